@@ -1,0 +1,176 @@
+/* rfm_b200.h -- C ABI of the B200-native FM / MF training and ranking-evaluation hot path.
+ *
+ * The reference (tatsuki1107/Relevance-FactorizationMachine) is pure Python and has no FFI:
+ * its boundary is the Python class API. Each entry point below names the reference
+ * interface (file:line under the reference root) it stands in for; the Python shim in
+ * relevance-factorizationmachine_b200/rfm_b200/ binds them with ctypes and re-creates the
+ * reference's classes on top.
+ *
+ * Conventions
+ *   - every function returns an int status (RFM_OK == 0); rfm_last_error() gives the text of
+ *     the last failure on the calling thread. Nothing here aborts the process.
+ *   - pointers are HOST pointers unless the name ends in _dev. Handles own device memory.
+ *   - all kernels are enqueued on the context's CUDA stream; calls that return host values
+ *     synchronise that stream, the others are asynchronous.
+ *   - there is no CPU fallback: without a CUDA device rfm_ctx_create fails with
+ *     RFM_ERR_NO_DEVICE.
+ */
+#ifndef RFM_B200_H_
+#define RFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFM_ABI_VERSION 1
+
+enum rfm_status {
+  RFM_OK = 0,
+  RFM_ERR_INVALID = 1,   /* bad argument (mirrors the reference's ValueError paths)      */
+  RFM_ERR_CUDA = 2,      /* a CUDA runtime call or kernel failed; see rfm_last_error()    */
+  RFM_ERR_NOMEM = 3,
+  RFM_ERR_NO_DEVICE = 4
+};
+
+/* arithmetic type of parameters and of every kernel that touches them. The reference is
+ * float64 throughout; RFM_F64 is the parity mode. */
+enum rfm_dtype { RFM_F32 = 0, RFM_F64 = 1 };
+
+typedef struct rfm_ctx rfm_ctx;
+typedef struct rfm_csr rfm_csr;
+typedef struct rfm_fm rfm_fm;
+typedef struct rfm_fm_trainer rfm_fm_trainer;
+typedef struct rfm_pairs rfm_pairs;
+typedef struct rfm_mf rfm_mf;
+typedef struct rfm_ranker rfm_ranker;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int rfm_abi_version(void);
+const char *rfm_last_error(void);
+int rfm_device_count(int *out);
+
+/* cuda_stream: a cudaStream_t (as void*) the caller owns, or NULL for the legacy default
+ * stream (which is what torch uses unless told otherwise). */
+int rfm_ctx_create(int device, void *cuda_stream, rfm_ctx **out);
+int rfm_ctx_destroy(rfm_ctx *ctx);
+int rfm_ctx_synchronize(rfm_ctx *ctx);
+/* number of kernels this library has launched through ctx (bench.py's gpu_launches). */
+int rfm_ctx_launch_count(rfm_ctx *ctx, int64_t *out);
+/* device-side timing on the context's stream (cudaEvent pair). */
+int rfm_ctx_timer_start(rfm_ctx *ctx);
+int rfm_ctx_timer_stop_ms(rfm_ctx *ctx, double *ms);
+
+/* page-locked host memory for the shim's staging buffers. */
+int rfm_host_alloc(size_t bytes, void **out);
+int rfm_host_free(void *p);
+
+/* ---- batch samplers ---------------------------------------------------------------------
+ * rfm_legacy_batch: sklearn.utils.resample(replace=False, n_samples=B, random_state=epoch) as
+ *   called at src/fm.py:72-79 and src/mf.py:88-95, i.e. RandomState(epoch).shuffle(arange(N))[:B]
+ *   (MT19937 + NumPy's legacy Fisher-Yates with masked rejection). Host code, bit-identical
+ *   to NumPy. scratch may be NULL or an int32[N] buffer to avoid the allocation.
+ * rfm_feistel_batch: this build's perf-mode sampler (not in the reference): first B images of
+ *   a keyed bijection of [0,N). Host statement of what the device kernel computes. */
+int rfm_legacy_batch(int64_t n_rows, int64_t batch, uint32_t epoch, int64_t *out_rows, int32_t *scratch);
+int rfm_feistel_batch(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epoch, int64_t *out_rows);
+
+/* ---- FM rows: scipy.sparse.csr_matrix + labels + pscores (the train/val dicts of
+ * src/fm.py:55-70; layout from utils/dataloader/coat/_preparer.py:154-170) --------------- */
+int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
+                   const void *indptr, int indptr_is_int64, const int32_t *indices,
+                   const double *data,
+                   const int64_t *labels,  /* may be NULL (predict-only rows)            */
+                   const double *pscores,  /* may be NULL                                */
+                   int dtype, rfm_csr **out);
+int rfm_csr_destroy(rfm_csr *rows);
+
+/* ---- FM model: w0, w, V (src/fm.py:31-53); parameter holders of utils/optimizer.py:10-64 */
+int rfm_fm_create(rfm_ctx *ctx, int64_t n_features, int32_t n_factors, int dtype, rfm_fm **out);
+int rfm_fm_destroy(rfm_fm *m);
+/* V is row-major (n_features, n_factors) float64, exactly the ndarray SGD.params holds. */
+int rfm_fm_set_params(rfm_fm *m, const double *w0, const double *w, const double *V);
+int rfm_fm_get_params(rfm_fm *m, double *w0, double *w, double *V);
+/* FactorizationMachines.predict, src/fm.py:114-133 (+ _sigmoid, src/base.py:63-66). */
+int rfm_fm_predict(rfm_fm *m, const rfm_csr *rows, double *out_scores);
+/* _cross_entropy_loss(labels, predict(rows), pscores), src/base.py:37-61. */
+int rfm_fm_logloss(rfm_fm *m, const rfm_csr *rows, double *out_loss);
+
+/* ---- FM training: one call == one reference "epoch" (one minibatch), src/fm.py:71-102 ----
+ * forward + IPS residual (fm.py:80), _update_w0/_update_w/_update_V (fm.py:135-187) as one
+ * simultaneous step with a deterministic segmented reduction per feature column, then the
+ * post-update batch loss (fm.py:90-96) and the full val loss (fm.py:98-102). Losses are
+ * kept on the device in slot `slot` and read back with rfm_fm_trainer_losses. */
+int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val /* may be NULL */,
+                          int64_t max_batch, int64_t max_slots, rfm_fm_trainer **out);
+int rfm_fm_trainer_destroy(rfm_fm_trainer *t);
+int rfm_fm_train_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch, double lr,
+                       int64_t slot);
+/* same step, batch drawn on the device by the Feistel sampler (perf mode). */
+int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t batch,
+                               double lr, int64_t slot);
+/* Data-parallel split of the same step: rank-local gradient of a batch
+ * slice into a dense buffer [sum_e | dw (n) | dV (n x kpad)], to be all-reduced by the
+ * caller, then applied identically on every rank. */
+int rfm_fm_grad_size(rfm_fm_trainer *t, int64_t *n_scalars);
+int rfm_fm_grad_ptr_dev(rfm_fm_trainer *t, void **grad_dev);
+int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch);
+int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr);
+/* post-update loss of a batch slice / of val rows [row_begin, row_end): SUM of the per-row
+ * terms (not divided) written to device slots so ranks can all-reduce them. */
+int rfm_fm_loss_sums_ptr_dev(rfm_fm_trainer *t, void **sums_dev /* double[2]: batch, val */);
+int rfm_fm_loss_sums(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch,
+                     int64_t val_begin, int64_t val_end);
+int rfm_fm_trainer_losses(rfm_fm_trainer *t, int64_t first_slot, int64_t n_slots,
+                          double *train_loss, double *val_loss);
+
+/* ---- MF rows and model (src/mf.py) ---------------------------------------------------- */
+int rfm_pairs_create(rfm_ctx *ctx, int64_t n_rows, const int64_t *user_item /* (n_rows,2) */,
+                     const int64_t *labels, const double *pscores, int dtype, rfm_pairs **out);
+int rfm_pairs_destroy(rfm_pairs *rows);
+int rfm_mf_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, int32_t n_factors, int dtype,
+                  rfm_mf **out);
+int rfm_mf_destroy(rfm_mf *m);
+int rfm_mf_set_params(rfm_mf *m, const double *P, const double *Q, const double *b_u,
+                      const double *b_i, double b);
+int rfm_mf_get_params(rfm_mf *m, double *P, double *Q, double *b_u, double *b_i);
+/* LogisticMatrixFactorization.predict, src/mf.py:136-170. */
+int rfm_mf_predict(rfm_mf *m, const rfm_pairs *rows, double *out_scores);
+int rfm_mf_logloss(rfm_mf *m, const rfm_pairs *rows, double *out_loss);
+/* one reference epoch, src/mf.py:97-124: strictly sequential per-sample SGD semantics
+ * (P then Q-with-new-P then b_u, b_i; residual taken first) executed as a wavefront
+ * schedule, then post-update batch loss and val loss. */
+int rfm_mf_train_epoch(rfm_mf *m, const rfm_pairs *train, const rfm_pairs *val /* may be NULL */,
+                       const int64_t *batch_rows, int64_t batch, double lr, double reg,
+                       double *train_loss, double *val_loss);
+
+/* ---- ranking evaluation (utils/evaluate.py, utils/metrics.py) ---------------------------
+ * rfm_ranker_create groups the rows of an interaction frame by user like
+ * interaction_df.groupby("user") (evaluate.py:129-156, 209-239).
+ * rfm_ranker_evaluate ranks every user's candidates by score (canonical order: score
+ * descending, later row first among exact ties -- argsort(kind="stable")[::-1]) and returns,
+ * per K[j]:  sums and valid-user counts for DCG (metrics.py:83-107), IPS-DCG (:53-80),
+ * ME (:110-127), Recall (:32-50), MAP (:9-29), and the per-item hit counts of the top-K[j]
+ * lists (CatalogCoverage :152-166 == non-zero count / n_items; Gini :130-149). Users whose
+ * labels sum to zero are skipped (evaluate.py:98-99, 201-202). */
+int rfm_ranker_create(rfm_ctx *ctx, int64_t n_rows, const int64_t *users, const int64_t *items,
+                      const double *labels, const double *pscores, int64_t n_items,
+                      rfm_ranker **out);
+int rfm_ranker_destroy(rfm_ranker *r);
+int rfm_ranker_num_users(rfm_ranker *r, int64_t *out);
+/* out_metrics: double[n_k][RFM_RANK_NCOLS]; out_item_hits: int32[n_k][n_items] or NULL;
+ * out_top_rows: int64[n_users][max K] row ids (-1 padded) or NULL. */
+#define RFM_RANK_NCOLS 12
+enum rfm_rank_col {
+  RFM_RANK_DCG_SUM = 0, RFM_RANK_IPSDCG_SUM = 1, RFM_RANK_ME_SUM = 2, RFM_RANK_ME_COUNT = 3,
+  RFM_RANK_RECALL_SUM = 4, RFM_RANK_MAP_SUM = 5, RFM_RANK_USERS = 6, RFM_RANK_COVERED = 7
+};
+int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, int32_t n_k,
+                        double *out_metrics, int32_t *out_item_hits, int64_t *out_top_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFM_B200_H_ */

@@ -1,0 +1,151 @@
+// common.cuh -- shared host/device helpers for librfm_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rfm_b200.h"
+
+namespace rfm {
+
+// ---- error plumbing -------------------------------------------------------------------------
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+
+#define RFM_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t err__ = (call);                                                            \
+    if (err__ != cudaSuccess)                                                              \
+      return ::rfm::fail(RFM_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                     \
+                         cudaGetErrorString(err__), __FILE__, __LINE__);                   \
+  } while (0)
+
+#define RFM_TRY(expr)                      \
+  do {                                     \
+    int rc__ = (expr);                     \
+    if (rc__ != RFM_OK) return rc__;       \
+  } while (0)
+
+#define RFM_REQUIRE(cond, ...)                                    \
+  do {                                                            \
+    if (!(cond)) return ::rfm::fail(RFM_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// ---- device memory --------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(RFM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T),
+                  cudaGetErrorString(e));
+    }
+    n = count;
+    return RFM_OK;
+  }
+  int ensure(size_t count) { return count <= n ? RFM_OK : alloc(count); }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf &) = delete;
+  PinnedBuf &operator=(const PinnedBuf &) = delete;
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  int ensure(size_t count) {
+    if (count <= n) return RFM_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&p), count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      n = 0;
+      return fail(RFM_ERR_NOMEM, "cudaMallocHost(%zu bytes) failed: %s", count * sizeof(T),
+                  cudaGetErrorString(e));
+    }
+    n = count;
+    return RFM_OK;
+  }
+};
+
+}  // namespace rfm
+
+// ---- the context ----------------------------------------------------------------------------
+struct rfm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // staging ring for small host->device / device->host transfers
+  rfm::PinnedBuf<unsigned char> stage;
+};
+
+namespace rfm {
+
+// every kernel launch goes through this so gpu_launches is an honest count
+#define RFM_LAUNCH(ctx, kernel, grid, block, smem, ...)                                     \
+  do {                                                                                      \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
+    (ctx)->launches++;                                                                      \
+    cudaError_t err__ = cudaGetLastError();                                                 \
+    if (err__ != cudaSuccess)                                                               \
+      return ::rfm::fail(RFM_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,          \
+                         cudaGetErrorString(err__), __FILE__, __LINE__);                    \
+  } while (0)
+
+inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// ---- device helpers -------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+template <typename T>
+struct Vec2;
+template <>
+struct Vec2<float> {
+  using type = float2;
+};
+template <>
+struct Vec2<double> {
+  using type = double2;
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+  // xor butterfly: every lane ends with the same, order-fixed total
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// host-callable device-wide utilities (scan.cu)
+int exclusive_scan_u32(rfm_ctx *ctx, const uint32_t *in_dev, uint32_t *out_dev, int64_t n,
+                       uint32_t *block_sums_dev /* >= ceil(n/4096)+1 */, uint32_t *total_dev);
+
+}  // namespace rfm

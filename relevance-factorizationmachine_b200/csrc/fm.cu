@@ -1,0 +1,1203 @@
+// fm.cu -- Factorization Machine hot path: predict, IPS log-loss, and the fused training epoch.
+//
+// Reference semantics (file:line under the reference root):
+//   predict      src/fm.py:114-133   y^ = w0 + X.w + 1/2 sum_f[(X.V)_f^2 - (X^2.V^2)_f], sigmoid
+//   residual     src/fm.py:80        e = y/ps - predict(batch)              (pre-update params)
+//   _update_w0   src/fm.py:135-143   w0 += lr * sum_t e_t
+//   _update_w    src/fm.py:145-154   w_j += lr * sum_t e_t x_tj
+//   _update_V    src/fm.py:156-187   v_j += lr * sum_t e_t (x_tj s_t - x_tj^2 v_j),  s_t = (X V)_t
+//   losses       src/base.py:37-61   on the batch after the update, and on the val rows
+//
+// Device layout (T = float or double, chosen at model creation):
+//   V    [n_features][kp]   row-major, kp = n_factors rounded up to a multiple of 64, zero padded;
+//        a warp reads one row as NCH = kp/64 coalesced 16- or 8-byte-per-lane loads
+//   w    [n_features],  w0 [1]
+//   rows CSR: row_ptr int64 [n_rows+1], col int32 [nnz], val T [nnz], yp T [n_rows] = y/ps
+//   S    [batch][kp]        s_t of the current batch (written by the row pass, read by the column pass)
+//   E    [batch]            e_t
+//
+// One epoch = row pass (forward, residual, emits (column, position, x) triples) -> stable radix
+// sort by column -> column pass (segmented reduction over 32-entry chunks of the sorted list,
+// in-place SGD for columns that live in one chunk, carry records otherwise) -> carry fix-up ->
+// loss pass on the batch -> loss pass on val. No floating-point atomics anywhere: every sum has a
+// fixed association, so results are bit-reproducible run to run.
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "sampler.cuh"
+
+using namespace rfm;
+
+// ---- handles ----------------------------------------------------------------------------------
+struct rfm_csr {
+  rfm_ctx *ctx = nullptr;
+  int dtype = RFM_F64;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0, max_row_len = 0;
+  bool has_targets = false;
+  DevBuf<int64_t> row_ptr;
+  DevBuf<int32_t> col;
+  DevBuf<unsigned char> val, yp;
+};
+
+struct rfm_fm {
+  rfm_ctx *ctx = nullptr;
+  int dtype = RFM_F64;
+  int64_t n = 0;
+  int k = 0, kp = 0, nch = 0;
+  DevBuf<unsigned char> w0, w, V;
+};
+
+namespace {
+
+constexpr int ROWS_THREADS = 256;
+constexpr int ROWS_WARPS = ROWS_THREADS / 32;
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int SHORT_RUN = 4;        // carry runs up to this many chunks are summed by one warp
+constexpr int LONG_RUN_THREADS = 1024;
+
+enum RowsMode { MODE_TRAIN = 0, MODE_LOSS = 1, MODE_PREDICT = 2 };
+
+size_t dsize(int dtype) { return dtype == RFM_F64 ? 8 : 4; }
+
+// ---- small conversion kernels -------------------------------------------------------------------
+template <typename T>
+__global__ void convert_f64_kernel(const double *__restrict__ in, T *__restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = static_cast<T>(in[i]);
+}
+
+__global__ void widen_i32_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+
+template <typename T>
+__global__ void targets_kernel(const int64_t *__restrict__ y, const double *__restrict__ ps,
+                               T *__restrict__ yp, int64_t n) {
+  // y / ps exactly as NumPy does it: int64 -> float64, one IEEE division (src/fm.py:80)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    yp[i] = static_cast<T>(static_cast<double>(y[i]) / ps[i]);
+}
+
+template <typename T>
+__global__ void pad_rows_kernel(const double *__restrict__ in, T *__restrict__ out, int64_t n, int k, int kp) {
+  const int64_t total = n * kp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kp;
+    const int f = static_cast<int>(i - r * kp);
+    out[i] = f < k ? static_cast<T>(in[r * k + f]) : T(0);
+  }
+}
+
+template <typename T>
+__global__ void unpad_rows_kernel(const T *__restrict__ in, double *__restrict__ out, int64_t n, int k, int kp) {
+  const int64_t total = n * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k;
+    const int f = static_cast<int>(i - r * k);
+    out[i] = static_cast<double>(in[r * kp + f]);
+  }
+}
+
+// ---- batch preparation --------------------------------------------------------------------------
+__global__ void feistel_sample_kernel(FeistelKey key, int64_t batch, int64_t *__restrict__ idx) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < batch; q += (int64_t)gridDim.x * blockDim.x)
+    idx[q] = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(q), key));
+}
+
+__global__ void row_len_kernel(const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ idx,
+                               int64_t batch, uint32_t *__restrict__ len) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < batch; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx[q];
+    len[q] = static_cast<uint32_t>(row_ptr[t + 1] - row_ptr[t]);
+  }
+}
+
+// ---- the row pass ---------------------------------------------------------------------------------
+template <typename T>
+struct RowsArgs {
+  const int64_t *row_ptr;
+  const int32_t *col;
+  const T *val;
+  const T *yp;
+  const int64_t *idx;     // batch row ids, or nullptr: rows [row0, row0 + n)
+  int64_t row0, n;
+  const T *w0, *w, *V;
+  int kp;
+  // MODE_TRAIN outputs
+  T *S, *E;
+  const uint32_t *bptr;   // exclusive scan of the batch's row lengths
+  uint32_t *keys, *pos;
+  T *xs;
+  // MODE_PREDICT output
+  double *out;
+  // MODE_TRAIN / MODE_LOSS: one partial sum per warp, in double
+  double *partials;
+};
+
+__device__ __forceinline__ double sigmoid_ref(double z) {
+  // src/base.py:63-66
+  z = fmin(fmax(z, -700.0), 700.0);
+  return 1.0 / (1.0 + exp(-z));
+}
+
+template <typename T, int NCH, int MODE>
+__global__ void __launch_bounds__(ROWS_THREADS)
+fm_rows_kernel(const RowsArgs<T> a) {
+  using V2 = typename Vec2<T>::type;
+  const int lane = lane_id();
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const T w0 = __ldg(a.w0);
+  double partial = 0.0;
+  for (int64_t q = gw; q < a.n; q += nw) {
+    const int64_t t = a.idx ? a.idx[q] : a.row0 + q;
+    const int64_t beg = a.row_ptr[t], end = a.row_ptr[t + 1];
+    V2 acc[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
+    T qsum = T(0), lin = T(0);
+    uint32_t out_base = 0;
+    if (MODE == MODE_TRAIN) out_base = a.bptr[q];
+    for (int64_t base = beg; base < end; base += 32) {
+      const int cnt = static_cast<int>(end - base < 32 ? end - base : 32);
+      int c = 0;
+      T x = T(0);
+      if (lane < cnt) {
+        c = a.col[base + lane];
+        x = a.val[base + lane];
+        lin += x * __ldg(a.w + c);
+        if (MODE == MODE_TRAIN) {
+          const uint32_t o = out_base + static_cast<uint32_t>(base - beg) + lane;
+          a.keys[o] = static_cast<uint32_t>(c);
+          a.pos[o] = static_cast<uint32_t>(q);
+          a.xs[o] = x;
+        }
+      }
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const int cj = __shfl_sync(FULL, c, i);
+        const T xj = __shfl_sync(FULL, x, i);
+        const V2 *vrow = reinterpret_cast<const V2 *>(a.V + (size_t)cj * a.kp) + lane;
+        const T xx = xj * xj;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const V2 v = __ldg(vrow + ch * 32);
+          acc[ch].x += xj * v.x;
+          acc[ch].y += xj * v.y;
+          qsum += xx * (v.x * v.x + v.y * v.y);
+        }
+      }
+    }
+    T ss = T(0);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) ss += acc[ch].x * acc[ch].x + acc[ch].y * acc[ch].y;
+    lin = warp_sum(lin);
+    ss = warp_sum(ss);
+    qsum = warp_sum(qsum);
+    const T z = (w0 + lin) + T(0.5) * (ss - qsum);
+    const double p = sigmoid_ref(static_cast<double>(z));
+    if (MODE == MODE_TRAIN) {
+      const double e = static_cast<double>(a.yp[t]) - p;
+      V2 *srow = reinterpret_cast<V2 *>(a.S + (size_t)q * a.kp) + lane;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) srow[ch * 32] = acc[ch];
+      if (lane == 0) a.E[q] = static_cast<T>(e);
+      partial += e;
+    } else if (MODE == MODE_LOSS) {
+      // src/base.py:56-59 term by term (1 - p formed by subtraction, eps inside both logs)
+      const double r = static_cast<double>(a.yp[t]);
+      partial -= r * log(p + 1e-8) + (1.0 - r) * log(1.0 - p + 1e-8);
+    } else {
+      if (lane == 0) a.out[q] = p;
+    }
+  }
+  if (MODE != MODE_PREDICT && lane == 0) a.partials[gw] = partial;
+}
+
+// Sum the per-warp partials in a fixed tree and finish the scalar it feeds.
+//   op 0: *dst_T += scale * sum   (w0 += lr * sum_e)      op 1: *dst_d = sum * scale  (loss mean)
+template <typename T>
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const double *__restrict__ partials, int n, int op, double scale, T *dst_T,
+                       double *dst_d) {
+  __shared__ double wsum[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) s += partials[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = wsum[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      if (op == 0) {
+        if (dst_T) *dst_T = static_cast<T>(static_cast<double>(*dst_T) + scale * v);
+        if (dst_d) *dst_d = v;
+      } else {
+        *dst_d = v * scale;
+      }
+    }
+  }
+}
+
+// ---- the column pass --------------------------------------------------------------------------------
+template <typename T>
+struct ColsArgs {
+  const uint32_t *keys, *pos;
+  const T *xs;
+  const uint32_t *count;
+  const T *E, *S;
+  T *V, *w;
+  int kp;
+  T lr;
+  T *carry_vec;      // [n_chunks][2][kp]   slot 0 = HEAD (segment began in an earlier chunk), 1 = TAIL
+  T *carry_ac;       // [n_chunks][2][2]    (a, c)
+  // data-parallel mode: write the gradient instead of applying it
+  T *grad_w, *grad_V;
+  // fix-up work list
+  uint32_t *long_runs;   // pairs (first chunk, last chunk)
+  uint32_t *n_long;
+  uint32_t long_cap;
+};
+
+template <typename T, int NCH, bool DP>
+__device__ __forceinline__ void finish_column(const ColsArgs<T> &a, uint32_t colj,
+                                              const typename Vec2<T>::type (&acc)[NCH], T sa, T sc, int lane) {
+  using V2 = typename Vec2<T>::type;
+  V2 *vrow = reinterpret_cast<V2 *>(a.V + (size_t)colj * a.kp) + lane;
+  if (DP) {
+    V2 *grow = reinterpret_cast<V2 *>(a.grad_V + (size_t)colj * a.kp) + lane;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const V2 v = vrow[ch * 32];
+      V2 g;
+      g.x = acc[ch].x - sc * v.x;
+      g.y = acc[ch].y - sc * v.y;
+      grow[ch * 32] = g;
+    }
+    if (lane == 0) a.grad_w[colj] = sa;
+  } else {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      V2 v = vrow[ch * 32];
+      v.x += a.lr * (acc[ch].x - sc * v.x);
+      v.y += a.lr * (acc[ch].y - sc * v.y);
+      vrow[ch * 32] = v;
+    }
+    if (lane == 0) a.w[colj] += a.lr * sa;
+  }
+}
+
+template <typename T, int NCH, bool DP>
+__global__ void __launch_bounds__(ROWS_THREADS)
+fm_cols_kernel(const ColsArgs<T> a) {
+  using V2 = typename Vec2<T>::type;
+  const int lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t M = *a.count;
+  const uint32_t n_chunks = (M + 31u) >> 5;
+  for (uint32_t chunk = gw; chunk < n_chunks; chunk += nw) {
+    const uint32_t base = chunk << 5;
+    const uint32_t e = base + lane;
+    const bool valid = e < M;
+    const uint32_t key = valid ? a.keys[e] : KEY_NONE;
+    const uint32_t p = valid ? a.pos[e] : 0u;
+    const T x = valid ? a.xs[e] : T(0);
+    const T ev = valid ? __ldg(a.E + p) : T(0);
+    const T xe = x * ev, xxe = x * x * ev;
+    const uint32_t prev_key = base > 0 ? a.keys[base - 1] : KEY_NONE;
+    const uint32_t next_key = base + 32u < M ? a.keys[base + 32u] : KEY_NONE;
+    const int n_valid = static_cast<int>(M - base < 32u ? M - base : 32u);
+
+    V2 acc[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
+    T sa = T(0), sc = T(0);
+    uint32_t cur = __shfl_sync(FULL, key, 0);
+    bool head = (cur == prev_key);
+#pragma unroll 4
+    for (int i = 0; i < n_valid; ++i) {
+      const uint32_t ki = __shfl_sync(FULL, key, i);
+      const uint32_t pi = __shfl_sync(FULL, p, i);
+      const T xei = __shfl_sync(FULL, xe, i);
+      const T xxei = __shfl_sync(FULL, xxe, i);
+      const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + lane;
+      V2 s[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) s[ch] = __ldg(srow + ch * 32);
+      if (ki != cur) {  // warp-uniform: the previous column's segment ended inside this chunk
+        if (head) {
+          V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)chunk * 2 + 0) * a.kp) + lane;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) cv[ch * 32] = acc[ch];
+          if (lane == 0) {
+            a.carry_ac[((size_t)chunk * 2 + 0) * 2 + 0] = sa;
+            a.carry_ac[((size_t)chunk * 2 + 0) * 2 + 1] = sc;
+          }
+        } else {
+          finish_column<T, NCH, DP>(a, cur, acc, sa, sc, lane);
+        }
+        head = false;
+        cur = ki;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
+        sa = sc = T(0);
+      }
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        acc[ch].x += xei * s[ch].x;
+        acc[ch].y += xei * s[ch].y;
+      }
+      sa += xei;
+      sc += xxei;
+    }
+    const bool tail = (cur == next_key);
+    if (head || tail) {
+      const int slot = head ? 0 : 1;
+      V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)chunk * 2 + slot) * a.kp) + lane;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) cv[ch * 32] = acc[ch];
+      if (lane == 0) {
+        a.carry_ac[((size_t)chunk * 2 + slot) * 2 + 0] = sa;
+        a.carry_ac[((size_t)chunk * 2 + slot) * 2 + 1] = sc;
+      }
+    } else {
+      finish_column<T, NCH, DP>(a, cur, acc, sa, sc, lane);
+    }
+  }
+}
+
+// Fix-up, part 1: the warp of the chunk where a multi-chunk column STARTS (its TAIL record) owns
+// that column. Short runs are summed here in chunk order; long ones are queued for part 2.
+template <typename T, int NCH, bool DP>
+__global__ void __launch_bounds__(ROWS_THREADS)
+fm_carry_kernel(const ColsArgs<T> a) {
+  using V2 = typename Vec2<T>::type;
+  const int lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t M = *a.count;
+  const uint32_t n_chunks = (M + 31u) >> 5;
+  for (uint32_t chunk = gw; chunk < n_chunks; chunk += nw) {
+    const uint32_t base = chunk << 5;
+    if (base + 32u >= M) continue;                      // last chunk cannot have a TAIL
+    const uint32_t klast = a.keys[base + 31u];
+    if (a.keys[base + 32u] != klast) continue;          // no segment runs on into the next chunk
+    if (a.keys[base] == klast && base > 0 && a.keys[base - 1] == klast) continue;  // a HEAD, not a TAIL
+    // upper bound of klast in [base+32, M): first index whose key differs
+    uint32_t lo = base + 32u, hi = M;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (a.keys[mid] == klast) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t last_chunk = (lo - 1u) >> 5;
+    if (last_chunk - chunk > SHORT_RUN) {
+      if (lane == 0) {
+        const uint32_t slot = atomicAdd(a.n_long, 1u);
+        if (slot < a.long_cap) {
+          a.long_runs[2 * slot] = chunk;
+          a.long_runs[2 * slot + 1] = last_chunk;
+        }
+      }
+      continue;
+    }
+    V2 acc[NCH];
+    const V2 *cv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)chunk * 2 + 1) * a.kp) + lane;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) acc[ch] = cv[ch * 32];
+    T sa = a.carry_ac[((size_t)chunk * 2 + 1) * 2 + 0], sc = a.carry_ac[((size_t)chunk * 2 + 1) * 2 + 1];
+    for (uint32_t c = chunk + 1; c <= last_chunk; ++c) {
+      const V2 *hv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)c * 2 + 0) * a.kp) + lane;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const V2 h = hv[ch * 32];
+        acc[ch].x += h.x;
+        acc[ch].y += h.y;
+      }
+      sa += a.carry_ac[((size_t)c * 2 + 0) * 2 + 0];
+      sc += a.carry_ac[((size_t)c * 2 + 0) * 2 + 1];
+    }
+    finish_column<T, NCH, DP>(a, klast, acc, sa, sc, lane);
+  }
+}
+
+// Fix-up, part 2: one CTA per long run. Warp w sums a contiguous block of the run's HEAD records
+// in chunk order; warp 0 then adds TAIL + block partials in warp order. The association depends
+// only on the run length and the CTA shape, never on timing.
+template <typename T, int NCH, bool DP>
+__global__ void __launch_bounds__(LONG_RUN_THREADS)
+fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
+  using V2 = typename Vec2<T>::type;
+  extern __shared__ unsigned char smem_raw[];
+  T *sm = reinterpret_cast<T *>(smem_raw);              // [n_warps_used][kp + 2]
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
+  uint32_t n_long = *a.n_long;
+  if (n_long > a.long_cap) n_long = a.long_cap;
+  const int stride = a.kp + 2;
+  for (uint32_t run = blockIdx.x; run < n_long; run += gridDim.x) {
+    const uint32_t first = a.long_runs[2 * run], last = a.long_runs[2 * run + 1];
+    const uint32_t n_heads = last - first;
+    const uint32_t per = (n_heads + n_warps_used - 1) / n_warps_used;
+    if (wid < n_warps_used) {
+      V2 acc[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
+      T sa = T(0), sc = T(0);
+      const uint32_t c0 = first + 1 + wid * per;
+      uint32_t c1 = c0 + per;
+      if (c1 > last + 1) c1 = last + 1;
+      for (uint32_t c = c0; c < c1; ++c) {
+        const V2 *hv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)c * 2 + 0) * a.kp) + lane;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const V2 h = hv[ch * 32];
+          acc[ch].x += h.x;
+          acc[ch].y += h.y;
+        }
+        sa += a.carry_ac[((size_t)c * 2 + 0) * 2 + 0];
+        sc += a.carry_ac[((size_t)c * 2 + 0) * 2 + 1];
+      }
+      T *mine = sm + (size_t)wid * stride;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        mine[ch * 64 + lane * 2] = acc[ch].x;
+        mine[ch * 64 + lane * 2 + 1] = acc[ch].y;
+      }
+      if (lane == 0) {
+        mine[a.kp] = sa;
+        mine[a.kp + 1] = sc;
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {
+      V2 acc[NCH];
+      const V2 *tv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)first * 2 + 1) * a.kp) + lane;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) acc[ch] = tv[ch * 32];
+      T sa = a.carry_ac[((size_t)first * 2 + 1) * 2 + 0], sc = a.carry_ac[((size_t)first * 2 + 1) * 2 + 1];
+      for (int w = 0; w < n_warps_used; ++w) {
+        const T *part = sm + (size_t)w * stride;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          acc[ch].x += part[ch * 64 + lane * 2];
+          acc[ch].y += part[ch * 64 + lane * 2 + 1];
+        }
+        sa += part[a.kp];
+        sc += part[a.kp + 1];
+      }
+      finish_column<T, NCH, DP>(a, a.keys[first * 32u + 31u], acc, sa, sc, lane);
+    }
+    __syncthreads();
+  }
+}
+
+// dense apply of an all-reduced gradient (data-parallel mode): identical on every rank
+template <typename T>
+__global__ void apply_grad_kernel(T *__restrict__ params, const T *__restrict__ grad, int64_t n, T lr) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    params[i] += lr * grad[i];
+}
+
+#define RFM_DISPATCH_NCH(nch, ...)                                 \
+  switch (nch) {                                                   \
+    case 1: { constexpr int NCH = 1; __VA_ARGS__; } break;         \
+    case 2: { constexpr int NCH = 2; __VA_ARGS__; } break;         \
+    case 3: { constexpr int NCH = 3; __VA_ARGS__; } break;         \
+    case 4: { constexpr int NCH = 4; __VA_ARGS__; } break;         \
+    case 5: { constexpr int NCH = 5; __VA_ARGS__; } break;         \
+    case 6: { constexpr int NCH = 6; __VA_ARGS__; } break;         \
+    case 7: { constexpr int NCH = 7; __VA_ARGS__; } break;         \
+    case 8: { constexpr int NCH = 8; __VA_ARGS__; } break;         \
+    default: return fail(RFM_ERR_INVALID, "n_factors too large (kp/64 = %d > 8)", nch); \
+  }
+
+int grid_for(rfm_ctx *ctx, int64_t work_items_per_block_unit, int blocks_per_sm) {
+  const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
+  int64_t g = work_items_per_block_unit < cap ? work_items_per_block_unit : cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+// copies a host array to the device through cudaMemcpyAsync on the context stream
+int upload(rfm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+  if (bytes == 0) return RFM_OK;
+  RFM_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return RFM_OK;
+}
+
+template <typename T>
+int launch_rows(rfm_ctx *ctx, int nch, int mode, const RowsArgs<T> &args, int grid) {
+  RFM_DISPATCH_NCH(nch, {
+    if (mode == MODE_TRAIN) {
+      auto kfn1 = fm_rows_kernel<T, NCH, MODE_TRAIN>;
+    RFM_LAUNCH(ctx, kfn1, grid, ROWS_THREADS, 0, args);
+    } else if (mode == MODE_LOSS) {
+      auto kfn2 = fm_rows_kernel<T, NCH, MODE_LOSS>;
+    RFM_LAUNCH(ctx, kfn2, grid, ROWS_THREADS, 0, args);
+    } else {
+      auto kfn3 = fm_rows_kernel<T, NCH, MODE_PREDICT>;
+    RFM_LAUNCH(ctx, kfn3, grid, ROWS_THREADS, 0, args);
+    }
+  });
+  return RFM_OK;
+}
+
+}  // namespace
+
+// ---- trainer handle -----------------------------------------------------------------------------
+struct rfm_fm_trainer {
+  rfm_fm *m = nullptr;
+  const rfm_csr *train = nullptr, *val = nullptr;
+  int64_t max_batch = 0, max_slots = 0, nnz_cap = 0;
+  int rows_grid = 0, n_row_warps = 0;
+  DevBuf<int64_t> idx;
+  DevBuf<uint32_t> row_len, bptr, scan_tmp, count, long_runs, n_long;
+  DevBuf<unsigned char> S, E, carry_vec, carry_ac, grad;
+  DevBuf<double> partials, losses, loss_sums;
+  RadixSorter<float> sort32;
+  RadixSorter<double> sort64;
+  // host staging ring for batch row ids
+  static constexpr int RING = 4;
+  PinnedBuf<int64_t> stage[RING];
+  cudaEvent_t stage_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+  bool stage_used[RING] = {false, false, false, false};
+  int ring_pos = 0;
+  uint32_t long_cap = 0;
+  int long_warps = 1;
+  size_t long_smem = 0;
+};
+
+namespace {
+
+template <typename T>
+RadixSorter<T> &sorter_of(rfm_fm_trainer *t);
+template <>
+RadixSorter<float> &sorter_of<float>(rfm_fm_trainer *t) { return t->sort32; }
+template <>
+RadixSorter<double> &sorter_of<double>(rfm_fm_trainer *t) { return t->sort64; }
+
+template <typename T>
+RowsArgs<T> rows_args(const rfm_fm *m, const rfm_csr *rows) {
+  RowsArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.row_ptr = rows->row_ptr.p;
+  a.col = rows->col.p;
+  a.val = reinterpret_cast<const T *>(rows->val.p);
+  a.yp = reinterpret_cast<const T *>(rows->yp.p);
+  a.w0 = reinterpret_cast<const T *>(m->w0.p);
+  a.w = reinterpret_cast<const T *>(m->w.p);
+  a.V = reinterpret_cast<const T *>(m->V.p);
+  a.kp = m->kp;
+  return a;
+}
+
+// loss pass over a batch (idx != null) or a row range, mean (scale = 1/count) or raw sum into *dst
+template <typename T>
+int loss_pass(rfm_fm_trainer *t, const rfm_csr *rows, const int64_t *idx_dev, int64_t row0, int64_t n,
+              double scale, double *dst_dev) {
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  if (n <= 0) {
+    RFM_CUDA(cudaMemsetAsync(dst_dev, 0, sizeof(double), ctx->stream));
+    return RFM_OK;
+  }
+  RowsArgs<T> a = rows_args<T>(m, rows);
+  a.idx = idx_dev;
+  a.row0 = row0;
+  a.n = n;
+  a.partials = t->partials.p;
+  const int grid = grid_for(ctx, ceil_div(n, ROWS_WARPS), t->rows_grid / ctx->sm_count);
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, a, grid));
+  RFM_LAUNCH(ctx, reduce_partials_kernel<T>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 1, scale,
+             (T *)nullptr, dst_dev);
+  return RFM_OK;
+}
+
+// forward + residual + triples + sort + column pass (+ fix-up). DP=false applies SGD in place.
+template <typename T, bool DP>
+int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  const rfm_csr *tr = t->train;
+  RadixSorter<T> &sorter = sorter_of<T>(t);
+  const int small_grid = grid_for(ctx, ceil_div(batch, 256), 4);
+  RFM_LAUNCH(ctx, row_len_kernel, small_grid, 256, 0, tr->row_ptr.p, t->idx.p, batch, t->row_len.p);
+  RFM_TRY(exclusive_scan_u32(ctx, t->row_len.p, t->bptr.p, batch, t->scan_tmp.p, t->count.p));
+
+  RowsArgs<T> a = rows_args<T>(m, tr);
+  a.idx = t->idx.p;
+  a.n = batch;
+  a.S = reinterpret_cast<T *>(t->S.p);
+  a.E = reinterpret_cast<T *>(t->E.p);
+  a.bptr = t->bptr.p;
+  a.keys = sorter.keys[0].p;
+  a.pos = sorter.pos[0].p;
+  a.xs = sorter.val[0].p;
+  a.partials = t->partials.p;
+  const int grid = grid_for(ctx, ceil_div(batch, ROWS_WARPS), t->rows_grid / ctx->sm_count);
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, a, grid));
+  int sorted = 0;
+  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted));
+
+  ColsArgs<T> c;
+  memset(&c, 0, sizeof(c));
+  c.keys = sorter.keys[sorted].p;
+  c.pos = sorter.pos[sorted].p;
+  c.xs = sorter.val[sorted].p;
+  c.count = t->count.p;
+  c.E = reinterpret_cast<const T *>(t->E.p);
+  c.S = reinterpret_cast<const T *>(t->S.p);
+  c.V = reinterpret_cast<T *>(m->V.p);
+  c.w = reinterpret_cast<T *>(m->w.p);
+  c.kp = m->kp;
+  c.lr = static_cast<T>(lr);
+  c.carry_vec = reinterpret_cast<T *>(t->carry_vec.p);
+  c.carry_ac = reinterpret_cast<T *>(t->carry_ac.p);
+  c.long_runs = t->long_runs.p;
+  c.n_long = t->n_long.p;
+  c.long_cap = t->long_cap;
+  if (DP) {
+    T *g = reinterpret_cast<T *>(t->grad.p);
+    c.grad_w = g + 1;
+    c.grad_V = g + 1 + m->n;
+    RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)(1 + m->n + m->n * m->kp) * sizeof(T), ctx->stream));
+    // sum_e goes to grad[0] as a plain sum (dst_d unused); w0 itself is updated in apply
+    RFM_LAUNCH(ctx, reduce_partials_kernel<double>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 0, 0.0,
+               (double *)nullptr, t->loss_sums.p + 2);
+  } else {
+    RFM_LAUNCH(ctx, reduce_partials_kernel<T>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 0, lr,
+               reinterpret_cast<T *>(m->w0.p), (double *)nullptr);
+  }
+  RFM_CUDA(cudaMemsetAsync(t->n_long.p, 0, sizeof(uint32_t), ctx->stream));
+  const int64_t chunk_cap = ceil_div(t->nnz_cap, 32);
+  const int cgrid = grid_for(ctx, ceil_div(chunk_cap, ROWS_WARPS), t->rows_grid / ctx->sm_count);
+  const int lgrid = t->long_cap < (uint32_t)ctx->sm_count * 2 ? (int)t->long_cap : ctx->sm_count * 2;
+  RFM_DISPATCH_NCH(m->nch, {
+    auto kfn4 = fm_cols_kernel<T, NCH, DP>;
+    RFM_LAUNCH(ctx, kfn4, cgrid, ROWS_THREADS, 0, c);
+    auto kfn5 = fm_carry_kernel<T, NCH, DP>;
+    RFM_LAUNCH(ctx, kfn5, cgrid, ROWS_THREADS, 0, c);
+    auto kfn6 = fm_long_runs_kernel<T, NCH, DP>;
+    RFM_LAUNCH(ctx, kfn6, lgrid < 1 ? 1 : lgrid, LONG_RUN_THREADS, t->long_smem, c,
+               t->long_warps);
+  });
+  return RFM_OK;
+}
+
+template <typename T>
+int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot) {
+  RFM_TRY((step_core<T, false>(t, batch, lr)));
+  RFM_TRY(loss_pass<T>(t, t->train, t->idx.p, 0, batch, 1.0 / (double)batch, t->losses.p + slot));
+  if (t->val)
+    RFM_TRY(loss_pass<T>(t, t->val, nullptr, 0, t->val->n_rows, 1.0 / (double)t->val->n_rows,
+                         t->losses.p + t->max_slots + slot));
+  return RFM_OK;
+}
+
+int stage_batch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
+  rfm_ctx *ctx = t->m->ctx;
+  const int r = t->ring_pos;
+  t->ring_pos = (r + 1) % rfm_fm_trainer::RING;
+  if (t->stage_used[r]) RFM_CUDA(cudaEventSynchronize(t->stage_ev[r]));
+  RFM_TRY(t->stage[r].ensure((size_t)batch));
+  memcpy(t->stage[r].p, batch_rows, (size_t)batch * sizeof(int64_t));
+  RFM_CUDA(cudaMemcpyAsync(t->idx.p, t->stage[r].p, (size_t)batch * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  RFM_CUDA(cudaEventRecord(t->stage_ev[r], ctx->stream));
+  t->stage_used[r] = true;
+  return RFM_OK;
+}
+
+int check_batch(const rfm_fm_trainer *t, int64_t batch, int64_t slot, const char *who) {
+  RFM_REQUIRE(t != nullptr, "%s: trainer is NULL", who);
+  RFM_REQUIRE(batch >= 1 && batch <= t->max_batch, "%s: batch %lld outside [1, %lld]", who, (long long)batch,
+              (long long)t->max_batch);
+  RFM_REQUIRE(batch <= t->train->n_rows,
+              "Cannot sample %lld out of arrays with dim %lld when replace is False", (long long)batch,
+              (long long)t->train->n_rows);
+  RFM_REQUIRE(slot >= 0 && slot < t->max_slots, "%s: slot %lld outside [0, %lld)", who, (long long)slot,
+              (long long)t->max_slots);
+  return RFM_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------
+extern "C" {
+
+int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *indptr, int indptr_is_int64,
+                   const int32_t *indices, const double *data, const int64_t *labels, const double *pscores,
+                   int dtype, rfm_csr **out) {
+  RFM_REQUIRE(ctx && out, "rfm_csr_create: NULL ctx/out");
+  *out = nullptr;
+  RFM_REQUIRE(n_rows >= 0 && n_cols >= 1, "rfm_csr_create: bad shape (%lld, %lld)", (long long)n_rows,
+              (long long)n_cols);
+  RFM_REQUIRE(n_cols < 0xFFFFFFFFLL, "rfm_csr_create: too many columns");
+  RFM_REQUIRE(indptr != nullptr, "rfm_csr_create: indptr is NULL");
+  RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "rfm_csr_create: bad dtype %d", dtype);
+  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "rfm_csr_create: labels and pscores go together");
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  const int64_t *p64 = static_cast<const int64_t *>(indptr);
+  const int32_t *p32 = static_cast<const int32_t *>(indptr);
+  auto ptr_at = [&](int64_t i) -> int64_t { return indptr_is_int64 ? p64[i] : (int64_t)p32[i]; };
+  const int64_t nnz = ptr_at(n_rows) - ptr_at(0);
+  RFM_REQUIRE(ptr_at(0) == 0 && nnz >= 0, "rfm_csr_create: indptr must start at 0 and be non-decreasing");
+  RFM_REQUIRE(nnz == 0 || (indices && data), "rfm_csr_create: indices/data are NULL");
+  int64_t max_len = 0;
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int64_t len = ptr_at(i + 1) - ptr_at(i);
+    RFM_REQUIRE(len >= 0, "rfm_csr_create: indptr decreases at row %lld", (long long)i);
+    if (len > max_len) max_len = len;
+  }
+  rfm_csr *r = new (std::nothrow) rfm_csr();
+  if (!r) return fail(RFM_ERR_NOMEM, "rfm_csr_create: out of host memory");
+  r->ctx = ctx;
+  r->dtype = dtype;
+  r->n_rows = n_rows;
+  r->n_cols = n_cols;
+  r->nnz = nnz;
+  r->max_row_len = max_len;
+  r->has_targets = labels != nullptr;
+  const size_t es = dsize(dtype);
+  int rc = RFM_OK;
+  auto body = [&]() -> int {
+    RFM_TRY(r->row_ptr.alloc(n_rows + 1));
+    RFM_TRY(r->col.alloc(nnz));
+    RFM_TRY(r->val.alloc((size_t)nnz * es));
+    RFM_TRY(r->yp.alloc((size_t)(n_rows ? n_rows : 1) * es));
+    DevBuf<unsigned char> tmp, tmp2;
+    if (indptr_is_int64) {
+      RFM_TRY(upload(ctx, r->row_ptr.p, indptr, (size_t)(n_rows + 1) * 8));
+    } else {
+      RFM_TRY(tmp.alloc((size_t)(n_rows + 1) * 4));
+      RFM_TRY(upload(ctx, tmp.p, indptr, (size_t)(n_rows + 1) * 4));
+      RFM_LAUNCH(ctx, widen_i32_kernel, grid_for(ctx, ceil_div(n_rows + 1, 256), 8), 256, 0,
+                 reinterpret_cast<const int32_t *>(tmp.p), r->row_ptr.p, n_rows + 1);
+    }
+    RFM_TRY(upload(ctx, r->col.p, indices, (size_t)nnz * 4));
+    if (dtype == RFM_F64) {
+      RFM_TRY(upload(ctx, r->val.p, data, (size_t)nnz * 8));
+    } else if (nnz > 0) {
+      RFM_TRY(tmp2.alloc((size_t)nnz * 8));
+      RFM_TRY(upload(ctx, tmp2.p, data, (size_t)nnz * 8));
+      RFM_LAUNCH(ctx, convert_f64_kernel<float>, grid_for(ctx, ceil_div(nnz, 256), 8), 256, 0,
+                 reinterpret_cast<const double *>(tmp2.p), reinterpret_cast<float *>(r->val.p), nnz);
+    }
+    DevBuf<int64_t> ytmp;
+    DevBuf<double> pstmp;
+    if (labels && n_rows > 0) {
+      RFM_TRY(ytmp.alloc(n_rows));
+      RFM_TRY(pstmp.alloc(n_rows));
+      RFM_TRY(upload(ctx, ytmp.p, labels, (size_t)n_rows * 8));
+      RFM_TRY(upload(ctx, pstmp.p, pscores, (size_t)n_rows * 8));
+      const int g = grid_for(ctx, ceil_div(n_rows, 256), 8);
+      if (dtype == RFM_F64) {
+        RFM_LAUNCH(ctx, targets_kernel<double>, g, 256, 0, ytmp.p, pstmp.p, reinterpret_cast<double *>(r->yp.p),
+                   n_rows);
+      } else {
+        RFM_LAUNCH(ctx, targets_kernel<float>, g, 256, 0, ytmp.p, pstmp.p, reinterpret_cast<float *>(r->yp.p),
+                   n_rows);
+      }
+    } else {
+      RFM_CUDA(cudaMemsetAsync(r->yp.p, 0, (size_t)(n_rows ? n_rows : 1) * es, ctx->stream));
+    }
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));  // temporaries are freed on return
+    return RFM_OK;
+  };
+  rc = body();
+  if (rc != RFM_OK) {
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return RFM_OK;
+}
+
+int rfm_csr_destroy(rfm_csr *rows) {
+  if (rows) {
+    cudaSetDevice(rows->ctx->device);
+    cudaStreamSynchronize(rows->ctx->stream);
+    delete rows;
+  }
+  return RFM_OK;
+}
+
+int rfm_fm_create(rfm_ctx *ctx, int64_t n_features, int32_t n_factors, int dtype, rfm_fm **out) {
+  RFM_REQUIRE(ctx && out, "rfm_fm_create: NULL ctx/out");
+  *out = nullptr;
+  RFM_REQUIRE(n_features >= 1 && n_factors >= 1, "rfm_fm_create: bad shape (%lld, %d)", (long long)n_features,
+              n_factors);
+  RFM_REQUIRE(n_factors <= 512, "rfm_fm_create: n_factors %d > 512 is not supported", n_factors);
+  RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "rfm_fm_create: bad dtype %d", dtype);
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  rfm_fm *m = new (std::nothrow) rfm_fm();
+  if (!m) return fail(RFM_ERR_NOMEM, "rfm_fm_create: out of host memory");
+  m->ctx = ctx;
+  m->dtype = dtype;
+  m->n = n_features;
+  m->k = n_factors;
+  m->nch = (n_factors + 63) / 64;
+  m->kp = m->nch * 64;
+  const size_t es = dsize(dtype);
+  int rc = m->w0.alloc(es);
+  if (rc == RFM_OK) rc = m->w.alloc((size_t)n_features * es);
+  if (rc == RFM_OK) rc = m->V.alloc((size_t)n_features * m->kp * es);
+  if (rc == RFM_OK) {
+    cudaMemsetAsync(m->w0.p, 0, es, ctx->stream);
+    cudaMemsetAsync(m->w.p, 0, (size_t)n_features * es, ctx->stream);
+    cudaMemsetAsync(m->V.p, 0, (size_t)n_features * m->kp * es, ctx->stream);
+  }
+  if (rc != RFM_OK) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return RFM_OK;
+}
+
+int rfm_fm_destroy(rfm_fm *m) {
+  if (m) {
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    delete m;
+  }
+  return RFM_OK;
+}
+
+int rfm_fm_set_params(rfm_fm *m, const double *w0, const double *w, const double *V) {
+  RFM_REQUIRE(m && w0 && w && V, "rfm_fm_set_params: NULL argument");
+  rfm_ctx *ctx = m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> tmp;
+  RFM_TRY(tmp.alloc((size_t)m->n * m->k + m->n + 1));
+  double *tV = tmp.p, *tw = tmp.p + (size_t)m->n * m->k, *tw0 = tw + m->n;
+  RFM_TRY(upload(ctx, tV, V, (size_t)m->n * m->k * 8));
+  RFM_TRY(upload(ctx, tw, w, (size_t)m->n * 8));
+  RFM_TRY(upload(ctx, tw0, w0, 8));
+  const int g = grid_for(ctx, ceil_div(m->n * m->kp, 256), 8);
+  if (m->dtype == RFM_F64) {
+    RFM_LAUNCH(ctx, pad_rows_kernel<double>, g, 256, 0, tV, reinterpret_cast<double *>(m->V.p), m->n, m->k, m->kp);
+    RFM_LAUNCH(ctx, convert_f64_kernel<double>, g, 256, 0, tw, reinterpret_cast<double *>(m->w.p), m->n);
+    RFM_LAUNCH(ctx, convert_f64_kernel<double>, 1, 32, 0, tw0, reinterpret_cast<double *>(m->w0.p), (int64_t)1);
+  } else {
+    RFM_LAUNCH(ctx, pad_rows_kernel<float>, g, 256, 0, tV, reinterpret_cast<float *>(m->V.p), m->n, m->k, m->kp);
+    RFM_LAUNCH(ctx, convert_f64_kernel<float>, g, 256, 0, tw, reinterpret_cast<float *>(m->w.p), m->n);
+    RFM_LAUNCH(ctx, convert_f64_kernel<float>, 1, 32, 0, tw0, reinterpret_cast<float *>(m->w0.p), (int64_t)1);
+  }
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RFM_OK;
+}
+
+}  // extern "C" (pause)
+namespace {
+template <typename T>
+__global__ void widen_to_f64_kernel(const T *__restrict__ in, double *__restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = static_cast<double>(in[i]);
+}
+}  // namespace
+extern "C" {
+
+int rfm_fm_get_params(rfm_fm *m, double *w0, double *w, double *V) {
+  RFM_REQUIRE(m && w0 && w && V, "rfm_fm_get_params: NULL argument");
+  rfm_ctx *ctx = m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> tmp;
+  RFM_TRY(tmp.alloc((size_t)m->n * m->k + m->n + 1));
+  double *tV = tmp.p, *tw = tmp.p + (size_t)m->n * m->k, *tw0 = tw + m->n;
+  const int g = grid_for(ctx, ceil_div(m->n * m->k, 256), 8);
+  if (m->dtype == RFM_F64) {
+    RFM_LAUNCH(ctx, unpad_rows_kernel<double>, g, 256, 0, reinterpret_cast<const double *>(m->V.p), tV, m->n, m->k,
+               m->kp);
+    RFM_LAUNCH(ctx, widen_to_f64_kernel<double>, g, 256, 0, reinterpret_cast<const double *>(m->w.p), tw, m->n);
+    RFM_LAUNCH(ctx, widen_to_f64_kernel<double>, 1, 32, 0, reinterpret_cast<const double *>(m->w0.p), tw0,
+               (int64_t)1);
+  } else {
+    RFM_LAUNCH(ctx, unpad_rows_kernel<float>, g, 256, 0, reinterpret_cast<const float *>(m->V.p), tV, m->n, m->k,
+               m->kp);
+    RFM_LAUNCH(ctx, widen_to_f64_kernel<float>, g, 256, 0, reinterpret_cast<const float *>(m->w.p), tw, m->n);
+    RFM_LAUNCH(ctx, widen_to_f64_kernel<float>, 1, 32, 0, reinterpret_cast<const float *>(m->w0.p), tw0, (int64_t)1);
+  }
+  RFM_CUDA(cudaMemcpyAsync(V, tV, (size_t)m->n * m->k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(w, tw, (size_t)m->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(w0, tw0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RFM_OK;
+}
+
+}  // extern "C" (pause)
+namespace {
+int check_rows(const rfm_fm *m, const rfm_csr *rows, const char *who) {
+  RFM_REQUIRE(m && rows, "%s: NULL argument", who);
+  RFM_REQUIRE(rows->ctx == m->ctx, "%s: rows and model live in different contexts", who);
+  RFM_REQUIRE(rows->dtype == m->dtype, "%s: rows dtype %d != model dtype %d", who, rows->dtype, m->dtype);
+  RFM_REQUIRE(rows->n_cols == m->n, "%s: rows have %lld columns, model has %lld features", who,
+              (long long)rows->n_cols, (long long)m->n);
+  return RFM_OK;
+}
+
+template <typename T>
+int predict_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
+  rfm_ctx *ctx = m->ctx;
+  if (rows->n_rows == 0) return RFM_OK;
+  DevBuf<double> out;
+  RFM_TRY(out.alloc(rows->n_rows));
+  RowsArgs<T> a = rows_args<T>(m, rows);
+  a.n = rows->n_rows;
+  a.out = out.p;
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_PREDICT, a, grid_for(ctx, ceil_div(rows->n_rows, ROWS_WARPS), 6)));
+  RFM_CUDA(cudaMemcpyAsync(out_host, out.p, (size_t)rows->n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RFM_OK;
+}
+
+template <typename T>
+int logloss_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
+  rfm_ctx *ctx = m->ctx;
+  const int grid = grid_for(ctx, ceil_div(rows->n_rows, ROWS_WARPS), 6);
+  DevBuf<double> partials, res;
+  RFM_TRY(partials.alloc((size_t)grid * ROWS_WARPS));
+  RFM_TRY(res.alloc(1));
+  RowsArgs<T> a = rows_args<T>(m, rows);
+  a.n = rows->n_rows;
+  a.partials = partials.p;
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, a, grid));
+  RFM_LAUNCH(ctx, reduce_partials_kernel<T>, 1, 1024, 0, partials.p, grid * ROWS_WARPS, 1,
+             1.0 / (double)rows->n_rows, (T *)nullptr, res.p);
+  RFM_CUDA(cudaMemcpyAsync(out_host, res.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RFM_OK;
+}
+}  // namespace
+extern "C" {
+
+int rfm_fm_predict(rfm_fm *m, const rfm_csr *rows, double *out_scores) {
+  RFM_TRY(check_rows(m, rows, "rfm_fm_predict"));
+  RFM_REQUIRE(out_scores || rows->n_rows == 0, "rfm_fm_predict: out_scores is NULL");
+  RFM_CUDA(cudaSetDevice(m->ctx->device));
+  return m->dtype == RFM_F64 ? predict_impl<double>(m, rows, out_scores) : predict_impl<float>(m, rows, out_scores);
+}
+
+int rfm_fm_logloss(rfm_fm *m, const rfm_csr *rows, double *out_loss) {
+  RFM_TRY(check_rows(m, rows, "rfm_fm_logloss"));
+  RFM_REQUIRE(out_loss, "rfm_fm_logloss: out_loss is NULL");
+  RFM_REQUIRE(rows->has_targets, "rfm_fm_logloss: rows were created without labels/pscores");
+  RFM_REQUIRE(rows->n_rows > 0, "rfm_fm_logloss: no rows");
+  RFM_CUDA(cudaSetDevice(m->ctx->device));
+  return m->dtype == RFM_F64 ? logloss_impl<double>(m, rows, out_loss) : logloss_impl<float>(m, rows, out_loss);
+}
+
+int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, int64_t max_batch,
+                          int64_t max_slots, rfm_fm_trainer **out) {
+  RFM_REQUIRE(out, "rfm_fm_trainer_create: out is NULL");
+  *out = nullptr;
+  RFM_TRY(check_rows(m, train, "rfm_fm_trainer_create(train)"));
+  if (val) RFM_TRY(check_rows(m, val, "rfm_fm_trainer_create(val)"));
+  RFM_REQUIRE(train->has_targets && (!val || val->has_targets), "rfm_fm_trainer_create: rows need labels/pscores");
+  RFM_REQUIRE(max_batch >= 1 && max_slots >= 1, "rfm_fm_trainer_create: bad max_batch/max_slots");
+  RFM_REQUIRE(max_batch <= 0x7fffffffLL, "rfm_fm_trainer_create: max_batch too large");
+  rfm_ctx *ctx = m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  if (max_batch > train->n_rows) max_batch = train->n_rows > 0 ? train->n_rows : 1;
+  int64_t nnz_cap = max_batch * train->max_row_len;
+  if (nnz_cap > train->nnz) nnz_cap = train->nnz;
+  if (nnz_cap < 1) nnz_cap = 1;
+  RFM_REQUIRE(nnz_cap < 0xFFFFFFF0LL, "rfm_fm_trainer_create: batch holds too many non-zeros (%lld)",
+              (long long)nnz_cap);
+  rfm_fm_trainer *t = new (std::nothrow) rfm_fm_trainer();
+  if (!t) return fail(RFM_ERR_NOMEM, "rfm_fm_trainer_create: out of host memory");
+  t->m = m;
+  t->train = train;
+  t->val = val;
+  t->max_batch = max_batch;
+  t->max_slots = max_slots;
+  t->nnz_cap = nnz_cap;
+  const size_t es = dsize(m->dtype);
+  auto body = [&]() -> int {
+    // resident CTAs per SM for the row/column kernels: 6 x 256 threads keeps 48 warps in flight
+    t->rows_grid = ctx->sm_count * 6;
+    t->n_row_warps = t->rows_grid * ROWS_WARPS;
+    RFM_TRY(t->idx.alloc(max_batch));
+    RFM_TRY(t->row_len.alloc(max_batch));
+    RFM_TRY(t->bptr.alloc(max_batch));
+    RFM_TRY(t->scan_tmp.alloc(ceil_div(max_batch, 4096) + 2));
+    RFM_TRY(t->count.alloc(1));
+    RFM_TRY(t->n_long.alloc(1));
+    RFM_TRY(t->S.alloc((size_t)max_batch * m->kp * es));
+    RFM_TRY(t->E.alloc((size_t)max_batch * es));
+    const int64_t chunk_cap = ceil_div(nnz_cap, 32);
+    RFM_TRY(t->carry_vec.alloc((size_t)chunk_cap * 2 * m->kp * es));
+    RFM_TRY(t->carry_ac.alloc((size_t)chunk_cap * 4 * es));
+    t->long_cap = (uint32_t)(chunk_cap / (SHORT_RUN + 1) + 1);
+    RFM_TRY(t->long_runs.alloc((size_t)t->long_cap * 2));
+    RFM_TRY(t->partials.alloc((size_t)t->n_row_warps));
+    RFM_TRY(t->losses.alloc((size_t)max_slots * 2));
+    RFM_TRY(t->loss_sums.alloc(4));
+    RFM_CUDA(cudaMemsetAsync(t->losses.p, 0, (size_t)max_slots * 2 * sizeof(double), ctx->stream));
+    if (m->dtype == RFM_F64) RFM_TRY(t->sort64.init(nnz_cap, m->n)); else RFM_TRY(t->sort32.init(nnz_cap, m->n));
+    const size_t per_warp = (size_t)(m->kp + 2) * es;
+    int lw = (int)(40 * 1024 / per_warp);
+    if (lw > 32) lw = 32;
+    if (lw < 1) lw = 1;
+    t->long_warps = lw;
+    t->long_smem = per_warp * lw;
+    for (int r = 0; r < rfm_fm_trainer::RING; ++r) RFM_CUDA(cudaEventCreateWithFlags(&t->stage_ev[r], cudaEventDisableTiming));
+    return RFM_OK;
+  };
+  const int rc = body();
+  if (rc != RFM_OK) {
+    rfm_fm_trainer_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return RFM_OK;
+}
+
+int rfm_fm_trainer_destroy(rfm_fm_trainer *t) {
+  if (t) {
+    cudaSetDevice(t->m->ctx->device);
+    cudaStreamSynchronize(t->m->ctx->stream);
+    for (int r = 0; r < rfm_fm_trainer::RING; ++r)
+      if (t->stage_ev[r]) cudaEventDestroy(t->stage_ev[r]);
+    delete t;
+  }
+  return RFM_OK;
+}
+
+int rfm_fm_train_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch, double lr, int64_t slot) {
+  RFM_TRY(check_batch(t, batch, slot, "rfm_fm_train_epoch"));
+  RFM_REQUIRE(batch_rows, "rfm_fm_train_epoch: batch_rows is NULL");
+  RFM_CUDA(cudaSetDevice(t->m->ctx->device));
+  for (int64_t q = 0; q < batch; ++q)
+    RFM_REQUIRE(batch_rows[q] >= 0 && batch_rows[q] < t->train->n_rows, "rfm_fm_train_epoch: row id %lld out of range",
+                (long long)batch_rows[q]);
+  RFM_TRY(stage_batch(t, batch_rows, batch));
+  return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot) : epoch_impl<float>(t, batch, lr, slot);
+}
+
+int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t batch, double lr,
+                               int64_t slot) {
+  RFM_TRY(check_batch(t, batch, slot, "rfm_fm_train_epoch_sampled"));
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_REQUIRE(t->train->n_rows <= (1LL << 32), "rfm_fm_train_epoch_sampled: at most 2^32 rows");
+  const FeistelKey key = make_feistel_key((uint64_t)t->train->n_rows, seed, epoch);
+  RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, key, batch, t->idx.p);
+  return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot) : epoch_impl<float>(t, batch, lr, slot);
+}
+
+int rfm_fm_grad_size(rfm_fm_trainer *t, int64_t *n_scalars) {
+  RFM_REQUIRE(t && n_scalars, "rfm_fm_grad_size: NULL argument");
+  *n_scalars = 1 + t->m->n + t->m->n * t->m->kp;
+  return RFM_OK;
+}
+
+int rfm_fm_grad_ptr_dev(rfm_fm_trainer *t, void **grad_dev) {
+  RFM_REQUIRE(t && grad_dev, "rfm_fm_grad_ptr_dev: NULL argument");
+  RFM_CUDA(cudaSetDevice(t->m->ctx->device));
+  if (!t->grad.p) {
+    int64_t n = 0;
+    rfm_fm_grad_size(t, &n);
+    RFM_TRY(t->grad.alloc((size_t)n * dsize(t->m->dtype)));
+  }
+  *grad_dev = t->grad.p;
+  return RFM_OK;
+}
+
+}  // extern "C" (pause)
+namespace {
+template <typename T>
+__global__ void store_sum_e_kernel(const double *__restrict__ src, T *__restrict__ grad0) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *grad0 = static_cast<T>(*src);
+}
+}  // namespace
+extern "C" {
+
+int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
+  RFM_TRY(check_batch(t, batch, 0, "rfm_fm_grad_epoch"));
+  RFM_REQUIRE(batch_rows, "rfm_fm_grad_epoch: batch_rows is NULL");
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  void *g = nullptr;
+  RFM_TRY(rfm_fm_grad_ptr_dev(t, &g));
+  RFM_TRY(stage_batch(t, batch_rows, batch));
+  if (t->m->dtype == RFM_F64) {
+    RFM_TRY((step_core<double, true>(t, batch, 0.0)));
+    RFM_LAUNCH(ctx, store_sum_e_kernel<double>, 1, 32, 0, t->loss_sums.p + 2, reinterpret_cast<double *>(g));
+  } else {
+    RFM_TRY((step_core<float, true>(t, batch, 0.0)));
+    RFM_LAUNCH(ctx, store_sum_e_kernel<float>, 1, 32, 0, t->loss_sums.p + 2, reinterpret_cast<float *>(g));
+  }
+  return RFM_OK;
+}
+
+int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
+  RFM_REQUIRE(t && t->grad.p, "rfm_fm_apply_grad: no gradient buffer (call rfm_fm_grad_epoch first)");
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  const int64_t nV = m->n * m->kp;
+  const int g = grid_for(ctx, ceil_div(nV, 256), 8);
+  if (m->dtype == RFM_F64) {
+    double *gr = reinterpret_cast<double *>(t->grad.p);
+    RFM_LAUNCH(ctx, apply_grad_kernel<double>, 1, 32, 0, reinterpret_cast<double *>(m->w0.p), gr, (int64_t)1, lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->w.p), gr + 1, m->n, lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->V.p), gr + 1 + m->n, nV, lr);
+  } else {
+    float *gr = reinterpret_cast<float *>(t->grad.p);
+    RFM_LAUNCH(ctx, apply_grad_kernel<float>, 1, 32, 0, reinterpret_cast<float *>(m->w0.p), gr, (int64_t)1, (float)lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->w.p), gr + 1, m->n, (float)lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->V.p), gr + 1 + m->n, nV,
+               (float)lr);
+  }
+  return RFM_OK;
+}
+
+int rfm_fm_loss_sums_ptr_dev(rfm_fm_trainer *t, void **sums_dev) {
+  RFM_REQUIRE(t && sums_dev, "rfm_fm_loss_sums_ptr_dev: NULL argument");
+  *sums_dev = t->loss_sums.p;
+  return RFM_OK;
+}
+
+int rfm_fm_loss_sums(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch, int64_t val_begin,
+                     int64_t val_end) {
+  RFM_REQUIRE(t, "rfm_fm_loss_sums: trainer is NULL");
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_REQUIRE(batch >= 0 && batch <= t->max_batch, "rfm_fm_loss_sums: bad batch");
+  const int64_t nv = t->val ? t->val->n_rows : 0;
+  RFM_REQUIRE(val_begin >= 0 && val_begin <= val_end && val_end <= nv, "rfm_fm_loss_sums: bad val range");
+  if (batch > 0) {
+    RFM_REQUIRE(batch_rows, "rfm_fm_loss_sums: batch_rows is NULL");
+    RFM_TRY(stage_batch(t, batch_rows, batch));
+  }
+  if (t->m->dtype == RFM_F64) {
+    RFM_TRY(loss_pass<double>(t, t->train, t->idx.p, 0, batch, 1.0, t->loss_sums.p));
+    RFM_TRY(loss_pass<double>(t, t->val ? t->val : t->train, nullptr, val_begin, val_end - val_begin, 1.0,
+                              t->loss_sums.p + 1));
+  } else {
+    RFM_TRY(loss_pass<float>(t, t->train, t->idx.p, 0, batch, 1.0, t->loss_sums.p));
+    RFM_TRY(loss_pass<float>(t, t->val ? t->val : t->train, nullptr, val_begin, val_end - val_begin, 1.0,
+                             t->loss_sums.p + 1));
+  }
+  return RFM_OK;
+}
+
+int rfm_fm_trainer_losses(rfm_fm_trainer *t, int64_t first_slot, int64_t n_slots, double *train_loss,
+                          double *val_loss) {
+  RFM_REQUIRE(t, "rfm_fm_trainer_losses: trainer is NULL");
+  RFM_REQUIRE(first_slot >= 0 && n_slots >= 0 && first_slot + n_slots <= t->max_slots,
+              "rfm_fm_trainer_losses: slot range out of bounds");
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  if (train_loss)
+    RFM_CUDA(cudaMemcpyAsync(train_loss, t->losses.p + first_slot, (size_t)n_slots * 8, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  if (val_loss)
+    RFM_CUDA(cudaMemcpyAsync(val_loss, t->losses.p + t->max_slots + first_slot, (size_t)n_slots * 8,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RFM_OK;
+}
+
+}  // extern "C"

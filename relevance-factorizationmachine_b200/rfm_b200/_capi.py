@@ -1,0 +1,223 @@
+"""ctypes binding of ``librfm_b200.so`` (C ABI declared in ``include/rfm_b200.h``).
+
+There is deliberately no fallback: if the library is missing or no B200 is visible, every
+compute entry point raises ``RuntimeError`` naming what is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librfm_b200.so")
+
+RFM_F32, RFM_F64 = 0, 1
+RANK_NCOLS = 12
+RANK_COLS = dict(DCG_SUM=0, IPSDCG_SUM=1, ME_SUM=2, ME_COUNT=3, RECALL_SUM=4, MAP_SUM=5, USERS=6, COVERED=7)
+
+_lib = None
+
+_P = c_void_p
+_SIGNATURES = {
+    "rfm_abi_version": ([], c_int),
+    "rfm_last_error": ([], c_char_p),
+    "rfm_device_count": ([POINTER(c_int)], c_int),
+    "rfm_ctx_create": ([c_int, _P, POINTER(_P)], c_int),
+    "rfm_ctx_destroy": ([_P], c_int),
+    "rfm_ctx_synchronize": ([_P], c_int),
+    "rfm_ctx_launch_count": ([_P, POINTER(c_int64)], c_int),
+    "rfm_ctx_timer_start": ([_P], c_int),
+    "rfm_ctx_timer_stop_ms": ([_P, POINTER(c_double)], c_int),
+    "rfm_host_alloc": ([c_size_t, POINTER(_P)], c_int),
+    "rfm_host_free": ([_P], c_int),
+    "rfm_legacy_batch": ([c_int64, c_int64, c_uint32, _P, _P], c_int),
+    "rfm_feistel_batch": ([c_int64, c_int64, c_uint32, c_uint32, _P], c_int),
+    "rfm_csr_create": ([_P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P, c_int, POINTER(_P)], c_int),
+    "rfm_csr_destroy": ([_P], c_int),
+    "rfm_fm_create": ([_P, c_int64, c_int32, c_int, POINTER(_P)], c_int),
+    "rfm_fm_destroy": ([_P], c_int),
+    "rfm_fm_set_params": ([_P, _P, _P, _P], c_int),
+    "rfm_fm_get_params": ([_P, _P, _P, _P], c_int),
+    "rfm_fm_predict": ([_P, _P, _P], c_int),
+    "rfm_fm_logloss": ([_P, _P, POINTER(c_double)], c_int),
+    "rfm_fm_trainer_create": ([_P, _P, _P, c_int64, c_int64, POINTER(_P)], c_int),
+    "rfm_fm_trainer_destroy": ([_P], c_int),
+    "rfm_fm_train_epoch": ([_P, _P, c_int64, c_double, c_int64], c_int),
+    "rfm_fm_train_epoch_sampled": ([_P, c_uint32, c_uint32, c_int64, c_double, c_int64], c_int),
+    "rfm_fm_grad_size": ([_P, POINTER(c_int64)], c_int),
+    "rfm_fm_grad_ptr_dev": ([_P, POINTER(_P)], c_int),
+    "rfm_fm_grad_epoch": ([_P, _P, c_int64], c_int),
+    "rfm_fm_apply_grad": ([_P, c_double], c_int),
+    "rfm_fm_loss_sums_ptr_dev": ([_P, POINTER(_P)], c_int),
+    "rfm_fm_loss_sums": ([_P, _P, c_int64, c_int64, c_int64], c_int),
+    "rfm_fm_trainer_losses": ([_P, c_int64, c_int64, _P, _P], c_int),
+    "rfm_pairs_create": ([_P, c_int64, _P, _P, _P, c_int, POINTER(_P)], c_int),
+    "rfm_pairs_destroy": ([_P], c_int),
+    "rfm_mf_create": ([_P, c_int64, c_int64, c_int32, c_int, POINTER(_P)], c_int),
+    "rfm_mf_destroy": ([_P], c_int),
+    "rfm_mf_set_params": ([_P, _P, _P, _P, _P, c_double], c_int),
+    "rfm_mf_get_params": ([_P, _P, _P, _P, _P], c_int),
+    "rfm_mf_predict": ([_P, _P, _P], c_int),
+    "rfm_mf_logloss": ([_P, _P, POINTER(c_double)], c_int),
+    "rfm_mf_train_epoch": ([_P, _P, _P, _P, c_int64, c_double, c_double, POINTER(c_double), POINTER(c_double)],
+                           c_int),
+    "rfm_ranker_create": ([_P, c_int64, _P, _P, _P, _P, c_int64, POINTER(_P)], c_int),
+    "rfm_ranker_destroy": ([_P], c_int),
+    "rfm_ranker_num_users": ([_P, POINTER(c_int64)], c_int),
+    "rfm_ranker_evaluate": ([_P, _P, _P, c_int32, _P, _P, _P], c_int),
+}
+
+# every symbol include/rfm_b200.h declares (tests check the library exports all of them)
+DECLARED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class RfmError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once; raise loudly when it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "rfm_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = lib().rfm_last_error().decode("utf-8", "replace")
+        if status == 1:
+            raise ValueError(msg)
+        raise RfmError("rfm_b200 (status %d): %s" % (status, msg))
+
+
+def ptr(a):
+    """Raw pointer of a C-contiguous ndarray (or None)."""
+    if a is None:
+        return None
+    assert a.flags.c_contiguous
+    return a.ctypes.data_as(c_void_p)
+
+
+def as_array(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def dtype_code(name) -> int:
+    name = np.dtype(name).name if not isinstance(name, str) else name
+    if name in ("float64", "f64", "double"):
+        return RFM_F64
+    if name in ("float32", "f32", "float"):
+        return RFM_F32
+    raise ValueError("dtype must be 'float64' or 'float32', got %r" % (name,))
+
+
+class Context:
+    """One device + one stream. Shared by every handle of a model."""
+
+    _default = {}
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self.handle = c_void_p()
+        n = c_int()
+        check(lib().rfm_device_count(byref(n)))
+        if n.value == 0:
+            raise RuntimeError("rfm_b200: no CUDA device is visible and there is no CPU fallback")
+        check(lib().rfm_ctx_create(device, c_void_p(stream) if stream else None, byref(self.handle)))
+        self.device = device
+
+    @classmethod
+    def default(cls, device: int = 0) -> "Context":
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def synchronize(self):
+        check(lib().rfm_ctx_synchronize(self.handle))
+
+    def launch_count(self) -> int:
+        out = c_int64()
+        check(lib().rfm_ctx_launch_count(self.handle, byref(out)))
+        return out.value
+
+    def timer_start(self):
+        check(lib().rfm_ctx_timer_start(self.handle))
+
+    def timer_stop_ms(self) -> float:
+        out = c_double()
+        check(lib().rfm_ctx_timer_stop_ms(self.handle, byref(out)))
+        return out.value
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self.handle = c_void_p()
+        self._keep = []
+
+    def close(self):
+        if self.handle and _lib is not None:
+            getattr(_lib, self._destroy)(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CsrRows(_Handle):
+    """Device copy of a scipy CSR matrix (+ labels / pscores)."""
+
+    _destroy = "rfm_csr_destroy"
+
+    def __init__(self, ctx: Context, X, labels=None, pscores=None, dtype="float64"):
+        super().__init__()
+        X = X.tocsr()
+        if not X.has_canonical_format:
+            X = X.copy()
+            X.sum_duplicates()
+        self.ctx, self.shape, self.dtype = ctx, X.shape, dtype
+        indptr = np.ascontiguousarray(X.indptr)
+        is64 = indptr.dtype == np.int64
+        if not is64:
+            indptr = as_array(indptr, np.int32)
+        indices = as_array(X.indices, np.int32)
+        data = as_array(X.data, np.float64)
+        if indices.size and (indices.min() < 0 or indices.max() >= X.shape[1]):
+            raise ValueError("CSR column index out of range")
+        y = None if labels is None else as_array(labels, np.int64)
+        ps = None if pscores is None else as_array(pscores, np.float64)
+        if y is not None and (y.shape[0] != X.shape[0] or ps is None or ps.shape[0] != X.shape[0]):
+            raise ValueError("labels/pscores must have one entry per row")
+        check(lib().rfm_csr_create(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
+                                   ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
+        self.n_rows = X.shape[0]
+        self.h2d_bytes = indptr.nbytes + indices.nbytes + data.nbytes + (y.nbytes + ps.nbytes if y is not None else 0)
+
+
+def legacy_batch(n_rows: int, batch: int, epoch: int, scratch=None) -> np.ndarray:
+    """``resample(replace=False, n_samples=batch, random_state=epoch)`` row ids (host, exact)."""
+    out = np.empty(batch, dtype=np.int64)
+    check(lib().rfm_legacy_batch(n_rows, batch, epoch & 0xFFFFFFFF, ptr(out), ptr(scratch)))
+    return out
+
+
+def feistel_batch(n_rows: int, batch: int, epoch: int, seed: int = 0) -> np.ndarray:
+    out = np.empty(batch, dtype=np.int64)
+    check(lib().rfm_feistel_batch(n_rows, batch, seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, ptr(out)))
+    return out

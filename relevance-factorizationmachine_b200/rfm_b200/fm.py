@@ -1,0 +1,189 @@
+"""``FactorizationMachines`` -- drop-in for the reference class (``src/fm.py:16-187``).
+
+Same dataclass fields in the same order (``estimator, n_epochs, n_factors, lr, batch_size,
+seed, n_features, alpha=2.0, evaluator=None``), same ``fit(train, val) -> (train_loss,
+val_loss)``, ``predict(X)``, parameter holders ``w0 / w / V`` and ``val_metrics``. Trailing
+optional fields select the device-side behaviour; their defaults reproduce the reference.
+
+The arithmetic runs in ``librfm_b200.so`` (``csrc/fm.cu``); this file is host plumbing:
+legacy-RNG initialisation (``src/fm.py:31-48``), batch order (``src/fm.py:72-79``), uploads,
+and the lazy host mirrors of the parameters.
+"""
+from __future__ import annotations
+
+import weakref
+from ctypes import byref, c_double, c_void_p
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib, ptr
+from .base import PointwiseBaseRecommender
+from .optimizer import SGD
+from .sampler import LegacyBatchPrefetcher
+
+
+class _FmDevice(_capi._Handle):
+    _destroy = "rfm_fm_destroy"
+
+    def __init__(self, ctx, n_features, n_factors, dtype):
+        super().__init__()
+        check(lib().rfm_fm_create(ctx.handle, n_features, n_factors, _capi.dtype_code(dtype), byref(self.handle)))
+
+
+class _FmTrainer(_capi._Handle):
+    _destroy = "rfm_fm_trainer_destroy"
+
+    def __init__(self, model, train, val, max_batch, max_slots):
+        super().__init__()
+        self._keep = [model, train, val]
+        check(lib().rfm_fm_trainer_create(model.handle, train.handle, val.handle if val is not None else None,
+                                          max_batch, max_slots, byref(self.handle)))
+
+
+@dataclass
+class FactorizationMachines(PointwiseBaseRecommender):
+    n_features: int
+    alpha: float = 2.0
+    evaluator: Optional[object] = None
+    # ---- extensions (not in the reference; defaults keep reference behaviour) ----
+    dtype: str = "float64"        # "float64" = parity mode, "float32" = perf mode
+    sampler: str = "legacy"       # "legacy" = RandomState(epoch) order, "feistel" = device sampler
+    device: int = 0
+    progress: bool = False        # tqdm bar like the reference's (src/fm.py:71)
+    _dev: object = field(default=None, init=False, repr=False, compare=False)
+
+    def __post_init__(self) -> None:
+        if self.sampler not in ("legacy", "feistel"):
+            raise ValueError("sampler must be 'legacy' or 'feistel'")
+        _capi.dtype_code(self.dtype)
+        np.random.seed(self.seed)                                   # global legacy RNG, like the reference
+        self.w0 = SGD(params=np.array([0.0]), lr=self.lr)
+        limit = self.alpha * np.sqrt(6 / self.n_features)
+        self.w = SGD(params=np.random.uniform(low=-limit, high=limit, size=self.n_features), lr=self.lr)
+        limit = self.alpha * np.sqrt(6 / self.n_factors)
+        self.V = SGD(params=np.random.uniform(low=-limit, high=limit, size=(self.n_features, self.n_factors)),
+                     lr=self.lr)
+        if self.evaluator is not None:
+            self.val_metrics = []
+            self.model_name = "FM"
+        self._ctx = None
+        self._synced = None            # versions of (w0, w, V) the device copy corresponds to
+        self._rows_cache: Dict[int, tuple] = {}
+        self.last_fit_stats = {}
+
+    # ---- device plumbing ---------------------------------------------------------------------
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = _capi.Context.default(self.device)
+            self._dev = _FmDevice(self._ctx, self.n_features, self.n_factors, self.dtype)
+        return self._ctx
+
+    def _host_state(self):
+        return (id(self.w0.params), self.w0.version, id(self.w.params), self.w.version,
+                id(self.V.params), self.V.version)
+
+    def sync_to_device(self, force: bool = False) -> None:
+        """Upload host parameters if a holder was updated on the host since the last sync."""
+        self._context()
+        if force or self._synced != self._host_state():
+            w0 = _capi.as_array(self.w0.params, np.float64).reshape(-1)
+            w = _capi.as_array(self.w.params, np.float64)
+            V = _capi.as_array(self.V.params, np.float64)
+            if w.shape != (self.n_features,) or V.shape != (self.n_features, self.n_factors):
+                raise ValueError("parameter arrays changed shape")
+            check(lib().rfm_fm_set_params(self._dev.handle, ptr(w0), ptr(w), ptr(V)))
+            self._synced = self._host_state()
+
+    def sync_to_host(self) -> None:
+        """Refresh the holders' ndarrays in place from the device master copy."""
+        w0 = np.empty(1)
+        w = np.empty(self.n_features)
+        V = np.empty((self.n_features, self.n_factors))
+        check(lib().rfm_fm_get_params(self._dev.handle, ptr(w0), ptr(w), ptr(V)))
+        for holder, new in ((self.w0, w0), (self.w, w), (self.V, V)):
+            if (isinstance(holder.params, np.ndarray) and holder.params.shape == new.shape
+                    and holder.params.dtype == np.float64 and holder.params.flags.writeable):
+                holder.params[...] = new
+            else:
+                holder.params = new
+        self._synced = self._host_state()
+
+    def _rows(self, X, labels=None, pscores=None):
+        """Device copy of a CSR matrix, cached per Python object so that the evaluator's features
+        and the val set are uploaded once, not every epoch."""
+        key = (id(X), id(labels), id(pscores))
+        hit = self._rows_cache.get(key)
+        if hit is not None and hit[0]() is X:
+            return hit[1]
+        rows = _capi.CsrRows(self._context(), X, labels, pscores, self.dtype)
+        try:
+            self._rows_cache[key] = (weakref.ref(X), rows)
+        except TypeError:
+            pass
+        if len(self._rows_cache) > 8:
+            self._rows_cache.pop(next(iter(self._rows_cache)))
+        return rows
+
+    # ---- reference API -----------------------------------------------------------------------
+    def fit(self, train, val) -> tuple:
+        ctx = self._context()
+        X = train["features"]
+        n_rows = X.shape[0]
+        if self.batch_size > n_rows:
+            raise ValueError("Cannot sample %d out of arrays with dim %d when replace is False"
+                             % (self.batch_size, n_rows))
+        train_rows = self._rows(X, train["labels"], train["pscores"])
+        val_rows = self._rows(val["features"], val["labels"], val["pscores"])
+        self.sync_to_device()
+        trainer = _FmTrainer(self._dev, train_rows, val_rows, self.batch_size, max(self.n_epochs, 1))
+        epochs = range(self.n_epochs)
+        prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
+        eval_rows = None
+        if self.evaluator is not None:
+            eval_rows = self._rows(self.evaluator.features[self.model_name])
+        it = epochs
+        if self.progress:
+            from tqdm import tqdm
+            it = tqdm(epochs)
+        launches0 = ctx.launch_count()
+        try:
+            for epoch in it:
+                if prefetch is not None:
+                    idx = prefetch.next()
+                    check(lib().rfm_fm_train_epoch(trainer.handle, ptr(idx), self.batch_size, self.lr, epoch))
+                else:
+                    check(lib().rfm_fm_train_epoch_sampled(trainer.handle, self.seed & 0xFFFFFFFF, epoch,
+                                                           self.batch_size, self.lr, epoch))
+                if eval_rows is not None:
+                    scores = np.empty(eval_rows.n_rows)
+                    check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
+                    self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
+            train_loss = np.empty(self.n_epochs)
+            val_loss = np.empty(self.n_epochs)
+            check(lib().rfm_fm_trainer_losses(trainer.handle, 0, self.n_epochs, ptr(train_loss), ptr(val_loss)))
+        finally:
+            if prefetch is not None:
+                prefetch.close()
+        self.last_fit_stats = {"gpu_launches": ctx.launch_count() - launches0,
+                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes}
+        trainer.close()
+        self.sync_to_host()
+        return train_loss.tolist(), val_loss.tolist()
+
+    def predict(self, X) -> np.ndarray:
+        self.sync_to_device()
+        rows = self._rows(X)
+        out = np.empty(rows.n_rows)
+        check(lib().rfm_fm_predict(self._dev.handle, rows.handle, ptr(out)))
+        return out
+
+    def logloss(self, data) -> float:
+        """``_cross_entropy_loss(labels, predict(features), pscores)`` evaluated on the device."""
+        self.sync_to_device()
+        rows = self._rows(data["features"], data["labels"], data["pscores"])
+        out = c_double()
+        check(lib().rfm_fm_logloss(self._dev.handle, rows.handle, byref(out)))
+        return out.value

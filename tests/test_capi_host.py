@@ -1,0 +1,78 @@
+"""CPU-side checks (no GPU needed): the C-ABI library loads, exports every declared symbol,
+its host-side samplers match NumPy / the oracle bit for bit, and it refuses to run without a
+device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import sampler_oracle
+from rfm_b200 import _capi
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rfm_b200.h")).read()
+    declared = set(re.findall(r"\b(rfm_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rfm_last_error"} - set(_capi.DECLARED_SYMBOLS)
+    handle = ctypes.CDLL(_capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(handle, s)]
+    assert not missing, "declared in include/rfm_b200.h but not exported: %s" % missing
+    assert set(_capi.DECLARED_SYMBOLS) == declared, set(_capi.DECLARED_SYMBOLS) ^ declared
+    assert _capi.lib().rfm_abi_version() == 1
+
+
+def test_legacy_sampler_matches_numpy_known_answers():
+    g = load_golden("legacy_sampler")
+    for key in g.files:
+        N, B, ep = (int(s[1:]) for s in key.split("_"))
+        np.testing.assert_array_equal(_capi.legacy_batch(N, B, ep), g[key], err_msg=key)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 16, 17, 255, 256, 257, 1000, 4097, 70000])
+def test_legacy_sampler_matches_numpy_live(N):
+    for epoch in (0, 1, 2, 499, 123456789):
+        ref = np.arange(N)
+        np.random.RandomState(epoch).shuffle(ref)
+        np.testing.assert_array_equal(_capi.legacy_batch(N, N, epoch), ref)
+        B = max(1, N // 3)
+        np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch), ref[:B])
+
+
+def test_legacy_sampler_rejects_oversized_batch_like_sklearn():
+    with pytest.raises(ValueError, match="Cannot sample 11 out of arrays with dim 10"):
+        _capi.legacy_batch(10, 11, 0)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 17, 256, 257, 3660, 65536, 100003, 12_000_000])
+def test_feistel_host_matches_oracle(N):
+    B = min(N, 4096)
+    for epoch, seed in ((0, 0), (1, 12345), (77, 2**32 - 1)):
+        np.testing.assert_array_equal(_capi.feistel_batch(N, B, epoch, seed),
+                                      sampler_oracle.feistel_batch(N, B, epoch, seed))
+
+
+def test_prefetcher_yields_epochs_in_order():
+    from rfm_b200.sampler import LegacyBatchPrefetcher
+    pf = LegacyBatchPrefetcher(5000, 100, range(3, 12), n_threads=3)
+    try:
+        for epoch in range(3, 12):
+            np.testing.assert_array_equal(pf.next(), sampler_oracle.legacy_batch(5000, 100, epoch))
+    finally:
+        pf.close()
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    n = ctypes.c_int()
+    _capi.check(_capi.lib().rfm_device_count(ctypes.byref(n)))
+    if n.value > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _capi.Context(0)
+    from rfm_b200.fm import FactorizationMachines
+    m = FactorizationMachines("IPS", 1, 4, 0.1, 2, 0, 5)
+    from scipy.sparse import identity
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.predict(X=identity(5, format="csr"))

@@ -1,0 +1,162 @@
+"""GPU parity tests of the FM path, through the C ABI (ctypes) and the drop-in Python class.
+
+Bar (BASELINE.json north_star): losses, embeddings within 1e-5 relative of the reference after N
+epochs in the deterministic minibatch mode. The float64 path is held to a much tighter 1e-9 here;
+the float32 perf mode is checked at the north-star tolerance where the arithmetic allows it.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_csr
+from oracle import fm_oracle, sampler_oracle
+
+pytestmark = pytest.mark.gpu
+
+FM_CASES = ["coat_fm_ips_alpha2", "coat_fm_ips_alpha01", "coat_fm_naive_alpha01",
+            "kuairec_small_fm_ips", "kuairec_small_fm_ips_alpha01"]
+
+
+def _model(g, n_features, **kw):
+    from rfm_b200.fm import FactorizationMachines
+    return FactorizationMachines(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]),
+                                 lr=float(g["lr"]), batch_size=int(g["B"]), seed=int(g["seed"]),
+                                 n_features=n_features, alpha=float(g["alpha"]), **kw)
+
+
+def _dicts(g):
+    train = {"features": golden_csr(g, "train"), "labels": g["train_labels"], "pscores": g["train_pscores"]}
+    val = {"features": golden_csr(g, "val"), "labels": g["val_labels"], "pscores": g["val_pscores"]}
+    return train, val
+
+
+@pytest.mark.parametrize("name", FM_CASES)
+def test_predict_matches_reference_golden(name):
+    g = load_golden(name)
+    m = _model(g, int(g["train_shape"][1]))
+    np.testing.assert_array_equal(m.V(), g["V_init"])            # legacy RNG init is the reference's
+    m.w0.params[...] = g["w0"]
+    m.w.params[...] = g["w"]
+    m.V.params[...] = g["V"]
+    m.sync_to_device(force=True)
+    p = m.predict(X=golden_csr(g, "test"))
+    np.testing.assert_allclose(p, g["test_scores"], rtol=1e-9, atol=1e-300)
+    train, _ = _dicts(g)
+    ref_loss = fm_oracle.ips_logloss(train["labels"], fm_oracle.fm_predict(train["features"], g["w0"], g["w"], g["V"]),
+                                     train["pscores"])
+    np.testing.assert_allclose(m.logloss(train), ref_loss, rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", FM_CASES)
+def test_fit_trajectory_matches_reference_golden(name):
+    """Full fit: same batches (RandomState(epoch) order), same losses every epoch, same final
+    parameters as the unmodified reference."""
+    g = load_golden(name)
+    train, val = _dicts(g)
+    m = _model(g, train["features"].shape[1])
+    tl, vl = m.fit(train, val)
+    np.testing.assert_allclose(tl, g["train_loss"], rtol=1e-9)
+    np.testing.assert_allclose(vl, g["val_loss"], rtol=1e-9)
+    np.testing.assert_allclose(m.w0(), g["w0"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.w(), g["w"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.V(), g["V"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.predict(X=golden_csr(g, "test")), g["test_scores"], rtol=1e-8, atol=1e-300)
+
+
+def test_fit_is_bit_reproducible():
+    g = load_golden("kuairec_small_fm_ips_alpha01")
+    train, val = _dicts(g)
+    runs = []
+    for _ in range(2):
+        m = _model(g, train["features"].shape[1])
+        tl, vl = m.fit(train, val)
+        runs.append((np.array(tl), np.array(vl), m.V().copy(), m.w().copy()))
+    for a, b in zip(*runs):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_float32_mode_tracks_reference():
+    g = load_golden("coat_fm_ips_alpha01")
+    train, val = _dicts(g)
+    m = _model(g, train["features"].shape[1], dtype="float32")
+    tl, vl = m.fit(train, val)
+    np.testing.assert_allclose(tl, g["train_loss"], rtol=1e-5)
+    np.testing.assert_allclose(vl, g["val_loss"], rtol=1e-5)
+    np.testing.assert_allclose(m.V(), g["V"], rtol=1e-4, atol=1e-6)
+
+
+def test_feistel_sampler_on_device_matches_oracle():
+    """perf-mode sampler: the device draws the same rows as the NumPy specification, so the
+    whole trajectory equals the oracle run with that sampler."""
+    g = load_golden("kuairec_small_fm_ips_alpha01")
+    train, val = _dicts(g)
+    m = _model(g, train["features"].shape[1], sampler="feistel")
+    w0, w, V = m.w0().copy(), m.w().copy(), m.V().copy()
+    tl, vl = m.fit(train, val)
+    seed = int(g["seed"])
+    (rw0, rw, rV), rtl, rvl = fm_oracle.fm_fit(
+        train, val, int(g["n_epochs"]), int(g["B"]), float(g["lr"]), w0, w, V,
+        sampler=lambda n, b, e: sampler_oracle.feistel_batch(n, b, e, seed))
+    np.testing.assert_allclose(tl, rtl, rtol=1e-9)
+    np.testing.assert_allclose(vl, rvl, rtol=1e-9)
+    np.testing.assert_allclose(m.V(), rV, rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("k", [1, 16, 64, 65, 130, 300])
+def test_factor_counts_and_padding(k):
+    """n_factors that are not multiples of the 64-wide row chunk, including the reference's own 300."""
+    rng = np.random.default_rng(k)
+    from scipy.sparse import random as sprandom
+    n, N = 50, 400
+    X = sprandom(N, n, density=0.15, random_state=3, format="csr", dtype=np.float64)
+    X.data = rng.normal(size=X.data.size)
+    y = rng.integers(0, 2, size=N)
+    ps = rng.uniform(0.2, 1.0, size=N)
+    train = {"features": X, "labels": y, "pscores": ps}
+    from rfm_b200.fm import FactorizationMachines
+    m = FactorizationMachines("IPS", 4, k, 1e-3, 128, 1, n, alpha=0.2)
+    w0, w, V = m.w0().copy(), m.w().copy(), m.V().copy()
+    tl, vl = m.fit(train, train)
+    (rw0, rw, rV), rtl, rvl = fm_oracle.fm_fit(train, train, 4, 128, 1e-3, w0, w, V)
+    np.testing.assert_allclose(tl, rtl, rtol=1e-9)
+    np.testing.assert_allclose(m.V(), rV, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.w(), rw, rtol=1e-9, atol=1e-13)
+
+
+def test_ragged_empty_rows_and_dense_columns():
+    """Rows with no stored entries, a column present in every row (long carry run), duplicate
+    columns across rows, batch == whole train set."""
+    rng = np.random.default_rng(0)
+    from scipy.sparse import csr_matrix, hstack, random as sprandom
+    N, n = 3000, 40
+    A = sprandom(N, n - 2, density=0.1, random_state=1, format="csr", dtype=np.float64)
+    A.data = rng.normal(size=A.data.size)
+    dense = csr_matrix(rng.normal(size=(N, 1)))
+    ones = csr_matrix(np.ones((N, 1)))
+    X = hstack([A, dense, ones]).tocsr()
+    # blank out some rows entirely
+    keep = np.ones(N, dtype=bool)
+    keep[::17] = False
+    X = csr_matrix(X.multiply(keep[:, None]))
+    X.eliminate_zeros()
+    y = rng.integers(0, 2, size=N)
+    ps = rng.uniform(0.2, 1.0, size=N)
+    train = {"features": X, "labels": y, "pscores": ps}
+    from rfm_b200.fm import FactorizationMachines
+    m = FactorizationMachines("IPS", 3, 8, 1e-4, N, 3, n, alpha=0.3)
+    w0, w, V = m.w0().copy(), m.w().copy(), m.V().copy()
+    tl, vl = m.fit(train, train)
+    (rw0, rw, rV), rtl, rvl = fm_oracle.fm_fit(train, train, 3, N, 1e-4, w0, w, V)
+    np.testing.assert_allclose(tl, rtl, rtol=1e-9)
+    np.testing.assert_allclose(vl, rvl, rtol=1e-9)
+    np.testing.assert_allclose(m.V(), rV, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.w(), rw, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.w0(), rw0, rtol=1e-9, atol=1e-13)
+
+
+def test_batch_larger_than_train_raises_like_sklearn():
+    g = load_golden("coat_fm_ips_alpha01")
+    train, val = _dicts(g)
+    from rfm_b200.fm import FactorizationMachines
+    m = FactorizationMachines("IPS", 1, 4, 0.1, train["features"].shape[0] + 1, 0, train["features"].shape[1])
+    with pytest.raises(ValueError, match="Cannot sample"):
+        m.fit(train, val)
