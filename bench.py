@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- train interactions/s of the fused IPS-FM epoch on synthetic KuaiRec-big-shaped data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one reference epoch (src/fm.py:71-102): one minibatch of B interactions through
+forward, IPS residual, the simultaneous w0/w/V update, the post-update batch loss and the val loss.
+
+ours:       value     = K*B*N / device time of K steps (CUDA events), dataset resident in HBM,
+                        batches drawn on the device (Feistel sampler, perf mode), float64.
+            e2e       = the same metric through the public API, FactorizationMachines.fit(train, val)
+                        on HOST (pinned) arrays: dataset upload, K epochs, loss read-back, parameter
+                        download, wall clock around the call.
+            roofline  = dominant kernel's algorithmic bytes / its CUDA-event time (separate profiled
+                        pass of the same steps), against MEASURED_PEAKS.json's HBM copy bandwidth.
+            cpu_baseline = the CPU oracle (NumPy/SciPy port of the reference step + the reference's
+                        own sampler) on a bounded sample of the same workload, on this box's cores.
+reference:  the CPU oracle port timed alone, same config / metric / unit (the reference is pure
+            Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "relevance-factorizationmachine_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "train_interactions_per_sec"
+UNIT = "interactions/s"
+N_USERS, N_ITEMS, N_TRAIN, N_VAL, K_FACTORS = 7176, 10728, 12_000_000, 2000, 64
+LR = 9e-6   # conf/setting/kuairec.yaml:59 (FM, IPS)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="interactions per step per GPU")
+    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--rows", type=int, default=N_TRAIN, help="train interactions in the job")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": "IPS-FM, synthetic KuaiRec big_matrix shape (BASELINE.json configs[2])",
+        "n_users": N_USERS, "n_items": N_ITEMS, "train_interactions": args.rows, "val_rows": N_VAL,
+        "n_factors": K_FACTORS, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+        "lr": LR, "parallelism": "dp%d" % world if world > 1 else "single",
+        "l2": "inputs larger than L2: each step gathers a fresh random batch from the resident "
+              "%.1f GB CSR; the parameter table V is legitimately L2-resident across steps" % 0.0,
+    }
+
+
+def make_data(rows, seed, rank=0):
+    from rfm_b200.synth import make_kuairec_shaped
+    t0 = time.perf_counter()
+    log = make_kuairec_shaped(seed=seed + rank, n_users=N_USERS, n_items=N_ITEMS, n_train=rows, n_val=N_VAL,
+                              build_mf=False, build_eval=False)
+    return log, time.perf_counter() - t0
+
+
+def algorithmic_bytes(X, batch_rows, k, s):
+    """bytes one interaction must move, per pass of the hot path."""
+    m = X.nnz / X.shape[0]
+    sub = X[batch_rows]
+    touched = np.unique(sub.indices).size
+    B = len(batch_rows)
+    stream = 4 + 4 + m * (4 + s) + 4 + s
+    step = stream + 2 * m * (k + 1) * s + 2 * (touched / B) * (k + 1) * s
+    per_kernel = {
+        # row pass: batch stream + gather of V rows and w + write of s_t, e_t and the sort triples
+        "fm_rows_train": 8 + 16 + m * (4 + s) + s + m * (k + 1) * s + k * s + s + m * (8 + s),
+        # column pass: sorted triples + e_t and s_t gathers + read/write of each touched row
+        "fm_cols": m * (8 + s) + m * s + m * k * s + 2 * (touched / B) * (k + 1) * s,
+        # loss pass: batch stream + gather of V rows and w
+        "fm_rows_loss": 8 + 16 + m * (4 + s) + s + m * (k + 1) * s,
+    }
+    return m, touched, step, per_kernel
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---- the CPU arm -----------------------------------------------------------------------------------
+def cpu_port_run(log, batch, steps, warmup, budget_s=25.0):
+    """Oracle port on the host: reference sampler + step + post-update loss + val loss per epoch
+    (oracle/fm_oracle.py::fm_fit == src/fm.py:55-112). Returns (interactions/s, description)."""
+    from oracle import fm_oracle
+    w0, w, V = fm_oracle.fm_init(12345, log.n_features, K_FACTORS)
+    t0 = time.perf_counter()
+    (w0, w, V), _, _ = fm_oracle.fm_fit(log.fm_train, log.fm_val, 1, batch, LR, w0, w, V)
+    one = time.perf_counter() - t0
+    if warmup + steps > 1 and one * (warmup + steps) > budget_s:
+        steps = max(1, int(budget_s / one) - warmup)
+    if warmup > 1:
+        (w0, w, V), _, _ = fm_oracle.fm_fit(log.fm_train, log.fm_val, warmup - 1, batch, LR, w0, w, V, first_epoch=1)
+    t0 = time.perf_counter()
+    fm_oracle.fm_fit(log.fm_train, log.fm_val, steps, batch, LR, w0, w, V, first_epoch=warmup)
+    dt = time.perf_counter() - t0
+    return steps * batch / dt, steps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log, gen_s = make_data(args.rows, 2024)
+    value, steps, dt = cpu_port_run(log, args.batch, args.steps, max(args.warmup, 1), budget_s=150.0)
+    sample = "%d epochs of B=%d on the %d-row train set (reference sampler included), %.1f s" % (
+        steps, args.batch, args.rows, dt)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python (NumPy/SciPy, single-threaded) and is not present on the GPU box; "
+                "this is its CPU restatement oracle/fm_oracle.py, which is ~8x faster than the reference's own "
+                "per-factor loop (BASELINE.md section 4)",
+    }
+    print(json.dumps(line))
+
+
+# ---- our arm ----------------------------------------------------------------------------------------
+def run_ours(args):
+    from ctypes import byref
+    from rfm_b200 import _capi
+    from rfm_b200._capi import check, lib, ptr
+    from rfm_b200.fm import FactorizationMachines, _FmTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d ...)"
+                             % (args.gpus, args.gpus))
+    dist = None
+    if world > 1:
+        from rfm_b200 import dist as rdist
+        dist = rdist.init(local_rank)
+
+    rows = args.rows // world
+    log, gen_s = make_data(rows, 2024, rank)
+    X = log.fm_train["features"]
+    pinned = []
+    for a in (X.indptr, X.indices, X.data, log.fm_train["labels"], log.fm_train["pscores"]):
+        if _capi.pin_array(a):
+            pinned.append(a)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    s = 8 if args.dtype == "float64" else 4
+    dtype_tag = "f64" if args.dtype == "float64" else "f32"
+
+    model = FactorizationMachines("IPS", K, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
+                                  sampler="feistel", device=local_rank)
+    ctx = model._context()
+    train_rows = model._rows(X, log.fm_train["labels"], log.fm_train["pscores"])
+    val_rows = model._rows(log.fm_val["features"], log.fm_val["labels"], log.fm_val["pscores"])
+    model.sync_to_device()
+    trainer = _FmTrainer(model._dev, train_rows, val_rows, B, W + 2 * K + 8)
+
+    if dist is not None:
+        stepper = dist.make_fm_stepper(model, trainer, train_rows, val_rows, B, LR)
+    else:
+        def stepper(epoch, slot):
+            check(lib().rfm_fm_train_epoch_sampled(trainer.handle, 12345, epoch, B, LR, slot))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+
+    for e in range(W):
+        stepper(e, e)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    launches0 = ctx.launch_count()
+    ctx.timer_start()
+    for e in range(K):
+        stepper(W + e, W + e)
+    ms = ctx.timer_stop_ms()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clk = clocks.stop()
+    if dist is not None:
+        ms = dist.max_over_ranks(ms)
+        launches = int(dist.sum_over_ranks(launches))
+    value = K * B * world / (ms * 1e-3)
+
+    # per-kernel share of the step: CUDA events around every launch, separate pass of the same steps
+    ctx.profile_begin()
+    for e in range(K):
+        stepper(W + K + e, W + K + e)
+    prof = ctx.profile_end()
+    tl = np.empty(W + 2 * K)
+    vl = np.empty(W + 2 * K)
+    check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + 2 * K, ptr(tl), ptr(vl)))
+    assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl)), "non-finite loss in the timed region"
+
+    if rank != 0:
+        if dist is not None:
+            e2e = measure_e2e(args, log, local_rank, dist, world)
+            dist.shutdown()
+        return
+
+    sample_rows = _capi.feistel_batch(X.shape[0], B, W, 12345)
+    m, touched, step_bytes, per_kernel = algorithmic_bytes(X, sample_rows, K_FACTORS, s)
+    total_prof_ms = sum(v[1] for v in prof.values())
+    top = max((k for k in prof if k in per_kernel), key=lambda k: prof[k][1])
+    top_ms = prof[top][1] / prof[top][0]
+    peaks, peak_kind = measured_peaks()
+    achieved = per_kernel[top] * B / (top_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind + " (HBM copy, burst)",
+        "algorithmic_bytes_per_interaction": per_kernel[top], "avg_launch_ms": top_ms,
+        "share_of_step": prof[top][1] / total_prof_ms,
+        "timing": "cudaEvent pair around each launch, separate pass of the same %d steps" % K,
+        "note": "V (%.1f MB) and S (%.1f MB) are L2-resident at this shape, so the algorithmic gather traffic is "
+                "served by L2, not HBM (SURVEY.md H7); achieved may therefore exceed the HBM peak"
+                % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6),
+        "step": {"algorithmic_bytes_per_interaction": step_bytes,
+                 "achieved": step_bytes * B * world / (ms / K * 1e-3) / 1e9 / world,
+                 "frac": step_bytes * B / (ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "kernels_ms_per_step": {k: round(v[1] / K, 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+
+    e2e = None if args.no_e2e else measure_e2e(args, log, local_rank, dist, world)
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, st, dt = cpu_port_run(log, B, 8, 1, budget_s=25.0)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+               "sample": "%d epochs of B=%d on the %d-row train set, reference sampler included, %.1f s"
+                         % (st, B, X.shape[0], dt)}
+    cfg = workload_config(args, world)
+    cfg["l2"] = cfg["l2"].replace("0.0 GB", "%.1f GB" % (train_rows.h2d_bytes / 1e9))
+    cfg.update(sampler="feistel (device, perf mode)", mean_nnz_per_row=round(m, 3),
+               touched_columns_per_step=int(touched), n_features=log.n_features, data_gen_s=round(gen_s, 1))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype_tag, "data": "synthetic", "config": cfg, "clocks": clk, "e2e": e2e,
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "final_train_loss": float(tl[W + K - 1]), "final_val_loss": float(vl[W + K - 1]),
+    }
+    print(json.dumps(line))
+    for a in pinned:
+        _capi.unpin_array(a)
+    if dist is not None:
+        dist.shutdown()
+
+
+def measure_e2e(args, log, device, dist, world):
+    """Public API on host arrays: FactorizationMachines.fit(train, val) for K epochs. Everything a
+    user pays is inside the timed region: CSR upload from pinned host memory, trainer set-up, K
+    epochs, loss read-back, parameter download."""
+    from rfm_b200.fm import FactorizationMachines
+    B, K = args.batch, args.steps
+    out = {}
+    for sampler in ("feistel", "legacy"):
+        n_ep = K if sampler == "feistel" else min(K, 16)
+        if dist is not None and sampler == "legacy":
+            continue
+        warm = FactorizationMachines("IPS", 2, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
+                                     sampler=sampler, device=device)
+        if dist is not None:
+            warm.distributed = dist
+        warm.fit(log.fm_train, log.fm_val)
+        del warm
+        model = FactorizationMachines("IPS", n_ep, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
+                                      sampler=sampler, device=device)
+        if dist is not None:
+            model.distributed = dist
+            dist.barrier()
+        model._context().synchronize()
+        t0 = time.perf_counter()
+        tl, vl = model.fit(log.fm_train, log.fm_val)
+        model._context().synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            dt = dist.max_over_ranks(dt)
+        rows_bytes = model.last_fit_stats["h2d_bytes_rows"]
+        out[sampler] = {
+            "value": n_ep * B * world / dt, "epochs": n_ep, "seconds": dt,
+            "h2d_bytes_per_step": rows_bytes / n_ep + (B * 8 if sampler == "legacy" else 0),
+            "d2h_bytes_per_step": 16 + (1 + log.n_features * (K_FACTORS + 1)) * 8 / n_ep,
+        }
+    main = out["feistel"]
+    res = {"value": main["value"], "unit": UNIT, "h2d_bytes_per_step": main["h2d_bytes_per_step"],
+           "d2h_bytes_per_step": main["d2h_bytes_per_step"], "seconds": main["seconds"], "epochs": main["epochs"],
+           "api": "FactorizationMachines(sampler='feistel').fit(train, val) on pinned host arrays; includes the "
+                  "one-time CSR upload, amortised over the epochs of this call"}
+    if "legacy" in out:
+        res["legacy_sampler"] = dict(out["legacy"], note="reference batch order (RandomState(epoch) shuffle of all "
+                                     "N ids on host threads, SURVEY.md F14): host-bound by design")
+    return res
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -63,9 +63,17 @@ int rfm_ctx_launch_count(rfm_ctx *ctx, int64_t *out);
 int rfm_ctx_timer_start(rfm_ctx *ctx);
 int rfm_ctx_timer_stop_ms(rfm_ctx *ctx, double *ms);
 
-/* page-locked host memory for the shim's staging buffers. */
+/* per-kernel timing: between begin and end every launch is bracketed by a cudaEvent pair on the
+ * context's stream; end writes "kernel-name<TAB>launches<TAB>total-ms" lines into out_text. */
+int rfm_ctx_profile_begin(rfm_ctx *ctx);
+int rfm_ctx_profile_end(rfm_ctx *ctx, char *out_text, size_t capacity);
+
+/* page-locked host memory for the shim's staging buffers; register/unregister pin an existing
+ * allocation (e.g. a NumPy array) in place so uploads run at full PCIe speed. */
 int rfm_host_alloc(size_t bytes, void **out);
 int rfm_host_free(void *p);
+int rfm_host_register(void *p, size_t bytes);
+int rfm_host_unregister(void *p);
 
 /* ---- batch samplers ---------------------------------------------------------------------
  * rfm_legacy_batch: sklearn.utils.resample(replace=False, n_samples=B, random_state=epoch) as

@@ -95,8 +95,15 @@ struct PinnedBuf {
 }  // namespace rfm
 
 // ---- the context ----------------------------------------------------------------------------
+struct rfm_prof_rec {
+  const char *name;
+  cudaEvent_t a, b;
+};
+
 struct rfm_ctx {
   int device = 0;
+  bool profiling = false;
+  std::vector<rfm_prof_rec> prof;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   int64_t launches = 0;
@@ -107,11 +114,17 @@ struct rfm_ctx {
 
 namespace rfm {
 
+// per-kernel CUDA-event timing (bench.py's roofline numbers); off unless rfm_ctx_profile_begin
+void prof_begin(rfm_ctx *ctx, const char *name);
+void prof_end(rfm_ctx *ctx);
+
 // every kernel launch goes through this so gpu_launches is an honest count
 #define RFM_LAUNCH(ctx, kernel, grid, block, smem, ...)                                     \
   do {                                                                                      \
+    if ((ctx)->profiling) ::rfm::prof_begin((ctx), #kernel);                                \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
     (ctx)->launches++;                                                                      \
+    if ((ctx)->profiling) ::rfm::prof_end((ctx));                                           \
     cudaError_t err__ = cudaGetLastError();                                                 \
     if (err__ != cudaSuccess)                                                               \
       return ::rfm::fail(RFM_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,          \

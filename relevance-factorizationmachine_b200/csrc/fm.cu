@@ -98,6 +98,16 @@ __global__ void unpad_rows_kernel(const T *__restrict__ in, double *__restrict__
   }
 }
 
+__global__ void check_columns_kernel(const int32_t *__restrict__ col, int64_t nnz, int64_t n_cols,
+                                     int *__restrict__ bad) {
+  bool mine = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = col[i];
+    mine |= (c < 0 || c >= n_cols);
+  }
+  if (mine) atomicOr(bad, 1);
+}
+
 // ---- batch preparation --------------------------------------------------------------------------
 __global__ void feistel_sample_kernel(FeistelKey key, int64_t batch, int64_t *__restrict__ idx) {
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < batch; q += (int64_t)gridDim.x * blockDim.x)
@@ -529,14 +539,19 @@ template <typename T>
 int launch_rows(rfm_ctx *ctx, int nch, int mode, const RowsArgs<T> &args, int grid) {
   RFM_DISPATCH_NCH(nch, {
     if (mode == MODE_TRAIN) {
-      auto kfn1 = fm_rows_kernel<T, NCH, MODE_TRAIN>;
-    RFM_LAUNCH(ctx, kfn1, grid, ROWS_THREADS, 0, args);
+      auto fm_rows_train = fm_rows_kernel<T, NCH, MODE_TRAIN>;
+    RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
     } else if (mode == MODE_LOSS) {
-      auto kfn2 = fm_rows_kernel<T, NCH, MODE_LOSS>;
-    RFM_LAUNCH(ctx, kfn2, grid, ROWS_THREADS, 0, args);
+      if (args.idx) {  // post-update loss of the batch vs. loss over a plain row range (val)
+        auto fm_rows_loss = fm_rows_kernel<T, NCH, MODE_LOSS>;
+        RFM_LAUNCH(ctx, fm_rows_loss, grid, ROWS_THREADS, 0, args);
+      } else {
+        auto fm_rows_loss_range = fm_rows_kernel<T, NCH, MODE_LOSS>;
+        RFM_LAUNCH(ctx, fm_rows_loss_range, grid, ROWS_THREADS, 0, args);
+      }
     } else {
-      auto kfn3 = fm_rows_kernel<T, NCH, MODE_PREDICT>;
-    RFM_LAUNCH(ctx, kfn3, grid, ROWS_THREADS, 0, args);
+      auto fm_rows_predict = fm_rows_kernel<T, NCH, MODE_PREDICT>;
+    RFM_LAUNCH(ctx, fm_rows_predict, grid, ROWS_THREADS, 0, args);
     }
   });
   return RFM_OK;
@@ -673,12 +688,12 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
   const int cgrid = grid_for(ctx, ceil_div(chunk_cap, ROWS_WARPS), t->rows_grid / ctx->sm_count);
   const int lgrid = t->long_cap < (uint32_t)ctx->sm_count * 2 ? (int)t->long_cap : ctx->sm_count * 2;
   RFM_DISPATCH_NCH(m->nch, {
-    auto kfn4 = fm_cols_kernel<T, NCH, DP>;
-    RFM_LAUNCH(ctx, kfn4, cgrid, ROWS_THREADS, 0, c);
-    auto kfn5 = fm_carry_kernel<T, NCH, DP>;
-    RFM_LAUNCH(ctx, kfn5, cgrid, ROWS_THREADS, 0, c);
-    auto kfn6 = fm_long_runs_kernel<T, NCH, DP>;
-    RFM_LAUNCH(ctx, kfn6, lgrid < 1 ? 1 : lgrid, LONG_RUN_THREADS, t->long_smem, c,
+    auto fm_cols = fm_cols_kernel<T, NCH, DP>;
+    RFM_LAUNCH(ctx, fm_cols, cgrid, ROWS_THREADS, 0, c);
+    auto fm_carry = fm_carry_kernel<T, NCH, DP>;
+    RFM_LAUNCH(ctx, fm_carry, cgrid, ROWS_THREADS, 0, c);
+    auto fm_long_runs = fm_long_runs_kernel<T, NCH, DP>;
+    RFM_LAUNCH(ctx, fm_long_runs, lgrid < 1 ? 1 : lgrid, LONG_RUN_THREADS, t->long_smem, c,
                t->long_warps);
   });
   return RFM_OK;
@@ -775,6 +790,12 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *ind
                  reinterpret_cast<const int32_t *>(tmp.p), r->row_ptr.p, n_rows + 1);
     }
     RFM_TRY(upload(ctx, r->col.p, indices, (size_t)nnz * 4));
+    DevBuf<int> bad;
+    RFM_TRY(bad.alloc(1));
+    RFM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+    if (nnz > 0)
+      RFM_LAUNCH(ctx, check_columns_kernel, grid_for(ctx, ceil_div(nnz, 256), 8), 256, 0, r->col.p, nnz, n_cols,
+                 bad.p);
     if (dtype == RFM_F64) {
       RFM_TRY(upload(ctx, r->val.p, data, (size_t)nnz * 8));
     } else if (nnz > 0) {
@@ -801,7 +822,10 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *ind
     } else {
       RFM_CUDA(cudaMemsetAsync(r->yp.p, 0, (size_t)(n_rows ? n_rows : 1) * es, ctx->stream));
     }
+    int bad_host = 0;
+    RFM_CUDA(cudaMemcpyAsync(&bad_host, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RFM_CUDA(cudaStreamSynchronize(ctx->stream));  // temporaries are freed on return
+    RFM_REQUIRE(bad_host == 0, "rfm_csr_create: CSR column index out of range [0, %lld)", (long long)n_cols);
     return RFM_OK;
   };
   rc = body();

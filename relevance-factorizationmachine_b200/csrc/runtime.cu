@@ -20,6 +20,19 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+void prof_begin(rfm_ctx *ctx, const char *name) {
+  rfm_prof_rec rec;
+  rec.name = name;
+  rec.a = rec.b = nullptr;
+  if (cudaEventCreate(&rec.a) != cudaSuccess || cudaEventCreate(&rec.b) != cudaSuccess) return;
+  cudaEventRecord(rec.a, ctx->stream);
+  ctx->prof.push_back(rec);
+}
+
+void prof_end(rfm_ctx *ctx) {
+  if (!ctx->prof.empty() && ctx->prof.back().b) cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}
+
 // ---- exclusive scan of uint32 ---------------------------------------------------------------
 // Three launches: per-tile totals, scan of the totals by one CTA, per-tile rescan + offset.
 // Integer adds, so the result does not depend on scheduling.
@@ -202,6 +215,57 @@ int rfm_ctx_timer_stop_ms(rfm_ctx *ctx, double *ms) {
   float f = 0.f;
   RFM_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
   *ms = f;
+  return RFM_OK;
+}
+
+int rfm_ctx_profile_begin(rfm_ctx *ctx) {
+  RFM_REQUIRE(ctx != nullptr, "rfm_ctx_profile_begin: ctx is NULL");
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->prof.clear();
+  ctx->profiling = true;
+  return RFM_OK;
+}
+
+int rfm_ctx_profile_end(rfm_ctx *ctx, char *out_text, size_t capacity) {
+  RFM_REQUIRE(ctx != nullptr && out_text != nullptr && capacity > 0, "rfm_ctx_profile_end: bad argument");
+  ctx->profiling = false;
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  struct Agg { const char *name; long count; double ms; };
+  std::vector<Agg> agg;
+  for (auto &rec : ctx->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, rec.a, rec.b) != cudaSuccess) ms = 0.f;
+    cudaEventDestroy(rec.a);
+    cudaEventDestroy(rec.b);
+    bool found = false;
+    for (auto &g : agg)
+      if (strcmp(g.name, rec.name) == 0) { g.count++; g.ms += ms; found = true; break; }
+    if (!found) agg.push_back({rec.name, 1, (double)ms});
+  }
+  ctx->prof.clear();
+  std::string text;
+  for (auto &g : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%ld\t%.6f\n", g.name, g.count, g.ms);
+    text += line;
+  }
+  RFM_REQUIRE(text.size() + 1 <= capacity, "rfm_ctx_profile_end: buffer too small (%zu needed)", text.size() + 1);
+  memcpy(out_text, text.c_str(), text.size() + 1);
+  return RFM_OK;
+}
+
+int rfm_host_register(void *p, size_t bytes) {
+  RFM_REQUIRE(p != nullptr, "rfm_host_register: NULL pointer");
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(RFM_ERR_CUDA, "rfm_host_register: cudaHostRegister(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  return RFM_OK;
+}
+
+int rfm_host_unregister(void *p) {
+  if (p && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
   return RFM_OK;
 }
 

@@ -31,6 +31,10 @@ _SIGNATURES = {
     "rfm_ctx_launch_count": ([_P, POINTER(c_int64)], c_int),
     "rfm_ctx_timer_start": ([_P], c_int),
     "rfm_ctx_timer_stop_ms": ([_P, POINTER(c_double)], c_int),
+    "rfm_ctx_profile_begin": ([_P], c_int),
+    "rfm_ctx_profile_end": ([_P, c_char_p, c_size_t], c_int),
+    "rfm_host_register": ([_P, c_size_t], c_int),
+    "rfm_host_unregister": ([_P], c_int),
     "rfm_host_alloc": ([c_size_t, POINTER(_P)], c_int),
     "rfm_host_free": ([_P], c_int),
     "rfm_legacy_batch": ([c_int64, c_int64, c_uint32, _P, _P], c_int),
@@ -152,6 +156,19 @@ class Context:
         check(lib().rfm_ctx_launch_count(self.handle, byref(out)))
         return out.value
 
+    def profile_begin(self):
+        check(lib().rfm_ctx_profile_begin(self.handle))
+
+    def profile_end(self) -> dict:
+        """{kernel name: (launches, total ms)} of every launch since profile_begin."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(lib().rfm_ctx_profile_end(self.handle, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, count, ms = line.split("\t")
+            out[name] = (int(count), float(ms))
+        return out
+
     def timer_start(self):
         check(lib().rfm_ctx_timer_start(self.handle))
 
@@ -198,8 +215,6 @@ class CsrRows(_Handle):
             indptr = as_array(indptr, np.int32)
         indices = as_array(X.indices, np.int32)
         data = as_array(X.data, np.float64)
-        if indices.size and (indices.min() < 0 or indices.max() >= X.shape[1]):
-            raise ValueError("CSR column index out of range")
         y = None if labels is None else as_array(labels, np.int64)
         ps = None if pscores is None else as_array(pscores, np.float64)
         if y is not None and (y.shape[0] != X.shape[0] or ps is None or ps.shape[0] != X.shape[0]):
@@ -208,6 +223,19 @@ class CsrRows(_Handle):
                                    ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
         self.n_rows = X.shape[0]
         self.h2d_bytes = indptr.nbytes + indices.nbytes + data.nbytes + (y.nbytes + ps.nbytes if y is not None else 0)
+
+
+def pin_array(a: np.ndarray) -> bool:
+    """Page-lock an ndarray in place (cudaHostRegister). Returns False if the driver refuses."""
+    try:
+        check(lib().rfm_host_register(ptr(a), a.nbytes))
+        return True
+    except RfmError:
+        return False
+
+
+def unpin_array(a: np.ndarray) -> None:
+    lib().rfm_host_unregister(ptr(a))
 
 
 def legacy_batch(n_rows: int, batch: int, epoch: int, scratch=None) -> np.ndarray:
