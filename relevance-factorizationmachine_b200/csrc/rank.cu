@@ -1,0 +1,311 @@
+// rank.cu -- per-user ranking metrics (reference utils/evaluate.py, utils/metrics.py).
+//
+//   group-by     utils/evaluate.py:129-156, 209-239   interaction_df.groupby("user"): users ascending,
+//                                                     rows inside a user in original order
+//   ranking      utils/evaluate.py:93, 197            scores.argsort()[::-1]; canonical tie rule here:
+//                                                     score descending, later row first among exact ties
+//                                                     (== argsort(kind="stable")[::-1])
+//   skip rule    utils/evaluate.py:98-99, 201-202     users whose labels sum to 0 contribute nothing
+//   DCG@k        utils/metrics.py:83-107    IPS-DCG@k  utils/metrics.py:53-80
+//   ME@k         utils/metrics.py:110-127 (nan when the list is shorter than k; nanmean'd by the caller)
+//   Recall@k     utils/metrics.py:32-50     MAP@k      utils/metrics.py:9-29
+//   coverage     utils/metrics.py:152-166   |union of kept users' top-k items| (integer, exact)
+//
+// One CTA per user selects the top max(K) candidates by repeated block-wide arg-max over the
+// user's list (keys are unique because the in-list position breaks ties), then one thread walks
+// the ranked prefix and emits the per-user metric terms. A second kernel sums the per-user terms
+// in a fixed order, so the aggregates are bit-reproducible. Item hit counts use integer atomics.
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+
+using namespace rfm;
+
+struct rfm_ranker {
+  rfm_ctx *ctx = nullptr;
+  int64_t n_rows = 0, n_users = 0, n_items = 0;
+  DevBuf<int32_t> order;       // grouped position -> original row id
+  DevBuf<int64_t> user_ptr;    // [n_users + 1]
+  DevBuf<int32_t> item;        // grouped
+  DevBuf<double> label, pscore;
+  DevBuf<double> scores;       // original row order
+  DevBuf<int32_t> K_dev;
+  DevBuf<double> per_user;     // [n_users][n_k][NTERMS]
+  DevBuf<double> metrics;      // [n_k][RFM_RANK_NCOLS]
+  DevBuf<int32_t> hits;        // [n_k][n_items]
+  DevBuf<int64_t> top_rows;    // [n_users][k_max]
+};
+
+namespace {
+
+constexpr int RK_THREADS = 128;
+constexpr int RK_MAX_K = 128;     // largest supported ranking position
+constexpr int RK_MAX_NK = 16;     // how many K values per call
+constexpr int NTERMS = 7;         // dcg, ipsdcg, me, me_valid, recall, map, kept
+
+struct Key {
+  double score;
+  int pos;   // position inside the user's list; -1 = none
+};
+
+__device__ __forceinline__ bool better(const Key &a, const Key &b) {
+  // true when a ranks before b
+  if (a.pos < 0) return false;
+  if (b.pos < 0) return true;
+  return a.score > b.score || (a.score == b.score && a.pos > b.pos);
+}
+
+__device__ __forceinline__ Key block_best(Key mine, Key *smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Key other;
+    other.score = __shfl_xor_sync(FULL, mine.score, o);
+    other.pos = __shfl_xor_sync(FULL, mine.pos, o);
+    if (better(other, mine)) mine = other;
+  }
+  if (lane == 0) smem[wid] = mine;
+  __syncthreads();
+  Key best = smem[0];
+  for (int w = 1; w < RK_THREADS / 32; ++w)
+    if (better(smem[w], best)) best = smem[w];
+  __syncthreads();
+  return best;
+}
+
+__global__ void __launch_bounds__(RK_THREADS)
+rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restrict__ order,
+                  const int32_t *__restrict__ item, const double *__restrict__ label,
+                  const double *__restrict__ pscore, const double *__restrict__ scores, int64_t n_users,
+                  const int32_t *__restrict__ K, int n_k, int k_max, int64_t n_items,
+                  double *__restrict__ per_user, int32_t *__restrict__ hits, int64_t *__restrict__ top_rows) {
+  __shared__ Key wbest[RK_THREADS / 32];
+  __shared__ double wsum[RK_THREADS / 32];
+  __shared__ int top_pos[RK_MAX_K];
+  __shared__ double total_y_s;
+  for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x) {
+    const int64_t beg = user_ptr[u];
+    const int L = static_cast<int>(user_ptr[u + 1] - beg);
+    // sum of labels decides whether the user counts at all
+    double ysum = 0.0;
+    for (int j = threadIdx.x; j < L; j += RK_THREADS) ysum += label[beg + j];
+    ysum = warp_sum(ysum);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = ysum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < RK_THREADS / 32; ++w) t += wsum[w];
+      total_y_s = t;
+    }
+    __syncthreads();
+    const double total_y = total_y_s;
+    const int n_top = L < k_max ? L : k_max;
+    // top-n_top by repeated arg-max below the previously selected key
+    Key last;
+    last.score = 0.0;
+    last.pos = -2;   // -2: nothing selected yet
+    for (int r = 0; r < n_top; ++r) {
+      Key mine;
+      mine.score = 0.0;
+      mine.pos = -1;
+      for (int j = threadIdx.x; j < L; j += RK_THREADS) {
+        Key c;
+        c.score = scores[order[beg + j]];
+        c.pos = j;
+        const bool below = last.pos == -2 || better(last, c);
+        if (below && better(c, mine)) mine = c;
+      }
+      last = block_best(mine, wbest);
+      if (threadIdx.x == 0) top_pos[r] = last.pos;
+    }
+    __syncthreads();
+    if (top_rows) {
+      for (int r = threadIdx.x; r < k_max; r += RK_THREADS)
+        top_rows[u * k_max + r] = r < n_top ? static_cast<int64_t>(order[beg + top_pos[r]]) : -1;
+    }
+    if (threadIdx.x < n_k) {
+      const int kk = threadIdx.x;
+      const int k = K[kk];
+      double *out = per_user + ((size_t)u * n_k + kk) * NTERMS;
+      if (total_y == 0.0) {
+        for (int c = 0; c < NTERMS; ++c) out[c] = 0.0;
+      } else {
+        const int n = L < k ? L : k;
+        double dcg = 0.0, ips = 0.0, hit = 0.0, ap = 0.0;
+        for (int j = 0; j < n; ++j) {
+          const double y = label[beg + top_pos[j]], ps = pscore[beg + top_pos[j]];
+          if (j == 0) {
+            dcg += y;
+            ips += y / ps;
+          } else {
+            const double d = log2(static_cast<double>(j + 1));
+            dcg += y / d;
+            ips += y / (ps * d);
+          }
+          hit += y;
+          if (y >= 1.0) ap += hit / static_cast<double>(j + 1);
+          if (hits) atomicAdd(hits + (size_t)kk * n_items + item[beg + top_pos[j]], 1);
+        }
+        out[0] = dcg;
+        out[1] = ips;
+        out[2] = L >= k ? pscore[beg + top_pos[k - 1]] : 0.0;
+        out[3] = L >= k ? 1.0 : 0.0;
+        out[4] = hit / total_y;
+        out[5] = ap;
+        out[6] = 1.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// fixed-order sum over users of every (k, term); one CTA per (k, term)
+__global__ void __launch_bounds__(256)
+rank_reduce_kernel(const double *__restrict__ per_user, int64_t n_users, int n_k, double *__restrict__ metrics) {
+  __shared__ double wsum[8];
+  const int kk = blockIdx.x / NTERMS, term = blockIdx.x % NTERMS;
+  double s = 0.0;
+  for (int64_t u = threadIdx.x; u < n_users; u += 256) s += per_user[((size_t)u * n_k + kk) * NTERMS + term];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    metrics[kk * RFM_RANK_NCOLS + term] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rank_covered_kernel(const int32_t *__restrict__ hits, int64_t n_items, double *__restrict__ metrics) {
+  __shared__ int wcnt[8];
+  const int kk = blockIdx.x;
+  int c = 0;
+  for (int64_t i = threadIdx.x; i < n_items; i += 256) c += hits[(size_t)kk * n_items + i] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += wcnt[w];
+    metrics[kk * RFM_RANK_NCOLS + RFM_RANK_COVERED] = static_cast<double>(t);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfm_ranker_create(rfm_ctx *ctx, int64_t n_rows, const int64_t *users, const int64_t *items,
+                      const double *labels, const double *pscores, int64_t n_items, rfm_ranker **out) {
+  RFM_REQUIRE(ctx && out, "rfm_ranker_create: NULL ctx/out");
+  *out = nullptr;
+  RFM_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffLL && n_items >= 1, "rfm_ranker_create: bad sizes");
+  RFM_REQUIRE(n_rows == 0 || (users && items && labels && pscores), "rfm_ranker_create: NULL column");
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  std::vector<int32_t> order((size_t)n_rows);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return users[a] < users[b]; });
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> g_item((size_t)n_rows);
+  std::vector<double> g_label((size_t)n_rows), g_ps((size_t)n_rows);
+  for (int64_t j = 0; j < n_rows; ++j) {
+    const int32_t r = order[(size_t)j];
+    if (j == 0 || users[r] != users[order[(size_t)j - 1]]) ptr.push_back(j);
+    RFM_REQUIRE(items[r] >= 0 && items[r] < n_items, "rfm_ranker_create: item id %lld outside [0, %lld)",
+                (long long)items[r], (long long)n_items);
+    g_item[(size_t)j] = (int32_t)items[r];
+    g_label[(size_t)j] = labels[r];
+    g_ps[(size_t)j] = pscores[r];
+  }
+  ptr.push_back(n_rows);
+  rfm_ranker *r = new (std::nothrow) rfm_ranker();
+  if (!r) return fail(RFM_ERR_NOMEM, "rfm_ranker_create: out of host memory");
+  r->ctx = ctx;
+  r->n_rows = n_rows;
+  r->n_users = (int64_t)ptr.size() - 1;
+  r->n_items = n_items;
+  auto body = [&]() -> int {
+    RFM_TRY(r->order.alloc(n_rows));
+    RFM_TRY(r->user_ptr.alloc(ptr.size()));
+    RFM_TRY(r->item.alloc(n_rows));
+    RFM_TRY(r->label.alloc(n_rows));
+    RFM_TRY(r->pscore.alloc(n_rows));
+    RFM_TRY(r->scores.alloc(n_rows));
+    RFM_TRY(r->K_dev.alloc(RK_MAX_NK));
+    RFM_TRY(r->metrics.alloc((size_t)RK_MAX_NK * RFM_RANK_NCOLS));
+    RFM_CUDA(cudaMemcpyAsync(r->order.p, order.data(), (size_t)n_rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(r->user_ptr.p, ptr.data(), ptr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(r->item.p, g_item.data(), (size_t)n_rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(r->label.p, g_label.data(), (size_t)n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(r->pscore.p, g_ps.data(), (size_t)n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RFM_OK;
+  };
+  const int rc = body();
+  if (rc != RFM_OK) {
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return RFM_OK;
+}
+
+int rfm_ranker_destroy(rfm_ranker *r) {
+  if (r) {
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    delete r;
+  }
+  return RFM_OK;
+}
+
+int rfm_ranker_num_users(rfm_ranker *r, int64_t *out) {
+  RFM_REQUIRE(r && out, "rfm_ranker_num_users: NULL argument");
+  *out = r->n_users;
+  return RFM_OK;
+}
+
+int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, int32_t n_k, double *out_metrics,
+                        int32_t *out_item_hits, int64_t *out_top_rows) {
+  RFM_REQUIRE(r && K && out_metrics, "rfm_ranker_evaluate: NULL argument");
+  RFM_REQUIRE(n_k >= 1 && n_k <= RK_MAX_NK, "rfm_ranker_evaluate: between 1 and %d ranking positions", RK_MAX_NK);
+  RFM_REQUIRE(r->n_rows == 0 || scores, "rfm_ranker_evaluate: scores is NULL");
+  int k_max = 0;
+  for (int j = 0; j < n_k; ++j) {
+    RFM_REQUIRE(K[j] >= 1 && K[j] <= RK_MAX_K, "rfm_ranker_evaluate: K[%d]=%d outside [1, %d]", j, K[j], RK_MAX_K);
+    k_max = std::max(k_max, (int)K[j]);
+  }
+  rfm_ctx *ctx = r->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_TRY(r->per_user.ensure((size_t)(r->n_users ? r->n_users : 1) * n_k * NTERMS));
+  RFM_TRY(r->hits.ensure((size_t)n_k * r->n_items));
+  if (out_top_rows) RFM_TRY(r->top_rows.ensure((size_t)(r->n_users ? r->n_users : 1) * k_max));
+  RFM_CUDA(cudaMemcpyAsync(r->scores.p, scores, (size_t)r->n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(r->K_dev.p, K, (size_t)n_k * 4, cudaMemcpyHostToDevice, ctx->stream));
+  RFM_CUDA(cudaMemsetAsync(r->hits.p, 0, (size_t)n_k * r->n_items * 4, ctx->stream));
+  RFM_CUDA(cudaMemsetAsync(r->metrics.p, 0, (size_t)RK_MAX_NK * RFM_RANK_NCOLS * 8, ctx->stream));
+  if (r->n_users > 0) {
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    const int grid = (int)(r->n_users < cap ? r->n_users : cap);
+    RFM_LAUNCH(ctx, rank_users_kernel, grid, RK_THREADS, 0, r->user_ptr.p, r->order.p, r->item.p, r->label.p,
+               r->pscore.p, r->scores.p, r->n_users, r->K_dev.p, (int)n_k, k_max, r->n_items, r->per_user.p,
+               r->hits.p, out_top_rows ? r->top_rows.p : (int64_t *)nullptr);
+    RFM_LAUNCH(ctx, rank_reduce_kernel, n_k * NTERMS, 256, 0, r->per_user.p, r->n_users, (int)n_k, r->metrics.p);
+  }
+  RFM_LAUNCH(ctx, rank_covered_kernel, n_k, 256, 0, r->hits.p, r->n_items, r->metrics.p);
+  RFM_CUDA(cudaMemcpyAsync(out_metrics, r->metrics.p, (size_t)n_k * RFM_RANK_NCOLS * 8, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  if (out_item_hits)
+    RFM_CUDA(cudaMemcpyAsync(out_item_hits, r->hits.p, (size_t)n_k * r->n_items * 4, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  if (out_top_rows && r->n_users > 0)
+    RFM_CUDA(cudaMemcpyAsync(out_top_rows, r->top_rows.p, (size_t)r->n_users * k_max * 8, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RFM_OK;
+}
+
+}  // extern "C"

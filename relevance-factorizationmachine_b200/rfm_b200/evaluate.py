@@ -1,0 +1,158 @@
+"""``TestEvaluator`` / ``ValEvaluator`` -- drop-ins for ``utils/evaluate.py:41-239``.
+
+Constructor fields, ``evaluate`` signatures, return types and error behaviour follow the
+reference; the per-user Python loop and the pandas group-by are replaced by one device call
+(``rfm_ranker_evaluate``, ``csrc/rank.cu``). ``interaction_df`` may be a pandas DataFrame (as in
+the reference) or any mapping of equally long columns ``user, item, label, pscore[, ones_pscore]``.
+
+Tie rule: score descending, later row first among exactly equal scores
+(``argsort(kind="stable")[::-1]``); the reference's default-sort order among exact ties is
+NumPy-build dependent.
+"""
+from __future__ import annotations
+
+import warnings
+from abc import ABC, abstractmethod
+from collections import defaultdict
+from ctypes import byref, c_int64
+from dataclasses import dataclass
+from typing import Dict, Tuple, Union
+
+import numpy as np
+
+from . import _capi
+from ._capi import RANK_COLS, RANK_NCOLS, check, lib, ptr
+from .metrics import calc_ips_of_dcg_at_k, gini_from_counts, metric_candidates
+
+METRIC_NAME_ERROR_MESSAGE = "metric_name must be in {}. metric_name: '{}'"
+
+
+class _Ranker(_capi._Handle):
+    _destroy = "rfm_ranker_destroy"
+
+    def __init__(self, ctx, users, items, labels, pscores, n_items):
+        super().__init__()
+        users = _capi.as_array(users, np.int64)
+        items = _capi.as_array(items, np.int64)
+        labels = _capi.as_array(labels, np.float64)
+        pscores = _capi.as_array(pscores, np.float64)
+        check(lib().rfm_ranker_create(ctx.handle, users.shape[0], ptr(users), ptr(items), ptr(labels),
+                                      ptr(pscores), n_items, byref(self.handle)))
+        self.n_rows, self.n_items = users.shape[0], n_items
+        n = c_int64()
+        check(lib().rfm_ranker_num_users(self.handle, byref(n)))
+        self.n_users = n.value
+
+    def evaluate(self, scores, K, want_hits=False, want_top=False):
+        scores = _capi.as_array(scores, np.float64)
+        if scores.shape[0] != self.n_rows:
+            raise ValueError("y_scores has %d entries, interaction_df has %d rows" % (scores.shape[0], self.n_rows))
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        metrics = np.zeros((len(K), RANK_NCOLS))
+        hits = np.zeros((len(K), self.n_items), dtype=np.int32) if want_hits else None
+        top = np.full((self.n_users, int(K.max())), -1, dtype=np.int64) if want_top else None
+        check(lib().rfm_ranker_evaluate(self.handle, ptr(scores), ptr(K), len(K), ptr(metrics), ptr(hits), ptr(top)))
+        return metrics, hits, top
+
+
+def _column(frame, name):
+    col = frame[name]
+    return col.to_numpy() if hasattr(col, "to_numpy") else np.asarray(col)
+
+
+@dataclass
+class _BaseEvaluator(ABC):
+    interaction_df: object
+    features: Dict[str, object]
+
+    @abstractmethod
+    def evaluate(self, *args, **kwargs):
+        ...
+
+    def _ranker(self, pscore_name="pscore", n_items=None, device=0):
+        cache = self.__dict__.setdefault("_rankers", {})
+        key = (pscore_name, len(_column(self.interaction_df, "user")))
+        if key not in cache:
+            items = _column(self.interaction_df, "item")
+            if n_items is None:
+                n_items = int(items.max()) + 1 if items.size else 1
+            cache[key] = _Ranker(_capi.Context.default(device), _column(self.interaction_df, "user"), items,
+                                 _column(self.interaction_df, "label"), _column(self.interaction_df, pscore_name),
+                                 n_items)
+        return cache[key]
+
+    def _record_scores(self, y_scores):
+        # the reference mutates interaction_df["y_score"] (evaluate.py:141, 223); keep that visible
+        try:
+            self.interaction_df["y_score"] = y_scores
+        except Exception:
+            pass
+
+
+@dataclass
+class TestEvaluator(_BaseEvaluator):
+    K: Tuple[int]
+    used_metrics: set
+    n_items: int
+
+    __test__ = False  # not a pytest class
+
+    def __post_init__(self) -> None:
+        self.metric_functions = {"ME": metric_candidates["ME"]}
+        for metric_name in self.used_metrics:
+            if metric_name not in metric_candidates:
+                raise ValueError(METRIC_NAME_ERROR_MESSAGE.format(metric_candidates.keys(), metric_name))
+            self.metric_functions[metric_name] = metric_candidates[metric_name]
+
+    def evaluate(self, y_scores: np.ndarray) -> defaultdict:
+        self._record_scores(y_scores)
+        need_hits = any(m in self.metric_functions for m in ("CatalogCoverage", "Gini"))
+        metrics, hits, _ = self._ranker(n_items=self.n_items).evaluate(y_scores, list(self.K), want_hits=need_hits)
+        results = defaultdict(list)
+        for j, _k in enumerate(self.K):
+            row = metrics[j]
+            kept = row[RANK_COLS["USERS"]]
+            for name in self.metric_functions:
+                if name == "CatalogCoverage":
+                    results[name].append(int(row[RANK_COLS["COVERED"]]) / self.n_items)
+                elif name == "Gini":
+                    results[name].append(gini_from_counts(hits[j].astype(np.int64)))
+                elif name == "ME":
+                    n = row[RANK_COLS["ME_COUNT"]]
+                    if n == 0:
+                        warnings.warn("Mean of empty slice", RuntimeWarning)
+                    results[name].append(row[RANK_COLS["ME_SUM"]] / n if n else np.nan)
+                else:
+                    col = {"DCG": "DCG_SUM", "Recall": "RECALL_SUM", "MAP": "MAP_SUM"}[name]
+                    results[name].append(row[RANK_COLS[col]] / kept if kept else np.nan)
+        return results
+
+    def top_rows(self, y_scores: np.ndarray, k: int) -> np.ndarray:
+        """(n_users, k) original row ids of every user's top-k (users ascending, -1 padded)."""
+        _, _, top = self._ranker(n_items=self.n_items).evaluate(y_scores, [k], want_top=True)
+        return top
+
+    def _group_by_user_data(self, *args, **kwargs):  # kept for API fidelity; grouping is done once on creation
+        raise NotImplementedError("grouping happens inside the device ranker")
+
+
+@dataclass
+class ValEvaluator(_BaseEvaluator):
+    k: int
+    metric_name: str
+
+    def __post_init__(self) -> None:
+        if self.metric_name == "DCG":
+            self.metric_func = calc_ips_of_dcg_at_k
+        else:
+            raise ValueError("You can use only DCG metric.")
+
+    def evaluate(self, y_scores: np.ndarray, estimator: str) -> float:
+        self._record_scores(y_scores)
+        pscore_name = "pscore" if estimator == "IPS" else "ones_pscore"
+        metrics, _, _ = self._ranker(pscore_name).evaluate(y_scores, [self.k])
+        kept = metrics[0, RANK_COLS["USERS"]]
+        return metrics[0, RANK_COLS["IPSDCG_SUM"]] / kept if kept else np.nan
+
+    def _group_by_user_data(self, *args, **kwargs):
+        raise NotImplementedError("grouping happens inside the device ranker")
