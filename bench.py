@@ -203,8 +203,8 @@ def run_ours(args):
         from rfm_b200 import dist as rdist
         dist = rdist.init(local_rank)
 
-    rows = args.rows // world
-    log, gen_s = make_data(rows, 2024, rank)
+    # data-parallel runs replicate the train set on every GPU (2.6 GB of 180 GB): same seed everywhere
+    log, gen_s = make_data(args.rows, 2024)
     X = log.fm_train["features"]
     pinned = []
     for a in (X.indptr, X.indices, X.data, log.fm_train["labels"], log.fm_train["pscores"]):
@@ -223,7 +223,12 @@ def run_ours(args):
     trainer = _FmTrainer(model._dev, train_rows, val_rows, B, W + 2 * K + 8)
 
     if dist is not None:
-        stepper = dist.make_fm_stepper(model, trainer, train_rows, val_rows, B, LR)
+        from rfm_b200 import dist as rdist
+        model.batch_size = B * world                       # weak scaling: B per GPU, global batch B*world
+        dp = rdist.make_fm_dp(model, trainer, dist, B * world, N_VAL, LR, lambda epoch: None)
+
+        def stepper(epoch, slot):
+            dp.step(epoch)
     else:
         def stepper(epoch, slot):
             check(lib().rfm_fm_train_epoch_sampled(trainer.handle, 12345, epoch, B, LR, slot))
@@ -257,13 +262,18 @@ def run_ours(args):
     prof = ctx.profile_end()
     tl = np.empty(W + 2 * K)
     vl = np.empty(W + 2 * K)
-    check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + 2 * K, ptr(tl), ptr(vl)))
+    if dist is None:
+        check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + 2 * K, ptr(tl), ptr(vl)))
+    else:
+        last = dp.loss_tensor.cpu().numpy()
+        tl[:] = last[0] / (B * world)
+        vl[:] = last[1] / N_VAL
     assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl)), "non-finite loss in the timed region"
 
     if rank != 0:
-        if dist is not None:
-            e2e = measure_e2e(args, log, local_rank, dist, world)
-            dist.shutdown()
+        if not args.no_e2e:
+            measure_e2e(args, log, local_rank, dist, world)
+        dist.shutdown()
         return
 
     sample_rows = _capi.feistel_batch(X.shape[0], B, W, 12345)
@@ -324,16 +334,13 @@ def measure_e2e(args, log, device, dist, world):
         n_ep = K if sampler == "feistel" else min(K, 16)
         if dist is not None and sampler == "legacy":
             continue
-        warm = FactorizationMachines("IPS", 2, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
-                                     sampler=sampler, device=device)
-        if dist is not None:
-            warm.distributed = dist
+        warm = FactorizationMachines("IPS", 2, K_FACTORS, LR, B * world, 12345, log.n_features, dtype=args.dtype,
+                                     sampler=sampler, device=device, distributed=dist)
         warm.fit(log.fm_train, log.fm_val)
         del warm
-        model = FactorizationMachines("IPS", n_ep, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
-                                      sampler=sampler, device=device)
+        model = FactorizationMachines("IPS", n_ep, K_FACTORS, LR, B * world, 12345, log.n_features,
+                                      dtype=args.dtype, sampler=sampler, device=device, distributed=dist)
         if dist is not None:
-            model.distributed = dist
             dist.barrier()
         model._context().synchronize()
         t0 = time.perf_counter()

@@ -120,14 +120,19 @@ int rfm_fm_train_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t bat
 int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t batch,
                                double lr, int64_t slot);
 /* Data-parallel split of the same step: rank-local gradient of a batch
- * slice into a dense buffer [sum_e | dw (n) | dV (n x kpad)], to be all-reduced by the
- * caller, then applied identically on every rank. */
+ * slice into a dense buffer [sum_e, 3 pad | dw (n, padded to a multiple of 4) | dV (n x kpad)]
+ * (rfm_fm_grad_size scalars of the model dtype), to be all-reduced by the caller, then applied
+ * identically on every rank. */
 int rfm_fm_grad_size(rfm_fm_trainer *t, int64_t *n_scalars);
 int rfm_fm_grad_ptr_dev(rfm_fm_trainer *t, void **grad_dev);
 int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch);
+/* same, the slice [q_begin, q_begin + batch) of the epoch's Feistel permutation drawn on the device. */
+int rfm_fm_grad_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t q_begin,
+                              int64_t batch);
 int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr);
 /* post-update loss of a batch slice / of val rows [row_begin, row_end): SUM of the per-row
- * terms (not divided) written to device slots so ranks can all-reduce them. */
+ * terms (not divided) written to device slots so ranks can all-reduce them. batch_rows == NULL
+ * reuses the batch that the last grad call left on the device. */
 int rfm_fm_loss_sums_ptr_dev(rfm_fm_trainer *t, void **sums_dev /* double[2]: batch, val */);
 int rfm_fm_loss_sums(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch,
                      int64_t val_begin, int64_t val_end);

@@ -53,8 +53,9 @@ def fm_predict(X: csr_matrix, w0, w, V):
     return sigmoid(fm_logits(X, float(np.asarray(w0).ravel()[0]), w, V))
 
 
-def fm_step(X: csr_matrix, y, ps, w0, w, V, lr: float):
-    """One reference epoch on an already-sampled batch. Returns new (w0, w, V)."""
+def fm_grad(X: csr_matrix, y, ps, w0, w, V):
+    """Descent direction of one batch (a plain SUM over its rows, so partial batches add up):
+    returns (sum_t e_t,  X^T e,  sum_t e_t (x_tj s_t - x_tj^2 v_j))."""
     w0 = float(np.asarray(w0).ravel()[0])
     e = y / ps - fm_predict(X, w0, w, V)                # fm.py:80, pre-update parameters
     S = X.dot(V)                                        # == (V.T @ X.T).T, fm.py:165
@@ -62,7 +63,13 @@ def fm_step(X: csr_matrix, y, ps, w0, w, V, lr: float):
     a = np.asarray(Xe.sum(axis=0)).ravel()              # X^T e           (fm.py:153)
     c = np.asarray(X.power(2).multiply(e[:, None]).sum(axis=0)).ravel()   # (X∘X)^T e
     G = Xe.T.dot(S) - c[:, None] * V                    # sum_t e_t (x_tj s_t - x_tj^2 v_j)
-    return np.array([w0 + lr * e.sum()]), w + lr * a, V + lr * G
+    return e.sum(), a, G
+
+
+def fm_step(X: csr_matrix, y, ps, w0, w, V, lr: float):
+    """One reference epoch on an already-sampled batch. Returns new (w0, w, V)."""
+    g0, a, G = fm_grad(X, y, ps, w0, w, V)
+    return np.array([float(np.asarray(w0).ravel()[0]) + lr * g0]), w + lr * a, V + lr * G
 
 
 def legacy_batch(n_rows: int, batch_size: int, epoch: int) -> np.ndarray:

@@ -58,6 +58,12 @@ enum RowsMode { MODE_TRAIN = 0, MODE_LOSS = 1, MODE_PREDICT = 2 };
 
 size_t dsize(int dtype) { return dtype == RFM_F64 ? 8 : 4; }
 
+// dense gradient buffer (data-parallel mode): [sum_e, pad x3 | dw (n, padded to x4) | dV (n x kp)].
+// Offsets are multiples of 4 elements so dV is 16-byte aligned for float and double vector stores.
+constexpr int64_t GRAD_W_OFF = 4;
+int64_t grad_v_off(int64_t n) { return GRAD_W_OFF + ((n + 3) / 4) * 4; }
+int64_t grad_total(int64_t n, int kp) { return grad_v_off(n) + n * kp; }
+
 // ---- small conversion kernels -------------------------------------------------------------------
 template <typename T>
 __global__ void convert_f64_kernel(const double *__restrict__ in, T *__restrict__ out, int64_t n) {
@@ -109,9 +115,10 @@ __global__ void check_columns_kernel(const int32_t *__restrict__ col, int64_t nn
 }
 
 // ---- batch preparation --------------------------------------------------------------------------
-__global__ void feistel_sample_kernel(FeistelKey key, int64_t batch, int64_t *__restrict__ idx) {
+__global__ void feistel_sample_kernel(FeistelKey key, int64_t q0, int64_t batch, int64_t *__restrict__ idx) {
+  // positions [q0, q0 + batch) of the epoch's permutation (q0 > 0: a rank's slice of a global batch)
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < batch; q += (int64_t)gridDim.x * blockDim.x)
-    idx[q] = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(q), key));
+    idx[q] = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(q0 + q), key));
 }
 
 __global__ void row_len_kernel(const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ idx,
@@ -673,9 +680,9 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
   c.long_cap = t->long_cap;
   if (DP) {
     T *g = reinterpret_cast<T *>(t->grad.p);
-    c.grad_w = g + 1;
-    c.grad_V = g + 1 + m->n;
-    RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)(1 + m->n + m->n * m->kp) * sizeof(T), ctx->stream));
+    c.grad_w = g + GRAD_W_OFF;
+    c.grad_V = g + grad_v_off(m->n);
+    RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)grad_total(m->n, m->kp) * sizeof(T), ctx->stream));
     // sum_e goes to grad[0] as a plain sum (dst_d unused); w0 itself is updated in apply
     RFM_LAUNCH(ctx, reduce_partials_kernel<double>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 0, 0.0,
                (double *)nullptr, t->loss_sums.p + 2);
@@ -1106,13 +1113,14 @@ int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch,
   RFM_CUDA(cudaSetDevice(ctx->device));
   RFM_REQUIRE(t->train->n_rows <= (1LL << 32), "rfm_fm_train_epoch_sampled: at most 2^32 rows");
   const FeistelKey key = make_feistel_key((uint64_t)t->train->n_rows, seed, epoch);
-  RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, key, batch, t->idx.p);
+  RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, key, (int64_t)0, batch,
+             t->idx.p);
   return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot) : epoch_impl<float>(t, batch, lr, slot);
 }
 
 int rfm_fm_grad_size(rfm_fm_trainer *t, int64_t *n_scalars) {
   RFM_REQUIRE(t && n_scalars, "rfm_fm_grad_size: NULL argument");
-  *n_scalars = 1 + t->m->n + t->m->n * t->m->kp;
+  *n_scalars = grad_total(t->m->n, t->m->kp);
   return RFM_OK;
 }
 
@@ -1137,14 +1145,10 @@ __global__ void store_sum_e_kernel(const double *__restrict__ src, T *__restrict
 }  // namespace
 extern "C" {
 
-int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
-  RFM_TRY(check_batch(t, batch, 0, "rfm_fm_grad_epoch"));
-  RFM_REQUIRE(batch_rows, "rfm_fm_grad_epoch: batch_rows is NULL");
+static int grad_epoch_tail(rfm_fm_trainer *t, int64_t batch) {
   rfm_ctx *ctx = t->m->ctx;
-  RFM_CUDA(cudaSetDevice(ctx->device));
   void *g = nullptr;
   RFM_TRY(rfm_fm_grad_ptr_dev(t, &g));
-  RFM_TRY(stage_batch(t, batch_rows, batch));
   if (t->m->dtype == RFM_F64) {
     RFM_TRY((step_core<double, true>(t, batch, 0.0)));
     RFM_LAUNCH(ctx, store_sum_e_kernel<double>, 1, 32, 0, t->loss_sums.p + 2, reinterpret_cast<double *>(g));
@@ -1153,6 +1157,31 @@ int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batc
     RFM_LAUNCH(ctx, store_sum_e_kernel<float>, 1, 32, 0, t->loss_sums.p + 2, reinterpret_cast<float *>(g));
   }
   return RFM_OK;
+}
+
+int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
+  RFM_TRY(check_batch(t, batch, 0, "rfm_fm_grad_epoch"));
+  RFM_REQUIRE(batch_rows, "rfm_fm_grad_epoch: batch_rows is NULL");
+  RFM_CUDA(cudaSetDevice(t->m->ctx->device));
+  for (int64_t q = 0; q < batch; ++q)
+    RFM_REQUIRE(batch_rows[q] >= 0 && batch_rows[q] < t->train->n_rows, "rfm_fm_grad_epoch: row id %lld out of range",
+                (long long)batch_rows[q]);
+  RFM_TRY(stage_batch(t, batch_rows, batch));
+  return grad_epoch_tail(t, batch);
+}
+
+int rfm_fm_grad_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t q_begin, int64_t batch) {
+  RFM_TRY(check_batch(t, batch, 0, "rfm_fm_grad_epoch_sampled"));
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_REQUIRE(q_begin >= 0 && q_begin + batch <= t->train->n_rows,
+              "Cannot sample %lld out of arrays with dim %lld when replace is False", (long long)(q_begin + batch),
+              (long long)t->train->n_rows);
+  RFM_REQUIRE(t->train->n_rows <= (1LL << 32), "rfm_fm_grad_epoch_sampled: at most 2^32 rows");
+  const FeistelKey key = make_feistel_key((uint64_t)t->train->n_rows, seed, epoch);
+  RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, key, q_begin, batch,
+             t->idx.p);
+  return grad_epoch_tail(t, batch);
 }
 
 int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
@@ -1165,13 +1194,13 @@ int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
   if (m->dtype == RFM_F64) {
     double *gr = reinterpret_cast<double *>(t->grad.p);
     RFM_LAUNCH(ctx, apply_grad_kernel<double>, 1, 32, 0, reinterpret_cast<double *>(m->w0.p), gr, (int64_t)1, lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->w.p), gr + 1, m->n, lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->V.p), gr + 1 + m->n, nV, lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->w.p), gr + GRAD_W_OFF, m->n, lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->V.p), gr + grad_v_off(m->n), nV, lr);
   } else {
     float *gr = reinterpret_cast<float *>(t->grad.p);
     RFM_LAUNCH(ctx, apply_grad_kernel<float>, 1, 32, 0, reinterpret_cast<float *>(m->w0.p), gr, (int64_t)1, (float)lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->w.p), gr + 1, m->n, (float)lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->V.p), gr + 1 + m->n, nV,
+    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->w.p), gr + GRAD_W_OFF, m->n, (float)lr);
+    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->V.p), gr + grad_v_off(m->n), nV,
                (float)lr);
   }
   return RFM_OK;
@@ -1191,10 +1220,7 @@ int rfm_fm_loss_sums(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch
   RFM_REQUIRE(batch >= 0 && batch <= t->max_batch, "rfm_fm_loss_sums: bad batch");
   const int64_t nv = t->val ? t->val->n_rows : 0;
   RFM_REQUIRE(val_begin >= 0 && val_begin <= val_end && val_end <= nv, "rfm_fm_loss_sums: bad val range");
-  if (batch > 0) {
-    RFM_REQUIRE(batch_rows, "rfm_fm_loss_sums: batch_rows is NULL");
-    RFM_TRY(stage_batch(t, batch_rows, batch));
-  }
+  if (batch > 0 && batch_rows) RFM_TRY(stage_batch(t, batch_rows, batch));  // NULL: reuse the batch on the device
   if (t->m->dtype == RFM_F64) {
     RFM_TRY(loss_pass<double>(t, t->train, t->idx.p, 0, batch, 1.0, t->loss_sums.p));
     RFM_TRY(loss_pass<double>(t, t->val ? t->val : t->train, nullptr, val_begin, val_end - val_begin, 1.0,

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "rfm_fm_grad_size": ([_P, POINTER(c_int64)], c_int),
     "rfm_fm_grad_ptr_dev": ([_P, POINTER(_P)], c_int),
     "rfm_fm_grad_epoch": ([_P, _P, c_int64], c_int),
+    "rfm_fm_grad_epoch_sampled": ([_P, c_uint32, c_uint32, c_int64, c_int64], c_int),
     "rfm_fm_apply_grad": ([_P, c_double], c_int),
     "rfm_fm_loss_sums_ptr_dev": ([_P, POINTER(_P)], c_int),
     "rfm_fm_loss_sums": ([_P, _P, c_int64, c_int64, c_int64], c_int),

@@ -1,0 +1,162 @@
+"""Data-parallel FM training over one 8xB200 box.
+
+One process per GPU (``torchrun``); ``torch.distributed`` is plumbing only: rendezvous and the
+all-reduce of the dense gradient ``[sum_e | dw (n) | dV (n x kpad)]`` that ``rfm_fm_grad_epoch``
+leaves in device memory. The FM gradient is a plain sum over batch rows (``src/fm.py:142,153,
+178-180``), so the step shards naturally:
+
+    every rank: same parameters, same global batch order (the sampler is deterministic)
+    rank r    : forward + residual + segmented column reduction over ITS slice of the batch
+    all ranks : all-reduce(sum) of the gradient buffer             <- the one exchange step
+    every rank: identical dense apply  w0 += lr*g0, w += lr*dw, V += lr*dV
+    losses    : per-rank partial sums over the batch slice / a val slice, all-reduced, then / count
+
+With one rank this is exactly the single-GPU step; with G ranks results differ from it only by the
+association of the cross-rank sum. MF's sequential per-sample semantics do not shard ("replicas only").
+
+``DataParallelFM`` holds the algorithm with the device work behind four callables so that the
+composition can be exercised on CPU with the ``gloo`` backend and the NumPy oracle
+(tests/test_dist_cpu.py); ``make_fm_stepper`` binds it to the C ABI for real runs.
+"""
+from __future__ import annotations
+
+import os
+from ctypes import byref, c_int64, c_void_p
+
+import numpy as np
+
+
+def slice_bounds(n: int, world: int, rank: int):
+    """Contiguous, balanced slices of range(n): the first n % world ranks get one extra element."""
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+class DistEnv:
+    """Thin wrapper over torch.distributed (NCCL on GPUs, gloo on CPU for tests)."""
+
+    def __init__(self, backend: str, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.device = device
+        if not dist.is_initialized():
+            kwargs = {}
+            if backend == "nccl" and device is not None:
+                kwargs["device_id"] = torch.device("cuda", device)
+            dist.init_process_group(backend=backend, **kwargs)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.backend = backend
+
+    def _scalar(self, value, op):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64,
+                              device="cuda:%d" % self.device if self.backend == "nccl" else "cpu")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, value):
+        return self._scalar(value, self.dist.ReduceOp.MAX)
+
+    def sum_over_ranks(self, value):
+        return self._scalar(value, self.dist.ReduceOp.SUM)
+
+    def barrier(self):
+        if self.backend == "nccl":
+            self.torch.cuda.synchronize(self.device)
+        self.dist.barrier()
+        if self.backend == "nccl":
+            self.torch.cuda.synchronize(self.device)
+
+    def all_reduce_sum(self, tensor):
+        self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM)
+
+    def shutdown(self):
+        if self.dist.is_initialized():
+            self.dist.destroy_process_group()
+
+
+def init(local_rank: int) -> DistEnv:
+    """NCCL process group for this rank's GPU; reads RANK/WORLD_SIZE/MASTER_* from the env."""
+    import torch
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local_rank)
+    return DistEnv("nccl", local_rank)
+
+
+class _DeviceArray:
+    """Exposes library-owned device memory to torch via __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def device_tensor(ptr: int, n: int, dtype: str, device: int):
+    import torch
+    typestr = "<f8" if dtype == "float64" else "<f4"
+    return torch.as_tensor(_DeviceArray(ptr, n, typestr), device="cuda:%d" % device)
+
+
+class DataParallelFM:
+    """The DP step, independent of where the arithmetic runs.
+
+    local_grad(begin, end, epoch) -> None   fill the gradient buffer for global-batch slice [begin, end)
+    grad_tensor                              torch tensor aliasing that buffer (all-reduced in place)
+    apply(lr) -> None                        params += lr * grad, identically on every rank
+    local_loss_sums(begin, end, vbegin, vend) -> None   fill loss_tensor[0:2] with this rank's partial sums
+    """
+
+    def __init__(self, env: DistEnv, global_batch: int, n_val: int, lr: float, local_grad, grad_tensor, apply,
+                 local_loss_sums, loss_tensor):
+        self.env, self.global_batch, self.n_val, self.lr = env, global_batch, n_val, lr
+        self.local_grad, self.grad_tensor, self.apply = local_grad, grad_tensor, apply
+        self.local_loss_sums, self.loss_tensor = local_loss_sums, loss_tensor
+        if global_batch < env.world:
+            raise ValueError("global batch (%d) must be at least the number of ranks (%d)" % (global_batch, env.world))
+        self.begin, self.end = slice_bounds(global_batch, env.world, env.rank)
+        self.vbegin, self.vend = slice_bounds(n_val, env.world, env.rank)
+
+    def step(self, epoch: int):
+        """One reference epoch over the global batch; returns the (device/CPU) tensor holding
+        [train_loss, val_loss] of this step (valid after the caller synchronises)."""
+        self.local_grad(self.begin, self.end, epoch)
+        self.env.all_reduce_sum(self.grad_tensor)
+        self.apply(self.lr)
+        self.local_loss_sums(self.begin, self.end, self.vbegin, self.vend)
+        self.env.all_reduce_sum(self.loss_tensor)
+        return self.loss_tensor
+
+
+def make_fm_dp(model, trainer, env: DistEnv, global_batch: int, n_val: int, lr: float, batch_source):
+    """Bind DataParallelFM to the C ABI.
+
+    batch_source(epoch) -> None | np.ndarray: None selects the device Feistel sampler; an int64
+    array is the epoch's GLOBAL batch order (legacy sampler), identical on every rank.
+    """
+    from . import _capi
+    from ._capi import check, lib, ptr
+    n = c_int64()
+    check(lib().rfm_fm_grad_size(trainer.handle, byref(n)))
+    gp, lp = c_void_p(), c_void_p()
+    check(lib().rfm_fm_grad_ptr_dev(trainer.handle, byref(gp)))
+    check(lib().rfm_fm_loss_sums_ptr_dev(trainer.handle, byref(lp)))
+    grad_tensor = device_tensor(gp.value, n.value, model.dtype, env.device)
+    loss_tensor = device_tensor(lp.value, 2, "float64", env.device)
+    state = {}
+
+    def local_grad(begin, end, epoch):
+        rows = batch_source(epoch)
+        state["rows"] = rows
+        if rows is None:
+            check(lib().rfm_fm_grad_epoch_sampled(trainer.handle, model.seed & 0xFFFFFFFF, epoch, begin, end - begin))
+        else:
+            mine = np.ascontiguousarray(rows[begin:end], dtype=np.int64)
+            check(lib().rfm_fm_grad_epoch(trainer.handle, ptr(mine), end - begin))
+
+    def apply(step_lr):
+        check(lib().rfm_fm_apply_grad(trainer.handle, step_lr))
+
+    def local_loss_sums(begin, end, vbegin, vend):
+        check(lib().rfm_fm_loss_sums(trainer.handle, None, end - begin, vbegin, vend))
+
+    return DataParallelFM(env, global_batch, n_val, lr, local_grad, grad_tensor, apply, local_loss_sums, loss_tensor)

@@ -53,6 +53,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
     sampler: str = "legacy"       # "legacy" = RandomState(epoch) order, "feistel" = device sampler
     device: int = 0
     progress: bool = False        # tqdm bar like the reference's (src/fm.py:71)
+    distributed: object = None    # rfm_b200.dist.DistEnv: data-parallel fit over its ranks
     _dev: object = field(default=None, init=False, repr=False, compare=False)
 
     def __post_init__(self) -> None:
@@ -138,6 +139,8 @@ class FactorizationMachines(PointwiseBaseRecommender):
         train_rows = self._rows(X, train["labels"], train["pscores"])
         val_rows = self._rows(val["features"], val["labels"], val["pscores"])
         self.sync_to_device()
+        if self.distributed is not None:
+            return self._fit_data_parallel(train_rows, val_rows, n_rows)
         trainer = _FmTrainer(self._dev, train_rows, val_rows, self.batch_size, max(self.n_epochs, 1))
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
@@ -172,6 +175,39 @@ class FactorizationMachines(PointwiseBaseRecommender):
         trainer.close()
         self.sync_to_host()
         return train_loss.tolist(), val_loss.tolist()
+
+    def _fit_data_parallel(self, train_rows, val_rows, n_rows) -> tuple:
+        """Same epochs, the batch cut into one contiguous slice per rank, one gradient all-reduce
+        per epoch, identical apply everywhere. Every rank returns the same losses/parameters."""
+        from . import dist as rdist
+        env = self.distributed
+        ctx = self._context()
+        begin, end = rdist.slice_bounds(self.batch_size, env.world, env.rank)
+        trainer = _FmTrainer(self._dev, train_rows, val_rows, max(end - begin, 1), 1)
+        epochs = range(self.n_epochs)
+        prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
+        source = (lambda epoch: prefetch.next()) if prefetch is not None else (lambda epoch: None)
+        dp = rdist.make_fm_dp(self, trainer, env, self.batch_size, val_rows.n_rows, self.lr, source)
+        torch = env.torch
+        hist = torch.zeros((max(self.n_epochs, 1), 2), dtype=torch.float64, device=dp.loss_tensor.device)
+        eval_rows = self._rows(self.evaluator.features[self.model_name]) if self.evaluator is not None else None
+        launches0 = ctx.launch_count()
+        try:
+            for epoch in epochs:
+                hist[epoch].copy_(dp.step(epoch))
+                if eval_rows is not None:
+                    scores = np.empty(eval_rows.n_rows)
+                    check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
+                    self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
+            out = hist.cpu().numpy()
+        finally:
+            if prefetch is not None:
+                prefetch.close()
+        self.last_fit_stats = {"gpu_launches": ctx.launch_count() - launches0,
+                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes}
+        trainer.close()
+        self.sync_to_host()
+        return (out[: self.n_epochs, 0] / self.batch_size).tolist(), (out[: self.n_epochs, 1] / val_rows.n_rows).tolist()
 
     def predict(self, X) -> np.ndarray:
         self.sync_to_device()
