@@ -43,7 +43,7 @@ struct rfm_fm {
   int dtype = RFM_F64;
   int64_t n = 0;
   int k = 0, kp = 0, nch = 0;
-  DevBuf<unsigned char> w0, w, V;
+  DevBuf<unsigned char> w0, w, V, vn;   // vn[j] = ||v_j||^2
 };
 
 namespace {
@@ -130,6 +130,19 @@ __global__ void row_len_kernel(const int64_t *__restrict__ row_ptr, const int64_
 }
 
 // ---- the row pass ---------------------------------------------------------------------------------
+// How a kernel's per-warp partial sums (sum of residuals, or of loss terms) become one scalar
+// without a second launch: every CTA writes its partial, takes a ticket, and the CTA that draws
+// the last ticket adds all CTA partials in a fixed order and finishes the scalar.
+struct Finish {
+  int op;                  // 0: *dst_T += scale * sum (w0 += lr * sum_e), also *dst_d = sum if set
+                           // 1: *dst_d = sum * scale  (loss mean)
+  double scale;
+  void *dst_T;
+  double *dst_d;
+  double *block_partials;  // [gridDim.x]
+  unsigned int *ticket;    // zero before the launch; reset by the finishing CTA
+};
+
 template <typename T>
 struct RowsArgs {
   const int64_t *row_ptr;
@@ -138,17 +151,22 @@ struct RowsArgs {
   const T *yp;
   const int64_t *idx;     // batch row ids, or nullptr: rows [row0, row0 + n)
   int64_t row0, n;
-  const T *w0, *w, *V;
+  const T *w0, *w, *V, *vn;   // vn[j] = ||v_j||^2, kept in step with V
   int kp;
   // MODE_TRAIN outputs
   T *S, *E;
-  const uint32_t *bptr;   // exclusive scan of the batch's row lengths
+  const uint32_t *bptr;   // ragged layout: exclusive scan of the batch's row lengths
+  uint32_t stride;        // fixed-stride layout when > 0: row q owns triples [q*stride, (q+1)*stride)
+  uint32_t sentinel;      // key written into unused slots of the fixed-stride layout (== n_features)
   uint32_t *keys, *pos;
   T *xs;
+  // SAMPLED: the batch is drawn here: row id of position q is feistel(q0 + q); also stored to idx_out
+  FeistelKey fkey;
+  int64_t q0;
+  int64_t *idx_out;
   // MODE_PREDICT output
   double *out;
-  // MODE_TRAIN / MODE_LOSS: one partial sum per warp, in double
-  double *partials;
+  Finish fin;
 };
 
 __device__ __forceinline__ double sigmoid_ref(double z) {
@@ -157,103 +175,166 @@ __device__ __forceinline__ double sigmoid_ref(double z) {
   return 1.0 / (1.0 + exp(-z));
 }
 
-template <typename T, int NCH, int MODE>
+template <typename T>
+__device__ __forceinline__ void block_finish(double warp_partial, const Finish &f) {
+  __shared__ double wsum[32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  if (lane == 0) wsum[wid] = warp_partial;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < n_warps; ++w) s += wsum[w];
+    f.block_partials[blockIdx.x] = s;
+    __threadfence();
+    is_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(f.block_partials + i);
+  s = warp_sum(s);
+  if (lane == 0) wsum[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < n_warps; ++w) tot += wsum[w];
+    if (f.op == 0) {
+      if (f.dst_T) {
+        T *d = static_cast<T *>(f.dst_T);
+        *d = static_cast<T>(static_cast<double>(*d) + f.scale * tot);
+      }
+      if (f.dst_d) *f.dst_d = tot;
+    } else {
+      *f.dst_d = tot * f.scale;
+    }
+    *f.ticket = 0u;
+  }
+}
+
+// sum over the TPR lanes of a row group (xor butterfly; every lane of the group gets the total)
+template <int TPR, typename T>
+__device__ __forceinline__ T group_sum(T v, unsigned mask) {
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+// TPR lanes cooperate on one row (32/TPR rows per warp); lane g of the group holds the NCV
+// 2-element chunks {(ch*TPR + g)*2, +1}, so each load instruction of a group reads TPR*2 contiguous
+// elements of a V row. The per-non-zero bookkeeping (broadcast of (column, x), address arithmetic,
+// loop control) and the scalar epilogue are shared by all rows of the warp.
+template <typename T, int TPR, int NCV, int MODE, bool SAMPLED>
 __global__ void __launch_bounds__(ROWS_THREADS)
 fm_rows_kernel(const RowsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
-  const int lane = lane_id();
+  constexpr int GPW = 32 / TPR;
+  const int lane = lane_id(), g = lane % TPR, grp = lane / TPR;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_groups = nw * GPW;
   const T w0 = __ldg(a.w0);
   double partial = 0.0;
-  for (int64_t q = gw; q < a.n; q += nw) {
-    const int64_t t = a.idx ? a.idx[q] : a.row0 + q;
-    const int64_t beg = a.row_ptr[t], end = a.row_ptr[t + 1];
-    V2 acc[NCH];
+  for (int64_t qb = gw * GPW; qb < a.n; qb += n_groups) {   // warp-uniform trip count
+    const int64_t q = qb + grp;
+    const bool active = q < a.n;
+    int64_t t = 0, beg = 0, end = 0;
+    if (active) {
+      if (SAMPLED) {
+        t = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(a.q0 + q), a.fkey));
+        if (g == 0) a.idx_out[q] = t;
+      } else {
+        t = a.idx ? a.idx[q] : a.row0 + q;
+      }
+      beg = a.row_ptr[t];
+      end = a.row_ptr[t + 1];
+    }
+    const int len = static_cast<int>(end - beg);
+    const int maxlen = __reduce_max_sync(FULL, len);
+    V2 acc[NCV];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
-    T qsum = T(0), lin = T(0);
+    for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
+    // scalar part of the logit owned by this lane: sum over its own entries of x w_j - x^2 ||v_j||^2 / 2
+    T sl = T(0);
     uint32_t out_base = 0;
-    if (MODE == MODE_TRAIN) out_base = a.bptr[q];
-    for (int64_t base = beg; base < end; base += 32) {
-      const int cnt = static_cast<int>(end - base < 32 ? end - base : 32);
+    if (MODE == MODE_TRAIN && active) out_base = a.stride ? static_cast<uint32_t>(q) * a.stride : a.bptr[q];
+    for (int off0 = 0; off0 < maxlen; off0 += TPR) {
+      const int off = off0 + g;
       int c = 0;
       T x = T(0);
-      if (lane < cnt) {
-        c = a.col[base + lane];
-        x = a.val[base + lane];
-        lin += x * __ldg(a.w + c);
+      if (off < len) {
+        c = a.col[beg + off];
+        x = a.val[beg + off];
+        sl += x * __ldg(a.w + c) - T(0.5) * (x * x) * __ldg(a.vn + c);
         if (MODE == MODE_TRAIN) {
-          const uint32_t o = out_base + static_cast<uint32_t>(base - beg) + lane;
+          const uint32_t o = out_base + static_cast<uint32_t>(off);
           a.keys[o] = static_cast<uint32_t>(c);
           a.pos[o] = static_cast<uint32_t>(q);
           a.xs[o] = x;
         }
       }
+      const int cnt = maxlen - off0 < TPR ? maxlen - off0 : TPR;
 #pragma unroll 4
       for (int i = 0; i < cnt; ++i) {
-        const int cj = __shfl_sync(FULL, c, i);
-        const T xj = __shfl_sync(FULL, x, i);
-        const V2 *vrow = reinterpret_cast<const V2 *>(a.V + (size_t)cj * a.kp) + lane;
-        const T xx = xj * xj;
+        const int cj = __shfl_sync(FULL, c, i, TPR);     // entries past a shorter row's end carry x = 0
+        const T xj = __shfl_sync(FULL, x, i, TPR);
+        const V2 *vrow = reinterpret_cast<const V2 *>(a.V + (size_t)cj * a.kp) + g;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          const V2 v = __ldg(vrow + ch * 32);
+        for (int ch = 0; ch < NCV; ++ch) {
+          const V2 v = __ldg(vrow + ch * TPR);
           acc[ch].x += xj * v.x;
           acc[ch].y += xj * v.y;
-          qsum += xx * (v.x * v.x + v.y * v.y);
         }
       }
     }
+    if (MODE == MODE_TRAIN && active && a.stride) {   // unused slots of this row sort behind every real column
+      for (uint32_t si = static_cast<uint32_t>(len) + g; si < a.stride; si += TPR) a.keys[out_base + si] = a.sentinel;
+    }
     T ss = T(0);
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) ss += acc[ch].x * acc[ch].x + acc[ch].y * acc[ch].y;
-    lin = warp_sum(lin);
-    ss = warp_sum(ss);
-    qsum = warp_sum(qsum);
-    const T z = (w0 + lin) + T(0.5) * (ss - qsum);
+    for (int ch = 0; ch < NCV; ++ch) ss += acc[ch].x * acc[ch].x + acc[ch].y * acc[ch].y;
+    const T z = w0 + group_sum<TPR>(sl + T(0.5) * ss, FULL);
     const double p = sigmoid_ref(static_cast<double>(z));
-    if (MODE == MODE_TRAIN) {
-      const double e = static_cast<double>(a.yp[t]) - p;
-      V2 *srow = reinterpret_cast<V2 *>(a.S + (size_t)q * a.kp) + lane;
+    if (active) {
+      if (MODE == MODE_TRAIN) {
+        const double e = static_cast<double>(a.yp[t]) - p;
+        V2 *srow = reinterpret_cast<V2 *>(a.S + (size_t)q * a.kp) + g;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) srow[ch * 32] = acc[ch];
-      if (lane == 0) a.E[q] = static_cast<T>(e);
-      partial += e;
-    } else if (MODE == MODE_LOSS) {
-      // src/base.py:56-59 term by term (1 - p formed by subtraction, eps inside both logs)
-      const double r = static_cast<double>(a.yp[t]);
-      partial -= r * log(p + 1e-8) + (1.0 - r) * log(1.0 - p + 1e-8);
-    } else {
-      if (lane == 0) a.out[q] = p;
-    }
-  }
-  if (MODE != MODE_PREDICT && lane == 0) a.partials[gw] = partial;
-}
-
-// Sum the per-warp partials in a fixed tree and finish the scalar it feeds.
-//   op 0: *dst_T += scale * sum   (w0 += lr * sum_e)      op 1: *dst_d = sum * scale  (loss mean)
-template <typename T>
-__global__ void __launch_bounds__(1024)
-reduce_partials_kernel(const double *__restrict__ partials, int n, int op, double scale, T *dst_T,
-                       double *dst_d) {
-  __shared__ double wsum[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) s += partials[i];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = wsum[threadIdx.x];
-    v = warp_sum(v);
-    if (threadIdx.x == 0) {
-      if (op == 0) {
-        if (dst_T) *dst_T = static_cast<T>(static_cast<double>(*dst_T) + scale * v);
-        if (dst_d) *dst_d = v;
+        for (int ch = 0; ch < NCV; ++ch) srow[ch * TPR] = acc[ch];
+        if (g == 0) {
+          a.E[q] = static_cast<T>(e);
+          partial += e;
+        }
+      } else if (MODE == MODE_LOSS) {
+        // src/base.py:56-59 term by term (1 - p formed by subtraction, eps inside both logs)
+        if (g == 0) {
+          const double r = static_cast<double>(a.yp[t]);
+          partial -= r * log(p + 1e-8) + (1.0 - r) * log(1.0 - p + 1e-8);
+        }
       } else {
-        *dst_d = v * scale;
+        if (g == 0) a.out[q] = p;
       }
     }
+  }
+  if (MODE != MODE_PREDICT) block_finish<T>(warp_sum(partial), a.fin);
+}
+
+// ||v_j||^2 for every row of V (after set_params and after a dense data-parallel apply)
+template <typename T>
+__global__ void __launch_bounds__(ROWS_THREADS)
+row_norms_kernel(const T *__restrict__ V, T *__restrict__ vn, int64_t n, int kp) {
+  const int lane = lane_id();
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = gw; j < n; j += nw) {
+    T s = T(0);
+    for (int f = lane * 2; f < kp; f += 64) {
+      const T v0 = V[j * kp + f], v1 = V[j * kp + f + 1];
+      s += v0 * v0 + v1 * v1;
+    }
+    s = warp_sum(s);
+    if (lane == 0) vn[j] = s;
   }
 }
 
@@ -263,130 +344,165 @@ struct ColsArgs {
   const uint32_t *keys, *pos;
   const T *xs;
   const uint32_t *count;
+  uint32_t sentinel;  // keys equal to this are padding of the fixed-stride layout (sorted last)
   const T *E, *S;
-  T *V, *w;
+  T *V, *w, *vn;
   int kp;
   T lr;
   T *carry_vec;      // [n_chunks][2][kp]   slot 0 = HEAD (segment began in an earlier chunk), 1 = TAIL
   T *carry_ac;       // [n_chunks][2][2]    (a, c)
   // data-parallel mode: write the gradient instead of applying it
   T *grad_w, *grad_V;
-  // fix-up work list
+  // fix-up work lists (order of the lists is irrelevant: every entry is handled independently)
+  uint32_t *tails;       // chunks that own a column continuing into later chunks
+  uint32_t *n_tails;
   uint32_t *long_runs;   // pairs (first chunk, last chunk)
   uint32_t *n_long;
   uint32_t long_cap;
 };
 
-template <typename T, int NCH, bool DP>
+template <typename T, int TPR, int NCV, bool DP>
 __device__ __forceinline__ void finish_column(const ColsArgs<T> &a, uint32_t colj,
-                                              const typename Vec2<T>::type (&acc)[NCH], T sa, T sc, int lane) {
+                                              const typename Vec2<T>::type (&acc)[NCV], T sa, T sc, int g,
+                                              unsigned gmask) {
   using V2 = typename Vec2<T>::type;
-  V2 *vrow = reinterpret_cast<V2 *>(a.V + (size_t)colj * a.kp) + lane;
+  V2 *vrow = reinterpret_cast<V2 *>(a.V + (size_t)colj * a.kp) + g;
   if (DP) {
-    V2 *grow = reinterpret_cast<V2 *>(a.grad_V + (size_t)colj * a.kp) + lane;
+    V2 *grow = reinterpret_cast<V2 *>(a.grad_V + (size_t)colj * a.kp) + g;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const V2 v = vrow[ch * 32];
-      V2 g;
-      g.x = acc[ch].x - sc * v.x;
-      g.y = acc[ch].y - sc * v.y;
-      grow[ch * 32] = g;
+    for (int ch = 0; ch < NCV; ++ch) {
+      const V2 v = vrow[ch * TPR];
+      V2 gr;
+      gr.x = acc[ch].x - sc * v.x;
+      gr.y = acc[ch].y - sc * v.y;
+      grow[ch * TPR] = gr;
     }
-    if (lane == 0) a.grad_w[colj] = sa;
+    if (g == 0) a.grad_w[colj] = sa;
   } else {
+    T nrm = T(0);
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      V2 v = vrow[ch * 32];
+    for (int ch = 0; ch < NCV; ++ch) {
+      V2 v = vrow[ch * TPR];
       v.x += a.lr * (acc[ch].x - sc * v.x);
       v.y += a.lr * (acc[ch].y - sc * v.y);
-      vrow[ch * 32] = v;
+      vrow[ch * TPR] = v;
+      nrm += v.x * v.x + v.y * v.y;
     }
-    if (lane == 0) a.w[colj] += a.lr * sa;
+    nrm = group_sum<TPR>(nrm, gmask);
+    if (g == 0) {
+      a.w[colj] += a.lr * sa;
+      a.vn[colj] = nrm;
+    }
   }
 }
 
-template <typename T, int NCH, bool DP>
+template <typename T, int TPR, int NCV>
+__device__ __forceinline__ void store_carry(const ColsArgs<T> &a, uint32_t chunk, int slot,
+                                            const typename Vec2<T>::type (&acc)[NCV], T sa, T sc, int g) {
+  using V2 = typename Vec2<T>::type;
+  V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)chunk * 2 + slot) * a.kp) + g;
+#pragma unroll
+  for (int ch = 0; ch < NCV; ++ch) cv[ch * TPR] = acc[ch];
+  if (g == 0) {
+    a.carry_ac[((size_t)chunk * 2 + slot) * 2 + 0] = sa;
+    a.carry_ac[((size_t)chunk * 2 + slot) * 2 + 1] = sc;
+  }
+}
+
+// A group of TPR lanes walks one chunk of 32 consecutive entries of the column-sorted list
+// (32/TPR chunks per warp). Entry i of the chunk lives in lane i % TPR, register i / TPR.
+template <typename T, int TPR, int NCV, bool DP>
 __global__ void __launch_bounds__(ROWS_THREADS)
 fm_cols_kernel(const ColsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
-  const int lane = lane_id();
+  constexpr int GPW = 32 / TPR, NJ = 32 / TPR;
+  const int lane = lane_id(), g = lane % TPR, grp = lane / TPR;
+  const unsigned gmask = TPR == 32 ? FULL : (((1u << TPR) - 1u) << (grp * TPR));
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_groups = nw * GPW;
   const uint32_t M = *a.count;
   const uint32_t n_chunks = (M + 31u) >> 5;
-  for (uint32_t chunk = gw; chunk < n_chunks; chunk += nw) {
+  for (uint32_t cb = gw * GPW; cb < n_chunks; cb += n_groups) {   // warp-uniform trip count
+    const uint32_t chunk = cb + grp;
     const uint32_t base = chunk << 5;
-    const uint32_t e = base + lane;
-    const bool valid = e < M;
-    const uint32_t key = valid ? a.keys[e] : KEY_NONE;
-    const uint32_t p = valid ? a.pos[e] : 0u;
-    const T x = valid ? a.xs[e] : T(0);
-    const T ev = valid ? __ldg(a.E + p) : T(0);
-    const T xe = x * ev, xxe = x * x * ev;
-    const uint32_t prev_key = base > 0 ? a.keys[base - 1] : KEY_NONE;
-    const uint32_t next_key = base + 32u < M ? a.keys[base + 32u] : KEY_NONE;
-    const int n_valid = static_cast<int>(M - base < 32u ? M - base : 32u);
-
-    V2 acc[NCH];
+    uint32_t key[NJ], p[NJ];
+    T xe[NJ], xxe[NJ];
+    int n_valid = 0;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
-    T sa = T(0), sc = T(0);
-    uint32_t cur = __shfl_sync(FULL, key, 0);
-    bool head = (cur == prev_key);
-#pragma unroll 4
-    for (int i = 0; i < n_valid; ++i) {
-      const uint32_t ki = __shfl_sync(FULL, key, i);
-      const uint32_t pi = __shfl_sync(FULL, p, i);
-      const T xei = __shfl_sync(FULL, xe, i);
-      const T xxei = __shfl_sync(FULL, xxe, i);
-      const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + lane;
-      V2 s[NCH];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) s[ch] = __ldg(srow + ch * 32);
-      if (ki != cur) {  // warp-uniform: the previous column's segment ended inside this chunk
-        if (head) {
-          V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)chunk * 2 + 0) * a.kp) + lane;
-#pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) cv[ch * 32] = acc[ch];
-          if (lane == 0) {
-            a.carry_ac[((size_t)chunk * 2 + 0) * 2 + 0] = sa;
-            a.carry_ac[((size_t)chunk * 2 + 0) * 2 + 1] = sc;
-          }
-        } else {
-          finish_column<T, NCH, DP>(a, cur, acc, sa, sc, lane);
-        }
-        head = false;
-        cur = ki;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
-        sa = sc = T(0);
-      }
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        acc[ch].x += xei * s[ch].x;
-        acc[ch].y += xei * s[ch].y;
-      }
-      sa += xei;
-      sc += xxei;
+    for (int j = 0; j < NJ; ++j) {
+      const uint32_t e = base + j * TPR + g;
+      uint32_t k = (chunk < n_chunks && e < M) ? a.keys[e] : KEY_NONE;
+      if (k == a.sentinel) k = KEY_NONE;
+      const bool valid = k != KEY_NONE;
+      key[j] = k;
+      p[j] = valid ? a.pos[e] : 0u;
+      const T x = valid ? a.xs[e] : T(0);
+      const T ev = valid ? __ldg(a.E + p[j]) : T(0);
+      xe[j] = x * ev;
+      xxe[j] = x * x * ev;
+      n_valid += __popc(__ballot_sync(FULL, valid) & gmask);   // padding sorts last: valid entries are a prefix
     }
-    const bool tail = (cur == next_key);
-    if (head || tail) {
-      const int slot = head ? 0 : 1;
-      V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)chunk * 2 + slot) * a.kp) + lane;
+    if (__all_sync(FULL, n_valid == 0)) break;                 // every later chunk of this warp is padding too
+    uint32_t prev_key = KEY_NONE, next_key = KEY_NONE;
+    if (n_valid > 0) {
+      if (base > 0) prev_key = a.keys[base - 1];
+      if (base + 32u < M) next_key = a.keys[base + 32u];
+      if (next_key == a.sentinel) next_key = KEY_NONE;
+    }
+    V2 acc[NCV];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) cv[ch * 32] = acc[ch];
-      if (lane == 0) {
-        a.carry_ac[((size_t)chunk * 2 + slot) * 2 + 0] = sa;
-        a.carry_ac[((size_t)chunk * 2 + slot) * 2 + 1] = sc;
+    for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
+    T sa = T(0), sc = T(0);
+    uint32_t cur = __shfl_sync(FULL, key[0], 0, TPR);
+    bool head = (n_valid > 0) && (cur == prev_key);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+#pragma unroll 2
+      for (int ii = 0; ii < TPR; ++ii) {
+        const int i = j * TPR + ii;
+        const uint32_t ki = __shfl_sync(FULL, key[j], ii, TPR);
+        const uint32_t pi = __shfl_sync(FULL, p[j], ii, TPR);
+        const T xei = __shfl_sync(FULL, xe[j], ii, TPR);
+        const T xxei = __shfl_sync(FULL, xxe[j], ii, TPR);
+        if (i < n_valid) {                                      // group-uniform
+          const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + g;
+          V2 sv[NCV];
+#pragma unroll
+          for (int ch = 0; ch < NCV; ++ch) sv[ch] = __ldg(srow + ch * TPR);
+          if (ki != cur) {  // the previous column's segment ended inside this chunk
+            if (head) store_carry<T, TPR, NCV>(a, chunk, 0, acc, sa, sc, g);
+            else finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
+            head = false;
+            cur = ki;
+#pragma unroll
+            for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
+            sa = sc = T(0);
+          }
+#pragma unroll
+          for (int ch = 0; ch < NCV; ++ch) {
+            acc[ch].x += xei * sv[ch].x;
+            acc[ch].y += xei * sv[ch].y;
+          }
+          sa += xei;
+          sc += xxei;
+        }
       }
-    } else {
-      finish_column<T, NCH, DP>(a, cur, acc, sa, sc, lane);
+    }
+    if (n_valid > 0) {
+      const bool tail = (cur == next_key);
+      if (head || tail) {
+        store_carry<T, TPR, NCV>(a, chunk, head ? 0 : 1, acc, sa, sc, g);
+        if (!head && g == 0) a.tails[atomicAdd(a.n_tails, 1u)] = chunk;   // this chunk owns the column's fix-up
+      } else {
+        finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
+      }
     }
   }
 }
 
-// Fix-up, part 1: the warp of the chunk where a multi-chunk column STARTS (its TAIL record) owns
-// that column. Short runs are summed here in chunk order; long ones are queued for part 2.
+// Fix-up, part 1: one warp per TAIL record, i.e. per column that starts in one chunk and runs on
+// into later ones. Short runs are summed here in chunk order; long ones are queued for part 2.
 template <typename T, int NCH, bool DP>
 __global__ void __launch_bounds__(ROWS_THREADS)
 fm_carry_kernel(const ColsArgs<T> a) {
@@ -395,13 +511,11 @@ fm_carry_kernel(const ColsArgs<T> a) {
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   const uint32_t M = *a.count;
-  const uint32_t n_chunks = (M + 31u) >> 5;
-  for (uint32_t chunk = gw; chunk < n_chunks; chunk += nw) {
+  const uint32_t n_tails = *a.n_tails;
+  for (uint32_t ti = gw; ti < n_tails; ti += nw) {
+    const uint32_t chunk = a.tails[ti];
     const uint32_t base = chunk << 5;
-    if (base + 32u >= M) continue;                      // last chunk cannot have a TAIL
-    const uint32_t klast = a.keys[base + 31u];
-    if (a.keys[base + 32u] != klast) continue;          // no segment runs on into the next chunk
-    if (a.keys[base] == klast && base > 0 && a.keys[base - 1] == klast) continue;  // a HEAD, not a TAIL
+    const uint32_t klast = a.keys[base + 31u];          // a TAIL chunk is full and its last key is the column
     // upper bound of klast in [base+32, M): first index whose key differs
     uint32_t lo = base + 32u, hi = M;
     while (lo < hi) {
@@ -435,18 +549,19 @@ fm_carry_kernel(const ColsArgs<T> a) {
       sa += a.carry_ac[((size_t)c * 2 + 0) * 2 + 0];
       sc += a.carry_ac[((size_t)c * 2 + 0) * 2 + 1];
     }
-    finish_column<T, NCH, DP>(a, klast, acc, sa, sc, lane);
+    finish_column<T, 32, NCH, DP>(a, klast, acc, sa, sc, lane, FULL);
   }
 }
 
 // Fix-up, part 2: one CTA per long run. Warp w sums a contiguous block of the run's HEAD records
-// in chunk order; warp 0 then adds TAIL + block partials in warp order. The association depends
-// only on the run length and the CTA shape, never on timing.
+// in chunk order (loads issued LONG_UNROLL at a time, additions in order); warp 0 then adds TAIL +
+// block partials in warp order. The association depends only on the run length and the CTA shape.
 template <typename T, int NCH, bool DP>
 __global__ void __launch_bounds__(LONG_RUN_THREADS)
 fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
   using V2 = typename Vec2<T>::type;
-  extern __shared__ unsigned char smem_raw[];
+  constexpr int LONG_UNROLL = NCH <= 1 ? 8 : NCH <= 2 ? 4 : NCH <= 4 ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *>(smem_raw);              // [n_warps_used][kp + 2]
   const int lane = lane_id(), wid = threadIdx.x >> 5;
   uint32_t n_long = *a.n_long;
@@ -464,16 +579,32 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
       const uint32_t c0 = first + 1 + wid * per;
       uint32_t c1 = c0 + per;
       if (c1 > last + 1) c1 = last + 1;
-      for (uint32_t c = c0; c < c1; ++c) {
-        const V2 *hv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)c * 2 + 0) * a.kp) + lane;
+      for (uint32_t c = c0; c < c1; c += LONG_UNROLL) {
+        V2 h[LONG_UNROLL][NCH];
+        T ha[LONG_UNROLL], hc[LONG_UNROLL];
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          const V2 h = hv[ch * 32];
-          acc[ch].x += h.x;
-          acc[ch].y += h.y;
+        for (int u = 0; u < LONG_UNROLL; ++u) {
+          const bool on = c + u < c1;
+          const size_t rec = (size_t)(on ? c + u : c) * 2;
+          const V2 *hv = reinterpret_cast<const V2 *>(a.carry_vec + rec * a.kp) + lane;
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            h[u][ch] = __ldcg(hv + ch * 32);
+            if (!on) h[u][ch].x = h[u][ch].y = T(0);
+          }
+          ha[u] = on ? __ldcg(a.carry_ac + rec * 2 + 0) : T(0);
+          hc[u] = on ? __ldcg(a.carry_ac + rec * 2 + 1) : T(0);
         }
-        sa += a.carry_ac[((size_t)c * 2 + 0) * 2 + 0];
-        sc += a.carry_ac[((size_t)c * 2 + 0) * 2 + 1];
+#pragma unroll
+        for (int u = 0; u < LONG_UNROLL; ++u) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            acc[ch].x += h[u][ch].x;
+            acc[ch].y += h[u][ch].y;
+          }
+          sa += ha[u];
+          sc += hc[u];
+        }
       }
       T *mine = sm + (size_t)wid * stride;
 #pragma unroll
@@ -503,7 +634,7 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
         sa += part[a.kp];
         sc += part[a.kp + 1];
       }
-      finish_column<T, NCH, DP>(a, a.keys[first * 32u + 31u], acc, sa, sc, lane);
+      finish_column<T, 32, NCH, DP>(a, a.keys[first * 32u + 31u], acc, sa, sc, lane, FULL);
     }
     __syncthreads();
   }
@@ -515,6 +646,20 @@ __global__ void apply_grad_kernel(T *__restrict__ params, const T *__restrict__ 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     params[i] += lr * grad[i];
 }
+
+// row / column kernels: (threads per row, chunks per lane) for kp = 64 * nch
+#define RFM_DISPATCH_TPR(nch, ...)                                                       \
+  switch (nch) {                                                                         \
+    case 1: { constexpr int TPR = 8, NCV = 4; __VA_ARGS__; } break;                      \
+    case 2: { constexpr int TPR = 16, NCV = 4; __VA_ARGS__; } break;                     \
+    case 3: { constexpr int TPR = 32, NCV = 3; __VA_ARGS__; } break;                     \
+    case 4: { constexpr int TPR = 32, NCV = 4; __VA_ARGS__; } break;                     \
+    case 5: { constexpr int TPR = 32, NCV = 5; __VA_ARGS__; } break;                     \
+    case 6: { constexpr int TPR = 32, NCV = 6; __VA_ARGS__; } break;                     \
+    case 7: { constexpr int TPR = 32, NCV = 7; __VA_ARGS__; } break;                     \
+    case 8: { constexpr int TPR = 32, NCV = 8; __VA_ARGS__; } break;                     \
+    default: return fail(RFM_ERR_INVALID, "n_factors too large (kp/64 = %d > 8)", nch);  \
+  }
 
 #define RFM_DISPATCH_NCH(nch, ...)                                 \
   switch (nch) {                                                   \
@@ -543,26 +688,34 @@ int upload(rfm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
 }
 
 template <typename T>
-int launch_rows(rfm_ctx *ctx, int nch, int mode, const RowsArgs<T> &args, int grid) {
-  RFM_DISPATCH_NCH(nch, {
+int launch_rows(rfm_ctx *ctx, int nch, int mode, bool sampled, const RowsArgs<T> &args, int grid) {
+  RFM_DISPATCH_TPR(nch, {
     if (mode == MODE_TRAIN) {
-      auto fm_rows_train = fm_rows_kernel<T, NCH, MODE_TRAIN>;
-    RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
+      if (sampled) {
+        auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, true>;
+        RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
+      } else {
+        auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, false>;
+        RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
+      }
     } else if (mode == MODE_LOSS) {
       if (args.idx) {  // post-update loss of the batch vs. loss over a plain row range (val)
-        auto fm_rows_loss = fm_rows_kernel<T, NCH, MODE_LOSS>;
+        auto fm_rows_loss = fm_rows_kernel<T, TPR, NCV, MODE_LOSS, false>;
         RFM_LAUNCH(ctx, fm_rows_loss, grid, ROWS_THREADS, 0, args);
       } else {
-        auto fm_rows_loss_range = fm_rows_kernel<T, NCH, MODE_LOSS>;
+        auto fm_rows_loss_range = fm_rows_kernel<T, TPR, NCV, MODE_LOSS, false>;
         RFM_LAUNCH(ctx, fm_rows_loss_range, grid, ROWS_THREADS, 0, args);
       }
     } else {
-      auto fm_rows_predict = fm_rows_kernel<T, NCH, MODE_PREDICT>;
-    RFM_LAUNCH(ctx, fm_rows_predict, grid, ROWS_THREADS, 0, args);
+      auto fm_rows_predict = fm_rows_kernel<T, TPR, NCV, MODE_PREDICT, false>;
+      RFM_LAUNCH(ctx, fm_rows_predict, grid, ROWS_THREADS, 0, args);
     }
   });
   return RFM_OK;
 }
+
+// rows (or 32-entry chunks) a CTA of ROWS_THREADS handles per pass of its loop
+int units_per_block(int nch) { return ROWS_WARPS * (nch == 1 ? 4 : nch == 2 ? 2 : 1); }
 
 }  // namespace
 
@@ -571,11 +724,13 @@ struct rfm_fm_trainer {
   rfm_fm *m = nullptr;
   const rfm_csr *train = nullptr, *val = nullptr;
   int64_t max_batch = 0, max_slots = 0, nnz_cap = 0;
-  int rows_grid = 0, n_row_warps = 0;
+  int rows_grid = 0;
+  uint32_t stride = 0;        // > 0: fixed-stride triple layout (rows of near-uniform length)
+  uint32_t count_host = 0;    // value currently stored in count (fixed-stride layout)
   DevBuf<int64_t> idx;
-  DevBuf<uint32_t> row_len, bptr, scan_tmp, count, long_runs, n_long;
+  DevBuf<uint32_t> row_len, bptr, scan_tmp, count, long_runs, n_long, tails, n_tails, ticket;
   DevBuf<unsigned char> S, E, carry_vec, carry_ac, grad;
-  DevBuf<double> partials, losses, loss_sums;
+  DevBuf<double> block_partials, losses, loss_sums;
   RadixSorter<float> sort32;
   RadixSorter<double> sort64;
   // host staging ring for batch row ids
@@ -609,8 +764,20 @@ RowsArgs<T> rows_args(const rfm_fm *m, const rfm_csr *rows) {
   a.w0 = reinterpret_cast<const T *>(m->w0.p);
   a.w = reinterpret_cast<const T *>(m->w.p);
   a.V = reinterpret_cast<const T *>(m->V.p);
+  a.vn = reinterpret_cast<const T *>(m->vn.p);
   a.kp = m->kp;
   return a;
+}
+
+Finish make_finish(int op, double scale, void *dst_T, double *dst_d, double *block_partials, uint32_t *ticket) {
+  Finish f;
+  f.op = op;
+  f.scale = scale;
+  f.dst_T = dst_T;
+  f.dst_d = dst_d;
+  f.block_partials = block_partials;
+  f.ticket = ticket;
+  return f;
 }
 
 // loss pass over a batch (idx != null) or a row range, mean (scale = 1/count) or raw sum into *dst
@@ -627,24 +794,34 @@ int loss_pass(rfm_fm_trainer *t, const rfm_csr *rows, const int64_t *idx_dev, in
   a.idx = idx_dev;
   a.row0 = row0;
   a.n = n;
-  a.partials = t->partials.p;
-  const int grid = grid_for(ctx, ceil_div(n, ROWS_WARPS), t->rows_grid / ctx->sm_count);
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, a, grid));
-  RFM_LAUNCH(ctx, reduce_partials_kernel<T>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 1, scale,
-             (T *)nullptr, dst_dev);
-  return RFM_OK;
+  a.fin = make_finish(1, scale, nullptr, dst_dev, t->block_partials.p, t->ticket.p);
+  const int grid = grid_for(ctx, ceil_div(n, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
+  return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid);
 }
 
 // forward + residual + triples + sort + column pass (+ fix-up). DP=false applies SGD in place.
+// sampled: the batch is positions [q0, q0+batch) of the epoch's Feistel permutation, drawn on the device.
 template <typename T, bool DP>
-int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
+int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const FeistelKey &fkey, int64_t q0) {
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
   const rfm_csr *tr = t->train;
   RadixSorter<T> &sorter = sorter_of<T>(t);
-  const int small_grid = grid_for(ctx, ceil_div(batch, 256), 4);
-  RFM_LAUNCH(ctx, row_len_kernel, small_grid, 256, 0, tr->row_ptr.p, t->idx.p, batch, t->row_len.p);
-  RFM_TRY(exclusive_scan_u32(ctx, t->row_len.p, t->bptr.p, batch, t->scan_tmp.p, t->count.p));
+  const bool fused_draw = sampled && t->stride > 0;
+  if (sampled && !fused_draw)   // ragged layout needs the row ids before the row pass (row lengths)
+    RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, fkey, q0, batch,
+               t->idx.p);
+  if (t->stride == 0) {
+    const int small_grid = grid_for(ctx, ceil_div(batch, 256), 4);
+    RFM_LAUNCH(ctx, row_len_kernel, small_grid, 256, 0, tr->row_ptr.p, t->idx.p, batch, t->row_len.p);
+    RFM_TRY(exclusive_scan_u32(ctx, t->row_len.p, t->bptr.p, batch, t->scan_tmp.p, t->count.p));
+  } else {
+    const uint32_t cnt = (uint32_t)batch * t->stride;
+    if (cnt != t->count_host) {
+      t->count_host = cnt;
+      RFM_CUDA(cudaMemcpyAsync(t->count.p, &t->count_host, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
 
   RowsArgs<T> a = rows_args<T>(m, tr);
   a.idx = t->idx.p;
@@ -652,12 +829,24 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
   a.S = reinterpret_cast<T *>(t->S.p);
   a.E = reinterpret_cast<T *>(t->E.p);
   a.bptr = t->bptr.p;
+  a.stride = t->stride;
+  a.sentinel = (uint32_t)m->n;
   a.keys = sorter.keys[0].p;
   a.pos = sorter.pos[0].p;
   a.xs = sorter.val[0].p;
-  a.partials = t->partials.p;
-  const int grid = grid_for(ctx, ceil_div(batch, ROWS_WARPS), t->rows_grid / ctx->sm_count);
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, a, grid));
+  a.fkey = fkey;
+  a.q0 = q0;
+  a.idx_out = t->idx.p;
+  if (DP) {
+    T *g = reinterpret_cast<T *>(t->grad.p);
+    RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)grad_total(m->n, m->kp) * sizeof(T), ctx->stream));
+    // sum_e lands in grad[0]; w0 itself is updated by the dense apply after the all-reduce
+    a.fin = make_finish(0, 1.0, g, nullptr, t->block_partials.p, t->ticket.p);
+  } else {
+    a.fin = make_finish(0, lr, m->w0.p, nullptr, t->block_partials.p, t->ticket.p);
+  }
+  const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, fused_draw, a, grid));
   int sorted = 0;
   RFM_TRY(sorter.sort(ctx, t->count.p, &sorted));
 
@@ -667,14 +856,18 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
   c.pos = sorter.pos[sorted].p;
   c.xs = sorter.val[sorted].p;
   c.count = t->count.p;
+  c.sentinel = t->stride ? (uint32_t)m->n : KEY_NONE;
   c.E = reinterpret_cast<const T *>(t->E.p);
   c.S = reinterpret_cast<const T *>(t->S.p);
   c.V = reinterpret_cast<T *>(m->V.p);
   c.w = reinterpret_cast<T *>(m->w.p);
+  c.vn = reinterpret_cast<T *>(m->vn.p);
   c.kp = m->kp;
   c.lr = static_cast<T>(lr);
   c.carry_vec = reinterpret_cast<T *>(t->carry_vec.p);
   c.carry_ac = reinterpret_cast<T *>(t->carry_ac.p);
+  c.tails = t->tails.p;
+  c.n_tails = t->n_tails.p;
   c.long_runs = t->long_runs.p;
   c.n_long = t->n_long.p;
   c.long_cap = t->long_cap;
@@ -682,23 +875,20 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
     T *g = reinterpret_cast<T *>(t->grad.p);
     c.grad_w = g + GRAD_W_OFF;
     c.grad_V = g + grad_v_off(m->n);
-    RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)grad_total(m->n, m->kp) * sizeof(T), ctx->stream));
-    // sum_e goes to grad[0] as a plain sum (dst_d unused); w0 itself is updated in apply
-    RFM_LAUNCH(ctx, reduce_partials_kernel<double>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 0, 0.0,
-               (double *)nullptr, t->loss_sums.p + 2);
-  } else {
-    RFM_LAUNCH(ctx, reduce_partials_kernel<T>, 1, 1024, 0, t->partials.p, grid * ROWS_WARPS, 0, lr,
-               reinterpret_cast<T *>(m->w0.p), (double *)nullptr);
   }
   RFM_CUDA(cudaMemsetAsync(t->n_long.p, 0, sizeof(uint32_t), ctx->stream));
+  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
   const int64_t chunk_cap = ceil_div(t->nnz_cap, 32);
-  const int cgrid = grid_for(ctx, ceil_div(chunk_cap, ROWS_WARPS), t->rows_grid / ctx->sm_count);
+  const int cgrid = grid_for(ctx, ceil_div(chunk_cap, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
+  const int tgrid = grid_for(ctx, ceil_div(chunk_cap, ROWS_WARPS * 4), 2);
   const int lgrid = t->long_cap < (uint32_t)ctx->sm_count * 2 ? (int)t->long_cap : ctx->sm_count * 2;
-  RFM_DISPATCH_NCH(m->nch, {
-    auto fm_cols = fm_cols_kernel<T, NCH, DP>;
+  RFM_DISPATCH_TPR(m->nch, {
+    auto fm_cols = fm_cols_kernel<T, TPR, NCV, DP>;
     RFM_LAUNCH(ctx, fm_cols, cgrid, ROWS_THREADS, 0, c);
+  });
+  RFM_DISPATCH_NCH(m->nch, {
     auto fm_carry = fm_carry_kernel<T, NCH, DP>;
-    RFM_LAUNCH(ctx, fm_carry, cgrid, ROWS_THREADS, 0, c);
+    RFM_LAUNCH(ctx, fm_carry, tgrid, ROWS_THREADS, 0, c);
     auto fm_long_runs = fm_long_runs_kernel<T, NCH, DP>;
     RFM_LAUNCH(ctx, fm_long_runs, lgrid < 1 ? 1 : lgrid, LONG_RUN_THREADS, t->long_smem, c,
                t->long_warps);
@@ -707,8 +897,8 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr) {
 }
 
 template <typename T>
-int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot) {
-  RFM_TRY((step_core<T, false>(t, batch, lr)));
+int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot, bool sampled, const FeistelKey &fkey) {
+  RFM_TRY((step_core<T, false>(t, batch, lr, sampled, fkey, 0)));
   RFM_TRY(loss_pass<T>(t, t->train, t->idx.p, 0, batch, 1.0 / (double)batch, t->losses.p + slot));
   if (t->val)
     RFM_TRY(loss_pass<T>(t, t->val, nullptr, 0, t->val->n_rows, 1.0 / (double)t->val->n_rows,
@@ -873,7 +1063,9 @@ int rfm_fm_create(rfm_ctx *ctx, int64_t n_features, int32_t n_factors, int dtype
   int rc = m->w0.alloc(es);
   if (rc == RFM_OK) rc = m->w.alloc((size_t)n_features * es);
   if (rc == RFM_OK) rc = m->V.alloc((size_t)n_features * m->kp * es);
+  if (rc == RFM_OK) rc = m->vn.alloc((size_t)n_features * es);
   if (rc == RFM_OK) {
+    cudaMemsetAsync(m->vn.p, 0, (size_t)n_features * es, ctx->stream);
     cudaMemsetAsync(m->w0.p, 0, es, ctx->stream);
     cudaMemsetAsync(m->w.p, 0, (size_t)n_features * es, ctx->stream);
     cudaMemsetAsync(m->V.p, 0, (size_t)n_features * m->kp * es, ctx->stream);
@@ -910,10 +1102,14 @@ int rfm_fm_set_params(rfm_fm *m, const double *w0, const double *w, const double
     RFM_LAUNCH(ctx, pad_rows_kernel<double>, g, 256, 0, tV, reinterpret_cast<double *>(m->V.p), m->n, m->k, m->kp);
     RFM_LAUNCH(ctx, convert_f64_kernel<double>, g, 256, 0, tw, reinterpret_cast<double *>(m->w.p), m->n);
     RFM_LAUNCH(ctx, convert_f64_kernel<double>, 1, 32, 0, tw0, reinterpret_cast<double *>(m->w0.p), (int64_t)1);
+    RFM_LAUNCH(ctx, row_norms_kernel<double>, grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8), ROWS_THREADS, 0,
+               reinterpret_cast<const double *>(m->V.p), reinterpret_cast<double *>(m->vn.p), m->n, m->kp);
   } else {
     RFM_LAUNCH(ctx, pad_rows_kernel<float>, g, 256, 0, tV, reinterpret_cast<float *>(m->V.p), m->n, m->k, m->kp);
     RFM_LAUNCH(ctx, convert_f64_kernel<float>, g, 256, 0, tw, reinterpret_cast<float *>(m->w.p), m->n);
     RFM_LAUNCH(ctx, convert_f64_kernel<float>, 1, 32, 0, tw0, reinterpret_cast<float *>(m->w0.p), (int64_t)1);
+    RFM_LAUNCH(ctx, row_norms_kernel<float>, grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8), ROWS_THREADS, 0,
+               reinterpret_cast<const float *>(m->V.p), reinterpret_cast<float *>(m->vn.p), m->n, m->kp);
   }
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
@@ -976,7 +1172,7 @@ int predict_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
   RowsArgs<T> a = rows_args<T>(m, rows);
   a.n = rows->n_rows;
   a.out = out.p;
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_PREDICT, a, grid_for(ctx, ceil_div(rows->n_rows, ROWS_WARPS), 6)));
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_PREDICT, false, a, grid_for(ctx, ceil_div(rows->n_rows, units_per_block(m->nch)), 6)));
   RFM_CUDA(cudaMemcpyAsync(out_host, out.p, (size_t)rows->n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
@@ -985,16 +1181,17 @@ int predict_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
 template <typename T>
 int logloss_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
   rfm_ctx *ctx = m->ctx;
-  const int grid = grid_for(ctx, ceil_div(rows->n_rows, ROWS_WARPS), 6);
+  const int grid = grid_for(ctx, ceil_div(rows->n_rows, units_per_block(m->nch)), 6);
   DevBuf<double> partials, res;
-  RFM_TRY(partials.alloc((size_t)grid * ROWS_WARPS));
+  DevBuf<uint32_t> ticket;
+  RFM_TRY(partials.alloc((size_t)grid));
   RFM_TRY(res.alloc(1));
+  RFM_TRY(ticket.alloc(1));
+  RFM_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(uint32_t), ctx->stream));
   RowsArgs<T> a = rows_args<T>(m, rows);
   a.n = rows->n_rows;
-  a.partials = partials.p;
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, a, grid));
-  RFM_LAUNCH(ctx, reduce_partials_kernel<T>, 1, 1024, 0, partials.p, grid * ROWS_WARPS, 1,
-             1.0 / (double)rows->n_rows, (T *)nullptr, res.p);
+  a.fin = make_finish(1, 1.0 / (double)rows->n_rows, nullptr, res.p, partials.p, ticket.p);
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid));
   RFM_CUDA(cudaMemcpyAsync(out_host, res.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
@@ -1030,8 +1227,13 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
   rfm_ctx *ctx = m->ctx;
   RFM_CUDA(cudaSetDevice(ctx->device));
   if (max_batch > train->n_rows) max_batch = train->n_rows > 0 ? train->n_rows : 1;
+  // Triple layout: when rows are of near-uniform length, row q of the batch owns a fixed stride of
+  // max_row_len slots (unused ones hold a sentinel key that sorts last); no row-length scan is needed
+  // and the element count is known on the host. Otherwise slots are packed with an exclusive scan.
+  const double mean_len = train->n_rows > 0 ? (double)train->nnz / (double)train->n_rows : 0.0;
+  const bool fixed_stride = train->max_row_len >= 1 && (double)train->max_row_len <= 1.25 * mean_len + 1.0;
   int64_t nnz_cap = max_batch * train->max_row_len;
-  if (nnz_cap > train->nnz) nnz_cap = train->nnz;
+  if (!fixed_stride && nnz_cap > train->nnz) nnz_cap = train->nnz;
   if (nnz_cap < 1) nnz_cap = 1;
   RFM_REQUIRE(nnz_cap < 0xFFFFFFF0LL, "rfm_fm_trainer_create: batch holds too many non-zeros (%lld)",
               (long long)nnz_cap);
@@ -1043,11 +1245,11 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
   t->max_batch = max_batch;
   t->max_slots = max_slots;
   t->nnz_cap = nnz_cap;
+  t->stride = fixed_stride ? (uint32_t)train->max_row_len : 0u;
   const size_t es = dsize(m->dtype);
   auto body = [&]() -> int {
     // resident CTAs per SM for the row/column kernels: 6 x 256 threads keeps 48 warps in flight
     t->rows_grid = ctx->sm_count * 6;
-    t->n_row_warps = t->rows_grid * ROWS_WARPS;
     RFM_TRY(t->idx.alloc(max_batch));
     RFM_TRY(t->row_len.alloc(max_batch));
     RFM_TRY(t->bptr.alloc(max_batch));
@@ -1061,11 +1263,16 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
     RFM_TRY(t->carry_ac.alloc((size_t)chunk_cap * 4 * es));
     t->long_cap = (uint32_t)(chunk_cap / (SHORT_RUN + 1) + 1);
     RFM_TRY(t->long_runs.alloc((size_t)t->long_cap * 2));
-    RFM_TRY(t->partials.alloc((size_t)t->n_row_warps));
+    RFM_TRY(t->block_partials.alloc((size_t)t->rows_grid));
+    RFM_TRY(t->ticket.alloc(1));
+    RFM_CUDA(cudaMemsetAsync(t->ticket.p, 0, sizeof(uint32_t), ctx->stream));
+    RFM_TRY(t->tails.alloc((size_t)chunk_cap));
+    RFM_TRY(t->n_tails.alloc(1));
     RFM_TRY(t->losses.alloc((size_t)max_slots * 2));
     RFM_TRY(t->loss_sums.alloc(4));
     RFM_CUDA(cudaMemsetAsync(t->losses.p, 0, (size_t)max_slots * 2 * sizeof(double), ctx->stream));
-    if (m->dtype == RFM_F64) RFM_TRY(t->sort64.init(nnz_cap, m->n)); else RFM_TRY(t->sort32.init(nnz_cap, m->n));
+    // keys go up to n (the sentinel of the fixed-stride layout), hence n + 1 key values
+    if (m->dtype == RFM_F64) RFM_TRY(t->sort64.init(nnz_cap, m->n + 1)); else RFM_TRY(t->sort32.init(nnz_cap, m->n + 1));
     const size_t per_warp = (size_t)(m->kp + 2) * es;
     int lw = (int)(40 * 1024 / per_warp);
     if (lw > 32) lw = 32;
@@ -1103,7 +1310,9 @@ int rfm_fm_train_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t bat
     RFM_REQUIRE(batch_rows[q] >= 0 && batch_rows[q] < t->train->n_rows, "rfm_fm_train_epoch: row id %lld out of range",
                 (long long)batch_rows[q]);
   RFM_TRY(stage_batch(t, batch_rows, batch));
-  return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot) : epoch_impl<float>(t, batch, lr, slot);
+  const FeistelKey none = make_feistel_key(1, 0, 0);
+  return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot, false, none)
+                                : epoch_impl<float>(t, batch, lr, slot, false, none);
 }
 
 int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t batch, double lr,
@@ -1113,9 +1322,8 @@ int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch,
   RFM_CUDA(cudaSetDevice(ctx->device));
   RFM_REQUIRE(t->train->n_rows <= (1LL << 32), "rfm_fm_train_epoch_sampled: at most 2^32 rows");
   const FeistelKey key = make_feistel_key((uint64_t)t->train->n_rows, seed, epoch);
-  RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, key, (int64_t)0, batch,
-             t->idx.p);
-  return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot) : epoch_impl<float>(t, batch, lr, slot);
+  return t->m->dtype == RFM_F64 ? epoch_impl<double>(t, batch, lr, slot, true, key)
+                                : epoch_impl<float>(t, batch, lr, slot, true, key);
 }
 
 int rfm_fm_grad_size(rfm_fm_trainer *t, int64_t *n_scalars) {
@@ -1145,18 +1353,11 @@ __global__ void store_sum_e_kernel(const double *__restrict__ src, T *__restrict
 }  // namespace
 extern "C" {
 
-static int grad_epoch_tail(rfm_fm_trainer *t, int64_t batch) {
-  rfm_ctx *ctx = t->m->ctx;
+static int grad_epoch_tail(rfm_fm_trainer *t, int64_t batch, bool sampled, const FeistelKey &key, int64_t q0) {
   void *g = nullptr;
   RFM_TRY(rfm_fm_grad_ptr_dev(t, &g));
-  if (t->m->dtype == RFM_F64) {
-    RFM_TRY((step_core<double, true>(t, batch, 0.0)));
-    RFM_LAUNCH(ctx, store_sum_e_kernel<double>, 1, 32, 0, t->loss_sums.p + 2, reinterpret_cast<double *>(g));
-  } else {
-    RFM_TRY((step_core<float, true>(t, batch, 0.0)));
-    RFM_LAUNCH(ctx, store_sum_e_kernel<float>, 1, 32, 0, t->loss_sums.p + 2, reinterpret_cast<float *>(g));
-  }
-  return RFM_OK;
+  if (t->m->dtype == RFM_F64) return step_core<double, true>(t, batch, 0.0, sampled, key, q0);
+  return step_core<float, true>(t, batch, 0.0, sampled, key, q0);
 }
 
 int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
@@ -1167,7 +1368,7 @@ int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batc
     RFM_REQUIRE(batch_rows[q] >= 0 && batch_rows[q] < t->train->n_rows, "rfm_fm_grad_epoch: row id %lld out of range",
                 (long long)batch_rows[q]);
   RFM_TRY(stage_batch(t, batch_rows, batch));
-  return grad_epoch_tail(t, batch);
+  return grad_epoch_tail(t, batch, false, make_feistel_key(1, 0, 0), 0);
 }
 
 int rfm_fm_grad_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t q_begin, int64_t batch) {
@@ -1179,9 +1380,7 @@ int rfm_fm_grad_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, 
               (long long)t->train->n_rows);
   RFM_REQUIRE(t->train->n_rows <= (1LL << 32), "rfm_fm_grad_epoch_sampled: at most 2^32 rows");
   const FeistelKey key = make_feistel_key((uint64_t)t->train->n_rows, seed, epoch);
-  RFM_LAUNCH(ctx, feistel_sample_kernel, grid_for(ctx, ceil_div(batch, 256), 4), 256, 0, key, q_begin, batch,
-             t->idx.p);
-  return grad_epoch_tail(t, batch);
+  return grad_epoch_tail(t, batch, true, key, q_begin);
 }
 
 int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
@@ -1196,12 +1395,16 @@ int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
     RFM_LAUNCH(ctx, apply_grad_kernel<double>, 1, 32, 0, reinterpret_cast<double *>(m->w0.p), gr, (int64_t)1, lr);
     RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->w.p), gr + GRAD_W_OFF, m->n, lr);
     RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->V.p), gr + grad_v_off(m->n), nV, lr);
+    RFM_LAUNCH(ctx, row_norms_kernel<double>, grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8), ROWS_THREADS, 0,
+               reinterpret_cast<const double *>(m->V.p), reinterpret_cast<double *>(m->vn.p), m->n, m->kp);
   } else {
     float *gr = reinterpret_cast<float *>(t->grad.p);
     RFM_LAUNCH(ctx, apply_grad_kernel<float>, 1, 32, 0, reinterpret_cast<float *>(m->w0.p), gr, (int64_t)1, (float)lr);
     RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->w.p), gr + GRAD_W_OFF, m->n, (float)lr);
     RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->V.p), gr + grad_v_off(m->n), nV,
                (float)lr);
+    RFM_LAUNCH(ctx, row_norms_kernel<float>, grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8), ROWS_THREADS, 0,
+               reinterpret_cast<const float *>(m->V.p), reinterpret_cast<float *>(m->vn.p), m->n, m->kp);
   }
   return RFM_OK;
 }
