@@ -103,6 +103,7 @@ struct rfm_prof_rec {
 struct rfm_ctx {
   int device = 0;
   bool profiling = false;
+  bool sync_launches = false;   // RFM_SYNC_LAUNCHES=1: synchronise after every kernel and name the one that faulted
   std::vector<rfm_prof_rec> prof;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
@@ -125,6 +126,12 @@ void prof_end(rfm_ctx *ctx);
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                        \
     (ctx)->launches++;                                                                      \
     if ((ctx)->profiling) ::rfm::prof_end((ctx));                                           \
+    if ((ctx)->sync_launches) {                                                             \
+      cudaError_t serr__ = cudaStreamSynchronize((ctx)->stream);                            \
+      if (serr__ != cudaSuccess)                                                            \
+        return ::rfm::fail(RFM_ERR_CUDA, "kernel %s faulted: %s (%s:%d)", #kernel,          \
+                           cudaGetErrorString(serr__), __FILE__, __LINE__);                 \
+    }                                                                                       \
     cudaError_t err__ = cudaGetLastError();                                                 \
     if (err__ != cudaSuccess)                                                               \
       return ::rfm::fail(RFM_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,          \

@@ -51,6 +51,9 @@ namespace {
 constexpr int ROWS_THREADS = 256;
 constexpr int ROWS_WARPS = ROWS_THREADS / 32;
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int COL_CHUNK = 32;      // sorted entries one lane group walks; carry records are per chunk
+                                   // (128 was measured: fewer carry records but a 60 % slower column pass)
+constexpr int COL_SUB = COL_CHUNK / 32;
 constexpr int SHORT_RUN = 4;        // carry runs up to this many chunks are summed by one warp
 constexpr int LONG_RUN_THREADS = 1024;
 
@@ -409,10 +412,12 @@ __device__ __forceinline__ void store_carry(const ColsArgs<T> &a, uint32_t chunk
   }
 }
 
-// A group of TPR lanes walks one chunk of 32 consecutive entries of the column-sorted list
-// (32/TPR chunks per warp). Entry i of the chunk lives in lane i % TPR, register i / TPR.
+// A group of TPR lanes walks one chunk of COL_CHUNK consecutive entries of the column-sorted list
+// (32/TPR chunks per warp), 32 entries at a time: entry i of a 32-entry slice lives in lane i % TPR,
+// register i / TPR. Columns that live entirely inside the chunk are finished here; the partial
+// sums of a column that crosses the chunk's start (HEAD) or end (TAIL) go to carry records.
 template <typename T, int TPR, int NCV, bool DP>
-__global__ void __launch_bounds__(ROWS_THREADS)
+__global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? 3 : 2)
 fm_cols_kernel(const ColsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
   constexpr int GPW = 32 / TPR, NJ = 32 / TPR;
@@ -422,74 +427,78 @@ fm_cols_kernel(const ColsArgs<T> a) {
   const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
   const uint32_t n_groups = nw * GPW;
   const uint32_t M = *a.count;
-  const uint32_t n_chunks = (M + 31u) >> 5;
+  const uint32_t n_chunks = (M + COL_CHUNK - 1u) / COL_CHUNK;
   for (uint32_t cb = gw * GPW; cb < n_chunks; cb += n_groups) {   // warp-uniform trip count
     const uint32_t chunk = cb + grp;
-    const uint32_t base = chunk << 5;
-    uint32_t key[NJ], p[NJ];
-    T xe[NJ], xxe[NJ];
-    int n_valid = 0;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const uint32_t e = base + j * TPR + g;
-      uint32_t k = (chunk < n_chunks && e < M) ? a.keys[e] : KEY_NONE;
-      if (k == a.sentinel) k = KEY_NONE;
-      const bool valid = k != KEY_NONE;
-      key[j] = k;
-      p[j] = valid ? a.pos[e] : 0u;
-      const T x = valid ? a.xs[e] : T(0);
-      const T ev = valid ? __ldg(a.E + p[j]) : T(0);
-      xe[j] = x * ev;
-      xxe[j] = x * x * ev;
-      n_valid += __popc(__ballot_sync(FULL, valid) & gmask);   // padding sorts last: valid entries are a prefix
-    }
-    if (__all_sync(FULL, n_valid == 0)) break;                 // every later chunk of this warp is padding too
-    uint32_t prev_key = KEY_NONE, next_key = KEY_NONE;
-    if (n_valid > 0) {
-      if (base > 0) prev_key = a.keys[base - 1];
-      if (base + 32u < M) next_key = a.keys[base + 32u];
-      if (next_key == a.sentinel) next_key = KEY_NONE;
-    }
+    const uint32_t base = chunk * COL_CHUNK;
     V2 acc[NCV];
 #pragma unroll
     for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
     T sa = T(0), sc = T(0);
-    uint32_t cur = __shfl_sync(FULL, key[0], 0, TPR);
-    bool head = (n_valid > 0) && (cur == prev_key);
+    uint32_t cur = KEY_NONE;
+    bool head = false, any = false;
+    for (int sub = 0; sub < COL_SUB; ++sub) {
+      const uint32_t sbase = base + sub * 32;
+      uint32_t key[NJ], p[NJ];
+      T xe[NJ], xxe[NJ];
+      int n_valid = 0;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
+      for (int j = 0; j < NJ; ++j) {
+        const uint32_t e = sbase + j * TPR + g;
+        uint32_t k = (chunk < n_chunks && e < M) ? a.keys[e] : KEY_NONE;
+        if (k == a.sentinel) k = KEY_NONE;
+        const bool valid = k != KEY_NONE;
+        key[j] = k;
+        p[j] = valid ? a.pos[e] : 0u;
+        const T x = valid ? a.xs[e] : T(0);
+        const T ev = valid ? __ldg(a.E + p[j]) : T(0);
+        xe[j] = x * ev;
+        xxe[j] = x * x * ev;
+        n_valid += __popc(__ballot_sync(FULL, valid) & gmask);   // padding sorts last: valid entries are a prefix
+      }
+      if (__all_sync(FULL, n_valid == 0)) break;                 // the rest of every group's chunk is padding
+      if (sub == 0 && n_valid > 0) {
+        cur = __shfl_sync(gmask, key[0], 0, TPR);
+        head = base > 0 && a.keys[base - 1] == cur;
+        any = true;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
 #pragma unroll 2
-      for (int ii = 0; ii < TPR; ++ii) {
-        const int i = j * TPR + ii;
-        const uint32_t ki = __shfl_sync(FULL, key[j], ii, TPR);
-        const uint32_t pi = __shfl_sync(FULL, p[j], ii, TPR);
-        const T xei = __shfl_sync(FULL, xe[j], ii, TPR);
-        const T xxei = __shfl_sync(FULL, xxe[j], ii, TPR);
-        if (i < n_valid) {                                      // group-uniform
-          const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + g;
-          V2 sv[NCV];
+        for (int ii = 0; ii < TPR; ++ii) {
+          const int i = j * TPR + ii;
+          const uint32_t ki = __shfl_sync(FULL, key[j], ii, TPR);
+          const uint32_t pi = __shfl_sync(FULL, p[j], ii, TPR);
+          const T xei = __shfl_sync(FULL, xe[j], ii, TPR);
+          const T xxei = __shfl_sync(FULL, xxe[j], ii, TPR);
+          if (i < n_valid) {                                      // group-uniform
+            const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + g;
+            V2 sv[NCV];
 #pragma unroll
-          for (int ch = 0; ch < NCV; ++ch) sv[ch] = __ldg(srow + ch * TPR);
-          if (ki != cur) {  // the previous column's segment ended inside this chunk
-            if (head) store_carry<T, TPR, NCV>(a, chunk, 0, acc, sa, sc, g);
-            else finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
-            head = false;
-            cur = ki;
+            for (int ch = 0; ch < NCV; ++ch) sv[ch] = __ldg(srow + ch * TPR);
+            if (ki != cur) {  // the previous column's segment ended inside this chunk
+              if (head) store_carry<T, TPR, NCV>(a, chunk, 0, acc, sa, sc, g);
+              else finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
+              head = false;
+              cur = ki;
 #pragma unroll
-            for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
-            sa = sc = T(0);
+              for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
+              sa = sc = T(0);
+            }
+#pragma unroll
+            for (int ch = 0; ch < NCV; ++ch) {
+              acc[ch].x += xei * sv[ch].x;
+              acc[ch].y += xei * sv[ch].y;
+            }
+            sa += xei;
+            sc += xxei;
           }
-#pragma unroll
-          for (int ch = 0; ch < NCV; ++ch) {
-            acc[ch].x += xei * sv[ch].x;
-            acc[ch].y += xei * sv[ch].y;
-          }
-          sa += xei;
-          sc += xxei;
         }
       }
     }
-    if (n_valid > 0) {
+    if (any) {
+      uint32_t next_key = base + COL_CHUNK < M ? a.keys[base + COL_CHUNK] : KEY_NONE;
+      if (next_key == a.sentinel) next_key = KEY_NONE;
       const bool tail = (cur == next_key);
       if (head || tail) {
         store_carry<T, TPR, NCV>(a, chunk, head ? 0 : 1, acc, sa, sc, g);
@@ -514,15 +523,20 @@ fm_carry_kernel(const ColsArgs<T> a) {
   const uint32_t n_tails = *a.n_tails;
   for (uint32_t ti = gw; ti < n_tails; ti += nw) {
     const uint32_t chunk = a.tails[ti];
-    const uint32_t base = chunk << 5;
-    const uint32_t klast = a.keys[base + 31u];          // a TAIL chunk is full and its last key is the column
-    // upper bound of klast in [base+32, M): first index whose key differs
-    uint32_t lo = base + 32u, hi = M;
-    while (lo < hi) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (a.keys[mid] == klast) lo = mid + 1; else hi = mid;
+    const uint32_t base = chunk * COL_CHUNK;
+    const uint32_t klast = a.keys[base + COL_CHUNK - 1u];   // a TAIL chunk is full; its last key is the column
+    // last chunk that still holds entries of the column. Most runs end inside the very next chunk:
+    // one probe of that chunk's last key settles it; otherwise binary-search the first differing key.
+    uint32_t last_chunk = chunk + 1u;
+    const uint32_t probe = base + 2u * COL_CHUNK - 1u;
+    if (probe < M && a.keys[probe] == klast) {
+      uint32_t lo = probe + 1u, hi = M;
+      while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a.keys[mid] == klast) lo = mid + 1; else hi = mid;
+      }
+      last_chunk = (lo - 1u) / COL_CHUNK;
     }
-    const uint32_t last_chunk = (lo - 1u) >> 5;
     if (last_chunk - chunk > SHORT_RUN) {
       if (lane == 0) {
         const uint32_t slot = atomicAdd(a.n_long, 1u);
@@ -634,7 +648,7 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
         sa += part[a.kp];
         sc += part[a.kp + 1];
       }
-      finish_column<T, 32, NCH, DP>(a, a.keys[first * 32u + 31u], acc, sa, sc, lane, FULL);
+      finish_column<T, 32, NCH, DP>(a, a.keys[first * COL_CHUNK + COL_CHUNK - 1u], acc, sa, sc, lane, FULL);
     }
     __syncthreads();
   }
@@ -878,7 +892,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   }
   RFM_CUDA(cudaMemsetAsync(t->n_long.p, 0, sizeof(uint32_t), ctx->stream));
   RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
-  const int64_t chunk_cap = ceil_div(t->nnz_cap, 32);
+  const int64_t chunk_cap = ceil_div(t->nnz_cap, COL_CHUNK);
   const int cgrid = grid_for(ctx, ceil_div(chunk_cap, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
   const int tgrid = grid_for(ctx, ceil_div(chunk_cap, ROWS_WARPS * 4), 2);
   const int lgrid = t->long_cap < (uint32_t)ctx->sm_count * 2 ? (int)t->long_cap : ctx->sm_count * 2;
@@ -1258,7 +1272,7 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
     RFM_TRY(t->n_long.alloc(1));
     RFM_TRY(t->S.alloc((size_t)max_batch * m->kp * es));
     RFM_TRY(t->E.alloc((size_t)max_batch * es));
-    const int64_t chunk_cap = ceil_div(nnz_cap, 32);
+    const int64_t chunk_cap = ceil_div(nnz_cap, COL_CHUNK);
     RFM_TRY(t->carry_vec.alloc((size_t)chunk_cap * 2 * m->kp * es));
     RFM_TRY(t->carry_ac.alloc((size_t)chunk_cap * 4 * es));
     t->long_cap = (uint32_t)(chunk_cap / (SHORT_RUN + 1) + 1);
@@ -1450,7 +1464,7 @@ int rfm_fm_trainer_losses(rfm_fm_trainer *t, int64_t first_slot, int64_t n_slots
     RFM_CUDA(cudaMemcpyAsync(val_loss, t->losses.p + t->max_slots + first_slot, (size_t)n_slots * 8,
                              cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  return RFM_OK;
+  return t->m->dtype == RFM_F64 ? t->sort64.check(ctx) : t->sort32.check(ctx);
 }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
 // runtime.cu -- context, error reporting, pinned memory, device-wide exclusive scan.
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -171,6 +172,8 @@ int rfm_ctx_create(int device, void *cuda_stream, rfm_ctx **out) {
   ctx->device = device;
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   ctx->sm_count = prop.multiProcessorCount;
+  const char *sl = getenv("RFM_SYNC_LAUNCHES");
+  ctx->sync_launches = sl && sl[0] == '1';
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx;
     return fail(RFM_ERR_CUDA, "rfm_ctx_create: cudaEventCreate failed");
