@@ -183,6 +183,27 @@ enum rfm_rank_col {
 int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, int32_t n_k,
                         double *out_metrics, int32_t *out_item_hits, int64_t *out_top_rows);
 
+/* ---- full-catalog scoring + exact top-K (new capability) ------------
+ * score(u, i) = bias + alpha[u] + beta[i] + <A_u, C_i>: MF with A = P, C = Q, alpha = b_u, beta = b_i,
+ * bias = b (src/mf.py:165-170); FM with the per-user / per-item sums of x_j v_j and their scalar parts
+ * (src/fm.py:125-132) when rows are [user features | item features]. The reference never scores the
+ * full grid (it ranks only the rows it is given, utils/evaluate.py:80-127); parity is "equal to
+ * predict on the Cartesian-product rows + per-user argsort".
+ * rfm_topk_run returns, for every user, the K best items of the catalog range [item_begin, item_end)
+ * in the canonical order (score descending, larger item id first among exact ties) with their exact
+ * float64 scores. mode 0: bf16 tcgen05 GEMM + fused per-user candidate filter, exact float64
+ * re-scoring, and a proof per user that pruning lost nothing (users without a proof are ranked
+ * exactly); mode 1: exact float64 only. stats[0] = 1 if the tensor-core path ran, stats[1] = number of
+ * users that needed the exact fallback. A, C are row-major float64 (n_users, k), (n_items, k);
+ * alpha / beta may be NULL. */
+typedef struct rfm_topk rfm_topk;
+int rfm_topk_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, int32_t n_factors, rfm_topk **out);
+int rfm_topk_destroy(rfm_topk *t);
+int rfm_topk_set_factors(rfm_topk *t, const double *A, const double *C, const double *alpha,
+                         const double *beta, double bias);
+int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64_t item_end,
+                 int32_t *out_items, double *out_scores, int64_t *stats);
+
 #ifdef __cplusplus
 }
 #endif

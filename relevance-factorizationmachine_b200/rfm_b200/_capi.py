@@ -69,6 +69,10 @@ _SIGNATURES = {
     "rfm_mf_logloss": ([_P, _P, POINTER(c_double)], c_int),
     "rfm_mf_train_epoch": ([_P, _P, _P, _P, c_int64, c_double, c_double, POINTER(c_double), POINTER(c_double)],
                            c_int),
+    "rfm_topk_create": ([_P, c_int64, c_int64, c_int32, POINTER(_P)], c_int),
+    "rfm_topk_destroy": ([_P], c_int),
+    "rfm_topk_set_factors": ([_P, _P, _P, _P, _P, c_double], c_int),
+    "rfm_topk_run": ([_P, c_int32, c_int32, c_int64, c_int64, _P, _P, _P], c_int),
     "rfm_ranker_create": ([_P, c_int64, _P, _P, _P, _P, c_int64, POINTER(_P)], c_int),
     "rfm_ranker_destroy": ([_P], c_int),
     "rfm_ranker_num_users": ([_P, POINTER(c_int64)], c_int),

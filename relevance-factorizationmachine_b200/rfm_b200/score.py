@@ -1,0 +1,88 @@
+"""Full-catalog scoring and exact per-user top-K on the device.
+
+``score(u, i) = bias + alpha[u] + beta[i] + <A_u, C_i>``. The reference never scores the whole
+user x item grid: ``predict`` scores the rows it is given (``src/fm.py:114-133``,
+``src/mf.py:136-152``) and the evaluators rank those (``utils/evaluate.py:80-127``). This module is
+the B200 path for "rank every item for every user": a bf16 tcgen05 GEMM prunes the catalog, the
+survivors are re-scored in float64 and the result is proven exact per user (``csrc/score.cu``). It
+equals ``predict`` on the Cartesian-product rows followed by the reference's per-user argsort.
+"""
+from __future__ import annotations
+
+from ctypes import byref, c_int64
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib, ptr
+
+
+def mf_factors(model):
+    """(A, C, alpha, beta, bias) of a LogisticMatrixFactorization: P, Q, b_u, b_i, b (src/mf.py:165-170)."""
+    return model.P(), model.Q(), model.b_u(), model.b_i(), float(getattr(model, "b", 0.0))
+
+
+def fm_side(table, w, V):
+    """Per-entity vector and scalar part of an FM side (user or item): for a CSR table whose row e holds
+    that entity's feature columns/values,  vec_e = sum_j x_j v_j  and
+    scal_e = sum_j x_j w_j + (||vec_e||^2 - sum_j x_j^2 ||v_j||^2) / 2   (src/fm.py:125-131 split by side)."""
+    table = table.tocsr()
+    vec = table.dot(V)
+    q = np.asarray(table.power(2).dot((V ** 2).sum(axis=1))).ravel()
+    scal = np.asarray(table.dot(w)).ravel() + 0.5 * ((vec ** 2).sum(axis=1) - q)
+    return np.ascontiguousarray(vec), scal
+
+
+def fm_factors(model, user_table, item_table):
+    """(A, C, alpha, beta, bias) of a FactorizationMachines whose rows are [user features | item features].
+    A per-pair context column with a fixed value belongs in ``user_table`` (same entry in every row)."""
+    w, V = model.w(), model.V()
+    A, alpha = fm_side(user_table, w, V)
+    C, beta = fm_side(item_table, w, V)
+    return A, C, alpha, beta, float(model.w0()[0])
+
+
+class TopKScorer(_capi._Handle):
+    _destroy = "rfm_topk_destroy"
+
+    def __init__(self, A, C, alpha=None, beta=None, bias=0.0, device=0):
+        super().__init__()
+        A = _capi.as_array(A, np.float64)
+        C = _capi.as_array(C, np.float64)
+        if A.ndim != 2 or C.ndim != 2 or A.shape[1] != C.shape[1]:
+            raise ValueError("A and C must be (n_users, k) and (n_items, k)")
+        alpha = None if alpha is None else _capi.as_array(alpha, np.float64)
+        beta = None if beta is None else _capi.as_array(beta, np.float64)
+        if alpha is not None and alpha.shape != (A.shape[0],):
+            raise ValueError("alpha must have one entry per user")
+        if beta is not None and beta.shape != (C.shape[0],):
+            raise ValueError("beta must have one entry per item")
+        self.ctx = _capi.Context.default(device)
+        self.n_users, self.n_items, self.k = A.shape[0], C.shape[0], A.shape[1]
+        check(lib().rfm_topk_create(self.ctx.handle, self.n_users, self.n_items, self.k, byref(self.handle)))
+        check(lib().rfm_topk_set_factors(self.handle, ptr(A), ptr(C), ptr(alpha), ptr(beta), float(bias)))
+        self.last_stats = {}
+
+    def topk(self, K: int, mode: str = "tensor", item_range=None):
+        """(items (n_users, K) int32, scores (n_users, K) float64): every user's K best items, best first;
+        -1 / -inf pad when the catalog range holds fewer than K items."""
+        if mode not in ("tensor", "exact"):
+            raise ValueError("mode must be 'tensor' or 'exact'")
+        begin, end = (0, self.n_items) if item_range is None else item_range
+        items = np.empty((self.n_users, K), dtype=np.int32)
+        scores = np.empty((self.n_users, K), dtype=np.float64)
+        stats = (c_int64 * 2)()
+        check(lib().rfm_topk_run(self.handle, K, 0 if mode == "tensor" else 1, begin, end, ptr(items), ptr(scores),
+                                 stats))
+        self.last_stats = {"tensor_core_path": bool(stats[0]), "users_ranked_exactly": int(stats[1])}
+        return items, scores
+
+
+def merge_topk(items_list, scores_list, K):
+    """Merge per-shard top-K lists (item-sharded scoring) into the global top-K
+    with the canonical order: score descending, larger item id first among exact ties."""
+    items = np.concatenate(items_list, axis=1)
+    scores = np.concatenate(scores_list, axis=1)
+    order = np.lexsort((-items.astype(np.int64), -scores), axis=1)[:, :K]
+    rows = np.arange(items.shape[0])[:, None]
+    return items[rows, order], scores[rows, order]
