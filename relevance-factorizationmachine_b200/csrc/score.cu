@@ -37,10 +37,11 @@ constexpr int BM = 128;          // users per CTA tile (= TMEM lanes)
 constexpr int BN = 256;          // items per MMA tile (= TMEM columns per accumulator stage)
 constexpr int BK = 64;           // bf16 elements per K block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int SCORE_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int SCORE_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
+constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter; each owns half of a tile's columns
+constexpr int EPI_HALVES = EPI_WARPS / 4;
 constexpr int MAX_KB = 2;        // k <= 128 on the tensor-core path
-constexpr int MAX_KC_SMEM = 32;  // candidate lists of up to this many entries live in shared memory
-constexpr int MAX_K = 128;
+constexpr int MAX_K = 120;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -129,14 +130,61 @@ struct FilterArgs {
   int32_t *glist_item;
 };
 
+// Candidate lists are two-level: kc entries in groups of 8, plus the minimum of every group (gm). An
+// insert finds the group holding the smallest kept score from the group minima, replaces that entry,
+// rescans only that group's 8 entries (independent loads) and refreshes the threshold tau = min(gm).
+// Everything is stored [index][row] so the 32 rows of a warp hit different banks / coalesce.
+// It has exactly one call site, inside a rolled loop (see the epilogue), so it costs no code in the hot path.
+__device__ __forceinline__ void insert_candidate(float s, int item, float *ls, int32_t *li, float *gm, int r, int n_groups,
+                                              float &tau) {
+  if (!(s > tau)) return;   // an earlier insert of the same 32-column slice may have raised the threshold
+  float m1 = gm[r], m2 = INFINITY;
+  int g1 = 0;
+  for (int g = 1; g < n_groups; ++g) {
+    const float x = gm[g * BM + r];
+    if (x < m1) {
+      m2 = m1;
+      m1 = x;
+      g1 = g;
+    } else if (x < m2) {
+      m2 = x;
+    }
+  }
+  float e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) e[j] = ls[(g1 * 8 + j) * BM + r];
+  // smallest (to be replaced) and second smallest entry of the group, positions tracked in registers
+  float e1 = e[0], e2 = INFINITY;
+  int j1 = 0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) {
+    if (e[j] < e1) {
+      e2 = e1;
+      e1 = e[j];
+      j1 = j;
+    } else if (e[j] < e2) {
+      e2 = e[j];
+    }
+  }
+  const float gmin = fminf(s, e2);
+  ls[(g1 * 8 + j1) * BM + r] = s;
+  li[(g1 * 8 + j1) * BM + r] = item;
+  gm[g1 * BM + r] = gmin;
+  tau = fminf(gmin, m2);
+}
+
 template <int KB>
 struct FilterSmem {
   static constexpr int STAGES = KB == 1 ? 3 : 2;
   static constexpr int A_BYTES = KB * BM * 128;
   static constexpr int B_STAGE_BYTES = KB * BN * 128;
   static constexpr int BAR_OFF = A_BYTES + STAGES * B_STAGE_BYTES;
-  static constexpr int LIST_OFF = BAR_OFF + 256;
-  static size_t bytes(int kc_smem) { return 1024 + LIST_OFF + (size_t)kc_smem * BM * 8; }
+  static constexpr int GM_OFF = BAR_OFF + 256;                 // group minima [EPI_HALVES][n_groups][BM] floats
+  __host__ __device__ static size_t list_off(int n_groups) { return GM_OFF + (size_t)EPI_HALVES * n_groups * BM * 4; }
+  // lists [EPI_HALVES][kc][BM] of (float score, int32 item) when they live in shared memory
+  static size_t bytes(int n_groups, int kc_smem) {
+    return 1024 + list_off(n_groups) + (size_t)EPI_HALVES * kc_smem * BM * 8;
+  }
 };
 
 template <int KB>
@@ -167,7 +215,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull + s, 1);
-      mbar_init(tempty + s, 4);     // one arrival per epilogue warp
+      mbar_init(tempty + s, EPI_WARPS);     // one arrival per epilogue warp
     }
     mbar_init(afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -223,15 +271,19 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp >= 4) {
     // ===== epilogue: thread r keeps the kc best (score, item) pairs of user row r =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;       // which half of every tile's columns this warp filters
     const int r = q * 32 + lane;
     const int kc = a.kc;
+    const int n_groups = kc >> 3;
+    float *gm = reinterpret_cast<float *>(smem + L::GM_OFF) + (size_t)half * n_groups * BM;
     float *ls;
     int32_t *li;
-    if (kc <= MAX_KC_SMEM) {
-      ls = reinterpret_cast<float *>(smem + L::LIST_OFF);
-      li = reinterpret_cast<int32_t *>(smem + L::LIST_OFF + (size_t)kc * BM * 4);
+    if (a.glist_score == nullptr) {
+      unsigned char *lists = smem + L::list_off(n_groups);
+      ls = reinterpret_cast<float *>(lists) + (size_t)half * kc * BM;
+      li = reinterpret_cast<int32_t *>(lists + (size_t)EPI_HALVES * kc * BM * 4) + (size_t)half * kc * BM;
     } else {
-      const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      const size_t cta = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * EPI_HALVES + half;
       ls = a.glist_score + cta * kc * BM;
       li = a.glist_item + cta * kc * BM;
     }
@@ -239,6 +291,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       ls[j * BM + r] = -INFINITY;
       li[j * BM + r] = -1;
     }
+    for (int g = 0; g < n_groups; ++g) gm[g * BM + r] = -INFINITY;
     float tau = -INFINITY;                  // smallest kept score
     for (int it = 0; it < n_tiles; ++it) {
       const int acc = it & 1;
@@ -247,34 +300,30 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const int item0 = (tile0 + it) * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * (BN / EPI_HALVES); c < (half + 1) * (BN / EPI_HALVES); c += 32) {
         uint32_t v[32];
         tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, v);
         const float4 *b4 = reinterpret_cast<const float4 *>(a.beta + item0 + c);
+        uint32_t pass = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b = __ldg(b4 + j4);
-          const float bb[4] = {b.x, b.y, b.z, b.w};
+          pass |= (__uint_as_float(v[j4 * 4 + 0]) + b.x > tau ? 1u : 0u) << (j4 * 4 + 0);
+          pass |= (__uint_as_float(v[j4 * 4 + 1]) + b.y > tau ? 1u : 0u) << (j4 * 4 + 1);
+          pass |= (__uint_as_float(v[j4 * 4 + 2]) + b.z > tau ? 1u : 0u) << (j4 * 4 + 2);
+          pass |= (__uint_as_float(v[j4 * 4 + 3]) + b.w > tau ? 1u : 0u) << (j4 * 4 + 3);
+        }
+        // Rare after warm-up. Every lane walks ITS OWN passing columns (lanes pass at different columns, so
+        // this takes max-over-lanes iterations, usually one, instead of one iteration per column). The
+        // lane's score is pulled out of the register tile with a select chain (no run-time indexed array).
+        while (__any_sync(FULL, pass != 0)) {
+          const int j = pass ? __ffs(pass) - 1 : 0;
+          float vj = 0.f;
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float s = __uint_as_float(v[j4 * 4 + jj]) + bb[jj];
-            if (s > tau) {   // rare after warm-up: replace the smallest kept entry, track the new smallest
-              float m1 = ls[r], m2 = INFINITY;
-              int j1 = 0;
-              for (int j = 1; j < kc; ++j) {
-                const float x = ls[j * BM + r];
-                if (x < m1) {
-                  m2 = m1;
-                  m1 = x;
-                  j1 = j;
-                } else if (x < m2) {
-                  m2 = x;
-                }
-              }
-              ls[j1 * BM + r] = s;
-              li[j1 * BM + r] = item0 + c + j4 * 4 + jj;
-              tau = s < m2 ? s : m2;
-            }
+          for (int jj = 0; jj < 32; ++jj) vj = (j == jj) ? __uint_as_float(v[jj]) : vj;
+          if (pass) {
+            pass &= pass - 1;
+            insert_candidate(vj + __ldg(a.beta + item0 + c + j), item0 + c + j, ls, li, gm, r, n_groups, tau);
           }
         }
       }
@@ -283,7 +332,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) mbar_arrive(tempty + acc);
     }
     // hand the list to the exact re-scoring pass
-    const size_t row = (size_t)split * a.n_users_pad + (size_t)user_block * BM + r;
+    const size_t row = ((size_t)split * EPI_HALVES + half) * a.n_users_pad + (size_t)user_block * BM + r;
     for (int j = 0; j < kc; ++j) {
       a.cand_score[row * kc + j] = ls[j * BM + r];
       a.cand_item[row * kc + j] = li[j * BM + r];
@@ -346,12 +395,19 @@ struct ExactArgs {
   int item_begin, item_end;   // catalog range this call ranks (item-sharded runs)
 };
 
-__device__ __forceinline__ double exact_score(const ExactArgs &e, int64_t u, int64_t i) {
+// The exact float64 score, computed by a whole warp: lane l accumulates factors l, l+32, ... in order
+// (coalesced reads of both rows), the 32 partial sums are combined by an xor butterfly, and every lane
+// returns the same value. Both the re-scoring pass and the exact fallback use this one association, so
+// a (user, item) pair gets the same bits whichever path scores it.
+__device__ __forceinline__ double warp_exact_dot(const ExactArgs &e, int64_t u, int64_t i, int lane) {
   const double *au = e.A + u * e.k, *ci = e.C + i * e.k;
   double dot = 0.0;
-  for (int f = 0; f < e.k; ++f) dot += au[f] * ci[f];
-  // association of the reference: (((dot + alpha_u) + beta_i) + bias), src/mf.py:165-170
-  return ((dot + (e.alpha ? e.alpha[u] : 0.0)) + (e.beta ? e.beta[i] : 0.0)) + e.bias;
+  for (int f = lane; f < e.k; f += 32) dot += au[f] * ci[f];
+  return warp_sum(dot);
+}
+__device__ __forceinline__ double warp_exact_score(const ExactArgs &e, int64_t u, int64_t i, int lane) {
+  // outer association of the reference: (((dot + alpha_u) + beta_i) + bias), src/mf.py:165-170
+  return ((warp_exact_dot(e, u, i, lane) + (e.alpha ? e.alpha[u] : 0.0)) + (e.beta ? e.beta[i] : 0.0)) + e.bias;
 }
 
 struct Best {
@@ -374,46 +430,84 @@ __device__ __forceinline__ Best warp_best(Best b) {
   return b;
 }
 
-// one warp per user: exact scores of the candidates, exact top-K, and the pruning proof
-__global__ void __launch_bounds__(256)
+// one warp per user: exact scores of the candidates, exact top-K, and the pruning proof. The warp's
+// candidates (item, exact score) are staged in shared memory so the K selection rounds never leave the SM.
+constexpr int RESCORE_WARPS = 4;
+
+__global__ void __launch_bounds__(RESCORE_WARPS * 32)
 score_rescore_kernel(const ExactArgs e, const float *__restrict__ cand_score, const int32_t *__restrict__ cand_item,
-                     const float *__restrict__ cand_tau, int n_splits, int n_users_pad, int kc, int K,
-                     const double *__restrict__ a_norm, const double *__restrict__ c_norm_max,
-                     const double *__restrict__ beta_abs_max, int32_t *__restrict__ out_items,
-                     double *__restrict__ out_scores, int32_t *__restrict__ fail_list, uint32_t *__restrict__ n_fail,
-                     double *__restrict__ cand_exact /* [n_users][n_splits*kc] scratch */) {
-  const int lane = threadIdx.x & 31;
+                     const float *__restrict__ cand_tau,
+                     int n_lists, int n_users_pad, int kc, int K, const double *__restrict__ a_norm,
+                     const double *__restrict__ c_norm_max, const double *__restrict__ beta_abs_max,
+                     int32_t *__restrict__ out_items, double *__restrict__ out_scores, int32_t *__restrict__ fail_list,
+                     uint32_t *__restrict__ n_fail) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n_cand = n_lists * kc;
+  double *ex = reinterpret_cast<double *>(rs_smem) + (size_t)wid * n_cand;
+  int32_t *it = reinterpret_cast<int32_t *>(rs_smem + (size_t)RESCORE_WARPS * n_cand * 8) + (size_t)wid * n_cand;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int n_cand = n_splits * kc;
   for (int64_t u = gw; u < e.n_users; u += nw) {
-    double *ex = cand_exact + u * n_cand;
-    float tau_max = -INFINITY;
+    // 1. stage (item, approximate score as an order-preserving uint key) of every list entry
+    uint32_t *key = reinterpret_cast<uint32_t *>(ex);     // the float64 slots are reused: keys first, scores later
+    int n_valid = 0;
     for (int c = lane; c < n_cand; c += 32) {
       const int sp = c / kc, j = c - sp * kc;
-      const size_t row = (size_t)sp * n_users_pad + u;
-      const int item = cand_item[row * kc + j];
-      ex[c] = item >= 0 && item < e.n_items ? exact_score(e, u, item) : -INFINITY;
+      const size_t at = ((size_t)sp * n_users_pad + u) * kc + j;
+      const int item = cand_item[at];
+      const bool ok = item >= 0 && item < e.n_items;
+      const uint32_t bits = __float_as_uint(cand_score[at]);
+      it[c] = ok ? item : -1;
+      key[2 * c] = ok ? (bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u)) : 0u;
+      n_valid += ok;
     }
-    for (int sp = lane; sp < n_splits; sp += 32) tau_max = fmaxf(tau_max, cand_tau[(size_t)sp * n_users_pad + u]);
+    n_valid = __reduce_add_sync(FULL, n_valid);
+    __syncwarp();
+    // 2. only the kc best approximate scores of the merged lists can matter; their kc-th value is a valid
+    //    pruning threshold (it is >= every list's own threshold). Find it by bisection on the key bits.
+    uint32_t thr = 0u;
+    float tau_max = -INFINITY;
+    if (n_valid > kc) {
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand_thr = thr | (1u << bit);
+        int cnt = 0;
+        for (int c = lane; c < n_cand; c += 32) cnt += (it[c] >= 0 && key[2 * c] >= cand_thr);
+        cnt = __reduce_add_sync(FULL, cnt);
+        if (cnt >= kc) thr = cand_thr;       // at least kc keys are >= cand_thr: the kc-th largest is too
+      }
+      const uint32_t bits = (thr & 0x80000000u) ? (thr ^ 0x80000000u) : ~thr;
+      tau_max = __uint_as_float(bits);
+    } else {
+      // every list entry is kept; items outside the lists are bounded by the lists' own thresholds
+      for (int sp = lane; sp < n_lists; sp += 32) tau_max = fmaxf(tau_max, cand_tau[(size_t)sp * n_users_pad + u]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tau_max = fmaxf(tau_max, __shfl_xor_sync(FULL, tau_max, o));
+      for (int o = 16; o > 0; o >>= 1) tau_max = fmaxf(tau_max, __shfl_xor_sync(FULL, tau_max, o));
+    }
+    for (int c = lane; c < n_cand; c += 32)
+      if (it[c] >= 0 && key[2 * c] < thr) it[c] = -1;
+    __syncwarp();
+    // 3. exact float64 scores of the survivors, one candidate at a time, all lanes on its dot product
+    for (int c = 0; c < n_cand; ++c) {
+      const int item = it[c];
+      if (item < 0) continue;
+      const double sc = warp_exact_score(e, u, item, lane);
+      __syncwarp();
+      if (lane == 0) ex[c] = sc;
+    }
     __syncwarp();
     Best last;
     last.s = 0.0;
     last.item = -2;
-    double kth = -INFINITY;
     for (int r = 0; r < K; ++r) {
       Best mine;
       mine.s = 0.0;
       mine.item = -1;
       for (int c = lane; c < n_cand; c += 32) {
-        const int sp = c / kc, j = c - sp * kc;
-        const int item = cand_item[((size_t)sp * n_users_pad + u) * kc + j];
-        if (item < 0 || item >= e.n_items) continue;
         Best b;
+        b.item = it[c];
+        if (b.item < 0) continue;
         b.s = ex[c];
-        b.item = item;
         const bool below = last.item == -2 || ranks_before(last, b);
         if (below && ranks_before(b, mine)) mine = b;
       }
@@ -422,25 +516,24 @@ score_rescore_kernel(const ExactArgs e, const float *__restrict__ cand_score, co
         out_items[u * K + r] = last.item;
         out_scores[u * K + r] = last.item >= 0 ? last.s : -INFINITY;
       }
-      if (last.item < 0) break;
-      kth = last.s;
-      if (r == K - 1 || r == e.n_items - 1) break;
+      if (last.item < 0) {   // fewer than K candidates: pad the rest
+        for (int rr = r + 1 + lane; rr < K; rr += 32) {
+          out_items[u * K + rr] = -1;
+          out_scores[u * K + rr] = -INFINITY;
+        }
+        break;
+      }
     }
     // Every item outside the lists has approximate ranking score (<A_u, C_i> + beta_i, what the tensor-core
     // pass sees) <= tau_max, hence exact ranking score <= tau_max + eps. Compare with the K-th item's exact
     // ranking score (alpha_u and the bias are constant per user and do not affect the order).
     double kth_rank = -INFINITY;
-    if (last.item >= 0) {
-      const double *au = e.A + u * e.k, *ci = e.C + (int64_t)last.item * e.k;
-      double dot = 0.0;
-      for (int f = 0; f < e.k; ++f) dot += au[f] * ci[f];
-      kth_rank = dot + (e.beta ? e.beta[last.item] : 0.0);
-    }
-    (void)kth;
+    if (last.item >= 0) kth_rank = warp_exact_dot(e, u, last.item, lane) + (e.beta ? e.beta[last.item] : 0.0);
     const double eps = ldexp(a_norm[u] * *c_norm_max, -7) + ldexp(fabs((double)tau_max) + *beta_abs_max, -20);
     const bool complete = tau_max == -INFINITY;          // lists never filled: every item is a candidate
     const bool proven = complete || (last.item >= 0 && kth_rank > (double)tau_max + eps);
     if (!proven && lane == 0) fail_list[atomicAdd(n_fail, 1u)] = (int32_t)u;
+    __syncwarp();
   }
 }
 
@@ -460,14 +553,13 @@ score_exact_kernel(const ExactArgs e, const int32_t *__restrict__ users, const u
       Best mine;
       mine.s = 0.0;
       mine.item = -1;
-      for (int64_t i = e.item_begin + threadIdx.x; i < e.item_end; i += blockDim.x) {
+      for (int64_t i = e.item_begin + wid; i < e.item_end; i += 8) {   // a warp per item
         Best b;
-        b.s = exact_score(e, u, i);
+        b.s = warp_exact_score(e, u, i, lane);
         b.item = (int)i;
         const bool below = last.item == -2 || ranks_before(last, b);
         if (below && ranks_before(b, mine)) mine = b;
       }
-      mine = warp_best(mine);
       if (lane == 0) wbest[wid] = mine;
       __syncthreads();
       Best best = wbest[0];
@@ -645,11 +737,11 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     int n_splits = std::max(1, std::min(n_item_tiles, (2 * ctx->sm_count + n_user_blocks - 1) / n_user_blocks));
     const int tiles_per_split = (n_item_tiles + n_splits - 1) / n_splits;
     n_splits = (n_item_tiles + tiles_per_split - 1) / tiles_per_split;
-    const size_t rows = (size_t)n_splits * t->n_users_pad;
+    const int n_lists = n_splits * EPI_HALVES;          // candidate lists per user
+    const size_t rows = (size_t)n_lists * t->n_users_pad;
     RFM_TRY(t->cand_score.ensure(rows * kc));
     RFM_TRY(t->cand_item.ensure(rows * kc));
     RFM_TRY(t->cand_tau.ensure(rows));
-    RFM_TRY(t->cand_exact.ensure((size_t)t->n_users * n_splits * kc));
     FilterArgs fa;
     fa.beta = t->beta32.p;
     fa.n_item_tiles = n_item_tiles;
@@ -661,30 +753,41 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     fa.cand_tau = t->cand_tau.p;
     fa.glist_score = nullptr;
     fa.glist_item = nullptr;
-    const int kc_smem = kc <= MAX_KC_SMEM ? kc : 0;
+    const int n_groups = kc / 8;
+    const size_t smem_limit = 227 * 1024;
+    const size_t smem_with_lists = t->kb == 1 ? FilterSmem<1>::bytes(n_groups, kc) : FilterSmem<2>::bytes(n_groups, kc);
+    const int kc_smem = smem_with_lists <= smem_limit ? kc : 0;     // otherwise the lists go to global memory
     if (!kc_smem) {
-      RFM_TRY(t->glist_score.ensure((size_t)n_user_blocks * n_splits * kc * BM));
-      RFM_TRY(t->glist_item.ensure((size_t)n_user_blocks * n_splits * kc * BM));
+      RFM_TRY(t->glist_score.ensure((size_t)n_user_blocks * n_splits * EPI_HALVES * kc * BM));
+      RFM_TRY(t->glist_item.ensure((size_t)n_user_blocks * n_splits * EPI_HALVES * kc * BM));
       fa.glist_score = t->glist_score.p;
       fa.glist_item = t->glist_item.p;
     }
     const dim3 grid(n_user_blocks, n_splits);
     if (t->kb == 1) {
-      const size_t smem = FilterSmem<1>::bytes(kc_smem);
+      const size_t smem = FilterSmem<1>::bytes(n_groups, kc_smem);
+      RFM_REQUIRE(smem <= smem_limit, "rfm_topk_run: K=%d needs %zu bytes of shared memory", K, smem);
       RFM_CUDA(cudaFuncSetAttribute(score_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       auto score_filter = score_filter_kernel<1>;
       RFM_LAUNCH(ctx, score_filter, grid, SCORE_THREADS, smem, t->tmap_a, t->tmap_c, fa);
     } else {
-      const size_t smem = FilterSmem<2>::bytes(kc_smem);
+      const size_t smem = FilterSmem<2>::bytes(n_groups, kc_smem);
+      RFM_REQUIRE(smem <= smem_limit, "rfm_topk_run: K=%d needs %zu bytes of shared memory", K, smem);
       RFM_CUDA(cudaFuncSetAttribute(score_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       auto score_filter = score_filter_kernel<2>;
       RFM_LAUNCH(ctx, score_filter, grid, SCORE_THREADS, smem, t->tmap_a, t->tmap_c, fa);
     }
     RFM_CUDA(cudaMemsetAsync(t->n_fail.p, 0, sizeof(uint32_t), ctx->stream));
-    const int rgrid = (int)std::min<int64_t>((t->n_users + 7) / 8, (int64_t)ctx->sm_count * 8);
-    RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, 256, 0, e, t->cand_score.p, t->cand_item.p, t->cand_tau.p, n_splits,
-               (int)t->n_users_pad, kc, (int)K, t->a_norm.p, t->c_norm_max.p, t->beta_abs_max.p, t->out_items.p,
-               t->out_scores.p, t->fail_list.p, t->n_fail.p, t->cand_exact.p);
+    const size_t rs_smem = (size_t)RESCORE_WARPS * n_lists * kc * 12;
+    RFM_REQUIRE(rs_smem <= 200 * 1024, "rfm_topk_run: %d candidates per user do not fit the re-scoring kernel",
+                n_lists * kc);
+    RFM_CUDA(cudaFuncSetAttribute(score_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    const int rgrid = (int)std::min<int64_t>((t->n_users + RESCORE_WARPS - 1) / RESCORE_WARPS,
+                                             (int64_t)ctx->sm_count * 8);
+    RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, RESCORE_WARPS * 32, rs_smem, e, t->cand_score.p, t->cand_item.p,
+               t->cand_tau.p,
+               n_lists, (int)t->n_users_pad, kc, (int)K, t->a_norm.p, t->c_norm_max.p, t->beta_abs_max.p,
+               t->out_items.p, t->out_scores.p, t->fail_list.p, t->n_fail.p);
     // users whose pruning could not be proven are ranked exactly against the whole catalog
     const int fgrid = (int)std::min<int64_t>(t->n_users, (int64_t)ctx->sm_count * 4);
     RFM_LAUNCH(ctx, score_exact_kernel, fgrid, 256, 0, e, t->fail_list.p, t->n_fail.p, (int64_t)0, (int)K,
