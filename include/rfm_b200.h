@@ -180,6 +180,10 @@ enum rfm_rank_col {
   RFM_RANK_DCG_SUM = 0, RFM_RANK_IPSDCG_SUM = 1, RFM_RANK_ME_SUM = 2, RFM_RANK_ME_COUNT = 3,
   RFM_RANK_RECALL_SUM = 4, RFM_RANK_MAP_SUM = 5, RFM_RANK_USERS = 6, RFM_RANK_COVERED = 7
 };
+/* Optional: label totals per user (users in ascending id order, rfm_ranker_num_users entries) to use for
+ * the skip rule and Recall's denominator instead of the sum over the rows given -- for callers that
+ * hand over only the top of every user's candidate list (full-catalog evaluation). NULL clears it. */
+int rfm_ranker_set_user_totals(rfm_ranker *r, const double *totals);
 int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, int32_t n_k,
                         double *out_metrics, int32_t *out_item_hits, int64_t *out_top_rows);
 

@@ -35,6 +35,8 @@ struct rfm_ranker {
   DevBuf<double> metrics;      // [n_k][RFM_RANK_NCOLS]
   DevBuf<int32_t> hits;        // [n_k][n_items]
   DevBuf<int64_t> top_rows;    // [n_users][k_max]
+  DevBuf<double> totals;       // optional per-user label totals supplied by the caller
+  bool has_totals = false;
 };
 
 namespace {
@@ -77,7 +79,8 @@ __device__ __forceinline__ Key block_best(Key mine, Key *smem) {
 __global__ void __launch_bounds__(RK_THREADS)
 rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restrict__ order,
                   const int32_t *__restrict__ item, const double *__restrict__ label,
-                  const double *__restrict__ pscore, const double *__restrict__ scores, int64_t n_users,
+                  const double *__restrict__ pscore, const double *__restrict__ scores,
+                  const double *__restrict__ user_totals, int64_t n_users,
                   const int32_t *__restrict__ K, int n_k, int k_max, int64_t n_items,
                   double *__restrict__ per_user, int32_t *__restrict__ hits, int64_t *__restrict__ top_rows) {
   __shared__ Key wbest[RK_THREADS / 32];
@@ -99,7 +102,9 @@ rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restric
       total_y_s = t;
     }
     __syncthreads();
-    const double total_y = total_y_s;
+    // label total that decides the skip rule and Recall's denominator: over the rows given, or the
+    // caller's total when the rows are only a prefix of the user's candidates (full-catalog evaluation)
+    const double total_y = user_totals ? user_totals[u] : total_y_s;
     const int n_top = L < k_max ? L : k_max;
     // top-n_top by repeated arg-max below the previously selected key
     Key last;
@@ -268,6 +273,21 @@ int rfm_ranker_num_users(rfm_ranker *r, int64_t *out) {
   return RFM_OK;
 }
 
+int rfm_ranker_set_user_totals(rfm_ranker *r, const double *totals) {
+  RFM_REQUIRE(r, "rfm_ranker_set_user_totals: ranker is NULL");
+  rfm_ctx *ctx = r->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  if (!totals) {
+    r->has_totals = false;
+    return RFM_OK;
+  }
+  RFM_TRY(r->totals.ensure((size_t)(r->n_users ? r->n_users : 1)));
+  RFM_CUDA(cudaMemcpyAsync(r->totals.p, totals, (size_t)r->n_users * 8, cudaMemcpyHostToDevice, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  r->has_totals = true;
+  return RFM_OK;
+}
+
 int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, int32_t n_k, double *out_metrics,
                         int32_t *out_item_hits, int64_t *out_top_rows) {
   RFM_REQUIRE(r && K && out_metrics, "rfm_ranker_evaluate: NULL argument");
@@ -291,7 +311,7 @@ int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, i
     const int64_t cap = (int64_t)ctx->sm_count * 8;
     const int grid = (int)(r->n_users < cap ? r->n_users : cap);
     RFM_LAUNCH(ctx, rank_users_kernel, grid, RK_THREADS, 0, r->user_ptr.p, r->order.p, r->item.p, r->label.p,
-               r->pscore.p, r->scores.p, r->n_users, r->K_dev.p, (int)n_k, k_max, r->n_items, r->per_user.p,
+               r->pscore.p, r->scores.p, r->has_totals ? r->totals.p : (const double *)nullptr, r->n_users, r->K_dev.p, (int)n_k, k_max, r->n_items, r->per_user.p,
                r->hits.p, out_top_rows ? r->top_rows.p : (int64_t *)nullptr);
     RFM_LAUNCH(ctx, rank_reduce_kernel, n_k * NTERMS, 256, 0, r->per_user.p, r->n_users, (int)n_k, r->metrics.p);
   }

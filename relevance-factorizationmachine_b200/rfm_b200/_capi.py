@@ -76,6 +76,7 @@ _SIGNATURES = {
     "rfm_ranker_create": ([_P, c_int64, _P, _P, _P, _P, c_int64, POINTER(_P)], c_int),
     "rfm_ranker_destroy": ([_P], c_int),
     "rfm_ranker_num_users": ([_P, POINTER(c_int64)], c_int),
+    "rfm_ranker_set_user_totals": ([_P, _P], c_int),
     "rfm_ranker_evaluate": ([_P, _P, _P, c_int32, _P, _P, _P], c_int),
 }
 

@@ -156,3 +156,76 @@ class ValEvaluator(_BaseEvaluator):
 
     def _group_by_user_data(self, *args, **kwargs):
         raise NotImplementedError("grouping happens inside the device ranker")
+
+
+@dataclass
+class FullCatalogEvaluator:
+    """TestEvaluator's metrics when EVERY item of the catalog is a candidate for every user.
+
+    The reference only ranks the rows of ``interaction_df`` (``utils/evaluate.py:80-127``); scoring the
+    whole user x item grid is a new capability. This class is defined to equal
+    ``TestEvaluator`` on the Cartesian-product frame whose label is the held-out label where one exists
+    and 0 elsewhere, and whose pscore is the item's exposure: scores come from the device scorer
+    (``rfm_b200.score.TopKScorer``: tcgen05 GEMM prune + exact float64 top-K), and the metric reductions
+    run in the device ranker on the top-max(K) rows of every user.
+    """
+
+    interaction_df: object          # held-out rows with columns user, item, label
+    item_pscores: np.ndarray        # (n_items,) exposure of every item (MeanExposure@K)
+    K: Tuple[int]
+    used_metrics: set
+    n_users: int
+    n_items: int
+
+    def __post_init__(self) -> None:
+        from scipy.sparse import csr_matrix
+        self.metric_names = ["ME"]
+        for metric_name in self.used_metrics:
+            if metric_name not in metric_candidates:
+                raise ValueError(METRIC_NAME_ERROR_MESSAGE.format(metric_candidates.keys(), metric_name))
+            if metric_name != "ME":
+                self.metric_names.append(metric_name)
+        users = _column(self.interaction_df, "user").astype(np.int64)
+        items = _column(self.interaction_df, "item").astype(np.int64)
+        labels = _column(self.interaction_df, "label").astype(np.float64)
+        self._labels = csr_matrix((labels, (users, items)), shape=(self.n_users, self.n_items))
+        self._totals = np.asarray(self._labels.sum(axis=1)).ravel().astype(np.float64)
+        self.item_pscores = _capi.as_array(self.item_pscores, np.float64)
+        self.last_stats = {}
+
+    def evaluate(self, scorer, mode: str = "tensor") -> defaultdict:
+        """``scorer`` is a ``TopKScorer`` (see ``rfm_b200.score.fm_factors`` / ``mf_factors``)."""
+        k_max = int(max(self.K))
+        items, scores = scorer.topk(k_max, mode=mode)
+        self.last_stats = dict(scorer.last_stats)
+        # reduced frame: every user's top rows, worst first so that the ranker's tie rule (later row first)
+        # reproduces the Cartesian frame's order (larger item id first among exact ties)
+        items = items[:, ::-1]
+        scores = scores[:, ::-1]
+        valid = (items >= 0).ravel()
+        u = np.repeat(np.arange(self.n_users, dtype=np.int64), k_max)[valid]
+        it = items.ravel()[valid].astype(np.int64)
+        lab = np.asarray(self._labels[u, it]).ravel()
+        ranker = _Ranker(scorer.ctx, u, it, lab, self.item_pscores[it], self.n_items)
+        present = np.unique(u)                                      # users in ascending order, as the ranker groups them
+        totals = np.ascontiguousarray(self._totals[present])
+        check(lib().rfm_ranker_set_user_totals(ranker.handle, ptr(totals)))
+        need_hits = any(m in self.metric_names for m in ("CatalogCoverage", "Gini"))
+        metrics, hits, _ = ranker.evaluate(scores.ravel()[valid], list(self.K), want_hits=need_hits)
+        ranker.close()
+        results = defaultdict(list)
+        for j, _k in enumerate(self.K):
+            row = metrics[j]
+            kept = row[RANK_COLS["USERS"]]
+            for name in self.metric_names:
+                if name == "CatalogCoverage":
+                    results[name].append(int(row[RANK_COLS["COVERED"]]) / self.n_items)
+                elif name == "Gini":
+                    results[name].append(gini_from_counts(hits[j].astype(np.int64)))
+                elif name == "ME":
+                    n = row[RANK_COLS["ME_COUNT"]]
+                    results[name].append(row[RANK_COLS["ME_SUM"]] / n if n else np.nan)
+                else:
+                    col = {"DCG": "DCG_SUM", "Recall": "RECALL_SUM", "MAP": "MAP_SUM"}[name]
+                    results[name].append(row[RANK_COLS[col]] / kept if kept else np.nan)
+        return results

@@ -113,3 +113,35 @@ def test_item_sharded_merge_equals_single_pass():
     items, scores = merge_topk([p[0] for p in parts], [p[1] for p in parts], 9)
     np.testing.assert_array_equal(items, full_items)
     np.testing.assert_array_equal(scores, full_scores)
+
+
+def test_full_catalog_evaluator_equals_test_evaluator_on_cartesian_frame():
+    """Metrics over the whole catalog == the oracle's TestEvaluator semantics on every (user, item) row."""
+    from oracle import metrics_oracle
+    from rfm_b200.evaluate import FullCatalogEvaluator
+    from rfm_b200.score import TopKScorer
+    rng = np.random.default_rng(8)
+    U, I, k = 90, 400, 64
+    A, C = rng.normal(size=(U, k)) * 0.4, rng.normal(size=(I, k)) * 0.4
+    beta = rng.normal(size=I) * 0.2
+    # held-out rows: ~12 per user, some users without any positive
+    hu = np.repeat(np.arange(U), 12)
+    hi = np.concatenate([rng.choice(I, 12, replace=False) for _ in range(U)])
+    hl = (rng.random(hu.size) < 0.4).astype(np.int64)
+    hl[hu % 9 == 0] = 0
+    theta = rng.uniform(0.1, 1.0, size=I)
+    K = [1, 3, 5, 9]
+    used = {"DCG", "CatalogCoverage", "Recall", "MAP", "Gini"}
+    ev = FullCatalogEvaluator({"user": hu, "item": hi, "label": hl}, theta, K, used, U, I)
+    res = ev.evaluate(TopKScorer(A, C, None, beta, 0.1))
+    # oracle on the Cartesian frame
+    uu, ii = np.meshgrid(np.arange(U), np.arange(I), indexing="ij")
+    lab = np.zeros((U, I), dtype=np.int64)
+    lab[hu, hi] = hl
+    frame = {"user": uu.ravel(), "item": ii.ravel(), "label": lab.ravel(), "pscore": theta[ii.ravel()],
+             "ones_pscore": np.ones(U * I)}
+    S = ((A @ C.T) + beta[None, :]) + 0.1
+    ref = metrics_oracle.test_evaluate(frame, S.ravel(), K, used, I)
+    for m in ["ME"] + sorted(used):
+        np.testing.assert_allclose(res[m], ref[m], rtol=1e-12, err_msg=m)
+    np.testing.assert_array_equal(np.array(res["CatalogCoverage"]), np.array(ref["CatalogCoverage"]))
