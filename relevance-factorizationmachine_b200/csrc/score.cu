@@ -119,7 +119,9 @@ constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) 
 
 struct FilterArgs {
   const float *beta;       // [n_items_pad], -inf beyond n_items
-  int n_item_tiles;        // tiles of BN items in the catalog
+  int tile_begin;          // first tile of the catalog range being ranked (item-sharded calls)
+  int n_item_tiles;        // tiles of BN items in that range
+  int item_end;            // items >= item_end are not candidates (the last tile may run past the range)
   int tiles_per_split;
   int kc;                  // candidates kept per user per split
   int n_users_pad;
@@ -203,8 +205,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int user_block = blockIdx.x, split = blockIdx.y;
-  const int tile0 = split * a.tiles_per_split;
-  int n_tiles = a.n_item_tiles - tile0;
+  const int tile0 = a.tile_begin + split * a.tiles_per_split;
+  int n_tiles = a.n_item_tiles - split * a.tiles_per_split;
   if (n_tiles > a.tiles_per_split) n_tiles = a.tiles_per_split;
   if (n_tiles < 0) n_tiles = 0;
 
@@ -323,7 +325,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int jj = 0; jj < 32; ++jj) vj = (j == jj) ? __uint_as_float(v[jj]) : vj;
           if (pass) {
             pass &= pass - 1;
-            insert_candidate(vj + __ldg(a.beta + item0 + c + j), item0 + c + j, ls, li, gm, r, n_groups, tau);
+            if (item0 + c + j < a.item_end)
+              insert_candidate(vj + __ldg(a.beta + item0 + c + j), item0 + c + j, ls, li, gm, r, n_groups, tau);
           }
         }
       }
@@ -456,7 +459,7 @@ score_rescore_kernel(const ExactArgs e, const float *__restrict__ cand_score, co
       const int sp = c / kc, j = c - sp * kc;
       const size_t at = ((size_t)sp * n_users_pad + u) * kc + j;
       const int item = cand_item[at];
-      const bool ok = item >= 0 && item < e.n_items;
+      const bool ok = item >= e.item_begin && item < e.item_end;
       const uint32_t bits = __float_as_uint(cand_score[at]);
       it[c] = ok ? item : -1;
       key[2 * c] = ok ? (bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u)) : 0u;
@@ -726,12 +729,13 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
   e.item_begin = (int)item_begin;
   e.item_end = (int)item_end;
   int64_t n_failed = 0;
-  // the tensor-core path ranks the whole catalog; item-sharded calls and wide k use the exact kernel
-  const bool tensor_path = mode == 0 && t->kb <= MAX_KB && item_begin == 0 && item_end == t->n_items;
+  // the tensor-core path needs a tile-aligned start (item shards are cut at multiples of 256) and k <= 128
+  const bool tensor_path = mode == 0 && t->kb <= MAX_KB && item_begin % BN == 0;
   if (tensor_path) {
     int kc = std::max(2 * K, K + 16);
     kc = (kc + 7) / 8 * 8;
-    const int n_item_tiles = (int)(t->n_items_pad / BN);
+    const int tile_begin = (int)(item_begin / BN);
+    const int n_item_tiles = (int)((item_end + BN - 1) / BN) - tile_begin;
     const int n_user_blocks = (int)(t->n_users_pad / BM);
     // split the catalog so that the grid covers the SMs about twice when there are few user blocks
     int n_splits = std::max(1, std::min(n_item_tiles, (2 * ctx->sm_count + n_user_blocks - 1) / n_user_blocks));
@@ -744,7 +748,9 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     RFM_TRY(t->cand_tau.ensure(rows));
     FilterArgs fa;
     fa.beta = t->beta32.p;
+    fa.tile_begin = tile_begin;
     fa.n_item_tiles = n_item_tiles;
+    fa.item_end = (int)item_end;
     fa.tiles_per_split = tiles_per_split;
     fa.kc = kc;
     fa.n_users_pad = (int)t->n_users_pad;

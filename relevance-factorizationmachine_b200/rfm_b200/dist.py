@@ -160,3 +160,33 @@ def make_fm_dp(model, trainer, env: DistEnv, global_batch: int, n_val: int, lr: 
         check(lib().rfm_fm_loss_sums(trainer.handle, None, end - begin, vbegin, vend))
 
     return DataParallelFM(env, global_batch, n_val, lr, local_grad, grad_tensor, apply, local_loss_sums, loss_tensor)
+
+
+def item_shard(n_items: int, world: int, rank: int, tile: int = 256):
+    """Contiguous item range of a rank, cut at multiples of the scoring kernel's item tile."""
+    n_tiles = (n_items + tile - 1) // tile
+    begin, end = slice_bounds(n_tiles, world, rank)
+    return min(begin * tile, n_items), min(end * tile, n_items)
+
+
+def sharded_topk(scorer, env: DistEnv, K: int, mode: str = "tensor"):
+    """Item-sharded full-catalog top-K: every rank holds all users' factors, ranks
+    its own slice of the catalog on its GPU, the per-rank (item, score) lists are all-gathered (the one
+    exchange step, n_users x K x 12 bytes per rank) and merged with the canonical order. Every rank returns
+    the same global top-K."""
+    from .score import merge_topk
+    torch = env.torch
+    begin, end = item_shard(scorer.n_items, env.world, env.rank)
+    if end > begin:
+        items, scores = scorer.topk(K, mode=mode, item_range=(begin, end))
+    else:
+        items = np.full((scorer.n_users, K), -1, dtype=np.int32)
+        scores = np.full((scorer.n_users, K), -np.inf)
+    dev = "cuda:%d" % env.device if env.backend == "nccl" else "cpu"
+    t_items = torch.from_numpy(items).to(dev)
+    t_scores = torch.from_numpy(scores).to(dev)
+    all_items = [torch.empty_like(t_items) for _ in range(env.world)]
+    all_scores = [torch.empty_like(t_scores) for _ in range(env.world)]
+    env.dist.all_gather(all_items, t_items)
+    env.dist.all_gather(all_scores, t_scores)
+    return merge_topk([t.cpu().numpy() for t in all_items], [t.cpu().numpy() for t in all_scores], K)

@@ -44,6 +44,16 @@ def main():
         env.dist.all_reduce(lo, op=env.dist.ReduceOp.MIN)
         env.dist.all_reduce(hi, op=env.dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks diverged"
+    # item-sharded full-catalog scoring: merged per-rank lists == one pass over the whole catalog
+    from rfm_b200.score import TopKScorer
+    rng = np.random.default_rng(21)
+    A, C, beta = rng.normal(size=(500, 64)) * 0.4, rng.normal(size=(3000, 64)) * 0.4, rng.normal(size=3000) * 0.2
+    sc = TopKScorer(A, C, None, beta, 0.0, device=local_rank)
+    full_items, full_scores = sc.topk(9)
+    items, scores = rdist.sharded_topk(sc, env, 9)
+    np.testing.assert_array_equal(items, full_items)
+    np.testing.assert_array_equal(scores, full_scores)
+    assert sc.last_stats["tensor_core_path"]
     if env.rank == 0:
         print("DP_OK world=%d" % env.world)
     env.shutdown()
