@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=N_TRAIN, help="train interactions in the job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
     return ap.parse_args()
 
 
@@ -184,6 +185,65 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---- full-catalog scoring (second half of BASELINE.json's metric) ------------------------------------
+def measure_scoring(device, dist, world, peaks, peak_kind):
+    """Scored user-item pairs/s of rank-all-items-for-all-users: bf16 tcgen05 GEMM prune + exact float64
+    top-K (csrc/score.cu). Two shapes: BASELINE configs[3]'s evaluation grid (1,411 x 3,327, k=64, top-9;
+    latency-bound: 0.6 GFLOP) and a grid large enough for the tensor pipe to matter. With N GPUs the
+    catalog is item-sharded and the per-rank lists are all-gathered and merged."""
+    from rfm_b200.score import TopKScorer
+    out = {"metric": "scored_user_item_pairs_per_sec", "unit": "pairs/s"}
+    rng = np.random.default_rng(11)
+    shapes = (("eval_grid_1411x3327", 1411, 3327, 64, 9, 20), ("large_32768x262144", 32768, 262144, 64, 9, 5))
+    for name, U, I, k, K, reps in shapes:
+        A = rng.normal(size=(U, k)) * 0.3
+        C = rng.normal(size=(I, k)) * 0.3
+        beta = rng.normal(size=I) * 0.2
+        sc = TopKScorer(A, C, None, beta, 0.0, device=device)
+        ctx = sc.ctx
+
+        def call():
+            if dist is not None:
+                from rfm_b200 import dist as rdist
+                return rdist.sharded_topk(sc, dist, K)
+            return sc.topk(K)
+
+        for _ in range(3):
+            call()
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            call()
+        ctx.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        if dist is not None:
+            dt = dist.max_over_ranks(dt)
+        ctx.profile_begin()
+        call()
+        prof = ctx.profile_end()
+        fk = prof.get("score_filter", (1, 0.0))[1]
+        i_local = I // world
+        upad, ipad = -(-U // 128) * 128, -(-i_local // 256) * 256
+        entry = {"users": U, "items": I, "n_factors": k, "top_k": K, "value": U * I / dt, "ms_per_call": dt * 1e3,
+                 "includes": "operands resident; per call: filter GEMM, exact re-score, proof, D2H of (items, scores)"
+                             + ("; all-gather + merge across ranks" if world > 1 else ""),
+                 "users_ranked_exactly": sc.last_stats.get("users_ranked_exactly"),
+                 "kernels_ms": {k2: round(v[1], 4) for k2, v in prof.items()}}
+        if fk > 0:
+            tf = 2.0 * upad * ipad * 64 * -(-k // 64) / (fk * 1e-3) / 1e12
+            entry["roofline"] = {"bound": "tensor", "kernel": "score_filter_kernel", "achieved": tf,
+                                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                 "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                                 "peak_kind": peak_kind + " (cuBLAS bf16, sustained)",
+                                 "note": "per rank; the epilogue (one compare per score per thread + candidate "
+                                         "inserts), not the MMA, bounds this kernel at k=64 (SURVEY.md H2)"}
+        out[name] = entry
+        sc.close()
+    return out
+
+
 # ---- our arm ----------------------------------------------------------------------------------------
 def run_ours(args):
     from ctypes import byref
@@ -273,6 +333,8 @@ def run_ours(args):
     if rank != 0:
         if not args.no_e2e:
             measure_e2e(args, log, local_rank, dist, world)
+        if not args.no_scoring:
+            measure_scoring(local_rank, dist, world, *measured_peaks())
         dist.shutdown()
         return
 
@@ -299,6 +361,7 @@ def run_ours(args):
     }
 
     e2e = None if args.no_e2e else measure_e2e(args, log, local_rank, dist, world)
+    scoring = None if args.no_scoring else measure_scoring(local_rank, dist, world, peaks, peak_kind)
     cpu = None
     if not args.no_cpu_baseline:
         v, st, dt = cpu_port_run(log, B, 8, 1, budget_s=25.0)
@@ -313,7 +376,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": dtype_tag, "data": "synthetic", "config": cfg, "clocks": clk, "e2e": e2e,
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "scoring": scoring,
         "final_train_loss": float(tl[W + K - 1]), "final_val_loss": float(vl[W + K - 1]),
     }
     print(json.dumps(line))
