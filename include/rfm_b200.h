@@ -207,6 +207,13 @@ int rfm_topk_set_factors(rfm_topk *t, const double *A, const double *C, const do
                          const double *beta, double bias);
 int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64_t item_end,
                  int32_t *out_items, double *out_scores, int64_t *stats);
+/* Item-sharded runs: rfm_topk_run with out_items == out_scores == NULL leaves the
+ * shard's result on the device; rfm_topk_result_ptr_dev exposes it (int32 [n_users][K], double
+ * [n_users][K]) for the caller's all-gather; rfm_topk_merge_dev merges n_lists gathered lists
+ * ([n_lists][n_users][K], device pointers) into the global top-K (host outputs), canonical order. */
+int rfm_topk_result_ptr_dev(rfm_topk *t, void **items_dev, void **scores_dev);
+int rfm_topk_merge_dev(rfm_ctx *ctx, int64_t n_users, int32_t K, int32_t n_lists, const int32_t *items_dev,
+                       const double *scores_dev, int32_t *out_items, double *out_scores);
 
 #ifdef __cplusplus
 }

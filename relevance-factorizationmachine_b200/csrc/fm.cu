@@ -654,11 +654,32 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
   }
 }
 
-// dense apply of an all-reduced gradient (data-parallel mode): identical on every rank
+// dense apply of an all-reduced gradient (data-parallel mode), identical on every rank: one warp per
+// feature row updates v_j, w_j and ||v_j||^2 in a single pass; the first thread also updates w0
 template <typename T>
-__global__ void apply_grad_kernel(T *__restrict__ params, const T *__restrict__ grad, int64_t n, T lr) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    params[i] += lr * grad[i];
+__global__ void __launch_bounds__(ROWS_THREADS)
+apply_grad_rows_kernel(T *__restrict__ w0, T *__restrict__ w, T *__restrict__ V, T *__restrict__ vn,
+                       const T *__restrict__ g0, const T *__restrict__ gw, const T *__restrict__ gV, int64_t n,
+                       int kp, T lr) {
+  const int lane = lane_id();
+  const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (gwarp == 0 && lane == 0) *w0 += lr * *g0;
+  for (int64_t j = gwarp; j < n; j += nw) {
+    T s = T(0);
+    for (int f = lane * 2; f < kp; f += 64) {      // same association as row_norms_kernel
+      const T v0 = V[j * kp + f] + lr * gV[j * kp + f];
+      const T v1 = V[j * kp + f + 1] + lr * gV[j * kp + f + 1];
+      V[j * kp + f] = v0;
+      V[j * kp + f + 1] = v1;
+      s += v0 * v0 + v1 * v1;
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      vn[j] = s;
+      w[j] += lr * gw[j];
+    }
+  }
 }
 
 // row / column kernels: (threads per row, chunks per lane) for kp = 64 * nch
@@ -1402,23 +1423,18 @@ int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
   RFM_CUDA(cudaSetDevice(ctx->device));
-  const int64_t nV = m->n * m->kp;
-  const int g = grid_for(ctx, ceil_div(nV, 256), 8);
+  const int g = grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8);
   if (m->dtype == RFM_F64) {
     double *gr = reinterpret_cast<double *>(t->grad.p);
-    RFM_LAUNCH(ctx, apply_grad_kernel<double>, 1, 32, 0, reinterpret_cast<double *>(m->w0.p), gr, (int64_t)1, lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->w.p), gr + GRAD_W_OFF, m->n, lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<double>, g, 256, 0, reinterpret_cast<double *>(m->V.p), gr + grad_v_off(m->n), nV, lr);
-    RFM_LAUNCH(ctx, row_norms_kernel<double>, grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8), ROWS_THREADS, 0,
-               reinterpret_cast<const double *>(m->V.p), reinterpret_cast<double *>(m->vn.p), m->n, m->kp);
+    RFM_LAUNCH(ctx, apply_grad_rows_kernel<double>, g, ROWS_THREADS, 0, reinterpret_cast<double *>(m->w0.p),
+               reinterpret_cast<double *>(m->w.p), reinterpret_cast<double *>(m->V.p),
+               reinterpret_cast<double *>(m->vn.p), gr, gr + GRAD_W_OFF, gr + grad_v_off(m->n), m->n, m->kp, lr);
   } else {
     float *gr = reinterpret_cast<float *>(t->grad.p);
-    RFM_LAUNCH(ctx, apply_grad_kernel<float>, 1, 32, 0, reinterpret_cast<float *>(m->w0.p), gr, (int64_t)1, (float)lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->w.p), gr + GRAD_W_OFF, m->n, (float)lr);
-    RFM_LAUNCH(ctx, apply_grad_kernel<float>, g, 256, 0, reinterpret_cast<float *>(m->V.p), gr + grad_v_off(m->n), nV,
+    RFM_LAUNCH(ctx, apply_grad_rows_kernel<float>, g, ROWS_THREADS, 0, reinterpret_cast<float *>(m->w0.p),
+               reinterpret_cast<float *>(m->w.p), reinterpret_cast<float *>(m->V.p),
+               reinterpret_cast<float *>(m->vn.p), gr, gr + GRAD_W_OFF, gr + grad_v_off(m->n), m->n, m->kp,
                (float)lr);
-    RFM_LAUNCH(ctx, row_norms_kernel<float>, grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8), ROWS_THREADS, 0,
-               reinterpret_cast<const float *>(m->V.p), reinterpret_cast<float *>(m->vn.p), m->n, m->kp);
   }
   return RFM_OK;
 }

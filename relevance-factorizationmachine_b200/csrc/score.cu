@@ -579,6 +579,44 @@ score_exact_kernel(const ExactArgs e, const int32_t *__restrict__ users, const u
   }
 }
 
+// merge per-shard top-K lists: one warp per user picks the K best of n_lists * K (item, score) pairs with
+// the canonical order. lists are [n_lists][n_users][K].
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const int32_t *__restrict__ items, const double *__restrict__ scores, int64_t n_users, int K,
+                  int n_lists, int32_t *__restrict__ out_items, double *__restrict__ out_scores) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int n_cand = n_lists * K;
+  for (int64_t u = gw; u < n_users; u += nw) {
+    Best last;
+    last.s = 0.0;
+    last.item = -2;
+    for (int r = 0; r < K; ++r) {
+      Best mine;
+      mine.s = 0.0;
+      mine.item = -1;
+      if (last.item != -1) {
+        for (int c = lane; c < n_cand; c += 32) {
+          const int l = c / K, j = c - l * K;
+          const size_t at = ((size_t)l * n_users + u) * K + j;
+          Best b;
+          b.item = items[at];
+          if (b.item < 0) continue;
+          b.s = scores[at];
+          const bool below = last.item == -2 || ranks_before(last, b);
+          if (below && ranks_before(b, mine)) mine = b;
+        }
+      }
+      last = warp_best(mine);
+      if (lane == 0) {
+        out_items[u * K + r] = last.item;
+        out_scores[u * K + r] = last.item >= 0 ? last.s : -INFINITY;
+      }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -707,7 +745,8 @@ int rfm_topk_set_factors(rfm_topk *t, const double *A, const double *C, const do
 
 int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64_t item_end, int32_t *out_items,
                  double *out_scores, int64_t *stats) {
-  RFM_REQUIRE(t && out_items && out_scores, "rfm_topk_run: NULL argument");
+  RFM_REQUIRE(t, "rfm_topk_run: NULL argument");
+  RFM_REQUIRE((out_items == nullptr) == (out_scores == nullptr), "rfm_topk_run: out_items and out_scores go together");
   RFM_REQUIRE(t->ready, "rfm_topk_run: call rfm_topk_set_factors first");
   RFM_REQUIRE(K >= 1 && K <= MAX_K, "rfm_topk_run: K=%d outside [1, %d]", K, MAX_K);
   RFM_REQUIRE(mode == 0 || mode == 1, "rfm_topk_run: mode must be 0 (tensor-core prune + exact) or 1 (exact only)");
@@ -807,14 +846,42 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     RFM_LAUNCH(ctx, score_exact_kernel, fgrid, 256, 0, e, (const int32_t *)nullptr, (const uint32_t *)nullptr,
                t->n_users, (int)K, t->out_items.p, t->out_scores.p);
   }
-  RFM_CUDA(cudaMemcpyAsync(out_items, t->out_items.p, (size_t)t->n_users * K * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  RFM_CUDA(cudaMemcpyAsync(out_scores, t->out_scores.p, (size_t)t->n_users * K * 8, cudaMemcpyDeviceToHost,
-                           ctx->stream));
+  if (out_items) {   // NULL: the caller reads the result on the device (rfm_topk_result_ptr_dev)
+    RFM_CUDA(cudaMemcpyAsync(out_items, t->out_items.p, (size_t)t->n_users * K * 4, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(out_scores, t->out_scores.p, (size_t)t->n_users * K * 8, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  }
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (stats) {
     stats[0] = tensor_path ? 1 : 0;
     stats[1] = n_failed;
   }
+  return RFM_OK;
+}
+
+int rfm_topk_result_ptr_dev(rfm_topk *t, void **items_dev, void **scores_dev) {
+  RFM_REQUIRE(t && items_dev && scores_dev, "rfm_topk_result_ptr_dev: NULL argument");
+  RFM_REQUIRE(t->out_items.p && t->out_scores.p, "rfm_topk_result_ptr_dev: call rfm_topk_run first");
+  *items_dev = t->out_items.p;
+  *scores_dev = t->out_scores.p;
+  return RFM_OK;
+}
+
+int rfm_topk_merge_dev(rfm_ctx *ctx, int64_t n_users, int32_t K, int32_t n_lists, const int32_t *items_dev,
+                       const double *scores_dev, int32_t *out_items, double *out_scores) {
+  RFM_REQUIRE(ctx && items_dev && scores_dev && out_items && out_scores, "rfm_topk_merge_dev: NULL argument");
+  RFM_REQUIRE(n_users >= 1 && K >= 1 && n_lists >= 1, "rfm_topk_merge_dev: bad sizes");
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<int32_t> oi;
+  DevBuf<double> os;
+  RFM_TRY(oi.alloc((size_t)n_users * K));
+  RFM_TRY(os.alloc((size_t)n_users * K));
+  const int grid = (int)std::min<int64_t>((n_users + 7) / 8, (int64_t)ctx->sm_count * 8);
+  RFM_LAUNCH(ctx, topk_merge_kernel, grid, 256, 0, items_dev, scores_dev, n_users, (int)K, (int)n_lists, oi.p, os.p);
+  RFM_CUDA(cudaMemcpyAsync(out_items, oi.p, (size_t)n_users * K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(out_scores, os.p, (size_t)n_users * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
 }
 

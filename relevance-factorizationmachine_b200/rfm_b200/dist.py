@@ -171,22 +171,33 @@ def item_shard(n_items: int, world: int, rank: int, tile: int = 256):
 
 def sharded_topk(scorer, env: DistEnv, K: int, mode: str = "tensor"):
     """Item-sharded full-catalog top-K: every rank holds all users' factors, ranks
-    its own slice of the catalog on its GPU, the per-rank (item, score) lists are all-gathered (the one
-    exchange step, n_users x K x 12 bytes per rank) and merged with the canonical order. Every rank returns
-    the same global top-K."""
-    from .score import merge_topk
+    its own slice of the catalog on its GPU, the per-rank (item, score) lists are all-gathered on the
+    device (the one exchange step, n_users x K x 12 bytes per rank) and merged by a kernel with the
+    canonical order. Every rank returns the same global top-K."""
+    from . import _capi
+    from ._capi import check, lib, ptr
+    if env.backend != "nccl":
+        raise RuntimeError("sharded_topk needs the NCCL backend (results stay on the device)")
     torch = env.torch
+    n_users = scorer.n_users
     begin, end = item_shard(scorer.n_items, env.world, env.rank)
+    dev = "cuda:%d" % env.device
     if end > begin:
-        items, scores = scorer.topk(K, mode=mode, item_range=(begin, end))
+        check(lib().rfm_topk_run(scorer.handle, K, 0 if mode == "tensor" else 1, begin, end, None, None, None))
+        ip, sp = c_void_p(), c_void_p()
+        check(lib().rfm_topk_result_ptr_dev(scorer.handle, byref(ip), byref(sp)))
+        mine_items = torch.as_tensor(_DeviceArray(ip.value, n_users * K, "<i4"), device=dev)
+        mine_scores = torch.as_tensor(_DeviceArray(sp.value, n_users * K, "<f8"), device=dev)
     else:
-        items = np.full((scorer.n_users, K), -1, dtype=np.int32)
-        scores = np.full((scorer.n_users, K), -np.inf)
-    dev = "cuda:%d" % env.device if env.backend == "nccl" else "cpu"
-    t_items = torch.from_numpy(items).to(dev)
-    t_scores = torch.from_numpy(scores).to(dev)
-    all_items = [torch.empty_like(t_items) for _ in range(env.world)]
-    all_scores = [torch.empty_like(t_scores) for _ in range(env.world)]
-    env.dist.all_gather(all_items, t_items)
-    env.dist.all_gather(all_scores, t_scores)
-    return merge_topk([t.cpu().numpy() for t in all_items], [t.cpu().numpy() for t in all_scores], K)
+        mine_items = torch.full((n_users * K,), -1, dtype=torch.int32, device=dev)
+        mine_scores = torch.full((n_users * K,), float("-inf"), dtype=torch.float64, device=dev)
+    all_items = torch.empty((env.world, n_users * K), dtype=torch.int32, device=dev)
+    all_scores = torch.empty((env.world, n_users * K), dtype=torch.float64, device=dev)
+    env.dist.all_gather_into_tensor(all_items, mine_items)
+    env.dist.all_gather_into_tensor(all_scores, mine_scores)
+    torch.cuda.current_stream(env.device).synchronize()
+    items = np.empty((n_users, K), dtype=np.int32)
+    scores = np.empty((n_users, K), dtype=np.float64)
+    check(lib().rfm_topk_merge_dev(scorer.ctx.handle, n_users, K, env.world, c_void_p(all_items.data_ptr()),
+                                   c_void_p(all_scores.data_ptr()), ptr(items), ptr(scores)))
+    return items, scores
