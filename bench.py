@@ -35,6 +35,7 @@ for p in (PKG, ROOT):
 
 import numpy as np  # noqa: E402
 
+WORKLOAD = "kuairec_big"
 METRIC = "train_interactions_per_sec"
 UNIT = "interactions/s"
 N_USERS, N_ITEMS, N_TRAIN, N_VAL, K_FACTORS = 7176, 10728, 12_000_000, 2000, 64
@@ -53,12 +54,17 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--workload", default="kuairec_big", choices=["kuairec_big", "stress"],
+                    help="kuairec_big = BASELINE configs[2] (the headline); stress = configs[4]-shaped: 1M users x 1M "
+                         "items, k=128, 8 non-zeros per row, parameter table far larger than L2")
     return ap.parse_args()
 
 
 def workload_config(args, world):
     return {
-        "workload": "IPS-FM, synthetic KuaiRec big_matrix shape (BASELINE.json configs[2])",
+        "workload": ("IPS-FM, synthetic KuaiRec big_matrix shape (BASELINE.json configs[2])" if WORKLOAD == "kuairec_big"
+                     else "IPS-FM stress, BASELINE.json configs[4] shape on one GPU's share: 1M users x 1M items, "
+                          "k=128, 8 non-zeros per row"),
         "n_users": N_USERS, "n_items": N_ITEMS, "train_interactions": args.rows, "val_rows": N_VAL,
         "n_factors": K_FACTORS, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
         "lr": LR, "parallelism": "dp%d" % world if world > 1 else "single",
@@ -67,7 +73,47 @@ def workload_config(args, world):
     }
 
 
+def make_stress_data(rows, seed):
+    """configs[4]-shaped rows: [user id | 3 user-side one-hots | item id | 3 item-side one-hots], m = 8,
+    n = 2,000,000 + 60 columns. Sorted columns per row, float64 values, vectorised."""
+    from scipy.sparse import csr_matrix
+    from rfm_b200.synth import SyntheticLog
+    rng = np.random.default_rng(seed)
+    U = I = 1_000_000
+    groups = (4, 8, 12, 6, 10, 20)
+    t0 = time.perf_counter()
+
+    def rows_of(n_rows):
+        u = rng.integers(0, U, n_rows)
+        i = rng.integers(0, I, n_rows)
+        cols = np.empty((n_rows, 8), dtype=np.int32)
+        cols[:, 0] = u
+        off = U
+        for g_idx in range(3):                       # user-side one-hots are a function of the user
+            cols[:, 1 + g_idx] = off + (u * (g_idx + 3) + g_idx) % groups[g_idx]
+            off += groups[g_idx]
+        cols[:, 4] = off + i
+        off += I
+        for g_idx in range(3, 6):
+            cols[:, 1 + g_idx + 1] = off + (i * (g_idx + 2) + g_idx) % groups[g_idx]
+            off += groups[g_idx]
+        X = csr_matrix((np.ones(n_rows * 8), cols.ravel(), np.arange(0, 8 * n_rows + 1, 8, dtype=np.int64)
+                        if n_rows * 8 >= 2**31 else np.arange(0, 8 * n_rows + 1, 8, dtype=np.int32)),
+                       shape=(n_rows, off))
+        X.has_sorted_indices = True
+        y = (rng.random(n_rows) < 0.3).astype(np.int64)
+        ps = rng.uniform(0.3, 1.0, n_rows)
+        return {"features": X, "labels": y, "pscores": ps}, off
+
+    train, n = rows_of(rows)
+    val, _ = rows_of(N_VAL)
+    log = SyntheticLog(U, I, n, train, val, None, None, {}, None, np.zeros((0, 2), np.int64), {})
+    return log, time.perf_counter() - t0
+
+
 def make_data(rows, seed, rank=0):
+    if WORKLOAD == "stress":
+        return make_stress_data(rows, seed)
     from rfm_b200.synth import make_kuairec_shaped
     t0 = time.perf_counter()
     log = make_kuairec_shaped(seed=seed + rank, n_users=N_USERS, n_items=N_ITEMS, n_train=rows, n_val=N_VAL,
@@ -345,15 +391,23 @@ def run_ours(args):
     top_ms = prof[top][1] / prof[top][0]
     peaks, peak_kind = measured_peaks()
     achieved = per_kernel[top] * B / (top_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and B == (65536 if WORKLOAD == "kuairec_big" else 1 << 20) and args.dtype == "float64":
+        with open(tpath) as f:     # DRAM bytes per launch from the committed ncu --set full capture of this workload
+            traffic = json.load(f).get(WORKLOAD, {}).get(top, {}).get("dram_bytes")
     roofline = {
         "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind + " (HBM copy, burst)",
+        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": per_kernel[top] * B,
+        "peak_kind": peak_kind + " (HBM copy, burst)",
         "algorithmic_bytes_per_interaction": per_kernel[top], "avg_launch_ms": top_ms,
         "share_of_step": prof[top][1] / total_prof_ms,
         "timing": "cudaEvent pair around each launch, separate pass of the same %d steps" % K,
-        "note": "V (%.1f MB) and S (%.1f MB) are L2-resident at this shape, so the algorithmic gather traffic is "
-                "served by L2, not HBM (SURVEY.md H7); achieved may therefore exceed the HBM peak"
-                % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6),
+        "note": ("V (%.1f MB) and S (%.1f MB) are L2-resident at this shape, so the algorithmic gather traffic is "
+                 "served by L2, not HBM (SURVEY.md H7); achieved may therefore exceed the HBM peak"
+                 % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6)) if WORKLOAD != "stress" else
+                ("V (%.1f GB) and S (%.1f GB) exceed L2: id-column gathers and the s_t gather are HBM traffic"
+                 % (log.n_features * K_FACTORS * s / 1e9, B * K_FACTORS * s / 1e9)),
         "step": {"algorithmic_bytes_per_interaction": step_bytes,
                  "achieved": step_bytes * B * world / (ms / K * 1e-3) / 1e9 / world,
                  "frac": step_bytes * B / (ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
@@ -370,6 +424,10 @@ def run_ours(args):
                          % (st, B, X.shape[0], dt)}
     cfg = workload_config(args, world)
     cfg["l2"] = cfg["l2"].replace("0.0 GB", "%.1f GB" % (train_rows.h2d_bytes / 1e9))
+    if WORKLOAD == "stress":
+        cfg["l2"] = ("inputs larger than L2: %.1f GB CSR, %.1f GB parameter table and %.1f GB of per-batch s_t rows, "
+                     "all far beyond the 126 MB L2" % (train_rows.h2d_bytes / 1e9,
+                                                        log.n_features * K_FACTORS * s / 1e9, B * K_FACTORS * s / 1e9))
     cfg.update(sampler="feistel (device, perf mode)", mean_nnz_per_row=round(m, 3),
                touched_columns_per_step=int(touched), n_features=log.n_features, data_gen_s=round(gen_s, 1))
     line = {
@@ -431,6 +489,13 @@ def measure_e2e(args, log, device, dist, world):
 
 if __name__ == "__main__":
     a = parse()
+    if a.workload == "stress":
+        WORKLOAD, N_USERS, N_ITEMS, K_FACTORS = "stress", 1_000_000, 1_000_000, 128
+        if a.rows == N_TRAIN:
+            a.rows = 20_000_000
+        if a.batch == 65536:
+            a.batch = 1 << 20
+        a.no_cpu_baseline = a.no_scoring = True
     if a.impl == "reference":
         run_reference(a)
     else:

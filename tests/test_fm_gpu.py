@@ -160,3 +160,31 @@ def test_batch_larger_than_train_raises_like_sklearn():
     m = FactorizationMachines("IPS", 1, 4, 0.1, train["features"].shape[0] + 1, 0, train["features"].shape[1])
     with pytest.raises(ValueError, match="Cannot sample"):
         m.fit(train, val)
+
+
+def test_many_features_three_sort_passes_and_k128():
+    """n_features > 65,536 (three 8-bit radix passes), k = 128 (16 lanes per row), id-like one-hot columns."""
+    rng = np.random.default_rng(12)
+    from scipy.sparse import csr_matrix
+    n_users, n_items, N, k, B = 60_000, 50_000, 6000, 128, 2500
+    n = n_users + n_items + 12
+    u = rng.integers(0, n_users, N)
+    i = rng.integers(0, n_items, N)
+    f1 = n_users + n_items + rng.integers(0, 5, N)
+    f2 = n_users + n_items + 5 + rng.integers(0, 7, N)
+    cols = np.stack([u, n_users + i, f1, f2], axis=1).astype(np.int32)
+    vals = np.ones((N, 4))
+    vals[:, 3] = rng.normal(size=N)
+    X = csr_matrix((vals.ravel(), cols.ravel(), np.arange(0, 4 * N + 1, 4)), shape=(N, n))
+    y = rng.integers(0, 2, N)
+    ps = rng.uniform(0.2, 1.0, N)
+    train = {"features": X, "labels": y, "pscores": ps}
+    from rfm_b200.fm import FactorizationMachines
+    m = FactorizationMachines("IPS", 3, k, 1e-3, B, 5, n, alpha=0.05)
+    w0, w, V = m.w0().copy(), m.w().copy(), m.V().copy()
+    tl, vl = m.fit(train, train)
+    (rw0, rw, rV), rtl, rvl = fm_oracle.fm_fit(train, train, 3, B, 1e-3, w0, w, V)
+    np.testing.assert_allclose(tl, rtl, rtol=1e-9)
+    np.testing.assert_allclose(vl, rvl, rtol=1e-9)
+    np.testing.assert_allclose(m.V(), rV, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.w(), rw, rtol=1e-9, atol=1e-13)
