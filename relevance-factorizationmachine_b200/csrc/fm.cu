@@ -48,14 +48,25 @@ struct rfm_fm {
 
 namespace {
 
+// Tuning knobs, measured on B200 at the KuaiRec-big shape (float64, k = 64, B = 65,536):
+// rows kernels capped at 85 registers (3 CTAs/SM), column kernel unrolled 4 deep at 2 CTAs/SM.
+#ifndef RFM_ROWS_MIN_BLOCKS
+#define RFM_ROWS_MIN_BLOCKS 3
+#endif
+#ifndef RFM_ROWS_UNROLL
+#define RFM_ROWS_UNROLL 4
+#endif
+#ifndef RFM_COLS_UNROLL
+#define RFM_COLS_UNROLL 4
+#endif
+#ifndef RFM_COLS_MIN_BLOCKS
+#define RFM_COLS_MIN_BLOCKS 2
+#endif
+#define RFM_PRAGMA(x) _Pragma(#x)
+#define RFM_UNROLL(n) RFM_PRAGMA(unroll n)
 constexpr int ROWS_THREADS = 256;
 constexpr int ROWS_WARPS = ROWS_THREADS / 32;
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
-constexpr int COL_CHUNK = 32;      // sorted entries one lane group walks; carry records are per chunk
-                                   // (128 was measured: fewer carry records but a 60 % slower column pass)
-constexpr int COL_SUB = COL_CHUNK / 32;
-constexpr int SHORT_RUN = 4;        // carry runs up to this many chunks are summed by one warp
-constexpr int LONG_RUN_THREADS = 1024;
 
 enum RowsMode { MODE_TRAIN = 0, MODE_LOSS = 1, MODE_PREDICT = 2 };
 
@@ -163,6 +174,8 @@ struct RowsArgs {
   uint32_t sentinel;      // key written into unused slots of the fixed-stride layout (== n_features)
   uint32_t *keys, *pos;
   T *xs;
+  uint32_t *ghist;        // [n_passes][256] digit histograms of the keys written here (for the radix sort)
+  int n_passes;
   // SAMPLED: the batch is drawn here: row id of position q is feistel(q0 + q); also stored to idx_out
   FeistelKey fkey;
   int64_t q0;
@@ -170,6 +183,14 @@ struct RowsArgs {
   // MODE_PREDICT output
   double *out;
   Finish fin;
+  // MODE_LOSS only: an optional second row set scored in the same launch (the val rows next to the batch);
+  // positions [n, n + n2) are rows [0, n2) of this set and feed fin2
+  const int64_t *row_ptr2;
+  const int32_t *col2;
+  const T *val2;
+  const T *yp2;
+  int64_t n2;
+  Finish fin2;
 };
 
 __device__ __forceinline__ double sigmoid_ref(double z) {
@@ -229,7 +250,7 @@ __device__ __forceinline__ T group_sum(T v, unsigned mask) {
 // elements of a V row. The per-non-zero bookkeeping (broadcast of (column, x), address arithmetic,
 // loop control) and the scalar epilogue are shared by all rows of the warp.
 template <typename T, int TPR, int NCV, int MODE, bool SAMPLED>
-__global__ void __launch_bounds__(ROWS_THREADS)
+__global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? RFM_ROWS_MIN_BLOCKS : 1)
 fm_rows_kernel(const RowsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
   constexpr int GPW = 32 / TPR;
@@ -238,20 +259,37 @@ fm_rows_kernel(const RowsArgs<T> a) {
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n_groups = nw * GPW;
   const T w0 = __ldg(a.w0);
-  double partial = 0.0;
-  for (int64_t qb = gw * GPW; qb < a.n; qb += n_groups) {   // warp-uniform trip count
+  // MODE_TRAIN: this kernel writes every sort key, so it also counts their digits (integer shared-memory
+  // atomics, flushed once per CTA) and the sort needs no histogram pass of its own
+  __shared__ uint32_t hist[MODE == MODE_TRAIN ? RS_MAX_PASSES * RS_RADIX : 1];
+  if (MODE == MODE_TRAIN) {
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += ROWS_THREADS) hist[i] = 0;
+    __syncthreads();
+  }
+  double partial = 0.0, partial2 = 0.0;
+  const int64_t n_total = a.n + (MODE == MODE_LOSS ? a.n2 : 0);
+  for (int64_t qb = gw * GPW; qb < n_total; qb += n_groups) {   // warp-uniform trip count
     const int64_t q = qb + grp;
-    const bool active = q < a.n;
+    const bool active = q < n_total;
+    const bool second = MODE == MODE_LOSS && q >= a.n;          // row of the second (val) row set
+    const int32_t *colp = second ? a.col2 : a.col;
+    const T *valp = second ? a.val2 : a.val;
     int64_t t = 0, beg = 0, end = 0;
     if (active) {
-      if (SAMPLED) {
-        t = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(a.q0 + q), a.fkey));
-        if (g == 0) a.idx_out[q] = t;
+      if (second) {
+        t = q - a.n;
+        beg = a.row_ptr2[t];
+        end = a.row_ptr2[t + 1];
       } else {
-        t = a.idx ? a.idx[q] : a.row0 + q;
+        if (SAMPLED) {
+          t = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(a.q0 + q), a.fkey));
+          if (g == 0) a.idx_out[q] = t;
+        } else {
+          t = a.idx ? a.idx[q] : a.row0 + q;
+        }
+        beg = a.row_ptr[t];
+        end = a.row_ptr[t + 1];
       }
-      beg = a.row_ptr[t];
-      end = a.row_ptr[t + 1];
     }
     const int len = static_cast<int>(end - beg);
     const int maxlen = __reduce_max_sync(FULL, len);
@@ -267,18 +305,20 @@ fm_rows_kernel(const RowsArgs<T> a) {
       int c = 0;
       T x = T(0);
       if (off < len) {
-        c = a.col[beg + off];
-        x = a.val[beg + off];
+        c = colp[beg + off];
+        x = valp[beg + off];
         sl += x * __ldg(a.w + c) - T(0.5) * (x * x) * __ldg(a.vn + c);
         if (MODE == MODE_TRAIN) {
           const uint32_t o = out_base + static_cast<uint32_t>(off);
           a.keys[o] = static_cast<uint32_t>(c);
           a.pos[o] = static_cast<uint32_t>(q);
           a.xs[o] = x;
+          for (int ps = 0; ps < a.n_passes; ++ps)
+            atomicAdd(&hist[ps * RS_RADIX + ((static_cast<uint32_t>(c) >> (8 * ps)) & 0xFF)], 1u);
         }
       }
       const int cnt = maxlen - off0 < TPR ? maxlen - off0 : TPR;
-#pragma unroll 4
+      RFM_UNROLL(RFM_ROWS_UNROLL)
       for (int i = 0; i < cnt; ++i) {
         const int cj = __shfl_sync(FULL, c, i, TPR);     // entries past a shorter row's end carry x = 0
         const T xj = __shfl_sync(FULL, x, i, TPR);
@@ -292,7 +332,11 @@ fm_rows_kernel(const RowsArgs<T> a) {
       }
     }
     if (MODE == MODE_TRAIN && active && a.stride) {   // unused slots of this row sort behind every real column
-      for (uint32_t si = static_cast<uint32_t>(len) + g; si < a.stride; si += TPR) a.keys[out_base + si] = a.sentinel;
+      for (uint32_t si = static_cast<uint32_t>(len) + g; si < a.stride; si += TPR) {
+        a.keys[out_base + si] = a.sentinel;
+        for (int ps = 0; ps < a.n_passes; ++ps)
+          atomicAdd(&hist[ps * RS_RADIX + ((a.sentinel >> (8 * ps)) & 0xFF)], 1u);
+      }
     }
     T ss = T(0);
 #pragma unroll
@@ -312,15 +356,22 @@ fm_rows_kernel(const RowsArgs<T> a) {
       } else if (MODE == MODE_LOSS) {
         // src/base.py:56-59 term by term (1 - p formed by subtraction, eps inside both logs)
         if (g == 0) {
-          const double r = static_cast<double>(a.yp[t]);
-          partial -= r * log(p + 1e-8) + (1.0 - r) * log(1.0 - p + 1e-8);
+          const double r = static_cast<double>(second ? a.yp2[t] : a.yp[t]);
+          const double term = r * log(p + 1e-8) + (1.0 - r) * log(1.0 - p + 1e-8);
+          if (second) partial2 -= term; else partial -= term;
         }
       } else {
         if (g == 0) a.out[q] = p;
       }
     }
   }
+  if (MODE == MODE_TRAIN) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.n_passes * RS_RADIX; i += ROWS_THREADS)
+      if (hist[i]) atomicAdd(a.ghist + i, hist[i]);
+  }
   if (MODE != MODE_PREDICT) block_finish<T>(warp_sum(partial), a.fin);
+  if (MODE == MODE_LOSS && a.n2 > 0) block_finish<T>(warp_sum(partial2), a.fin2);
 }
 
 // ||v_j||^2 for every row of V (after set_params and after a dense data-parallel apply)
@@ -352,16 +403,14 @@ struct ColsArgs {
   T *V, *w, *vn;
   int kp;
   T lr;
-  T *carry_vec;      // [n_chunks][2][kp]   slot 0 = HEAD (segment began in an earlier chunk), 1 = TAIL
-  T *carry_ac;       // [n_chunks][2][2]    (a, c)
+  uint32_t unit;     // sorted entries covered by one carry record = one CTA iteration of the column pass
+  T *carry_vec;      // [n_units][2][kp]    slot 0 = HEAD (run began in an earlier unit), 1 = TAIL
+  T *carry_ac;       // [n_units][2][2]     (a, c)
   // data-parallel mode: write the gradient instead of applying it
   T *grad_w, *grad_V;
   // fix-up work lists (order of the lists is irrelevant: every entry is handled independently)
   uint32_t *tails;       // chunks that own a column continuing into later chunks
   uint32_t *n_tails;
-  uint32_t *long_runs;   // pairs (first chunk, last chunk)
-  uint32_t *n_long;
-  uint32_t long_cap;
 };
 
 template <typename T, int TPR, int NCV, bool DP>
@@ -412,180 +461,222 @@ __device__ __forceinline__ void store_carry(const ColsArgs<T> &a, uint32_t chunk
   }
 }
 
-// A group of TPR lanes walks one chunk of COL_CHUNK consecutive entries of the column-sorted list
-// (32/TPR chunks per warp), 32 entries at a time: entry i of a 32-entry slice lives in lane i % TPR,
-// register i / TPR. Columns that live entirely inside the chunk are finished here; the partial
-// sums of a column that crosses the chunk's start (HEAD) or end (TAIL) go to carry records.
+// Column pass. A group of TPR lanes walks one chunk of 32 consecutive entries of the column-sorted list
+// (entry i lives in lane i % TPR, register i / TPR); a CTA covers GPC = 8 * 32/TPR consecutive chunks per
+// iteration ("unit"). Columns that live inside one chunk are finished by their group. Partial sums of a
+// column that crosses a chunk's start (HEAD) or end (TAIL) are parked in shared memory; after a CTA barrier
+// the group where a run starts walks the following chunks' HEAD partials in chunk order and either finishes
+// the column (the run ends inside the unit) or emits ONE carry record for the unit. Only runs that cross
+// unit boundaries reach the global fix-up kernels.
 template <typename T, int TPR, int NCV, bool DP>
-__global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? 3 : 2)
+__global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? RFM_COLS_MIN_BLOCKS : 1)
 fm_cols_kernel(const ColsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
-  constexpr int GPW = 32 / TPR, NJ = 32 / TPR;
+  constexpr int GPW = 32 / TPR, NJ = 32 / TPR, GPC = ROWS_WARPS * GPW;
+  extern __shared__ __align__(16) unsigned char cols_smem[];
+  const int pstride = a.kp + 2;                                  // partial = kp values + (a, c)
+  T *part = reinterpret_cast<T *>(cols_smem);                    // [GPC][2][pstride]
+  uint32_t *hkey = reinterpret_cast<uint32_t *>(part + (size_t)GPC * 2 * pstride);   // [GPC] key of the HEAD partial
+  uint32_t *tkey = hkey + GPC;                                   // [GPC] key of the TAIL partial
+  uint32_t *flag = tkey + GPC;                                   // [GPC] bit0 HEAD, bit1 TAIL, bit2 HEAD runs on past the chunk
   const int lane = lane_id(), g = lane % TPR, grp = lane / TPR;
+  const int wid = threadIdx.x >> 5;
+  const int gi = wid * GPW + grp;                                // this group's chunk inside the unit
   const unsigned gmask = TPR == 32 ? FULL : (((1u << TPR) - 1u) << (grp * TPR));
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n_groups = nw * GPW;
   const uint32_t M = *a.count;
-  const uint32_t n_chunks = (M + COL_CHUNK - 1u) / COL_CHUNK;
-  for (uint32_t cb = gw * GPW; cb < n_chunks; cb += n_groups) {   // warp-uniform trip count
-    const uint32_t chunk = cb + grp;
-    const uint32_t base = chunk * COL_CHUNK;
+  const uint32_t n_chunks = (M + 31u) >> 5;
+  const uint32_t n_units = (n_chunks + GPC - 1) / GPC;
+  for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {   // CTA-uniform trip count
+    const uint32_t chunk = unit * GPC + gi;
+    const uint32_t base = chunk << 5;
+    uint32_t key[NJ], p[NJ];
+    T xe[NJ], xxe[NJ];
+    int n_valid = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const uint32_t e = base + j * TPR + g;
+      uint32_t k = (chunk < n_chunks && e < M) ? a.keys[e] : KEY_NONE;
+      if (k == a.sentinel) k = KEY_NONE;
+      const bool valid = k != KEY_NONE;
+      key[j] = k;
+      p[j] = valid ? a.pos[e] : 0u;
+      const T x = valid ? a.xs[e] : T(0);
+      const T ev = valid ? __ldg(a.E + p[j]) : T(0);
+      xe[j] = x * ev;
+      xxe[j] = x * x * ev;
+      n_valid += __popc(__ballot_sync(FULL, valid) & gmask);   // padding sorts last: valid entries are a prefix
+    }
+    uint32_t prev_key = KEY_NONE, next_key = KEY_NONE;
+    if (n_valid > 0) {
+      if (base > 0) prev_key = a.keys[base - 1];
+      if (base + 32u < M) next_key = a.keys[base + 32u];
+      if (next_key == a.sentinel) next_key = KEY_NONE;
+    }
     V2 acc[NCV];
 #pragma unroll
     for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
     T sa = T(0), sc = T(0);
-    uint32_t cur = KEY_NONE;
-    bool head = false, any = false;
-    for (int sub = 0; sub < COL_SUB; ++sub) {
-      const uint32_t sbase = base + sub * 32;
-      uint32_t key[NJ], p[NJ];
-      T xe[NJ], xxe[NJ];
-      int n_valid = 0;
+    uint32_t cur = __shfl_sync(FULL, key[0], 0, TPR);
+    bool head = (n_valid > 0) && (cur == prev_key);
+    uint32_t my_flag = 0;
+    T *my_head = part + ((size_t)gi * 2 + 0) * pstride, *my_tail = part + ((size_t)gi * 2 + 1) * pstride;
+    auto park = [&](T *dst) {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const uint32_t e = sbase + j * TPR + g;
-        uint32_t k = (chunk < n_chunks && e < M) ? a.keys[e] : KEY_NONE;
-        if (k == a.sentinel) k = KEY_NONE;
-        const bool valid = k != KEY_NONE;
-        key[j] = k;
-        p[j] = valid ? a.pos[e] : 0u;
-        const T x = valid ? a.xs[e] : T(0);
-        const T ev = valid ? __ldg(a.E + p[j]) : T(0);
-        xe[j] = x * ev;
-        xxe[j] = x * x * ev;
-        n_valid += __popc(__ballot_sync(FULL, valid) & gmask);   // padding sorts last: valid entries are a prefix
+      for (int ch = 0; ch < NCV; ++ch) {
+        dst[(ch * TPR + g) * 2] = acc[ch].x;
+        dst[(ch * TPR + g) * 2 + 1] = acc[ch].y;
       }
-      if (__all_sync(FULL, n_valid == 0)) break;                 // the rest of every group's chunk is padding
-      if (sub == 0 && n_valid > 0) {
-        cur = __shfl_sync(gmask, key[0], 0, TPR);
-        head = base > 0 && a.keys[base - 1] == cur;
-        any = true;
+      if (g == 0) {
+        dst[a.kp] = sa;
+        dst[a.kp + 1] = sc;
       }
+    };
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-#pragma unroll 2
-        for (int ii = 0; ii < TPR; ++ii) {
-          const int i = j * TPR + ii;
-          const uint32_t ki = __shfl_sync(FULL, key[j], ii, TPR);
-          const uint32_t pi = __shfl_sync(FULL, p[j], ii, TPR);
-          const T xei = __shfl_sync(FULL, xe[j], ii, TPR);
-          const T xxei = __shfl_sync(FULL, xxe[j], ii, TPR);
-          if (i < n_valid) {                                      // group-uniform
-            const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + g;
-            V2 sv[NCV];
+    for (int j = 0; j < NJ; ++j) {
+      RFM_UNROLL(RFM_COLS_UNROLL)
+      for (int ii = 0; ii < TPR; ++ii) {
+        const int i = j * TPR + ii;
+        const uint32_t ki = __shfl_sync(FULL, key[j], ii, TPR);
+        const uint32_t pi = __shfl_sync(FULL, p[j], ii, TPR);
+        const T xei = __shfl_sync(FULL, xe[j], ii, TPR);
+        const T xxei = __shfl_sync(FULL, xxe[j], ii, TPR);
+        if (i < n_valid) {                                      // group-uniform
+          const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + g;
+          V2 sv[NCV];
 #pragma unroll
-            for (int ch = 0; ch < NCV; ++ch) sv[ch] = __ldg(srow + ch * TPR);
-            if (ki != cur) {  // the previous column's segment ended inside this chunk
-              if (head) store_carry<T, TPR, NCV>(a, chunk, 0, acc, sa, sc, g);
-              else finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
-              head = false;
-              cur = ki;
-#pragma unroll
-              for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
-              sa = sc = T(0);
+          for (int ch = 0; ch < NCV; ++ch) sv[ch] = __ldg(srow + ch * TPR);
+          if (ki != cur) {  // the previous column's segment ended inside this chunk
+            if (head) {
+              park(my_head);
+              if (g == 0) hkey[gi] = cur;
+              my_flag |= 1u;
+            } else {
+              finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
             }
+            head = false;
+            cur = ki;
 #pragma unroll
-            for (int ch = 0; ch < NCV; ++ch) {
-              acc[ch].x += xei * sv[ch].x;
-              acc[ch].y += xei * sv[ch].y;
-            }
-            sa += xei;
-            sc += xxei;
+            for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
+            sa = sc = T(0);
           }
+#pragma unroll
+          for (int ch = 0; ch < NCV; ++ch) {
+            acc[ch].x += xei * sv[ch].x;
+            acc[ch].y += xei * sv[ch].y;
+          }
+          sa += xei;
+          sc += xxei;
         }
       }
     }
-    if (any) {
-      uint32_t next_key = base + COL_CHUNK < M ? a.keys[base + COL_CHUNK] : KEY_NONE;
-      if (next_key == a.sentinel) next_key = KEY_NONE;
+    if (n_valid > 0) {
       const bool tail = (cur == next_key);
-      if (head || tail) {
-        store_carry<T, TPR, NCV>(a, chunk, head ? 0 : 1, acc, sa, sc, g);
-        if (!head && g == 0) a.tails[atomicAdd(a.n_tails, 1u)] = chunk;   // this chunk owns the column's fix-up
+      if (head) {                 // the chunk's only segment began earlier; bit2: it also runs on
+        park(my_head);
+        if (g == 0) hkey[gi] = cur;
+        my_flag |= 1u | (tail ? 4u : 0u);
+      } else if (tail) {
+        park(my_tail);
+        if (g == 0) tkey[gi] = cur;
+        my_flag |= 2u;
       } else {
         finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
       }
     }
-  }
-}
-
-// Fix-up, part 1: one warp per TAIL record, i.e. per column that starts in one chunk and runs on
-// into later ones. Short runs are summed here in chunk order; long ones are queued for part 2.
-template <typename T, int NCH, bool DP>
-__global__ void __launch_bounds__(ROWS_THREADS)
-fm_carry_kernel(const ColsArgs<T> a) {
-  using V2 = typename Vec2<T>::type;
-  const int lane = lane_id();
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t M = *a.count;
-  const uint32_t n_tails = *a.n_tails;
-  for (uint32_t ti = gw; ti < n_tails; ti += nw) {
-    const uint32_t chunk = a.tails[ti];
-    const uint32_t base = chunk * COL_CHUNK;
-    const uint32_t klast = a.keys[base + COL_CHUNK - 1u];   // a TAIL chunk is full; its last key is the column
-    // last chunk that still holds entries of the column. Most runs end inside the very next chunk:
-    // one probe of that chunk's last key settles it; otherwise binary-search the first differing key.
-    uint32_t last_chunk = chunk + 1u;
-    const uint32_t probe = base + 2u * COL_CHUNK - 1u;
-    if (probe < M && a.keys[probe] == klast) {
-      uint32_t lo = probe + 1u, hi = M;
-      while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (a.keys[mid] == klast) lo = mid + 1; else hi = mid;
+    if (g == 0) flag[gi] = my_flag;
+    __syncthreads();
+    // ---- combine inside the unit: the group where a run starts owns it ----
+    // which = 0: the run entering the unit from an earlier one (only group 0 can own it); which = 1: a run
+    // that starts in this chunk (TAIL).
+    for (int which = 0; which < 2; ++which) {
+      const bool own = which == 0 ? (gi == 0 && (my_flag & 1u)) : (my_flag & 2u) != 0;
+      if (!own) continue;
+      const T *src = which == 0 ? my_head : my_tail;
+      const uint32_t rkey = which == 0 ? hkey[gi] : tkey[gi];
+#pragma unroll
+      for (int ch = 0; ch < NCV; ++ch) {
+        acc[ch].x = src[(ch * TPR + g) * 2];
+        acc[ch].y = src[(ch * TPR + g) * 2 + 1];
       }
-      last_chunk = (lo - 1u) / COL_CHUNK;
-    }
-    if (last_chunk - chunk > SHORT_RUN) {
-      if (lane == 0) {
-        const uint32_t slot = atomicAdd(a.n_long, 1u);
-        if (slot < a.long_cap) {
-          a.long_runs[2 * slot] = chunk;
-          a.long_runs[2 * slot + 1] = last_chunk;
+      sa = src[a.kp];
+      sc = src[a.kp + 1];
+      bool open = which == 0 ? (my_flag & 4u) != 0 : true;      // does the run continue past this chunk?
+      int nx = gi + 1;
+      while (open && nx < GPC) {
+        const uint32_t f = flag[nx];
+        if (!(f & 1u) || hkey[nx] != rkey) break;               // cannot happen for a consistent list
+        const T *hp = part + ((size_t)nx * 2 + 0) * pstride;
+#pragma unroll
+        for (int ch = 0; ch < NCV; ++ch) {
+          acc[ch].x += hp[(ch * TPR + g) * 2];
+          acc[ch].y += hp[(ch * TPR + g) * 2 + 1];
+        }
+        sa += hp[a.kp];
+        sc += hp[a.kp + 1];
+        open = (f & 4u) != 0;
+        ++nx;
+      }
+      if (which == 1 && !open) {
+        finish_column<T, TPR, NCV, DP>(a, rkey, acc, sa, sc, g, gmask);       // began and ended inside the unit
+      } else {
+        // crosses a unit boundary: one carry record for the whole unit (slot 0 = entering run, 1 = leaving run)
+        V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)unit * 2 + which) * a.kp) + g;
+#pragma unroll
+        for (int ch = 0; ch < NCV; ++ch) cv[ch * TPR] = acc[ch];
+        if (g == 0) {
+          a.carry_ac[((size_t)unit * 2 + which) * 2 + 0] = sa;
+          a.carry_ac[((size_t)unit * 2 + which) * 2 + 1] = sc;
+          if (which == 1) a.tails[atomicAdd(a.n_tails, 1u)] = unit;            // this unit owns the column's fix-up
         }
       }
-      continue;
     }
-    V2 acc[NCH];
-    const V2 *cv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)chunk * 2 + 1) * a.kp) + lane;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) acc[ch] = cv[ch * 32];
-    T sa = a.carry_ac[((size_t)chunk * 2 + 1) * 2 + 0], sc = a.carry_ac[((size_t)chunk * 2 + 1) * 2 + 1];
-    for (uint32_t c = chunk + 1; c <= last_chunk; ++c) {
-      const V2 *hv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)c * 2 + 0) * a.kp) + lane;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const V2 h = hv[ch * 32];
-        acc[ch].x += h.x;
-        acc[ch].y += h.y;
-      }
-      sa += a.carry_ac[((size_t)c * 2 + 0) * 2 + 0];
-      sc += a.carry_ac[((size_t)c * 2 + 0) * 2 + 1];
-    }
-    finish_column<T, 32, NCH, DP>(a, klast, acc, sa, sc, lane, FULL);
+    __syncthreads();
   }
 }
 
-// Fix-up, part 2: one CTA per long run. Warp w sums a contiguous block of the run's HEAD records
-// in chunk order (loads issued LONG_UNROLL at a time, additions in order); warp 0 then adds TAIL +
-// block partials in warp order. The association depends only on the run length and the CTA shape.
+// Fix-up: one CTA per run that leaves a unit of the column pass (its TAIL record). Thread 0 finds the last
+// unit the column reaches (one probe settles the common case, a binary search the rest); warp w then sums a
+// contiguous block of the following units' HEAD records in unit order (loads issued FIX_UNROLL at a time,
+// additions in order) and warp 0 adds TAIL + the warp blocks in warp order. The association depends only on
+// the run length and the CTA shape, never on timing.
+constexpr int FIX_THREADS = 256;
+constexpr int FIX_WARPS = FIX_THREADS / 32;
+
 template <typename T, int NCH, bool DP>
-__global__ void __launch_bounds__(LONG_RUN_THREADS)
-fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
+__global__ void __launch_bounds__(FIX_THREADS)
+fm_fixup_kernel(const ColsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
-  constexpr int LONG_UNROLL = NCH <= 1 ? 8 : NCH <= 2 ? 4 : NCH <= 4 ? 2 : 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sm = reinterpret_cast<T *>(smem_raw);              // [n_warps_used][kp + 2]
+  constexpr int FIX_UNROLL = NCH <= 1 ? 8 : NCH <= 2 ? 4 : NCH <= 4 ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char fix_smem[];
+  T *sm = reinterpret_cast<T *>(fix_smem);              // [FIX_WARPS][kp + 2]
+  __shared__ uint32_t s_last, s_key;
   const int lane = lane_id(), wid = threadIdx.x >> 5;
-  uint32_t n_long = *a.n_long;
-  if (n_long > a.long_cap) n_long = a.long_cap;
+  const uint32_t M = *a.count;
+  const uint32_t n_tails = *a.n_tails;
   const int stride = a.kp + 2;
-  for (uint32_t run = blockIdx.x; run < n_long; run += gridDim.x) {
-    const uint32_t first = a.long_runs[2 * run], last = a.long_runs[2 * run + 1];
+  for (uint32_t ti = blockIdx.x; ti < n_tails; ti += gridDim.x) {
+    const uint32_t first = a.tails[ti];
+    if (threadIdx.x == 0) {
+      const uint32_t base = first * a.unit;
+      const uint32_t klast = a.keys[base + a.unit - 1u];   // a unit with a leaving run is full; its last key is the column
+      uint32_t last_unit = first + 1u;
+      const uint32_t probe = base + 2u * a.unit - 1u;
+      if (probe < M && a.keys[probe] == klast) {            // the next unit is entirely this column: search on
+        uint32_t lo = probe + 1u, hi = M;
+        while (lo < hi) {
+          const uint32_t mid = lo + ((hi - lo) >> 1);
+          if (a.keys[mid] == klast) lo = mid + 1; else hi = mid;
+        }
+        last_unit = (lo - 1u) / a.unit;
+      }
+      s_last = last_unit;
+      s_key = klast;
+    }
+    __syncthreads();
+    const uint32_t last = s_last, klast = s_key;
     const uint32_t n_heads = last - first;
-    const uint32_t per = (n_heads + n_warps_used - 1) / n_warps_used;
-    if (wid < n_warps_used) {
+    const uint32_t per = (n_heads + FIX_WARPS - 1) / FIX_WARPS;
+    {
       V2 acc[NCH];
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) acc[ch].x = acc[ch].y = T(0);
@@ -593,11 +684,11 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
       const uint32_t c0 = first + 1 + wid * per;
       uint32_t c1 = c0 + per;
       if (c1 > last + 1) c1 = last + 1;
-      for (uint32_t c = c0; c < c1; c += LONG_UNROLL) {
-        V2 h[LONG_UNROLL][NCH];
-        T ha[LONG_UNROLL], hc[LONG_UNROLL];
+      for (uint32_t c = c0; c < c1; c += FIX_UNROLL) {
+        V2 h[FIX_UNROLL][NCH];
+        T ha[FIX_UNROLL], hc[FIX_UNROLL];
 #pragma unroll
-        for (int u = 0; u < LONG_UNROLL; ++u) {
+        for (int u = 0; u < FIX_UNROLL; ++u) {
           const bool on = c + u < c1;
           const size_t rec = (size_t)(on ? c + u : c) * 2;
           const V2 *hv = reinterpret_cast<const V2 *>(a.carry_vec + rec * a.kp) + lane;
@@ -610,7 +701,7 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
           hc[u] = on ? __ldcg(a.carry_ac + rec * 2 + 1) : T(0);
         }
 #pragma unroll
-        for (int u = 0; u < LONG_UNROLL; ++u) {
+        for (int u = 0; u < FIX_UNROLL; ++u) {
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
             acc[ch].x += h[u][ch].x;
@@ -636,9 +727,9 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
       V2 acc[NCH];
       const V2 *tv = reinterpret_cast<const V2 *>(a.carry_vec + ((size_t)first * 2 + 1) * a.kp) + lane;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) acc[ch] = tv[ch * 32];
-      T sa = a.carry_ac[((size_t)first * 2 + 1) * 2 + 0], sc = a.carry_ac[((size_t)first * 2 + 1) * 2 + 1];
-      for (int w = 0; w < n_warps_used; ++w) {
+      for (int ch = 0; ch < NCH; ++ch) acc[ch] = __ldcg(tv + ch * 32);
+      T sa = __ldcg(a.carry_ac + ((size_t)first * 2 + 1) * 2 + 0), sc = __ldcg(a.carry_ac + ((size_t)first * 2 + 1) * 2 + 1);
+      for (int w = 0; w < FIX_WARPS; ++w) {
         const T *part = sm + (size_t)w * stride;
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
@@ -648,7 +739,7 @@ fm_long_runs_kernel(const ColsArgs<T> a, int n_warps_used) {
         sa += part[a.kp];
         sc += part[a.kp + 1];
       }
-      finish_column<T, 32, NCH, DP>(a, a.keys[first * COL_CHUNK + COL_CHUNK - 1u], acc, sa, sc, lane, FULL);
+      finish_column<T, 32, NCH, DP>(a, klast, acc, sa, sc, lane, FULL);
     }
     __syncthreads();
   }
@@ -751,6 +842,12 @@ int launch_rows(rfm_ctx *ctx, int nch, int mode, bool sampled, const RowsArgs<T>
 
 // rows (or 32-entry chunks) a CTA of ROWS_THREADS handles per pass of its loop
 int units_per_block(int nch) { return ROWS_WARPS * (nch == 1 ? 4 : nch == 2 ? 2 : 1); }
+// sorted entries one CTA iteration of the column pass covers (= entries per carry record)
+int64_t cols_unit(int nch) { return 32 * (int64_t)units_per_block(nch); }
+size_t cols_smem_bytes(int nch, int kp, size_t es) {
+  const size_t gpc = (size_t)units_per_block(nch);
+  return gpc * 2 * (size_t)(kp + 2) * es + 3 * gpc * sizeof(uint32_t);
+}
 
 }  // namespace
 
@@ -763,7 +860,7 @@ struct rfm_fm_trainer {
   uint32_t stride = 0;        // > 0: fixed-stride triple layout (rows of near-uniform length)
   uint32_t count_host = 0;    // value currently stored in count (fixed-stride layout)
   DevBuf<int64_t> idx;
-  DevBuf<uint32_t> row_len, bptr, scan_tmp, count, long_runs, n_long, tails, n_tails, ticket;
+  DevBuf<uint32_t> row_len, bptr, scan_tmp, count, tails, n_tails, ticket;
   DevBuf<unsigned char> S, E, carry_vec, carry_ac, grad;
   DevBuf<double> block_partials, losses, loss_sums;
   RadixSorter<float> sort32;
@@ -774,9 +871,6 @@ struct rfm_fm_trainer {
   cudaEvent_t stage_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
   bool stage_used[RING] = {false, false, false, false};
   int ring_pos = 0;
-  uint32_t long_cap = 0;
-  int long_warps = 1;
-  size_t long_smem = 0;
 };
 
 namespace {
@@ -872,6 +966,9 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   a.fkey = fkey;
   a.q0 = q0;
   a.idx_out = t->idx.p;
+  RFM_TRY(sorter.clear_histograms(ctx));
+  a.ghist = sorter.ghist();
+  a.n_passes = sorter.passes;
   if (DP) {
     T *g = reinterpret_cast<T *>(t->grad.p);
     RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)grad_total(m->n, m->kp) * sizeof(T), ctx->stream));
@@ -883,7 +980,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
   RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, fused_draw, a, grid));
   int sorted = 0;
-  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted));
+  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true));
 
   ColsArgs<T> c;
   memset(&c, 0, sizeof(c));
@@ -899,34 +996,31 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   c.vn = reinterpret_cast<T *>(m->vn.p);
   c.kp = m->kp;
   c.lr = static_cast<T>(lr);
+  c.unit = (uint32_t)cols_unit(m->nch);
   c.carry_vec = reinterpret_cast<T *>(t->carry_vec.p);
   c.carry_ac = reinterpret_cast<T *>(t->carry_ac.p);
   c.tails = t->tails.p;
   c.n_tails = t->n_tails.p;
-  c.long_runs = t->long_runs.p;
-  c.n_long = t->n_long.p;
-  c.long_cap = t->long_cap;
   if (DP) {
     T *g = reinterpret_cast<T *>(t->grad.p);
     c.grad_w = g + GRAD_W_OFF;
     c.grad_V = g + grad_v_off(m->n);
   }
-  RFM_CUDA(cudaMemsetAsync(t->n_long.p, 0, sizeof(uint32_t), ctx->stream));
   RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
-  const int64_t chunk_cap = ceil_div(t->nnz_cap, COL_CHUNK);
-  const int cgrid = grid_for(ctx, ceil_div(chunk_cap, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
-  const int tgrid = grid_for(ctx, ceil_div(chunk_cap, ROWS_WARPS * 4), 2);
-  const int lgrid = t->long_cap < (uint32_t)ctx->sm_count * 2 ? (int)t->long_cap : ctx->sm_count * 2;
+  const int64_t unit_cap = ceil_div(t->nnz_cap, cols_unit(m->nch));
+  const int cgrid = grid_for(ctx, unit_cap, t->rows_grid / ctx->sm_count);
+  const int tgrid = grid_for(ctx, unit_cap, 4);   // one CTA per leaving run; there are at most unit_cap of them
+  const size_t csmem = cols_smem_bytes(m->nch, m->kp, sizeof(T));
   RFM_DISPATCH_TPR(m->nch, {
     auto fm_cols = fm_cols_kernel<T, TPR, NCV, DP>;
-    RFM_LAUNCH(ctx, fm_cols, cgrid, ROWS_THREADS, 0, c);
+    if (csmem > 48 * 1024)
+      RFM_CUDA(cudaFuncSetAttribute(fm_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    RFM_LAUNCH(ctx, fm_cols, cgrid, ROWS_THREADS, csmem, c);
   });
   RFM_DISPATCH_NCH(m->nch, {
-    auto fm_carry = fm_carry_kernel<T, NCH, DP>;
-    RFM_LAUNCH(ctx, fm_carry, tgrid, ROWS_THREADS, 0, c);
-    auto fm_long_runs = fm_long_runs_kernel<T, NCH, DP>;
-    RFM_LAUNCH(ctx, fm_long_runs, lgrid < 1 ? 1 : lgrid, LONG_RUN_THREADS, t->long_smem, c,
-               t->long_warps);
+    auto fm_fixup = fm_fixup_kernel<T, NCH, DP>;
+    const size_t fsmem = (size_t)FIX_WARPS * (m->kp + 2) * sizeof(T);
+    RFM_LAUNCH(ctx, fm_fixup, tgrid, FIX_THREADS, fsmem, c);
   });
   return RFM_OK;
 }
@@ -934,11 +1028,26 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
 template <typename T>
 int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot, bool sampled, const FeistelKey &fkey) {
   RFM_TRY((step_core<T, false>(t, batch, lr, sampled, fkey, 0)));
-  RFM_TRY(loss_pass<T>(t, t->train, t->idx.p, 0, batch, 1.0 / (double)batch, t->losses.p + slot));
-  if (t->val)
-    RFM_TRY(loss_pass<T>(t, t->val, nullptr, 0, t->val->n_rows, 1.0 / (double)t->val->n_rows,
-                         t->losses.p + t->max_slots + slot));
-  return RFM_OK;
+  // post-update batch loss and val loss in ONE launch (the val rows ride along as a second row set)
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  RowsArgs<T> a = rows_args<T>(m, t->train);
+  a.idx = t->idx.p;
+  a.n = batch;
+  a.fin = make_finish(1, 1.0 / (double)batch, nullptr, t->losses.p + slot, t->block_partials.p, t->ticket.p);
+  int64_t n_all = batch;
+  if (t->val && t->val->n_rows > 0) {
+    a.row_ptr2 = t->val->row_ptr.p;
+    a.col2 = t->val->col.p;
+    a.val2 = reinterpret_cast<const T *>(t->val->val.p);
+    a.yp2 = reinterpret_cast<const T *>(t->val->yp.p);
+    a.n2 = t->val->n_rows;
+    a.fin2 = make_finish(1, 1.0 / (double)t->val->n_rows, nullptr, t->losses.p + t->max_slots + slot,
+                         t->block_partials.p + t->rows_grid, t->ticket.p + 1);
+    n_all += a.n2;
+  }
+  const int grid = grid_for(ctx, ceil_div(n_all, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
+  return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid);
 }
 
 int stage_batch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
@@ -1290,17 +1399,14 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
     RFM_TRY(t->bptr.alloc(max_batch));
     RFM_TRY(t->scan_tmp.alloc(ceil_div(max_batch, 4096) + 2));
     RFM_TRY(t->count.alloc(1));
-    RFM_TRY(t->n_long.alloc(1));
     RFM_TRY(t->S.alloc((size_t)max_batch * m->kp * es));
     RFM_TRY(t->E.alloc((size_t)max_batch * es));
-    const int64_t chunk_cap = ceil_div(nnz_cap, COL_CHUNK);
+    const int64_t chunk_cap = ceil_div(nnz_cap, cols_unit(m->nch)) + 1;   // carry records: one per column-pass unit
     RFM_TRY(t->carry_vec.alloc((size_t)chunk_cap * 2 * m->kp * es));
     RFM_TRY(t->carry_ac.alloc((size_t)chunk_cap * 4 * es));
-    t->long_cap = (uint32_t)(chunk_cap / (SHORT_RUN + 1) + 1);
-    RFM_TRY(t->long_runs.alloc((size_t)t->long_cap * 2));
-    RFM_TRY(t->block_partials.alloc((size_t)t->rows_grid));
-    RFM_TRY(t->ticket.alloc(1));
-    RFM_CUDA(cudaMemsetAsync(t->ticket.p, 0, sizeof(uint32_t), ctx->stream));
+    RFM_TRY(t->block_partials.alloc((size_t)t->rows_grid * 2));
+    RFM_TRY(t->ticket.alloc(2));
+    RFM_CUDA(cudaMemsetAsync(t->ticket.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     RFM_TRY(t->tails.alloc((size_t)chunk_cap));
     RFM_TRY(t->n_tails.alloc(1));
     RFM_TRY(t->losses.alloc((size_t)max_slots * 2));
@@ -1308,12 +1414,6 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
     RFM_CUDA(cudaMemsetAsync(t->losses.p, 0, (size_t)max_slots * 2 * sizeof(double), ctx->stream));
     // keys go up to n (the sentinel of the fixed-stride layout), hence n + 1 key values
     if (m->dtype == RFM_F64) RFM_TRY(t->sort64.init(nnz_cap, m->n + 1)); else RFM_TRY(t->sort32.init(nnz_cap, m->n + 1));
-    const size_t per_warp = (size_t)(m->kp + 2) * es;
-    int lw = (int)(40 * 1024 / per_warp);
-    if (lw > 32) lw = 32;
-    if (lw < 1) lw = 1;
-    t->long_warps = lw;
-    t->long_smem = per_warp * lw;
     for (int r = 0; r < rfm_fm_trainer::RING; ++r) RFM_CUDA(cudaEventCreateWithFlags(&t->stage_ev[r], cudaEventDisableTiming));
     return RFM_OK;
   };

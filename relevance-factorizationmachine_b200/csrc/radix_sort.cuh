@@ -217,15 +217,22 @@ struct RadixSorter {
     RFM_CUDA(cudaMemset(scratch.p, 0, scratch_words * sizeof(uint32_t)));
     return RFM_OK;
   }
-  // input is in buffer 0; returns the index of the buffer holding the sorted output
-  int sort(rfm_ctx *ctx, const uint32_t *count_dev, int *out_buf) {
-    int cur = 0;
-    // zero the histograms, tile counters and status words; the error flag in between is sticky
+  int clear_histograms(rfm_ctx *ctx) {
     RFM_CUDA(cudaMemsetAsync(ghist(), 0, (size_t)RS_MAX_PASSES * RS_RADIX * sizeof(uint32_t), ctx->stream));
+    return RFM_OK;
+  }
+  // input is in buffer 0; returns the index of the buffer holding the sorted output. histograms_ready: the
+  // producer of the keys already accumulated ghist() (after clear_histograms), so the histogram pass is skipped.
+  int sort(rfm_ctx *ctx, const uint32_t *count_dev, int *out_buf, bool histograms_ready = false) {
+    int cur = 0;
+    // zero the tile counters and status words; the error flag in between is sticky
     RFM_CUDA(cudaMemsetAsync(tile_counter(0), 0, RS_MAX_PASSES * sizeof(uint32_t), ctx->stream));
     RFM_CUDA(cudaMemsetAsync(status(0), 0, (size_t)passes * n_tiles_cap * RS_RADIX * sizeof(uint32_t), ctx->stream));
-    const int hgrid = n_tiles_cap < ctx->sm_count * 4 ? n_tiles_cap : ctx->sm_count * 4;
-    RFM_LAUNCH(ctx, rs_global_hist_kernel, hgrid, RS_THREADS, 0, keys[0].p, count_dev, passes, ghist());
+    if (!histograms_ready) {
+      RFM_TRY(clear_histograms(ctx));
+      const int hgrid = n_tiles_cap < ctx->sm_count * 4 ? n_tiles_cap : ctx->sm_count * 4;
+      RFM_LAUNCH(ctx, rs_global_hist_kernel, hgrid, RS_THREADS, 0, keys[0].p, count_dev, passes, ghist());
+    }
     const int grid = n_tiles_cap < ctx->sm_count * 4 ? n_tiles_cap : ctx->sm_count * 4;
     for (int p = 0; p < passes; ++p) {
       RFM_LAUNCH(ctx, rs_onesweep_kernel<T>, grid, RS_THREADS, 0, keys[cur].p, pos[cur].p, val[cur].p,
