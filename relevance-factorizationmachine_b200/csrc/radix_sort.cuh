@@ -22,7 +22,10 @@ namespace rfm {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                      // elements per thread
+#ifndef RFM_RS_ITEMS
+#define RFM_RS_ITEMS 8
+#endif
+constexpr int RS_ITEMS = RFM_RS_ITEMS;            // elements per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 4096 elements per tile
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
@@ -66,8 +69,12 @@ rs_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restr
                    uint32_t *error_flag) {
   __shared__ uint32_t wcnt[RS_WARPS][RS_RADIX];
   __shared__ uint32_t digit_base[RS_RADIX];
+  __shared__ uint32_t gbase[RS_RADIX];        // global position of tile-local slot 0 of each digit's run
   __shared__ uint32_t warp_tot[RS_WARPS];
   __shared__ uint32_t s_tile;
+  // the tile in tile-sorted order, so the write-out below is coalesced inside every digit run
+  __shared__ uint32_t sk[RS_TILE], sp[RS_TILE];
+  __shared__ T sv[RS_TILE];
   const uint32_t count = *count_dev;
   const uint32_t n_tiles = (count + RS_TILE - 1) / RS_TILE;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -94,12 +101,22 @@ rs_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restr
     const uint32_t tile = s_tile;
     if (tile >= n_tiles) break;
     const uint32_t warp_base = tile * RS_TILE + wid * (32 * RS_ITEMS);
-    uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+    // all of this thread's elements are loaded up front (independent loads in flight together); the scatter
+    // phase below only stores
+    uint32_t key[RS_ITEMS], rank[RS_ITEMS], ppos[RS_ITEMS];
+    T pval[RS_ITEMS];
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
       const uint32_t e = warp_base + r * 32 + lane;
       const bool valid = e < count;
       key[r] = valid ? keys_in[e] : 0u;
+      ppos[r] = valid ? pos_in[e] : 0u;
+      pval[r] = valid ? val_in[e] : T(0);
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const uint32_t e = warp_base + r * 32 + lane;
+      const bool valid = e < count;
       const uint32_t d = valid ? ((key[r] >> shift) & 0xFF) : 0xFFFFFFFFu;
       const uint32_t peers = __match_any_sync(FULL, d);
       const uint32_t before = valid ? wcnt[wid][d] : 0u;
@@ -122,7 +139,10 @@ rs_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restr
         st_volatile_u32(mine, RS_FLAG_AGG | tile_count);
         // walk back over earlier tiles, LB predecessors per round trip; stop at the first inclusive
         // prefix; re-poll from the first status word that is not published yet
-        constexpr int LB = 8;
+#ifndef RFM_RS_LOOKBACK
+#define RFM_RS_LOOKBACK 8
+#endif
+        constexpr int LB = RFM_RS_LOOKBACK;
         int64_t t = (int64_t)tile - 1;
         uint32_t spins = 0;
         bool done = false;
@@ -154,32 +174,54 @@ rs_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restr
         }
         st_volatile_u32(mine, RS_FLAG_PREFIX | ((excl + tile_count) & RS_VALUE_MASK));
       }
-      uint32_t run = digit_base[d] + excl;
+      // tile-local start of this digit's run (exclusive scan of the tile's digit counts over the CTA)
+      uint32_t inc = tile_count;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t2 = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t2;
+      }
+      if (lane == 31) warp_tot[wid] = inc;
+      __syncthreads();
+      uint32_t before = 0;
+      for (int w = 0; w < wid; ++w) before += warp_tot[w];
+      const uint32_t tstart = before + inc - tile_count;
+      gbase[d] = digit_base[d] + excl - tstart;
+      uint32_t run = tstart;
 #pragma unroll
       for (int w = 0; w < RS_WARPS; ++w) {
         const uint32_t c = wcnt[w][d];
-        wcnt[w][d] = run;
+        wcnt[w][d] = run;          // tile-local slot where warp w's first element of this digit goes
         run += c;
       }
     }
     __syncthreads();
+    const uint32_t tile_n = count - tile * RS_TILE < (uint32_t)RS_TILE ? count - tile * RS_TILE : (uint32_t)RS_TILE;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
       const uint32_t e = warp_base + r * 32 + lane;
       if (e < count) {
-        const uint32_t dst = wcnt[wid][(key[r] >> shift) & 0xFF] + rank[r];
-        if (dst >= count) {   // cannot happen unless a prefix is wrong: record it instead of faulting
-          if (atomicCAS(error_flag, 0u, 2u) == 0u) {
-            error_flag[5] = tile;
-            error_flag[6] = ((key[r] >> shift) & 0xFF) | (uint32_t)shift << 16;
-            error_flag[7] = dst;
-          }
-          continue;
-        }
-        keys_out[dst] = key[r];
-        pos_out[dst] = pos_in[e];
-        val_out[dst] = val_in[e];
+        const uint32_t slot = wcnt[wid][(key[r] >> shift) & 0xFF] + rank[r];
+        sk[slot] = key[r];
+        sp[slot] = ppos[r];
+        sv[slot] = pval[r];
       }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+      const uint32_t k = sk[i];
+      const uint32_t dst = gbase[(k >> shift) & 0xFF] + i;
+      if (dst >= count) {   // cannot happen unless a prefix is wrong: record it instead of faulting
+        if (atomicCAS(error_flag, 0u, 2u) == 0u) {
+          error_flag[5] = tile;
+          error_flag[6] = ((k >> shift) & 0xFF) | (uint32_t)shift << 16;
+          error_flag[7] = dst;
+        }
+        continue;
+      }
+      keys_out[dst] = k;
+      pos_out[dst] = sp[i];
+      val_out[dst] = sv[i];
     }
   }
 }
