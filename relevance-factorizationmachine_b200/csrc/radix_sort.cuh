@@ -256,7 +256,7 @@ struct RadixSorter {
     }
     scratch_words = (size_t)RS_MAX_PASSES * RS_RADIX + 8 + (size_t)passes * n_tiles_cap * RS_RADIX;
     RFM_TRY(scratch.alloc(scratch_words));
-    RFM_CUDA(cudaMemset(scratch.p, 0, scratch_words * sizeof(uint32_t)));
+    RFM_CUDA(cudaMemsetAsync(scratch.p, 0, scratch_words * sizeof(uint32_t), nullptr));
     return RFM_OK;
   }
   int clear_histograms(rfm_ctx *ctx) {

@@ -172,6 +172,14 @@ int rfm_ctx_create(int device, void *cuda_stream, rfm_ctx **out) {
   ctx->device = device;
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   ctx->sm_count = prop.multiProcessorCount;
+  {  // keep freed device memory in the default pool instead of returning it to the driver
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   const char *sl = getenv("RFM_SYNC_LAUNCHES");
   ctx->sync_launches = sl && sl[0] == '1';
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {

@@ -11,6 +11,7 @@ and the lazy host mirrors of the parameters.
 """
 from __future__ import annotations
 
+import time
 import weakref
 from ctypes import byref, c_double, c_void_p
 from dataclasses import dataclass, field
@@ -136,12 +137,16 @@ class FactorizationMachines(PointwiseBaseRecommender):
         if self.batch_size > n_rows:
             raise ValueError("Cannot sample %d out of arrays with dim %d when replace is False"
                              % (self.batch_size, n_rows))
+        t_up = time.perf_counter()
         train_rows = self._rows(X, train["labels"], train["pscores"])
         val_rows = self._rows(val["features"], val["labels"], val["pscores"])
         self.sync_to_device()
+        self._upload_seconds = time.perf_counter() - t_up
         if self.distributed is not None:
             return self._fit_data_parallel(train_rows, val_rows, n_rows)
+        t_phase = time.perf_counter()
         trainer = _FmTrainer(self._dev, train_rows, val_rows, self.batch_size, max(self.n_epochs, 1))
+        phases = {"upload": self._upload_seconds, "trainer_create": time.perf_counter() - t_phase}
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
         eval_rows = None
@@ -152,6 +157,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
             from tqdm import tqdm
             it = tqdm(epochs)
         launches0 = ctx.launch_count()
+        t_phase = time.perf_counter()
         try:
             for epoch in it:
                 if prefetch is not None:
@@ -164,16 +170,26 @@ class FactorizationMachines(PointwiseBaseRecommender):
                     scores = np.empty(eval_rows.n_rows)
                     check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
                     self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
+            phases["enqueue_epochs"] = time.perf_counter() - t_phase
+            t_phase = time.perf_counter()
             train_loss = np.empty(self.n_epochs)
             val_loss = np.empty(self.n_epochs)
             check(lib().rfm_fm_trainer_losses(trainer.handle, 0, self.n_epochs, ptr(train_loss), ptr(val_loss)))
+            phases["drain_and_read_losses"] = time.perf_counter() - t_phase
         finally:
             if prefetch is not None:
                 prefetch.close()
-        self.last_fit_stats = {"gpu_launches": ctx.launch_count() - launches0,
-                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes}
+        launches = ctx.launch_count() - launches0
+        t_phase = time.perf_counter()
         trainer.close()
+        phases["trainer_destroy"] = time.perf_counter() - t_phase
+        t_phase = time.perf_counter()
         self.sync_to_host()
+        phases["download_params"] = time.perf_counter() - t_phase
+        self.last_fit_stats = {"gpu_launches": launches,
+                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes,
+                               "upload_seconds": self._upload_seconds,
+                               "phase_seconds": {k: round(v, 5) for k, v in phases.items()}}
         return train_loss.tolist(), val_loss.tolist()
 
     def _fit_data_parallel(self, train_rows, val_rows, n_rows) -> tuple:
@@ -204,7 +220,8 @@ class FactorizationMachines(PointwiseBaseRecommender):
             if prefetch is not None:
                 prefetch.close()
         self.last_fit_stats = {"gpu_launches": ctx.launch_count() - launches0,
-                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes}
+                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes,
+                               "upload_seconds": self._upload_seconds}
         trainer.close()
         self.sync_to_host()
         return (out[: self.n_epochs, 0] / self.batch_size).tolist(), (out[: self.n_epochs, 1] / val_rows.n_rows).tolist()
