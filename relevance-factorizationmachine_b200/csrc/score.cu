@@ -37,8 +37,11 @@ constexpr int BM = 128;          // users per CTA tile (= TMEM lanes)
 constexpr int BN = 256;          // items per MMA tile (= TMEM columns per accumulator stage)
 constexpr int BK = 64;           // bf16 elements per K block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int SCORE_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
-constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter; each owns half of a tile's columns
+#ifndef RFM_EPI_WARPS
+#define RFM_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = RFM_EPI_WARPS;             // EPI_WARPS/4 per TMEM lane quarter; each owns a slice of a tile's columns
+constexpr int SCORE_THREADS = 128 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue
 constexpr int EPI_HALVES = EPI_WARPS / 4;
 constexpr int MAX_KB = 2;        // k <= 128 on the tensor-core path
 constexpr int MAX_K = 120;
@@ -65,6 +68,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+  }
+}
+// same, for the producer / MMA threads: they run far ahead of the epilogue, and a bare spin would steal issue
+// slots from the epilogue warps that share their schedulers (measured: 30 % of all issued instructions)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(200);
   }
 }
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1) {
@@ -177,7 +194,7 @@ __device__ __forceinline__ void insert_candidate(float s, int item, float *ls, i
 
 template <int KB>
 struct FilterSmem {
-  static constexpr int STAGES = KB == 1 ? 3 : 2;
+  static constexpr int STAGES = (KB == 1 && EPI_WARPS <= 8) ? 3 : 2;
   static constexpr int A_BYTES = KB * BM * 128;
   static constexpr int B_STAGE_BYTES = KB * BN * 128;
   static constexpr int BAR_OFF = A_BYTES + STAGES * B_STAGE_BYTES;
@@ -238,7 +255,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
+        mbar_wait_relaxed(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, L::B_STAGE_BYTES);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(sB + s * L::B_STAGE_BYTES + kb * BN * 128, &tmap_c, full + s, kb * BK, (tile0 + it) * BN);
@@ -252,8 +269,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t ph = (it / STAGES) & 1;
         const int acc = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(tempty + acc, aph ^ 1);
-        mbar_wait(full + s, ph);
+        mbar_wait_relaxed(tempty + acc, aph ^ 1);
+        mbar_wait_relaxed(full + s, ph);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -306,23 +323,33 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t v[32];
         tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, v);
         const float4 *b4 = reinterpret_cast<const float4 *>(a.beta + item0 + c);
-        uint32_t pass = 0;
+        // four independent partial masks: a single "pass |= ..." chain is 32 dependent instructions long
+        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b = __ldg(b4 + j4);
-          pass |= (__uint_as_float(v[j4 * 4 + 0]) + b.x > tau ? 1u : 0u) << (j4 * 4 + 0);
-          pass |= (__uint_as_float(v[j4 * 4 + 1]) + b.y > tau ? 1u : 0u) << (j4 * 4 + 1);
-          pass |= (__uint_as_float(v[j4 * 4 + 2]) + b.z > tau ? 1u : 0u) << (j4 * 4 + 2);
-          pass |= (__uint_as_float(v[j4 * 4 + 3]) + b.w > tau ? 1u : 0u) << (j4 * 4 + 3);
+          p0 |= (__uint_as_float(v[j4 * 4 + 0]) + b.x > tau ? 1u : 0u) << (j4 * 4 + 0);
+          p1 |= (__uint_as_float(v[j4 * 4 + 1]) + b.y > tau ? 1u : 0u) << (j4 * 4 + 1);
+          p2 |= (__uint_as_float(v[j4 * 4 + 2]) + b.z > tau ? 1u : 0u) << (j4 * 4 + 2);
+          p3 |= (__uint_as_float(v[j4 * 4 + 3]) + b.w > tau ? 1u : 0u) << (j4 * 4 + 3);
         }
+        uint32_t pass = (p0 | p1) | (p2 | p3);
         // Rare after warm-up. Every lane walks ITS OWN passing columns (lanes pass at different columns, so
         // this takes max-over-lanes iterations, usually one, instead of one iteration per column). The
         // lane's score is pulled out of the register tile with a select chain (no run-time indexed array).
         while (__any_sync(FULL, pass != 0)) {
           const int j = pass ? __ffs(pass) - 1 : 0;
-          float vj = 0.f;
+          // v[j] for a run-time j without a run-time indexed array: 5-level select tree on the bits of j
+          uint32_t t16[16], t8[8], t4[4], t2[2];
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) vj = (j == jj) ? __uint_as_float(v[jj]) : vj;
+          for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) t2[i] = (j & 8) ? t4[2 * i + 1] : t4[2 * i];
+          const float vj = __uint_as_float((j & 16) ? t2[1] : t2[0]);
           if (pass) {
             pass &= pass - 1;
             if (item0 + c + j < a.item_end)
