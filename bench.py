@@ -373,7 +373,7 @@ def run_ours(args):
     if dist is None:
         check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + 2 * K, ptr(tl), ptr(vl)))
     else:
-        last = dp.loss_tensor.cpu().numpy()
+        last = dp.flush().cpu().numpy()
         tl[:] = last[0] / (B * world)
         vl[:] = last[1] / N_VAL
     assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl)), "non-finite loss in the timed region"

@@ -9,7 +9,8 @@ leaves in device memory. The FM gradient is a plain sum over batch rows (``src/f
     rank r    : forward + residual + segmented column reduction over ITS slice of the batch
     all ranks : all-reduce(sum) of the gradient buffer             <- the one exchange step
     every rank: identical dense apply  w0 += lr*g0, w += lr*dw, V += lr*dV
-    losses    : per-rank partial sums over the batch slice / a val slice, all-reduced, then / count
+    losses    : per-rank partial sums over the batch slice / a val slice; they ride along in the NEXT
+                step's gradient all-reduce (two spare header slots), so a step has ONE collective
 
 With one rank this is exactly the single-GPU step; with G ranks results differ from it only by the
 association of the cross-rank sum. MF's sequential per-sample semantics do not shard ("replicas only").
@@ -117,14 +118,28 @@ class DataParallelFM:
         self.vbegin, self.vend = slice_bounds(n_val, env.world, env.rank)
 
     def step(self, epoch: int):
-        """One reference epoch over the global batch; returns the (device/CPU) tensor holding
-        [train_loss, val_loss] of this step (valid after the caller synchronises)."""
+        """One reference epoch over the global batch, with ONE collective: the gradient all-reduce. The
+        loss sums of the PREVIOUS step ride along in two spare slots of the gradient buffer's header
+        ([sum_e, loss_batch, loss_val, pad | dw | dV]), so this returns the previous step's global
+        [batch loss sum, val loss sum] (None on the first step); call ``flush()`` after the last step."""
         self.local_grad(self.begin, self.end, epoch)
+        pending = getattr(self, "_pending", False)
+        if pending:
+            self.grad_tensor[1:3].copy_(self.loss_tensor)        # previous step's local sums (dtype-converting copy)
         self.env.all_reduce_sum(self.grad_tensor)
+        prev = self.grad_tensor[1:3].to(self.loss_tensor.dtype).clone() if pending else None
         self.apply(self.lr)
         self.local_loss_sums(self.begin, self.end, self.vbegin, self.vend)
+        self._pending = True
+        return prev
+
+    def flush(self):
+        """Global loss sums of the last step (its own small all-reduce)."""
+        if not getattr(self, "_pending", False):
+            return None
         self.env.all_reduce_sum(self.loss_tensor)
-        return self.loss_tensor
+        self._pending = False
+        return self.loss_tensor.clone()
 
 
 def make_fm_dp(model, trainer, env: DistEnv, global_batch: int, n_val: int, lr: float, batch_source):

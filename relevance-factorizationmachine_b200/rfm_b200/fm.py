@@ -210,11 +210,16 @@ class FactorizationMachines(PointwiseBaseRecommender):
         launches0 = ctx.launch_count()
         try:
             for epoch in epochs:
-                hist[epoch].copy_(dp.step(epoch))
+                prev = dp.step(epoch)                       # global loss sums of the previous epoch
+                if prev is not None:
+                    hist[epoch - 1].copy_(prev)
                 if eval_rows is not None:
                     scores = np.empty(eval_rows.n_rows)
                     check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
                     self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
+            last = dp.flush()
+            if last is not None:
+                hist[self.n_epochs - 1].copy_(last)
             out = hist.cpu().numpy()
         finally:
             if prefetch is not None:

@@ -38,7 +38,8 @@ def _worker(rank, world, port, n_epochs, out_dir):
     n = X.shape[1]
     params = {"w0": g["w0_init"].copy(), "w": g["w_init"].copy(), "V": g["V_init"].copy()}
     env = DistEnv("gloo")
-    grad = torch.zeros(1 + n + n * k, dtype=torch.float64)
+    H = 4    # header of the gradient buffer: [sum_e, loss_batch, loss_val, pad], as in csrc/fm.cu (GRAD_W_OFF)
+    grad = torch.zeros(H + n + n * k, dtype=torch.float64)
     loss = torch.zeros(2, dtype=torch.float64)
     state = {}
 
@@ -47,15 +48,16 @@ def _worker(rank, world, port, n_epochs, out_dir):
         state["idx"] = idx
         mine = idx[begin:end]
         g0, a, G = fm_oracle.fm_grad(X[mine], y[mine], ps[mine], params["w0"], params["w"], params["V"])
+        grad[:H] = 0.0                      # the device path zeroes the whole buffer before accumulating
         grad[0] = g0
-        grad[1:1 + n] = torch.from_numpy(a)
-        grad[1 + n:] = torch.from_numpy(G.reshape(-1))
+        grad[H:H + n] = torch.from_numpy(a)
+        grad[H + n:] = torch.from_numpy(G.reshape(-1))
 
     def apply(step_lr):
         gnp = grad.numpy()
         params["w0"] = params["w0"] + step_lr * gnp[0]
-        params["w"] = params["w"] + step_lr * gnp[1:1 + n]
-        params["V"] = params["V"] + step_lr * gnp[1 + n:].reshape(n, k)
+        params["w"] = params["w"] + step_lr * gnp[H:H + n]
+        params["V"] = params["V"] + step_lr * gnp[H + n:].reshape(n, k)
 
     def term_sum(Xs, ys, pss):
         p = fm_oracle.fm_predict(Xs, params["w0"], params["w"], params["V"])
@@ -70,9 +72,13 @@ def _worker(rank, world, port, n_epochs, out_dir):
     dp = DataParallelFM(env, B, Xv.shape[0], lr, local_grad, grad, apply, local_loss_sums, loss)
     tl, vl = [], []
     for epoch in range(n_epochs):
-        out = dp.step(epoch).numpy().copy()
-        tl.append(out[0] / B)
-        vl.append(out[1] / Xv.shape[0])
+        prev = dp.step(epoch)                  # the previous epoch's global loss sums ride in this all-reduce
+        if prev is not None:
+            tl.append(float(prev[0]) / B)
+            vl.append(float(prev[1]) / Xv.shape[0])
+    out = dp.flush().numpy()
+    tl.append(out[0] / B)
+    vl.append(out[1] / Xv.shape[0])
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), tl=tl, vl=vl, **params)
     env.shutdown()
 
