@@ -195,11 +195,13 @@ int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, i
  * predict on the Cartesian-product rows + per-user argsort".
  * rfm_topk_run returns, for every user, the K best items of the catalog range [item_begin, item_end)
  * in the canonical order (score descending, larger item id first among exact ties) with their exact
- * float64 scores. mode 0: bf16 tcgen05 GEMM + fused per-user candidate filter, exact float64
- * re-scoring, and a proof per user that pruning lost nothing (users without a proof are ranked
- * exactly); mode 1: exact float64 only. stats[0] = 1 if the tensor-core path ran, stats[1] = number of
- * users that needed the exact fallback. A, C are row-major float64 (n_users, k), (n_items, k);
- * alpha / beta may be NULL. */
+ * float64 scores. mode 0: two bf16 tcgen05 GEMM passes with fused epilogues -- the first finds, per
+ * user, a threshold that provably lies below the K-th best score (minus the bf16 error bound), the
+ * second collects every item that reaches it -- then exact float64 re-scoring of the collected items
+ * (users whose candidate buffer overflowed are ranked exactly); mode 1: exact float64 only.
+ * stats (int64[4], may be NULL): [0] = 1 if the tensor-core path ran, [1] = users that needed the
+ * exact fallback, [2] = candidates collected over all users, [3] = tile stride of the first pass.
+ * A, C are row-major float64 (n_users, k), (n_items, k); alpha / beta may be NULL. */
 typedef struct rfm_topk rfm_topk;
 int rfm_topk_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, int32_t n_factors, rfm_topk **out);
 int rfm_topk_destroy(rfm_topk *t);

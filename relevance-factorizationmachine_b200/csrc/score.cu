@@ -7,25 +7,36 @@
 // Cartesian-product rows followed by its per-user argsort", checked in tests/test_score_gpu.py.
 //
 // Pipeline (all on the device):
-//   1. A, C -> bf16 tiles, K padded to 64, rows padded to the tile; row norms in float64.
-//   2. score_filter_kernel: a persistent warp-specialised tcgen05 GEMM. One CTA owns a block of 128
-//      users and a range of 256-item tiles. TMA (cp.async.bulk.tensor, 128B swizzle) stages the
-//      operands, one elected thread issues tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32 in TMEM,
-//      two accumulator stages), and four epilogue warps read the accumulator with tcgen05.ld: thread r
-//      streams the scores of user r, adds beta, and keeps the Kc best (score, item) candidates above a
-//      running threshold. Scores are never written to memory.
-//   3. score_rescore_kernel: exact float64 scores of the candidates, exact top-K with the canonical tie
-//      rule (score descending, larger item id first), and a proof that no item outside the candidate
-//      list can belong to the top-K:  exact_K(u) > threshold(u) + eps(u), with
-//      eps(u) = 2^-7 ||A_u|| max_i ||C_i|| bounding the bf16 rounding of both operands.
-//   4. score_exact_kernel: users that fail the proof (or every user, in exact mode / for k > 128) are
-//      scored in float64 against the whole catalog.
-// The result is therefore always the exact float64 top-K; the tensor-core pass only prunes.
+//   1. A, C -> bf16 tiles, K padded to 64, rows padded to the tile; row norms and rounding-residual norms in
+//      float64; the item terms beta as a 16-wide bf16 operand (three-way split, exact to 2^-24).
+//   2. score_pass_kernel<PASS 0> ("score_sample"): a warp-specialised tcgen05 GEMM over every stride-th 256-item
+//      tile. One CTA keeps up to four blocks of 128 users resident; TMA (cp.async.bulk.tensor, 128B swizzle)
+//      stages the item tiles, one elected thread issues tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32 in TMEM,
+//      two accumulator stages; the first MMA of a step adds beta), and 16 epilogue warps read the accumulator
+//      with tcgen05.ld: thread r streams the scores of user row r through FMNMX3 and writes one maximum per
+//      group of 64 items. Scores are never written to memory.
+//   3. score_threshold_kernel: per user, the K-th largest group maximum. K different items reach it, so it is a
+//      lower bound on the K-th best approximate score; tau = bound - 2 eps(u), where eps(u) bounds
+//      |approximate - exact| rigorously from the data (score_error_bound).
+//   4. score_pass_kernel<PASS 1> ("score_collect"): the same GEMM over every tile; the epilogue compares each
+//      32-column slice's maximum with tau and appends the few items that reach it (about K * stride per user)
+//      to the user's candidate buffer. Every item whose exact score can reach the exact K-th best is collected.
+//   5. score_rescore_kernel: candidates within 2 eps of the K-th best approximate score are re-scored in
+//      float64 (a candidate per lane) and ranked with the canonical tie rule (score descending, larger item id
+//      first).
+//   6. score_exact_kernel: users whose candidate buffer overflowed (or every user, in exact mode / for k > 128)
+//      are scored in float64 against the whole catalog.
+// The result is therefore always the exact float64 top-K; the tensor-core passes only prune. Both passes are
+// bound by reading the accumulator out of TMEM (128 KB per 128 x 256 step at ~100 B/clk/SM, measured), not by
+// the MMA (640 cycles per step at k = 64) or the epilogue math.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
 
 #include "common.cuh"
 
@@ -38,11 +49,18 @@ constexpr int BN = 256;          // items per MMA tile (= TMEM columns per accum
 constexpr int BK = 64;           // bf16 elements per K block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 #ifndef RFM_EPI_WARPS
-#define RFM_EPI_WARPS 8
+#define RFM_EPI_WARPS 16
 #endif
 constexpr int EPI_WARPS = RFM_EPI_WARPS;             // EPI_WARPS/4 per TMEM lane quarter; each owns a slice of a tile's columns
 constexpr int SCORE_THREADS = 128 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue
-constexpr int EPI_HALVES = EPI_WARPS / 4;
+#ifndef RFM_EPI_PINGPONG
+#define RFM_EPI_PINGPONG 0
+#endif
+// 0: every epilogue warp filters every accumulator (4 TMEM lane quarters x EPI_PARTS column ranges), so the MMA of
+//    step i + 1 overlaps the whole epilogue of step i; 1: two warp groups, one per accumulator stage
+constexpr int EPI_GROUPS = RFM_EPI_PINGPONG ? 2 : 1;
+constexpr int EPI_PARTS = EPI_WARPS / (4 * EPI_GROUPS);
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "8 or 16 epilogue warps");
 constexpr int MAX_KB = 2;        // k <= 128 on the tensor-core path
 constexpr int MAX_K = 120;
 
@@ -81,7 +99,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(200);
+    __nanosleep(32);
   }
 }
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1) {
@@ -103,20 +121,6 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, ui
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups of
 // 1024 B. Descriptor fields: start address >> 4 (bits 0-13), leading byte offset (16-29, unused for
 // swizzled K-major), stride byte offset = 1024 >> 4 (32-45), version 1 (46-47), layout SWIZZLE_128B = 2 (61-63).
@@ -130,102 +134,203 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// K-major operand tile without swizzle (canonical "interleave" layout): element (row, k) of a 16-bit type lives at
+// (row % 8) * 16 + (row / 8) * SBO + (k / 8) * LBO + (k % 8) * 2 bytes.
+__device__ __forceinline__ uint64_t umma_desc_interleaved(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
 // kind::f16 instruction descriptor: D = fp32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), both
 // K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
-struct FilterArgs {
-  const float *beta;       // [n_items_pad], -inf beyond n_items
-  int tile_begin;          // first tile of the catalog range being ranked (item-sharded calls)
-  int n_item_tiles;        // tiles of BN items in that range
-  int item_end;            // items >= item_end are not candidates (the last tile may run past the range)
-  int tiles_per_split;
-  int kc;                  // candidates kept per user per split
-  int n_users_pad;
-  float *cand_score;       // [n_splits][n_users_pad][kc]
-  int32_t *cand_item;
-  float *cand_tau;         // [n_splits][n_users_pad]  smallest kept score when the list is full, else -inf
-  float *glist_score;      // global candidate lists when kc > MAX_KC_SMEM: [grid][kc][BM]
-  int32_t *glist_item;
+struct PassArgs {
+  const __nv_bfloat16 *beta16;   // [n_items_pad / 8][2][8][8]: item terms as three bf16 parts, canonical operand order
+  int tile_begin;          // first 256-item tile of the catalog range being ranked (item-sharded calls)
+  int tile_stride;         // pass 1 visits every tile_stride-th tile (the sample), pass 2 every tile
+  int n_visit;             // tiles this pass visits
+  int tiles_per_split;     // visited tiles per CTA (blockIdx.y)
+  int item_end;            // end of the catalog range (padding columns of the last tile are never candidates)
+  int user_block0;         // first 128-user block of this chunk of users
+  int n_user_blocks;       // 128-user blocks in this chunk
+  int ub;                  // user blocks per CTA (<= PassSmem::UB)
+  int64_t n_groups;        // pass 1: group maxima per user row
+  float *gmax;             // pass 1 out: [chunk users (padded)][n_groups]
+  const float *tau;        // pass 2 in: [chunk users (padded)] collect threshold (+inf for padding rows)
+  int kc;                  // pass 2: capacity of a user's candidate buffer
+  uint32_t *cand_cnt;      // pass 2 out: [chunk users (padded)] candidates seen (may exceed kc: overflow)
+  int2 *cand;              // pass 2 out: [chunk users (padded)][kc] (item, approximate score bits)
 };
 
-// Candidate lists are two-level: kc entries in groups of 8, plus the minimum of every group (gm). An
-// insert finds the group holding the smallest kept score from the group minima, replaces that entry,
-// rescans only that group's 8 entries (independent loads) and refreshes the threshold tau = min(gm).
-// Everything is stored [index][row] so the 32 rows of a warp hit different banks / coalesce.
-// It has exactly one call site, inside a rolled loop (see the epilogue), so it costs no code in the hot path.
-__device__ __forceinline__ void insert_candidate(float s, int item, float *ls, int32_t *li, float *gm, int r, int n_groups,
-                                              float &tau) {
-  if (!(s > tau)) return;   // an earlier insert of the same 32-column slice may have raised the threshold
-  float m1 = gm[r], m2 = INFINITY;
-  int g1 = 0;
-  for (int g = 1; g < n_groups; ++g) {
-    const float x = gm[g * BM + r];
-    if (x < m1) {
-      m2 = m1;
-      m1 = x;
-      g1 = g;
-    } else if (x < m2) {
-      m2 = x;
-    }
-  }
-  float e[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) e[j] = ls[(g1 * 8 + j) * BM + r];
-  // smallest (to be replaced) and second smallest entry of the group, positions tracked in registers
-  float e1 = e[0], e2 = INFINITY;
-  int j1 = 0;
-#pragma unroll
-  for (int j = 1; j < 8; ++j) {
-    if (e[j] < e1) {
-      e2 = e1;
-      e1 = e[j];
-      j1 = j;
-    } else if (e[j] < e2) {
-      e2 = e[j];
-    }
-  }
-  const float gmin = fminf(s, e2);
-  ls[(g1 * 8 + j1) * BM + r] = s;
-  li[(g1 * 8 + j1) * BM + r] = item;
-  gm[g1 * BM + r] = gmin;
-  tau = fminf(gmin, m2);
+constexpr int WARP_COLS = BN / EPI_PARTS;      // columns of an accumulator one epilogue warp filters
+static_assert(WARP_COLS % 64 == 0, "an epilogue warp owns whole groups of 64 columns");
+constexpr int MAX_GCOLS = WARP_COLS >= 128 ? 128 : 64;   // widest pass-1 group one warp can produce alone
+
+// The item term beta_i is added by the tensor core as well: every step starts with one extra K = 16 MMA of a
+// constant operand [1 1 1 0 ... 0] against [b0 b1 b2 0 ... 0], beta split into three bf16 terms (exact to
+// 2^-24 |beta|), so the accumulator the epilogue reads already holds <A_u, C_i> + beta_i. Both small operands
+// use the no-swizzle K-major canonical layout (8-row x 16-byte core matrices; LBO = 128 B between the two K
+// halves, SBO = 256 B between 8-row groups); the item operand is stored in global memory in exactly that order,
+// so a tile's 8 KB arrive with one 1-D bulk copy.
+// A CTA keeps UB blocks of 128 users resident and runs every B tile it stages against all of them (the
+// accumulator stages alternate between consecutive (tile, user block) steps), so the catalog is streamed from L2
+// once per UB * 128 users: with one block per CTA the B-tile traffic, not the tensor pipe, bounds the pass.
+template <int KB>
+struct PassSmem {
+  static constexpr int UB = KB == 1 ? 4 : 2;
+  static constexpr int STAGES = KB == 1 ? 3 : 2;
+  static constexpr int A_BLOCK_BYTES = KB * BM * 128;
+  static constexpr int A_BYTES = UB * A_BLOCK_BYTES;
+  static constexpr int ONES_OFF = A_BYTES;                           // the [1 1 1 0 ...] operand, BM x 16 bf16
+  static constexpr int ONES_BYTES = BM * 32;
+  static constexpr int B_OFF = ONES_OFF + ONES_BYTES;
+  static constexpr int B_MAIN_BYTES = KB * BN * 128;
+  static constexpr int B_BETA_BYTES = BN * 32;                       // the item-term operand, BN x 16 bf16
+  static constexpr int B_STAGE_BYTES = B_MAIN_BYTES + B_BETA_BYTES;
+  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  static constexpr size_t BYTES = 1024 + BAR_OFF + 256;
+};
+
+// 1-D bulk copy global -> shared, completing on an mbarrier (the item terms of a tile ride with its B tile)
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-template <int KB>
-struct FilterSmem {
-  static constexpr int STAGES = (KB == 1 && EPI_WARPS <= 8) ? 3 : 2;
-  static constexpr int A_BYTES = KB * BM * 128;
-  static constexpr int B_STAGE_BYTES = KB * BN * 128;
-  static constexpr int BAR_OFF = A_BYTES + STAGES * B_STAGE_BYTES;
-  static constexpr int GM_OFF = BAR_OFF + 256;                 // group minima [EPI_HALVES][n_groups][BM] floats
-  __host__ __device__ static size_t list_off(int n_groups) { return GM_OFF + (size_t)EPI_HALVES * n_groups * BM * 4; }
-  // lists [EPI_HALVES][kc][BM] of (float score, int32 item) when they live in shared memory
-  static size_t bytes(int n_groups, int kc_smem) {
-    return 1024 + list_off(n_groups) + (size_t)EPI_HALVES * kc_smem * BM * 8;
-  }
-};
+__device__ __forceinline__ void tc_ld_issue_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are listed so that no use of them is scheduled above it
+__device__ __forceinline__ void tc_ld_wait_x32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+// Scheduling fence: the values listed are complete before anything after this point is issued. Used to finish
+// the math of one slice before the TMEM load that overwrites its registers' twin buffer is issued.
+__device__ __forceinline__ void pin4(float (&m)[4]) {
+  asm volatile("" : "+f"(m[0]), "+f"(m[1]), "+f"(m[2]), "+f"(m[3])::"memory");
+}
+// three-input max (FMNMX3): one instruction per three elements
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
-template <int KB>
+// m8[i] = max of columns 8i .. 8i+7 of a 32-column slice of the accumulator (which already includes beta)
+__device__ __forceinline__ void slice_max(const uint32_t (&v)[32], float (&m8)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    m8[i] = max3(max3(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]), __uint_as_float(v[8 * i + 2])),
+                 max3(__uint_as_float(v[8 * i + 3]), __uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                 fmaxf(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+}
+
+// pass 1: write the group maxima of one 32-column slice (groups of GCOLS <= 32 columns)
+template <int GCOLS>
+__device__ __forceinline__ void store_group_max(float *__restrict__ dst, const float (&m8)[4]) {
+  if (GCOLS == 8) {
+    *reinterpret_cast<float4 *>(dst) = make_float4(m8[0], m8[1], m8[2], m8[3]);
+  } else if (GCOLS == 16) {
+    *reinterpret_cast<float2 *>(dst) = make_float2(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  } else {
+    *dst = fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]);
+  }
+}
+
+// pass 2: append every item of a slice whose approximate score reaches the user's threshold (cold path). Only
+// the 8-column sub-groups whose maximum passes are walked: typically one lane and one sub-group per call.
+// The slot comes from a global atomic whose round trip (~1 us) must not stall the warp: an append only issues
+// the atomic and parks (slot, row, item); the store happens at the thread's next append (or at the end).
+struct PendingAppend {
+  uint32_t pos;
+  int row, item;      // item < 0: nothing pending
+  float score;
+};
+__device__ __forceinline__ void flush_append(const PendingAppend &p, int kc, int2 *__restrict__ cand) {
+  if (p.item >= 0 && p.pos < (uint32_t)kc) cand[(size_t)p.row * kc + p.pos] = make_int2(p.item, __float_as_int(p.score));
+}
+__device__ __forceinline__ void collect_slice(const uint32_t (&v)[32], const float (&m8)[4], float tau, int item_first,
+                                              int item_end, int kc, int row, uint32_t *__restrict__ cand_cnt,
+                                              int2 *__restrict__ cand, PendingAppend &pend) {
+  // warp-uniform control flow: a sub-group of 8 columns is examined only if some lane's maximum over it passes,
+  // and then every lane builds its 8-bit pass mask without branching (all but one or two lanes get zero)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (__any_sync(FULL, m8[i] >= tau)) {
+      uint32_t mask = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mask |= (__uint_as_float(v[8 * i + j]) >= tau ? 1u : 0u) << j;
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        uint32_t bits = v[8 * i];
+#pragma unroll
+        for (int jj = 1; jj < 8; ++jj)
+          if (j == jj) bits = v[8 * i + jj];
+        const int item = item_first + 8 * i + j;
+        if (item < item_end) {
+          flush_append(pend, kc, cand);
+          pend.pos = atomicAdd(cand_cnt + row, 1u);
+          pend.row = row;
+          pend.item = item;
+          pend.score = __uint_as_float(bits);
+        }
+      }
+    }
+}
+
+// The tensor-core pass. PASS 0 (the sample): per user row, the maximum approximate score of every group of GCOLS
+// items of the visited tiles goes to gmax. PASS 1 (collect): every item whose approximate score reaches the
+// user's threshold is appended to the user's candidate buffer. Neither pass keeps a sorted list: thread r
+// streams row r of the accumulator through FADD2 + FMNMX3 (one instruction per element) and the append
+// happens for a handful of items per user over the whole catalog.
+template <int KB, int PASS, int GCOLS>
 __global__ void __launch_bounds__(SCORE_THREADS, 1)
-score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_c,
-                    const FilterArgs a) {
-  using L = FilterSmem<KB>;
+score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_c,
+                  const PassArgs a) {
+  using L = PassSmem<KB>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char *sA = smem;
-  unsigned char *sB = smem + L::A_BYTES;
+  unsigned char *sOnes = smem + L::ONES_OFF;
+  unsigned char *sB = smem + L::B_OFF;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::BAR_OFF);
   uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
   uint64_t *afull = bars + 2 * STAGES + 4;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int user_block = blockIdx.x, split = blockIdx.y;
-  const int tile0 = a.tile_begin + split * a.tiles_per_split;
-  int n_tiles = a.n_item_tiles - split * a.tiles_per_split;
+  constexpr int UB = L::UB;
+  const int split = blockIdx.y;
+  const int block0 = blockIdx.x * a.ub;                 // first user block of this CTA, inside the chunk
+  const int nh = min(a.ub, a.n_user_blocks - block0);   // user blocks this CTA holds
+  const int visit0 = split * a.tiles_per_split;       // index of this CTA's first visited tile
+  int n_tiles = a.n_visit - visit0;
   if (n_tiles > a.tiles_per_split) n_tiles = a.tiles_per_split;
   if (n_tiles < 0) n_tiles = 0;
+  auto tile_of = [&](int it) { return a.tile_begin + (visit0 + it) * a.tile_stride; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -234,7 +339,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull + s, 1);
-      mbar_init(tempty + s, EPI_WARPS);     // one arrival per epilogue warp
+      mbar_init(tempty + s, EPI_WARPS / EPI_GROUPS);   // one arrival per epilogue warp serving the stage
     }
     mbar_init(afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,6 +348,17 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // the constant operand: row r = [1 1 1 0 ... 0] (16 bf16), canonical no-swizzle K-major layout
+  for (int i = threadIdx.x; i < BM * 2; i += SCORE_THREADS) {
+    const int row = i >> 1, khalf = i & 1;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (khalf == 0) {
+      w.x = 0x3F803F80u;   // bf16 1.0, 1.0
+      w.y = 0x00003F80u;   // bf16 1.0, 0.0
+    }
+    *reinterpret_cast<uint4 *>(sOnes + (row >> 3) * 256 + khalf * 128 + (row & 7) * 16) = w;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes, read by the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -250,15 +366,20 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
-      mbar_expect_tx(afull, L::A_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * BM * 128, &tmap_a, afull, kb * BK, user_block * BM);
+      mbar_expect_tx(afull, nh * L::A_BLOCK_BYTES);
+      for (int h = 0; h < nh; ++h)
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(sA + h * L::A_BLOCK_BYTES + kb * BM * 128, &tmap_a, afull, kb * BK,
+                      (a.user_block0 + block0 + h) * BM);
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait_relaxed(empty + s, ph ^ 1);
         mbar_expect_tx(full + s, L::B_STAGE_BYTES);
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sB + s * L::B_STAGE_BYTES + kb * BN * 128, &tmap_c, full + s, kb * BK, (tile0 + it) * BN);
+          tma_load_2d(sB + s * L::B_STAGE_BYTES + kb * BN * 128, &tmap_c, full + s, kb * BK, tile_of(it) * BN);
+        bulk_load_1d(sB + s * L::B_STAGE_BYTES + L::B_MAIN_BYTES, a.beta16 + (size_t)tile_of(it) * BN * 16,
+                     L::B_BETA_BYTES, full + s);
       }
     }
   } else if (warp == 1) {
@@ -267,93 +388,99 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        const int acc = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait_relaxed(tempty + acc, aph ^ 1);
         mbar_wait_relaxed(full + s, ph);
-        tc_fence_after();
+        for (int h = 0; h < nh; ++h) {
+          const int step = it * nh + h;
+          const int acc = step & 1;
+          const uint32_t aph = (step >> 1) & 1;
+          mbar_wait_relaxed(tempty + acc, aph ^ 1);
+          tc_fence_after();
+          // accumulator = 1 * beta (overwrite), then += <A_u, C_i> over the K blocks
+          tc_mma_bf16(tmem_base + acc * BN, umma_desc_interleaved(smem_u32(sOnes), 128, 256),
+                      umma_desc_interleaved(smem_u32(sB + s * L::B_STAGE_BYTES + L::B_MAIN_BYTES), 128, 256),
+                      UMMA_IDESC, 0u);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t a_base = smem_u32(sA + kb * BM * 128);
-          const uint32_t b_base = smem_u32(sB + s * L::B_STAGE_BYTES + kb * BN * 128);
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t a_base = smem_u32(sA + h * L::A_BLOCK_BYTES + kb * BM * 128);
+            const uint32_t b_base = smem_u32(sB + s * L::B_STAGE_BYTES + kb * BN * 128);
 #pragma unroll
-          for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom
-            tc_mma_bf16(tmem_base + acc * BN, umma_desc_sw128(a_base + k4 * 32), umma_desc_sw128(b_base + k4 * 32),
-                        UMMA_IDESC, (kb | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom
+              tc_mma_bf16(tmem_base + acc * BN, umma_desc_sw128(a_base + k4 * 32), umma_desc_sw128(b_base + k4 * 32),
+                          UMMA_IDESC, 1u);
+            }
           }
+          tc_commit(tfull + acc);    // the accumulator is complete
         }
-        tc_commit(empty + s);      // the B stage is free once these MMAs have read it
-        tc_commit(tfull + acc);    // the accumulator is complete
+        tc_commit(empty + s);        // the B stage is free once the MMAs of every user block have read it
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread r keeps the kc best (score, item) pairs of user row r =====
+    // ===== epilogue: thread r streams the scores of row r of every user block =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;       // which half of every tile's columns this warp filters
+    const int group = EPI_GROUPS == 2 ? ((warp - 4) >> 2) & 1 : 0;        // accumulator stage this warp serves
+    const int part = EPI_GROUPS == 2 ? (warp - 4) >> 3 : (warp - 4) >> 2;  // its range of the accumulator's columns
     const int r = q * 32 + lane;
-    const int kc = a.kc;
-    const int n_groups = kc >> 3;
-    float *gm = reinterpret_cast<float *>(smem + L::GM_OFF) + (size_t)half * n_groups * BM;
-    float *ls;
-    int32_t *li;
-    if (a.glist_score == nullptr) {
-      unsigned char *lists = smem + L::list_off(n_groups);
-      ls = reinterpret_cast<float *>(lists) + (size_t)half * kc * BM;
-      li = reinterpret_cast<int32_t *>(lists + (size_t)EPI_HALVES * kc * BM * 4) + (size_t)half * kc * BM;
-    } else {
-      const size_t cta = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * EPI_HALVES + half;
-      ls = a.glist_score + cta * kc * BM;
-      li = a.glist_item + cta * kc * BM;
-    }
-    for (int j = 0; j < kc; ++j) {
-      ls[j * BM + r] = -INFINITY;
-      li[j * BM + r] = -1;
-    }
-    for (int g = 0; g < n_groups; ++g) gm[g * BM + r] = -INFINITY;
-    float tau = -INFINITY;                  // smallest kept score
-    for (int it = 0; it < n_tiles; ++it) {
-      const int acc = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
+    PendingAppend pend;
+    pend.pos = 0u;
+    pend.row = 0;
+    pend.item = -1;
+    pend.score = 0.f;
+    float tau_h[UB];
+#pragma unroll
+    for (int h = 0; h < UB; ++h)
+      tau_h[h] = (PASS == 1 && h < nh) ? a.tau[(size_t)(block0 + h) * BM + r] : INFINITY;
+    for (int step = group; step < n_tiles * nh; step += EPI_GROUPS) {
+      const int it = step / nh, h = step - it * nh;
+      const int acc = step & 1;
+      const uint32_t aph = (step >> 1) & 1;
+      const size_t row = (size_t)(block0 + h) * BM + r;      // row inside this chunk of users
+      float tau = tau_h[0];
+#pragma unroll
+      for (int hh = 1; hh < UB; ++hh)
+        if (h == hh) tau = tau_h[hh];
+      float *grow = PASS == 0 ? a.gmax + row * a.n_groups : nullptr;
       mbar_wait(tfull + acc, aph);
       tc_fence_after();
-      const int item0 = (tile0 + it) * BN;
+      const int item0 = tile_of(it) * BN;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const int c_begin = part * WARP_COLS;
+      uint32_t v0[32], v1[32];
+      float gacc = -INFINITY;
+      tc_ld_issue_x32(tbase + c_begin, v0);
 #pragma unroll 1
-      for (int c = half * (BN / EPI_HALVES); c < (half + 1) * (BN / EPI_HALVES); c += 32) {
-        uint32_t v[32];
-        tc_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, v);
-        const float4 *b4 = reinterpret_cast<const float4 *>(a.beta + item0 + c);
-        // four independent partial masks: a single "pass |= ..." chain is 32 dependent instructions long
-        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b = __ldg(b4 + j4);
-          p0 |= (__uint_as_float(v[j4 * 4 + 0]) + b.x > tau ? 1u : 0u) << (j4 * 4 + 0);
-          p1 |= (__uint_as_float(v[j4 * 4 + 1]) + b.y > tau ? 1u : 0u) << (j4 * 4 + 1);
-          p2 |= (__uint_as_float(v[j4 * 4 + 2]) + b.z > tau ? 1u : 0u) << (j4 * 4 + 2);
-          p3 |= (__uint_as_float(v[j4 * 4 + 3]) + b.w > tau ? 1u : 0u) << (j4 * 4 + 3);
+      for (int c = c_begin; c < c_begin + WARP_COLS; c += 64) {
+        // software pipeline over 32-column slices: the next slice's TMEM load is in flight during the math
+        float m0[4], m1[4];
+        tc_ld_wait_x32(v0);
+        tc_ld_issue_x32(tbase + c + 32, v1);
+        slice_max(v0, m0);
+        pin4(m0);
+        if (PASS == 1) {
+          const float mx = fmaxf(max3(m0[0], m0[1], m0[2]), m0[3]);
+          if (__any_sync(FULL, mx >= tau))
+            collect_slice(v0, m0, tau, item0 + c, a.item_end, a.kc, (int)row, a.cand_cnt, a.cand, pend);
         }
-        uint32_t pass = (p0 | p1) | (p2 | p3);
-        // Rare after warm-up. Every lane walks ITS OWN passing columns (lanes pass at different columns, so
-        // this takes max-over-lanes iterations, usually one, instead of one iteration per column). The
-        // lane's score is pulled out of the register tile with a select chain (no run-time indexed array).
-        while (__any_sync(FULL, pass != 0)) {
-          const int j = pass ? __ffs(pass) - 1 : 0;
-          // v[j] for a run-time j without a run-time indexed array: 5-level select tree on the bits of j
-          uint32_t t16[16], t8[8], t4[4], t2[2];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) t2[i] = (j & 8) ? t4[2 * i + 1] : t4[2 * i];
-          const float vj = __uint_as_float((j & 16) ? t2[1] : t2[0]);
-          if (pass) {
-            pass &= pass - 1;
-            if (item0 + c + j < a.item_end)
-              insert_candidate(vj + __ldg(a.beta + item0 + c + j), item0 + c + j, ls, li, gm, r, n_groups, tau);
+        tc_ld_wait_x32(v1);
+        if (c + 64 < c_begin + WARP_COLS) tc_ld_issue_x32(tbase + c + 64, v0);
+        slice_max(v1, m1);
+        pin4(m1);
+        if (PASS == 1) {
+          const float mx = fmaxf(max3(m1[0], m1[1], m1[2]), m1[3]);
+          if (__any_sync(FULL, mx >= tau))
+            collect_slice(v1, m1, tau, item0 + c + 32, a.item_end, a.kc, (int)row, a.cand_cnt, a.cand, pend);
+        }
+        if (PASS == 0) {
+          float *dst = grow + (int64_t)(visit0 + it) * (BN / GCOLS) + c / GCOLS;
+          if (GCOLS == 128 && MAX_GCOLS >= 128) {         // a group spans two iterations of this loop
+            const float m = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
+            if ((c & 64) == 0) gacc = m;
+            else *dst = fmaxf(gacc, m);
+          } else if (GCOLS == 64) {
+            *dst = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
+          } else {
+            store_group_max<GCOLS>(dst, m0);
+            store_group_max<GCOLS>(dst + 32 / GCOLS, m1);
           }
         }
       }
@@ -361,13 +488,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + acc);
     }
-    // hand the list to the exact re-scoring pass
-    const size_t row = ((size_t)split * EPI_HALVES + half) * a.n_users_pad + (size_t)user_block * BM + r;
-    for (int j = 0; j < kc; ++j) {
-      a.cand_score[row * kc + j] = ls[j * BM + r];
-      a.cand_item[row * kc + j] = li[j * BM + r];
-    }
-    a.cand_tau[row] = tau;
+    if (PASS == 1) flush_append(pend, a.kc, a.cand);
   }
   tc_fence_before();
   __syncthreads();
@@ -377,29 +498,144 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// eps(u) >= |approximate score - exact ranking score| for every item, where the approximate score is what the
+// tensor core accumulates, sum_f bf16(a_f) bf16(c_f) + b0 + b1 + b2, and the exact one is <a, c> + beta:
+//   operands:      |sum a^c^ - sum ac| <= ||a^|| ||c^ - c|| + ||a^ - a|| ||c||   (Cauchy-Schwarz; the residual
+//                  norms are computed from the data, not from the worst-case 2^-8 relative rounding error)
+//   beta split:    |b0 + b1 + b2 - beta| <= 2^-24 |beta|
+//   accumulation:  n = kpad + 16 products (exact in float32) summed with at most one ulp of error each
+//                  (the tensor core may truncate): <= n 2^-23 (||a^|| ||c^|| + |beta|); doubled for margin.
+__device__ __forceinline__ double score_error_bound(double a_norm, double a_res, double c_norm_max, double c_res_max,
+                                                    double beta_abs_max, int kpad) {
+  const double a_hat = a_norm + a_res, c_hat = c_norm_max + c_res_max;
+  const double operands = a_hat * c_res_max + a_res * c_norm_max;
+  const double accumulation = ldexp((double)(2 * (kpad + 16)), -23) * (a_hat * c_hat + beta_abs_max);
+  return (operands + accumulation + ldexp(beta_abs_max, -23)) * (1.0 + 0x1p-20) + 1e-300;
+}
+
+// One warp per user: the K-th largest group maximum of the sample is a lower bound on the user's K-th best
+// approximate score (K different items reach it). tau = that bound - 2 eps: every item whose EXACT score can
+// reach the exact K-th best has an approximate score >= tau (eps bounds |approximate - exact|).
+constexpr int SELECT_WARPS = 4;
+// NJ > 0: every lane keeps its NJ keys (groups lane, lane + 32, ...) in registers; NJ = 0: keys staged in shared memory
+template <int NJ>
+__global__ void __launch_bounds__(SELECT_WARPS * 32)
+score_threshold_kernel(const float *__restrict__ gmax, int64_t n_groups, int fold, int64_t n_rows,
+                       int64_t n_users_chunk, int K,
+                       const double *__restrict__ a_norm, const double *__restrict__ a_res,
+                       const double *__restrict__ c_norm_max, const double *__restrict__ c_res_max,
+                       const double *__restrict__ beta_abs_max, int kpad, float *__restrict__ tau,
+                       float *__restrict__ eps_out, uint32_t *__restrict__ cand_cnt) {
+  extern __shared__ __align__(16) unsigned char th_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t *skey = reinterpret_cast<uint32_t *>(th_smem) + (size_t)wid * (NJ > 0 ? 0 : n_groups);
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto to_key = [](float x) {              // order-preserving uint key
+    const uint32_t bits = __float_as_uint(x);
+    return bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+  };
+  for (int64_t u = gw; u < n_rows; u += nw) {
+    if (lane == 0) cand_cnt[u] = 0u;
+    if (u >= n_users_chunk) {           // padding rows never collect
+      if (lane == 0) tau[u] = INFINITY;
+      continue;
+    }
+    // fold == 2: adjacent stored groups are merged on load (the maximum of two group maxima is the maximum of
+    // the doubled group), halving the keys when the sample holds more groups than the threshold needs
+    const float *g = gmax + u * n_groups * fold;
+    auto group_max = [&](int64_t i) {
+      if (fold == 1) return g[i];
+      const float2 p = *reinterpret_cast<const float2 *>(g + 2 * i);
+      return fmaxf(p.x, p.y);
+    };
+    uint32_t key[NJ > 0 ? NJ : 1];
+    if (NJ > 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) key[j] = lane + 32 * j < n_groups ? to_key(group_max(lane + 32 * j)) : 0u;
+    } else {
+      for (int64_t i = lane; i < n_groups; i += 32) skey[i] = to_key(group_max(i));
+      __syncwarp();
+    }
+    float t0 = -INFINITY;
+    if (n_groups >= K) {
+      uint32_t thr = 0u;                // bisection on the key bits for the K-th largest key
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand_thr = thr | (1u << bit);
+        int cnt = 0;
+        if (NJ > 0) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) cnt += key[j] >= cand_thr;
+        } else {
+          for (int64_t i = lane; i < n_groups; i += 32) cnt += skey[i] >= cand_thr;
+        }
+        cnt = __reduce_add_sync(FULL, cnt);
+        if (cnt >= K) thr = cand_thr;
+      }
+      const uint32_t bits = (thr & 0x80000000u) ? (thr ^ 0x80000000u) : ~thr;
+      t0 = __uint_as_float(bits);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const double eps = score_error_bound(a_norm[u], a_res[u], *c_norm_max, *c_res_max, *beta_abs_max, kpad);
+      tau[u] = t0 > -INFINITY ? __double2float_rd((double)t0 - 2.0 * eps) : -INFINITY;
+      eps_out[u] = __double2float_ru(eps);
+    }
+  }
+}
+
 // ---- operand preparation ---------------------------------------------------------------------------------
-// float64 [rows][k] -> bf16 [rows_pad][kpad] (zero padded) and float64 row norms
+// float64 [rows][k] -> bf16 [rows_pad][kpad] (zero padded), float64 row norms and the norms of the rounding
+// residuals row - bf16(row) (what the error bound of the tensor-core scores is made of)
 __global__ void to_bf16_kernel(const double *__restrict__ in, int64_t rows, int k, int64_t rows_pad, int kpad,
-                               __nv_bfloat16 *__restrict__ out, double *__restrict__ norms) {
+                               __nv_bfloat16 *__restrict__ out, double *__restrict__ norms,
+                               double *__restrict__ res_norms) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t rrow = gw; rrow < rows_pad; rrow += nw) {
-    double s = 0.0;
+    double s = 0.0, d = 0.0;
     for (int f = lane; f < kpad; f += 32) {
       const double v = (rrow < rows && f < k) ? in[rrow * k + f] : 0.0;
-      out[rrow * kpad + f] = __double2bfloat16(v);
+      const __nv_bfloat16 h = __double2bfloat16(v);
+      out[rrow * kpad + f] = h;
+      const double e = v - (double)__bfloat162float(h);
       s += v * v;
+      d += e * e;
     }
     s = warp_sum(s);
-    if (lane == 0 && rrow < rows) norms[rrow] = sqrt(s);
+    d = warp_sum(d);
+    if (lane == 0 && rrow < rows) {
+      norms[rrow] = sqrt(s) * (1.0 + 0x1p-40);        // rounded up: these feed an upper bound
+      res_norms[rrow] = sqrt(d) * (1.0 + 0x1p-40);
+    }
   }
 }
 
-__global__ void beta_f32_kernel(const double *__restrict__ beta, int64_t n_items, int64_t n_pad,
-                                float *__restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = i < n_items ? static_cast<float>(beta ? beta[i] : 0.0) : -INFINITY;
+// item terms as a bf16 MMA operand: beta = b0 + b1 + b2 (bf16 each, residual <= 2^-24 |beta|) in columns 0..2 of a
+// 16-wide row, rows stored in the canonical no-swizzle K-major order (see PassSmem). Items beyond the catalog
+// get -inf so that they never reach a threshold.
+__global__ void beta_operand_kernel(const double *__restrict__ beta, int64_t n_items, int64_t n_pad,
+                                    __nv_bfloat16 *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16 *row = out + (i >> 3) * 128 + (i & 7) * 8;      // first K half; the second is 64 elements on
+    const __nv_bfloat16 zero = __float2bfloat16(0.f);
+    __nv_bfloat16 b0 = zero, b1 = zero, b2 = zero;
+    if (i >= n_items) {
+      b0 = __float2bfloat16(-INFINITY);
+    } else if (beta) {
+      const double v = beta[i];
+      b0 = __double2bfloat16(v);
+      const double r1 = v - (double)__bfloat162float(b0);
+      b1 = __double2bfloat16(r1);
+      b2 = __double2bfloat16(r1 - (double)__bfloat162float(b1));
+    }
+    row[0] = b0;
+    row[1] = b1;
+    row[2] = b2;
+    for (int k = 3; k < 8; ++k) row[k] = zero;
+    for (int k = 0; k < 8; ++k) row[64 + k] = zero;
+  }
 }
 
 __global__ void max_reduce_kernel(const double *__restrict__ v, int64_t n, double *__restrict__ out) {
@@ -440,6 +676,31 @@ __device__ __forceinline__ double warp_exact_score(const ExactArgs &e, int64_t u
   return ((warp_exact_dot(e, u, i, lane) + (e.alpha ? e.alpha[u] : 0.0)) + (e.beta ? e.beta[i] : 0.0)) + e.bias;
 }
 
+// The same value computed by ONE lane (32 candidates of a user are re-scored in parallel, one per lane): 32
+// strided partial sums, each the same fma chain a lane of warp_exact_dot runs, combined in the butterfly's order
+// (lane 0's view of it: x[l] + x[l + o] for o = 16, 8, 4, 2, 1). au is the user's row staged in shared memory.
+__device__ __forceinline__ double lane_exact_dot(const double *__restrict__ au, const double *__restrict__ ci, int k) {
+  double x[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) x[l] = 0.0;
+  for (int f0 = 0; f0 < k; f0 += 32) {
+    if (f0 + 32 <= k) {
+#pragma unroll
+      for (int l = 0; l < 32; ++l) x[l] += au[f0 + l] * ci[f0 + l];
+    } else {
+#pragma unroll
+      for (int l = 0; l < 32; ++l)
+        if (f0 + l < k) x[l] += au[f0 + l] * ci[f0 + l];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int l = 0; l < o; ++l) x[l] += x[l + o];
+  }
+  return x[0];
+}
+
 struct Best {
   double s;
   int item;   // -1 = none
@@ -460,122 +721,121 @@ __device__ __forceinline__ Best warp_best(Best b) {
   return b;
 }
 
-// one warp per user: exact scores of the candidates, exact top-K, and the pruning proof. The warp's
+// one warp per user: exact float64 scores of the collected candidates and the exact top-K among them with the
+// canonical tie rule. A user whose buffer overflowed goes to the exact fallback instead. The warp's
 // candidates (item, exact score) are staged in shared memory so the K selection rounds never leave the SM.
 constexpr int RESCORE_WARPS = 4;
 
 __global__ void __launch_bounds__(RESCORE_WARPS * 32)
-score_rescore_kernel(const ExactArgs e, const float *__restrict__ cand_score, const int32_t *__restrict__ cand_item,
-                     const float *__restrict__ cand_tau,
-                     int n_lists, int n_users_pad, int kc, int K, const double *__restrict__ a_norm,
-                     const double *__restrict__ c_norm_max, const double *__restrict__ beta_abs_max,
+score_rescore_kernel(const ExactArgs e, int64_t user0, int64_t n_users_chunk, const uint32_t *__restrict__ cand_cnt,
+                     const int2 *__restrict__ cand, const float *__restrict__ eps, int kc, int K,
                      int32_t *__restrict__ out_items, double *__restrict__ out_scores, int32_t *__restrict__ fail_list,
-                     uint32_t *__restrict__ n_fail) {
+                     uint32_t *__restrict__ n_fail, unsigned long long *__restrict__ n_cand_total) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n_cand = n_lists * kc;
-  double *ex = reinterpret_cast<double *>(rs_smem) + (size_t)wid * n_cand;
-  int32_t *it = reinterpret_cast<int32_t *>(rs_smem + (size_t)RESCORE_WARPS * n_cand * 8) + (size_t)wid * n_cand;
+  double *ex = reinterpret_cast<double *>(rs_smem) + (size_t)wid * kc;
+  double *au = reinterpret_cast<double *>(rs_smem) + (size_t)RESCORE_WARPS * kc + (size_t)wid * e.k;
+  int32_t *it = reinterpret_cast<int32_t *>(rs_smem + (size_t)RESCORE_WARPS * (kc + e.k) * 8) + (size_t)wid * 2 * kc;
+  uint32_t *key = reinterpret_cast<uint32_t *>(it + kc);
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t u = gw; u < e.n_users; u += nw) {
-    // 1. stage (item, approximate score as an order-preserving uint key) of every list entry
-    uint32_t *key = reinterpret_cast<uint32_t *>(ex);     // the float64 slots are reused: keys first, scores later
-    int n_valid = 0;
-    for (int c = lane; c < n_cand; c += 32) {
-      const int sp = c / kc, j = c - sp * kc;
-      const size_t at = ((size_t)sp * n_users_pad + u) * kc + j;
-      const int item = cand_item[at];
-      const bool ok = item >= e.item_begin && item < e.item_end;
-      const uint32_t bits = __float_as_uint(cand_score[at]);
-      it[c] = ok ? item : -1;
-      key[2 * c] = ok ? (bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u)) : 0u;
-      n_valid += ok;
+  for (int64_t row = gw; row < n_users_chunk; row += nw) {
+    const int64_t u = user0 + row;
+    const uint32_t cnt = cand_cnt[row];
+    if (lane == 0) atomicAdd(n_cand_total, (unsigned long long)cnt);
+    if (cnt > (uint32_t)kc) {            // more candidates than the buffer holds: rank this user exactly
+      if (lane == 0) fail_list[atomicAdd(n_fail, 1u)] = (int32_t)u;
+      continue;
     }
-    n_valid = __reduce_add_sync(FULL, n_valid);
+    int n_cand = (int)cnt;
+    for (int f = lane; f < e.k; f += 32) au[f] = e.A[u * e.k + f];
+    for (int c = lane; c < n_cand; c += 32) {
+      const int2 v = cand[row * kc + c];
+      const uint32_t bits = (uint32_t)v.y;
+      it[c] = v.x;
+      key[c] = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);      // order-preserving uint key
+    }
     __syncwarp();
-    // 2. only the kc best approximate scores of the merged lists can matter; their kc-th value is a valid
-    //    pruning threshold (it is >= every list's own threshold). Find it by bisection on the key bits.
-    uint32_t thr = 0u;
-    float tau_max = -INFINITY;
-    if (n_valid > kc) {
+    if (n_cand > K) {
+      // The K-th largest approximate score over ALL collected items is a tighter bound than the sampled
+      // threshold: only candidates within 2 eps of it can reach the exact top-K. Bisection on the key bits.
+      uint32_t thr = 0u;
       for (int bit = 31; bit >= 0; --bit) {
         const uint32_t cand_thr = thr | (1u << bit);
-        int cnt = 0;
-        for (int c = lane; c < n_cand; c += 32) cnt += (it[c] >= 0 && key[2 * c] >= cand_thr);
-        cnt = __reduce_add_sync(FULL, cnt);
-        if (cnt >= kc) thr = cand_thr;       // at least kc keys are >= cand_thr: the kc-th largest is too
+        int above = 0;
+        for (int c = lane; c < n_cand; c += 32) above += key[c] >= cand_thr;
+        above = __reduce_add_sync(FULL, above);
+        if (above >= K) thr = cand_thr;
       }
       const uint32_t bits = (thr & 0x80000000u) ? (thr ^ 0x80000000u) : ~thr;
-      tau_max = __uint_as_float(bits);
-    } else {
-      // every list entry is kept; items outside the lists are bounded by the lists' own thresholds
-      for (int sp = lane; sp < n_lists; sp += 32) tau_max = fmaxf(tau_max, cand_tau[(size_t)sp * n_users_pad + u]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tau_max = fmaxf(tau_max, __shfl_xor_sync(FULL, tau_max, o));
+      const float cut = __double2float_rd((double)__uint_as_float(bits) - 2.0 * (double)eps[row]);
+      const uint32_t cbits = __float_as_uint(cut);
+      const uint32_t cut_key = cbits ^ ((cbits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+      int kept = 0;                      // compact the survivors to the front of it[]
+      for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        const int c = c0 + lane;
+        const bool keep = c < n_cand && key[c] >= cut_key;
+        const int item = c < n_cand ? it[c] : -1;
+        const uint32_t m = __ballot_sync(FULL, keep);
+        __syncwarp();
+        if (keep) it[kept + __popc(m & ((1u << lane) - 1u))] = item;
+        kept += __popc(m);
+        __syncwarp();
+      }
+      n_cand = kept;
     }
-    for (int c = lane; c < n_cand; c += 32)
-      if (it[c] >= 0 && key[2 * c] < thr) it[c] = -1;
-    __syncwarp();
-    // 3. exact float64 scores of the survivors, one candidate at a time, all lanes on its dot product
-    for (int c = 0; c < n_cand; ++c) {
+    const double alpha_u = e.alpha ? e.alpha[u] : 0.0;
+    for (int c = lane; c < n_cand; c += 32) {        // a candidate per lane
       const int item = it[c];
-      if (item < 0) continue;
-      const double sc = warp_exact_score(e, u, item, lane);
-      __syncwarp();
-      if (lane == 0) ex[c] = sc;
+      // outer association of the reference: (((dot + alpha_u) + beta_i) + bias), src/mf.py:165-170
+      ex[c] = ((lane_exact_dot(au, e.C + (size_t)item * e.k, e.k) + alpha_u) + (e.beta ? e.beta[item] : 0.0)) + e.bias;
     }
     __syncwarp();
-    Best last;
-    last.s = 0.0;
-    last.item = -2;
-    for (int r = 0; r < K; ++r) {
+    // rank by counting: the canonical order is a strict total order (items are distinct), so the number of
+    // candidates ranking before c is c's position; positions below K are the answer
+    for (int c = lane; c < n_cand; c += 32) {
       Best mine;
-      mine.s = 0.0;
-      mine.item = -1;
-      for (int c = lane; c < n_cand; c += 32) {
-        Best b;
-        b.item = it[c];
-        if (b.item < 0) continue;
-        b.s = ex[c];
-        const bool below = last.item == -2 || ranks_before(last, b);
-        if (below && ranks_before(b, mine)) mine = b;
+      mine.s = ex[c];
+      mine.item = it[c];
+      int rank = 0;
+      for (int d = 0; d < n_cand; ++d) {
+        Best other;
+        other.s = ex[d];
+        other.item = it[d];
+        rank += ranks_before(other, mine) ? 1 : 0;
       }
-      last = warp_best(mine);
-      if (lane == 0) {
-        out_items[u * K + r] = last.item;
-        out_scores[u * K + r] = last.item >= 0 ? last.s : -INFINITY;
-      }
-      if (last.item < 0) {   // fewer than K candidates: pad the rest
-        for (int rr = r + 1 + lane; rr < K; rr += 32) {
-          out_items[u * K + rr] = -1;
-          out_scores[u * K + rr] = -INFINITY;
-        }
-        break;
+      if (rank < K) {
+        out_items[u * K + rank] = mine.item;
+        out_scores[u * K + rank] = mine.s;
       }
     }
-    // Every item outside the lists has approximate ranking score (<A_u, C_i> + beta_i, what the tensor-core
-    // pass sees) <= tau_max, hence exact ranking score <= tau_max + eps. Compare with the K-th item's exact
-    // ranking score (alpha_u and the bias are constant per user and do not affect the order).
-    double kth_rank = -INFINITY;
-    if (last.item >= 0) kth_rank = warp_exact_dot(e, u, last.item, lane) + (e.beta ? e.beta[last.item] : 0.0);
-    const double eps = ldexp(a_norm[u] * *c_norm_max, -7) + ldexp(fabs((double)tau_max) + *beta_abs_max, -20);
-    const bool complete = tau_max == -INFINITY;          // lists never filled: every item is a candidate
-    const bool proven = complete || (last.item >= 0 && kth_rank > (double)tau_max + eps);
-    if (!proven && lane == 0) fail_list[atomicAdd(n_fail, 1u)] = (int32_t)u;
+    for (int r = n_cand + lane; r < K; r += 32) {    // fewer than K items in the range: pad the rest
+      out_items[u * K + r] = -1;
+      out_scores[u * K + r] = -INFINITY;
+    }
     __syncwarp();
   }
 }
 
-// one CTA per user: exact top-K over the whole catalog range (fallback and exact mode)
-__global__ void __launch_bounds__(256)
+// one CTA per user: exact top-K over the whole catalog range (fallback and exact mode). The float64 scores of
+// the range are computed once (a warp per item) into the CTA's scratch row, then K selection rounds read them back.
+constexpr int EXACT_THREADS = 256;
+__global__ void __launch_bounds__(EXACT_THREADS)
 score_exact_kernel(const ExactArgs e, const int32_t *__restrict__ users, const uint32_t *__restrict__ n_users_dev,
-                   int64_t n_users_host, int K, int32_t *__restrict__ out_items, double *__restrict__ out_scores) {
-  __shared__ Best wbest[8];
+                   int64_t n_users_host, int K, double *__restrict__ scratch, int32_t *__restrict__ out_items,
+                   double *__restrict__ out_scores) {
+  __shared__ Best wbest[EXACT_THREADS / 32];
   const int64_t n_u = n_users_dev ? (int64_t)*n_users_dev : n_users_host;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_range = e.item_end - e.item_begin;
+  double *sc = scratch + (size_t)blockIdx.x * n_range;
   for (int64_t ui = blockIdx.x; ui < n_u; ui += gridDim.x) {
     const int64_t u = users ? users[ui] : ui;
+    for (int64_t i = wid; i < n_range; i += EXACT_THREADS / 32) {
+      const double v = warp_exact_score(e, u, e.item_begin + i, lane);
+      if (lane == 0) sc[i] = v;
+    }
+    __syncthreads();
     Best last;
     last.s = 0.0;
     last.item = -2;
@@ -583,17 +843,18 @@ score_exact_kernel(const ExactArgs e, const int32_t *__restrict__ users, const u
       Best mine;
       mine.s = 0.0;
       mine.item = -1;
-      for (int64_t i = e.item_begin + wid; i < e.item_end; i += 8) {   // a warp per item
+      for (int64_t i = threadIdx.x; i < n_range; i += EXACT_THREADS) {
         Best b;
-        b.s = warp_exact_score(e, u, i, lane);
-        b.item = (int)i;
+        b.s = sc[i];
+        b.item = (int)(e.item_begin + i);
         const bool below = last.item == -2 || ranks_before(last, b);
         if (below && ranks_before(b, mine)) mine = b;
       }
+      mine = warp_best(mine);
       if (lane == 0) wbest[wid] = mine;
       __syncthreads();
       Best best = wbest[0];
-      for (int w = 1; w < 8; ++w)
+      for (int w = 1; w < EXACT_THREADS / 32; ++w)
         if (ranks_before(wbest[w], best)) best = wbest[w];
       __syncthreads();
       last = best;
@@ -601,8 +862,15 @@ score_exact_kernel(const ExactArgs e, const int32_t *__restrict__ users, const u
         out_items[u * K + r] = last.item;
         out_scores[u * K + r] = last.item >= 0 ? last.s : -INFINITY;
       }
-      if (last.item < 0) break;
+      if (last.item < 0) {   // fewer than K items in the range: pad the rest
+        for (int rr = r + 1 + threadIdx.x; rr < K; rr += EXACT_THREADS) {
+          out_items[u * K + rr] = -1;
+          out_scores[u * K + rr] = -INFINITY;
+        }
+        break;
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -668,6 +936,86 @@ int make_tmap(CUtensorMap *tm, void *base, int64_t rows_pad, int kpad, int box_r
   return RFM_OK;
 }
 
+// CTAs of the exact kernel: each keeps the float64 scores of the whole range, within a 512 MiB scratch budget
+int exact_grid(const rfm_ctx *ctx, int64_t n_users, int64_t n_range) {
+  const int64_t by_scratch = std::max<int64_t>(1, ((int64_t)512 << 20) / (8 * n_range));
+  return (int)std::min<int64_t>(std::min<int64_t>(n_users, (int64_t)ctx->sm_count * 4), by_scratch);
+}
+
+constexpr int MAX_GROUPS = 8192;     // group maxima per user the threshold kernel stages in shared memory
+
+// Split the visited tiles of a pass over blockIdx.y so that the grid fills whole waves of the SMs. Every CTA
+// pays about one and a half tiles of prologue (TMEM allocation, the A tile, pipeline fill).
+int pick_splits(int n_user_blocks, int n_visit, int sm_count) {
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= std::min(n_visit, 256); ++s) {
+    const int per = (n_visit + s - 1) / s;
+    const int s_eff = (n_visit + per - 1) / per;
+    const int64_t ctas = (int64_t)n_user_blocks * s_eff;
+    const int64_t waves = (ctas + sm_count - 1) / sm_count;
+    const double score = (double)ctas / (double)(waves * sm_count) * (per / (per + 1.5));
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = s_eff;
+    }
+  }
+  return best;
+}
+
+template <int KB, int PASS, int GCOLS>
+int launch_pass_as(rfm_ctx *ctx, dim3 grid, const CUtensorMap &tmap_a, const CUtensorMap &tmap_c, const PassArgs &pa) {
+  auto kernel = score_pass_kernel<KB, PASS, GCOLS>;
+  RFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<KB>::BYTES));
+  if (PASS == 0) {
+    auto score_sample = kernel;
+    RFM_LAUNCH(ctx, score_sample, grid, SCORE_THREADS, PassSmem<KB>::BYTES, tmap_a, tmap_c, pa);
+  } else {
+    auto score_collect = kernel;
+    RFM_LAUNCH(ctx, score_collect, grid, SCORE_THREADS, PassSmem<KB>::BYTES, tmap_a, tmap_c, pa);
+  }
+  return RFM_OK;
+}
+template <int KB>
+int launch_pass_kb(rfm_ctx *ctx, int pass, int gcols, dim3 grid, const CUtensorMap &tmap_a, const CUtensorMap &tmap_c,
+                   const PassArgs &pa) {
+  if (pass == 1) return launch_pass_as<KB, 1, 64>(ctx, grid, tmap_a, tmap_c, pa);
+  switch (gcols) {
+    case 128: return launch_pass_as<KB, 0, 128>(ctx, grid, tmap_a, tmap_c, pa);
+    case 64: return launch_pass_as<KB, 0, 64>(ctx, grid, tmap_a, tmap_c, pa);
+    case 32: return launch_pass_as<KB, 0, 32>(ctx, grid, tmap_a, tmap_c, pa);
+    case 16: return launch_pass_as<KB, 0, 16>(ctx, grid, tmap_a, tmap_c, pa);
+    default: return launch_pass_as<KB, 0, 8>(ctx, grid, tmap_a, tmap_c, pa);
+  }
+}
+int launch_pass(rfm_ctx *ctx, int kb, int pass, int gcols, dim3 grid, const CUtensorMap &tmap_a,
+                const CUtensorMap &tmap_c, const PassArgs &pa) {
+  return kb == 1 ? launch_pass_kb<1>(ctx, pass, gcols, grid, tmap_a, tmap_c, pa)
+                 : launch_pass_kb<2>(ctx, pass, gcols, grid, tmap_a, tmap_c, pa);
+}
+
+template <int NJ>
+int launch_threshold_as(rfm_ctx *ctx, int grid, const float *gmax, int64_t n_groups, int fold, int64_t n_rows,
+                        int64_t n_users_chunk, int K, const double *a_norm, const double *a_res, const double *c_norm_max,
+                        const double *c_res_max, const double *beta_abs_max, int kpad, float *tau, float *eps_out,
+                        uint32_t *cand_cnt) {
+  auto score_threshold = score_threshold_kernel<NJ>;
+  const size_t smem = NJ > 0 ? 0 : (size_t)SELECT_WARPS * n_groups * 4;
+  if (smem) RFM_CUDA(cudaFuncSetAttribute(score_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RFM_LAUNCH(ctx, score_threshold, grid, SELECT_WARPS * 32, smem, gmax, n_groups, fold, n_rows, n_users_chunk, K, a_norm,
+             a_res, c_norm_max, c_res_max, beta_abs_max, kpad, tau, eps_out, cand_cnt);
+  return RFM_OK;
+}
+template <typename... Args>
+int launch_threshold(rfm_ctx *ctx, int grid, const float *gmax, int64_t n_groups, Args... args) {
+  const int64_t per_lane = (n_groups + 31) / 32;
+  if (per_lane <= 8) return launch_threshold_as<8>(ctx, grid, gmax, n_groups, args...);
+  if (per_lane <= 16) return launch_threshold_as<16>(ctx, grid, gmax, n_groups, args...);
+  if (per_lane <= 32) return launch_threshold_as<32>(ctx, grid, gmax, n_groups, args...);
+  if (per_lane <= 64) return launch_threshold_as<64>(ctx, grid, gmax, n_groups, args...);
+  return launch_threshold_as<0>(ctx, grid, gmax, n_groups, args...);
+}
+
 }  // namespace
 
 struct rfm_topk {
@@ -676,12 +1024,16 @@ struct rfm_topk {
   int k = 0, kpad = 0, kb = 0;
   double bias = 0.0;
   bool has_alpha = false, has_beta = false, ready = false;
-  DevBuf<double> A, C, alpha, beta, a_norm, c_norm, c_norm_max, beta_abs_max;
-  DevBuf<__nv_bfloat16> A16, C16;
-  DevBuf<float> beta32, cand_score, cand_tau, glist_score;
-  DevBuf<int32_t> cand_item, glist_item, out_items, fail_list;
-  DevBuf<double> out_scores, cand_exact;
-  DevBuf<uint32_t> n_fail;
+  DevBuf<double> A, C, alpha, beta, a_norm, a_res, c_norm, c_res, c_norm_max, c_res_max, beta_abs_max;
+  DevBuf<__nv_bfloat16> A16, C16, beta16;
+  DevBuf<float> gmax, tau, eps;
+  DevBuf<int32_t> out_items, fail_list;
+  DevBuf<int2> cand;
+  PinnedBuf<int32_t> stage_items;
+  PinnedBuf<double> stage_scores;
+  DevBuf<double> out_scores, exact_scratch;
+  DevBuf<uint32_t> n_fail, cand_cnt;
+  DevBuf<unsigned long long> n_cand;
   CUtensorMap tmap_a, tmap_c;
 };
 
@@ -710,6 +1062,9 @@ int rfm_topk_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, int32_t n_fa
     RFM_TRY(t->beta.alloc(n_items));
     RFM_TRY(t->a_norm.alloc(n_users));
     RFM_TRY(t->c_norm.alloc(n_items));
+    RFM_TRY(t->a_res.alloc(n_users));
+    RFM_TRY(t->c_res.alloc(n_items));
+    RFM_TRY(t->c_res_max.alloc(1));
     RFM_TRY(t->c_norm_max.alloc(1));
     RFM_TRY(t->beta_abs_max.alloc(1));
     RFM_TRY(t->n_fail.alloc(1));
@@ -717,7 +1072,7 @@ int rfm_topk_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, int32_t n_fa
     if (t->kb <= MAX_KB) {
       RFM_TRY(t->A16.alloc((size_t)t->n_users_pad * t->kpad));
       RFM_TRY(t->C16.alloc((size_t)t->n_items_pad * t->kpad));
-      RFM_TRY(t->beta32.alloc(t->n_items_pad));
+      RFM_TRY(t->beta16.alloc((size_t)t->n_items_pad * 16));
     }
     return RFM_OK;
   };
@@ -755,12 +1110,13 @@ int rfm_topk_set_factors(rfm_topk *t, const double *A, const double *C, const do
   if (t->kb <= MAX_KB) {
     const int g = ctx->sm_count * 8;
     RFM_LAUNCH(ctx, to_bf16_kernel, g, 256, 0, t->A.p, t->n_users, t->k, t->n_users_pad, t->kpad, t->A16.p,
-               t->a_norm.p);
+               t->a_norm.p, t->a_res.p);
     RFM_LAUNCH(ctx, to_bf16_kernel, g, 256, 0, t->C.p, t->n_items, t->k, t->n_items_pad, t->kpad, t->C16.p,
-               t->c_norm.p);
-    RFM_LAUNCH(ctx, beta_f32_kernel, g, 256, 0, beta ? t->beta.p : (const double *)nullptr, t->n_items,
-               t->n_items_pad, t->beta32.p);
+               t->c_norm.p, t->c_res.p);
+    RFM_LAUNCH(ctx, beta_operand_kernel, g, 256, 0, beta ? t->beta.p : (const double *)nullptr, t->n_items,
+               t->n_items_pad, t->beta16.p);
     RFM_LAUNCH(ctx, max_reduce_kernel, 1, 1024, 0, t->c_norm.p, t->n_items, t->c_norm_max.p);
+    RFM_LAUNCH(ctx, max_reduce_kernel, 1, 1024, 0, t->c_res.p, t->n_items, t->c_res_max.p);
     RFM_LAUNCH(ctx, max_reduce_kernel, 1, 1024, 0, t->beta.p, t->n_items, t->beta_abs_max.p);
     RFM_TRY(make_tmap(&t->tmap_a, t->A16.p, t->n_users_pad, t->kpad, BM));
     RFM_TRY(make_tmap(&t->tmap_c, t->C16.p, t->n_items_pad, t->kpad, BN));
@@ -780,6 +1136,12 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
   if (item_end <= 0) item_end = t->n_items;
   RFM_REQUIRE(item_begin >= 0 && item_begin < item_end && item_end <= t->n_items, "rfm_topk_run: bad item range");
   rfm_ctx *ctx = t->ctx;
+  const bool timing = getenv("RFM_SCORE_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t_start = now();
   RFM_CUDA(cudaSetDevice(ctx->device));
   RFM_TRY(t->out_items.ensure((size_t)t->n_users * K));
   RFM_TRY(t->out_scores.ensure((size_t)t->n_users * K));
@@ -794,95 +1156,145 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
   e.k = t->k;
   e.item_begin = (int)item_begin;
   e.item_end = (int)item_end;
-  int64_t n_failed = 0;
-  // the tensor-core path needs a tile-aligned start (item shards are cut at multiples of 256) and k <= 128
-  const bool tensor_path = mode == 0 && t->kb <= MAX_KB && item_begin % BN == 0;
+  int64_t n_failed = 0, n_candidates = 0, sample_stride = 0;
+  // the tensor-core path needs a tile-aligned range (item shards are cut at multiples of 256; the catalog's own
+  // end is padded with beta = -inf) and k <= 128
+  const bool tensor_path = mode == 0 && t->kb <= MAX_KB && item_begin % BN == 0 &&
+                           (item_end % BN == 0 || item_end == t->n_items);
   if (tensor_path) {
-    int kc = std::max(2 * K, K + 16);
-    kc = (kc + 7) / 8 * 8;
     const int tile_begin = (int)(item_begin / BN);
     const int n_item_tiles = (int)((item_end + BN - 1) / BN) - tile_begin;
     const int n_user_blocks = (int)(t->n_users_pad / BM);
-    // split the catalog so that the grid covers the SMs about twice when there are few user blocks
-    int n_splits = std::max(1, std::min(n_item_tiles, (2 * ctx->sm_count + n_user_blocks - 1) / n_user_blocks));
-    const int tiles_per_split = (n_item_tiles + n_splits - 1) / n_splits;
-    n_splits = (n_item_tiles + tiles_per_split - 1) / tiles_per_split;
-    const int n_lists = n_splits * EPI_HALVES;          // candidate lists per user
-    const size_t rows = (size_t)n_lists * t->n_users_pad;
-    RFM_TRY(t->cand_score.ensure(rows * kc));
-    RFM_TRY(t->cand_item.ensure(rows * kc));
-    RFM_TRY(t->cand_tau.ensure(rows));
-    FilterArgs fa;
-    fa.beta = t->beta32.p;
-    fa.tile_begin = tile_begin;
-    fa.n_item_tiles = n_item_tiles;
-    fa.item_end = (int)item_end;
-    fa.tiles_per_split = tiles_per_split;
-    fa.kc = kc;
-    fa.n_users_pad = (int)t->n_users_pad;
-    fa.cand_score = t->cand_score.p;
-    fa.cand_item = t->cand_item.p;
-    fa.cand_tau = t->cand_tau.p;
-    fa.glist_score = nullptr;
-    fa.glist_item = nullptr;
-    const int n_groups = kc / 8;
-    const size_t smem_limit = 227 * 1024;
-    const size_t smem_with_lists = t->kb == 1 ? FilterSmem<1>::bytes(n_groups, kc) : FilterSmem<2>::bytes(n_groups, kc);
-    const int kc_smem = smem_with_lists <= smem_limit ? kc : 0;     // otherwise the lists go to global memory
-    if (!kc_smem) {
-      RFM_TRY(t->glist_score.ensure((size_t)n_user_blocks * n_splits * EPI_HALVES * kc * BM));
-      RFM_TRY(t->glist_item.ensure((size_t)n_user_blocks * n_splits * EPI_HALVES * kc * BM));
-      fa.glist_score = t->glist_score.p;
-      fa.glist_item = t->glist_item.p;
-    }
-    const dim3 grid(n_user_blocks, n_splits);
-    if (t->kb == 1) {
-      const size_t smem = FilterSmem<1>::bytes(n_groups, kc_smem);
-      RFM_REQUIRE(smem <= smem_limit, "rfm_topk_run: K=%d needs %zu bytes of shared memory", K, smem);
-      RFM_CUDA(cudaFuncSetAttribute(score_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      auto score_filter = score_filter_kernel<1>;
-      RFM_LAUNCH(ctx, score_filter, grid, SCORE_THREADS, smem, t->tmap_a, t->tmap_c, fa);
-    } else {
-      const size_t smem = FilterSmem<2>::bytes(n_groups, kc_smem);
-      RFM_REQUIRE(smem <= smem_limit, "rfm_topk_run: K=%d needs %zu bytes of shared memory", K, smem);
-      RFM_CUDA(cudaFuncSetAttribute(score_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      auto score_filter = score_filter_kernel<2>;
-      RFM_LAUNCH(ctx, score_filter, grid, SCORE_THREADS, smem, t->tmap_a, t->tmap_c, fa);
-    }
+    // Pass 1 scores a sample of the catalog, every stride-th tile. A sparser sample is cheaper but gives a
+    // lower threshold: about K * stride items per user reach it (negative binomial, sd stride * sqrt(K (1 - 1/stride))).
+    int stride = K <= 16 ? 4 : (K <= 64 ? 2 : 1);
+    if (const char *env = getenv("RFM_SCORE_STRIDE")) stride = std::max(1, atoi(env));
+    // The threshold is the K-th largest group maximum, so the sample must hold many more groups than K: small
+    // catalogs are sampled densely and in narrower groups (128 -> 8 items).
+    int gcols = MAX_GCOLS;
+    auto groups_of = [&](int st, int g) { return (int64_t)((n_item_tiles + st - 1) / st) * (BN / g); };
+    const int64_t want_groups = 8 * (int64_t)K + 64;
+    while (stride > 1 && groups_of(stride, gcols) < want_groups) stride /= 2;
+    while (gcols > 8 && groups_of(stride, gcols) < want_groups) gcols /= 2;
+    while (groups_of(stride, gcols) > MAX_GROUPS) ++stride;
+    const int n_sample = (n_item_tiles + stride - 1) / stride;
+    const int64_t n_groups = groups_of(stride, gcols);
+    // About c K stride items per user reach the threshold (negative binomial in the sampling, sd
+    // stride sqrt(K (1 - 1/stride)); c = -ln(1 - f) / f corrects for top items sharing a group, f = K / groups).
+    const int fold = (n_groups % 2 == 0 && n_groups / 2 >= want_groups) ? 2 : 1;   // threshold over pairs of groups
+    const double f = std::min(0.5, (double)K * fold / (double)n_groups);
+    const double cf = -std::log1p(-f) / f;
+    const double sd = stride * std::sqrt((double)K * (1.0 - 1.0 / stride));
+    // The 2 eps safety margin lowers the threshold further (how much depends on the score distribution), so the
+    // buffer is four times the expected count: an overflow costs an exact re-rank of that user.
+    int kc = (int)std::ceil(cf * (4.0 * K * stride + 6.0 * sd)) + 32;
+    kc = std::max<int64_t>(kc, std::min<int64_t>(item_end - item_begin, 256));
+    kc = (kc + 7) / 8 * 8;
+    // users are processed in chunks so that the group maxima of a chunk stay within a fixed scratch budget
+    const int64_t scratch_rows = std::max<int64_t>(BM, ((int64_t)1 << 30) / (n_groups * 4) / BM * BM);
+    const int chunk_blocks = (int)std::min<int64_t>(n_user_blocks, scratch_rows / BM);
+    const size_t chunk_rows = (size_t)chunk_blocks * BM;
+    RFM_TRY(t->gmax.ensure(chunk_rows * n_groups));
+    RFM_TRY(t->tau.ensure(chunk_rows));
+    RFM_TRY(t->cand_cnt.ensure(chunk_rows));
+    RFM_TRY(t->cand.ensure(chunk_rows * kc));
+    RFM_TRY(t->eps.ensure(chunk_rows));
+    RFM_TRY(t->n_cand.ensure(1));
     RFM_CUDA(cudaMemsetAsync(t->n_fail.p, 0, sizeof(uint32_t), ctx->stream));
-    const size_t rs_smem = (size_t)RESCORE_WARPS * n_lists * kc * 12;
-    RFM_REQUIRE(rs_smem <= 200 * 1024, "rfm_topk_run: %d candidates per user do not fit the re-scoring kernel",
-                n_lists * kc);
+    RFM_CUDA(cudaMemsetAsync(t->n_cand.p, 0, sizeof(unsigned long long), ctx->stream));
+    const size_t rs_smem = (size_t)RESCORE_WARPS * ((size_t)kc * 16 + (size_t)t->k * 8);
+    RFM_REQUIRE(rs_smem <= 200 * 1024, "rfm_topk_run: %d candidates per user do not fit the re-scoring kernel", kc);
     RFM_CUDA(cudaFuncSetAttribute(score_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-    const int rgrid = (int)std::min<int64_t>((t->n_users + RESCORE_WARPS - 1) / RESCORE_WARPS,
-                                             (int64_t)ctx->sm_count * 8);
-    RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, RESCORE_WARPS * 32, rs_smem, e, t->cand_score.p, t->cand_item.p,
-               t->cand_tau.p,
-               n_lists, (int)t->n_users_pad, kc, (int)K, t->a_norm.p, t->c_norm_max.p, t->beta_abs_max.p,
-               t->out_items.p, t->out_scores.p, t->fail_list.p, t->n_fail.p);
-    // users whose pruning could not be proven are ranked exactly against the whole catalog
-    const int fgrid = (int)std::min<int64_t>(t->n_users, (int64_t)ctx->sm_count * 4);
-    RFM_LAUNCH(ctx, score_exact_kernel, fgrid, 256, 0, e, t->fail_list.p, t->n_fail.p, (int64_t)0, (int)K,
-               t->out_items.p, t->out_scores.p);
+    for (int ub0 = 0; ub0 < n_user_blocks; ub0 += chunk_blocks) {
+      const int nb = std::min(chunk_blocks, n_user_blocks - ub0);
+      const int64_t user0 = (int64_t)ub0 * BM;
+      const int64_t users_here = std::min<int64_t>((int64_t)nb * BM, t->n_users - user0);
+      PassArgs pa;
+      pa.beta16 = t->beta16.p;
+      pa.tile_begin = tile_begin;
+      pa.item_end = (int)item_end;
+      pa.user_block0 = ub0;
+      pa.n_user_blocks = nb;
+      // every CTA holds up to ub blocks of 128 users, as many as still leave two waves of CTAs
+      int ub = t->kb == 1 ? PassSmem<1>::UB : PassSmem<2>::UB;
+      while (ub > 1 && (int64_t)((nb + ub - 1) / ub) * n_sample < 2 * (int64_t)ctx->sm_count) ub /= 2;
+      pa.ub = ub;
+      const int n_ctas_x = (nb + ub - 1) / ub;
+      pa.n_groups = n_groups;
+      pa.gmax = t->gmax.p;
+      pa.tau = t->tau.p;
+      pa.kc = kc;
+      pa.cand_cnt = t->cand_cnt.p;
+      pa.cand = t->cand.p;
+      // pass 1: group maxima of the sample
+      pa.tile_stride = stride;
+      pa.n_visit = n_sample;
+      int n_splits = pick_splits(n_ctas_x, n_sample, ctx->sm_count);
+      pa.tiles_per_split = (n_sample + n_splits - 1) / n_splits;
+      n_splits = (n_sample + pa.tiles_per_split - 1) / pa.tiles_per_split;
+      RFM_TRY(launch_pass(ctx, t->kb, 0, gcols, dim3(n_ctas_x, n_splits), t->tmap_a, t->tmap_c, pa));
+      const int tgrid = (int)std::min<int64_t>(((int64_t)nb * BM + SELECT_WARPS - 1) / SELECT_WARPS,
+                                               (int64_t)ctx->sm_count * 8);
+      RFM_TRY(launch_threshold(ctx, tgrid, t->gmax.p, n_groups / fold, fold, (int64_t)nb * BM, users_here, (int)K,
+                               t->a_norm.p + user0, t->a_res.p + user0, t->c_norm_max.p, t->c_res_max.p,
+                               t->beta_abs_max.p, t->kpad, t->tau.p, t->eps.p, t->cand_cnt.p));
+      // pass 2: collect every item that reaches the threshold
+      pa.tile_stride = 1;
+      pa.n_visit = n_item_tiles;
+      n_splits = pick_splits(n_ctas_x, n_item_tiles, ctx->sm_count);
+      pa.tiles_per_split = (n_item_tiles + n_splits - 1) / n_splits;
+      n_splits = (n_item_tiles + pa.tiles_per_split - 1) / pa.tiles_per_split;
+      RFM_TRY(launch_pass(ctx, t->kb, 1, 64, dim3(n_ctas_x, n_splits), t->tmap_a, t->tmap_c, pa));
+      const int rgrid = (int)std::min<int64_t>((users_here + RESCORE_WARPS - 1) / RESCORE_WARPS,
+                                               (int64_t)ctx->sm_count * 8);
+      RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
+                 t->cand.p, t->eps.p, kc, (int)K, t->out_items.p, t->out_scores.p, t->fail_list.p, t->n_fail.p,
+                 t->n_cand.p);
+    }
+    // users whose candidate buffer overflowed are ranked exactly against the whole catalog range
+    const int fgrid = exact_grid(ctx, t->n_users, item_end - item_begin);
+    RFM_TRY(t->exact_scratch.ensure((size_t)fgrid * (item_end - item_begin)));
+    RFM_LAUNCH(ctx, score_exact_kernel, fgrid, EXACT_THREADS, 0, e, t->fail_list.p, t->n_fail.p, (int64_t)0, (int)K,
+               t->exact_scratch.p, t->out_items.p, t->out_scores.p);
     uint32_t nf = 0;
+    unsigned long long nc = 0;
     RFM_CUDA(cudaMemcpyAsync(&nf, t->n_fail.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(&nc, t->n_cand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     RFM_CUDA(cudaStreamSynchronize(ctx->stream));
     n_failed = nf;
+    n_candidates = (int64_t)nc;
+    sample_stride = stride;
   } else {
-    const int fgrid = (int)std::min<int64_t>(t->n_users, (int64_t)ctx->sm_count * 4);
-    RFM_LAUNCH(ctx, score_exact_kernel, fgrid, 256, 0, e, (const int32_t *)nullptr, (const uint32_t *)nullptr,
-               t->n_users, (int)K, t->out_items.p, t->out_scores.p);
+    const int fgrid = exact_grid(ctx, t->n_users, item_end - item_begin);
+    RFM_TRY(t->exact_scratch.ensure((size_t)fgrid * (item_end - item_begin)));
+    RFM_LAUNCH(ctx, score_exact_kernel, fgrid, EXACT_THREADS, 0, e, (const int32_t *)nullptr, (const uint32_t *)nullptr,
+               t->n_users, (int)K, t->exact_scratch.p, t->out_items.p, t->out_scores.p);
   }
+  const auto t_launched = now();
+  if (timing) RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  const auto t_computed = now();
   if (out_items) {   // NULL: the caller reads the result on the device (rfm_topk_result_ptr_dev)
-    RFM_CUDA(cudaMemcpyAsync(out_items, t->out_items.p, (size_t)t->n_users * K * 4, cudaMemcpyDeviceToHost,
-                             ctx->stream));
-    RFM_CUDA(cudaMemcpyAsync(out_scores, t->out_scores.p, (size_t)t->n_users * K * 8, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+    // through page-locked staging: a device-to-host copy into pageable memory runs at a fraction of the link rate
+    const size_t n_out = (size_t)t->n_users * K;
+    RFM_TRY(t->stage_items.ensure(n_out));
+    RFM_TRY(t->stage_scores.ensure(n_out));
+    RFM_CUDA(cudaMemcpyAsync(t->stage_items.p, t->out_items.p, n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(t->stage_scores.p, t->out_scores.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    const auto t_d2h = now();
+    memcpy(out_items, t->stage_items.p, n_out * 4);
+    memcpy(out_scores, t->stage_scores.p, n_out * 8);
+    if (timing)
+      fprintf(stderr, "rfm_topk_run: launch %.3f ms, device %.3f ms, d2h %.3f ms, host copy %.3f ms\n",
+              ms(t_start, t_launched), ms(t_launched, t_computed), ms(t_computed, t_d2h), ms(t_d2h, now()));
+  } else {
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   if (stats) {
     stats[0] = tensor_path ? 1 : 0;
     stats[1] = n_failed;
+    stats[2] = n_candidates;
+    stats[3] = sample_stride;
   }
   return RFM_OK;
 }

@@ -71,10 +71,11 @@ class TopKScorer(_capi._Handle):
         begin, end = (0, self.n_items) if item_range is None else item_range
         items = np.empty((self.n_users, K), dtype=np.int32)
         scores = np.empty((self.n_users, K), dtype=np.float64)
-        stats = (c_int64 * 2)()
+        stats = (c_int64 * 4)()
         check(lib().rfm_topk_run(self.handle, K, 0 if mode == "tensor" else 1, begin, end, ptr(items), ptr(scores),
                                  stats))
-        self.last_stats = {"tensor_core_path": bool(stats[0]), "users_ranked_exactly": int(stats[1])}
+        self.last_stats = {"tensor_core_path": bool(stats[0]), "users_ranked_exactly": int(stats[1]),
+                           "candidates": int(stats[2]), "sample_stride": int(stats[3])}
         return items, scores
 
 

@@ -48,6 +48,20 @@ def test_mf_style_topk_matches_numpy(U, I, k, K):
     check(A, C, alpha, beta, 0.25, K, mode="exact")
 
 
+def test_item_terms_alone_rank_the_catalog():
+    """A = 0: the approximate score is the item term added by the extra MMA step, so a wrong operand layout or
+    split of beta shows up directly (the candidate sets would miss the true top items)."""
+    rng = np.random.default_rng(4)
+    U, I, k = 300, 5000, 64
+    beta = rng.normal(size=I) * 3.0
+    sc = check(np.zeros((U, k)), rng.normal(size=(I, k)), None, beta, 0.0, 9)
+    assert sc.last_stats["users_ranked_exactly"] == 0
+    assert sc.last_stats["candidates"] <= 40 * U            # thresholds are tight: a handful of items per user
+    # a large common offset plus tiny differences: only the low-order parts of the split separate the items
+    beta = 1000.0 + rng.normal(size=I) * 1e-3
+    check(rng.normal(size=(U, k)) * 1e-4, rng.normal(size=(I, k)) * 1e-4, None, beta, 0.0, 9)
+
+
 def test_k_wider_than_the_tensor_path_uses_exact_kernel():
     rng = np.random.default_rng(0)
     check(rng.normal(size=(40, 300)), rng.normal(size=(90, 300)), None, None, 0.0, 7, expect_tensor=False)
