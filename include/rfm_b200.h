@@ -130,6 +130,22 @@ int rfm_fm_grad_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batc
 int rfm_fm_grad_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t q_begin,
                               int64_t batch);
 int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr);
+/* The same exchange over NVLink peer memory, one kernel per step and rank instead of {all-reduce, apply}
+ * (SURVEY.md section 8e "fuse ... deterministic: fixed rank-order summation"). rfm_fm_dp_export moves the
+ * gradient buffer into a CUDA-IPC region (call it before the first rfm_fm_grad_*; rfm_fm_grad_ptr_dev
+ * then changes every step) and returns its handle; the caller gathers the handles of all ranks (at most
+ * 8, one process per GPU of one node) and passes them, in rank order, to rfm_fm_dp_connect.
+ * rfm_fm_dp_exchange_apply then: barrier -> every rank sums its slice over all ranks in rank order, in
+ * place -> barrier -> every rank applies the reduced gradient read from the slice owners. The loss sums
+ * of the previous step (rfm_fm_loss_sums) ride in the buffer header; their global values land in the
+ * device doubles returned by rfm_fm_dp_prev_loss_ptr_dev (status: 0 = ok, else a barrier timed out). */
+#define RFM_DP_HANDLE_BYTES 64
+int rfm_fm_dp_export(rfm_fm_trainer *t, void *handle_out /* RFM_DP_HANDLE_BYTES */);
+int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world,
+                      const void *all_handles /* world x RFM_DP_HANDLE_BYTES */);
+int rfm_fm_dp_exchange_apply(rfm_fm_trainer *t, double lr);
+int rfm_fm_dp_prev_loss_ptr_dev(rfm_fm_trainer *t, void **sums_dev /* double[2] */,
+                                void **status_dev /* uint32, may be NULL */);
 /* post-update loss of a batch slice / of val rows [row_begin, row_end): SUM of the per-row
  * terms (not divided) written to device slots so ranks can all-reduce them. batch_rows == NULL
  * reuses the batch that the last grad call left on the device. */

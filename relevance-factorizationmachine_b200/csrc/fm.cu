@@ -76,6 +76,7 @@ size_t dsize(int dtype) { return dtype == RFM_F64 ? 8 : 4; }
 // Offsets are multiples of 4 elements so dV is 16-byte aligned for float and double vector stores.
 constexpr int64_t GRAD_W_OFF = 4;
 int64_t grad_v_off(int64_t n) { return GRAD_W_OFF + ((n + 3) / 4) * 4; }
+__device__ __forceinline__ int64_t grad_v_off_dev(int64_t n) { return GRAD_W_OFF + ((n + 3) / 4) * 4; }
 int64_t grad_total(int64_t n, int kp) { return grad_v_off(n) + n * kp; }
 
 // ---- small conversion kernels -------------------------------------------------------------------
@@ -884,6 +885,18 @@ struct rfm_fm_trainer {
   DevBuf<uint32_t> row_len, bptr, scan_tmp, count, tails, n_tails, ticket;
   DevBuf<unsigned char> S, E, carry_vec, carry_ac, grad;
   DevBuf<double> block_partials, losses, loss_sums;
+  // NVLink peer exchange of the data-parallel step (rfm_fm_dp_*): a cudaMalloc'ed region every rank maps
+  // through CUDA IPC: [gradient buffer, parity 0 | gradient buffer, parity 1 | flags]
+  static constexpr int DP_MAX_WORLD = 8;
+  unsigned char *xchg = nullptr;
+  size_t xchg_grad_bytes = 0;
+  unsigned char *peer_base[DP_MAX_WORLD] = {nullptr};
+  int dp_rank = -1, dp_world = 0, dp_parity = 0;
+  uint32_t dp_seq = 0;
+  bool dp_pending_loss = false;
+  DevBuf<double> dp_prev_loss;
+  DevBuf<uint32_t> dp_local;   // [arrive counter, go flag, error flag]
+  unsigned char *grad_ptr() const { return xchg ? xchg + (size_t)dp_parity * xchg_grad_bytes : grad.p; }
   RadixSorter<float> sort32;
   RadixSorter<double> sort64;
   // host staging ring for batch row ids
@@ -991,7 +1004,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   a.ghist = sorter.ghist();
   a.n_passes = sorter.passes;
   if (DP) {
-    T *g = reinterpret_cast<T *>(t->grad.p);
+    T *g = reinterpret_cast<T *>(t->grad_ptr());
     RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)grad_total(m->n, m->kp) * sizeof(T), ctx->stream));
     // sum_e lands in grad[0]; w0 itself is updated by the dense apply after the all-reduce
     a.fin = make_finish(0, 1.0, g, nullptr, t->block_partials.p, t->ticket.p);
@@ -1023,7 +1036,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   c.tails = t->tails.p;
   c.n_tails = t->n_tails.p;
   if (DP) {
-    T *g = reinterpret_cast<T *>(t->grad.p);
+    T *g = reinterpret_cast<T *>(t->grad_ptr());
     c.grad_w = g + GRAD_W_OFF;
     c.grad_V = g + grad_v_off(m->n);
   }
@@ -1453,6 +1466,9 @@ int rfm_fm_trainer_destroy(rfm_fm_trainer *t) {
     cudaStreamSynchronize(t->m->ctx->stream);
     for (int r = 0; r < rfm_fm_trainer::RING; ++r)
       if (t->stage_ev[r]) cudaEventDestroy(t->stage_ev[r]);
+    for (int q = 0; q < t->dp_world; ++q)
+      if (q != t->dp_rank && t->peer_base[q]) cudaIpcCloseMemHandle(t->peer_base[q]);
+    if (t->xchg) cudaFree(t->xchg);
     delete t;
   }
   return RFM_OK;
@@ -1491,12 +1507,12 @@ int rfm_fm_grad_size(rfm_fm_trainer *t, int64_t *n_scalars) {
 int rfm_fm_grad_ptr_dev(rfm_fm_trainer *t, void **grad_dev) {
   RFM_REQUIRE(t && grad_dev, "rfm_fm_grad_ptr_dev: NULL argument");
   RFM_CUDA(cudaSetDevice(t->m->ctx->device));
-  if (!t->grad.p) {
+  if (!t->xchg && !t->grad.p) {
     int64_t n = 0;
     rfm_fm_grad_size(t, &n);
     RFM_TRY(t->grad.alloc((size_t)n * dsize(t->m->dtype)));
   }
-  *grad_dev = t->grad.p;
+  *grad_dev = t->grad_ptr();
   return RFM_OK;
 }
 
@@ -1540,23 +1556,294 @@ int rfm_fm_grad_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, 
 }
 
 int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
-  RFM_REQUIRE(t && t->grad.p, "rfm_fm_apply_grad: no gradient buffer (call rfm_fm_grad_epoch first)");
+  RFM_REQUIRE(t && t->grad_ptr(), "rfm_fm_apply_grad: no gradient buffer (call rfm_fm_grad_epoch first)");
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
   RFM_CUDA(cudaSetDevice(ctx->device));
   const int g = grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8);
   if (m->dtype == RFM_F64) {
-    double *gr = reinterpret_cast<double *>(t->grad.p);
+    double *gr = reinterpret_cast<double *>(t->grad_ptr());
     RFM_LAUNCH(ctx, apply_grad_rows_kernel<double>, g, ROWS_THREADS, 0, reinterpret_cast<double *>(m->w0.p),
                reinterpret_cast<double *>(m->w.p), reinterpret_cast<double *>(m->V.p),
                reinterpret_cast<double *>(m->vn.p), gr, gr + GRAD_W_OFF, gr + grad_v_off(m->n), m->n, m->kp, lr);
   } else {
-    float *gr = reinterpret_cast<float *>(t->grad.p);
+    float *gr = reinterpret_cast<float *>(t->grad_ptr());
     RFM_LAUNCH(ctx, apply_grad_rows_kernel<float>, g, ROWS_THREADS, 0, reinterpret_cast<float *>(m->w0.p),
                reinterpret_cast<float *>(m->w.p), reinterpret_cast<float *>(m->V.p),
                reinterpret_cast<float *>(m->vn.p), gr, gr + GRAD_W_OFF, gr + grad_v_off(m->n), m->n, m->kp,
                (float)lr);
   }
+  return RFM_OK;
+}
+
+}  // extern "C" (pause)
+namespace {
+
+// ---- data-parallel step over NVLink peer memory ---------------------------------------------------------------
+// One kernel per step and rank replaces {all-reduce, dense apply}: after a cross-GPU barrier every rank sums ITS
+// slice of the gradient over all ranks' buffers (peer loads, fixed rank order, so every rank later sees the same
+// bits) and writes it back in place; after a second barrier every rank reads each slice from its owner and
+// applies it to its replica of the parameters. 2 (N - 1) / N of the gradient crosses NVLink per rank, nothing is
+// staged, and the buffers alternate between two parities so that a fast rank never overwrites what a slow one
+// still reads. Flags are monotonically increasing step numbers written with system-scope release stores.
+constexpr int DPX_THREADS = 256;
+constexpr uint32_t DPX_SPIN_LIMIT = 1u << 23;   // a few seconds of polling, then the status flag is raised
+
+struct DpxArgs {
+  const unsigned char *peer[rfm_fm_trainer::DP_MAX_WORLD];   // every rank's exchange region (own included)
+  size_t grad_off;          // byte offset of this step's parity inside a region
+  size_t flags_off;         // byte offset of the flag block: uint32 [2 phases][DP_MAX_WORLD]
+  int rank, world;
+  uint32_t seq;             // this step's number (>= 1)
+  int64_t total, slice;     // scalars in a gradient buffer; scalars per rank slice (a multiple of 2)
+  uint32_t *local;          // [arrive counter, go flag, error flag] of this rank
+  const double *loss_in;    // this rank's previous-step loss sums, or nullptr
+  double *loss_out;         // global loss sums of the previous step (read back from the header)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all CTAs of this rank and all ranks: CTA 0 collects the local arrivals, exchanges flags with the peers, then
+// releases the local CTAs. go values are 2 * seq + phase, so they only ever grow.
+__device__ void dpx_barrier(const DpxArgs &a, int phase) {
+  __syncthreads();
+  const uint32_t go = 2u * a.seq + (uint32_t)phase;
+  if (blockIdx.x == 0) {     // block-uniform branch
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.local, 1u);
+      uint32_t spins = 0;
+      const uint32_t want = gridDim.x * (2u * (a.seq - 1u) + (uint32_t)phase + 1u);   // the counter never resets
+      while (ld_acquire_gpu(a.local) < want)
+        if (++spins > DPX_SPIN_LIMIT) { a.local[2] = 1u; break; }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < a.world) {   // one thread per peer: the stores and the polls overlap
+      const int q = threadIdx.x;
+      uint32_t *f = reinterpret_cast<uint32_t *>(const_cast<unsigned char *>(a.peer[q]) + a.flags_off);
+      st_release_sys(f + phase * rfm_fm_trainer::DP_MAX_WORLD + a.rank, a.seq);
+      const uint32_t *mine = reinterpret_cast<const uint32_t *>(a.peer[a.rank] + a.flags_off);
+      uint32_t spins = 0;
+      while (ld_acquire_sys(mine + phase * rfm_fm_trainer::DP_MAX_WORLD + q) < a.seq)
+        if (++spins > DPX_SPIN_LIMIT) { a.local[2] = 2u + (uint32_t)q; break; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(a.local + 1, go);
+  } else if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(a.local, 1u);
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(a.local + 1) < go)
+      if (++spins > DPX_SPIN_LIMIT) break;
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DPX_THREADS, 4)
+fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__ w, T *__restrict__ V,
+                            T *__restrict__ vn, int64_t n, int kp, T lr) {
+  T *mine = reinterpret_cast<T *>(const_cast<unsigned char *>(a.peer[a.rank]) + a.grad_off);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_in) {   // the previous step's loss sums ride in the header
+    mine[1] = static_cast<T>(a.loss_in[0]);
+    mine[2] = static_cast<T>(a.loss_in[1]);
+  }
+  dpx_barrier(a, 0);          // every rank's gradient is complete
+  {
+    const int64_t lo = min(a.total, (int64_t)a.rank * a.slice), hi = min(a.total, lo + a.slice);
+    using V2 = typename Vec2<T>::type;
+    const int64_t pairs = (hi - lo) / 2;       // total and slice are even
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;                       // peer loads in flight per thread: NVLink latency is ~2 us
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < pairs; i0 += U * stride) {
+      V2 acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = V2{T(0), T(0)};
+      for (int q = 0; q < a.world; ++q) {      // fixed rank order: identical bits whoever owns the slice
+        const V2 *src = reinterpret_cast<const V2 *>(reinterpret_cast<const T *>(a.peer[q] + a.grad_off) + lo);
+        V2 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i0 + u * stride < pairs) x[u] = src[i0 + u * stride];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (q == 0) {
+            acc[u] = x[u];
+          } else {
+            acc[u].x += x[u].x;
+            acc[u].y += x[u].y;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * stride < pairs) reinterpret_cast<V2 *>(mine + lo)[i0 + u * stride] = acc[u];
+    }
+  }
+  dpx_barrier(a, 1);          // every slice is reduced
+  auto at = [&](int64_t i) -> const T * {      // element i of the reduced gradient, in its owner's buffer
+    const int64_t owner = min((int64_t)a.world - 1, i / a.slice);
+    return reinterpret_cast<const T *>(a.peer[owner] + a.grad_off) + i;
+  };
+  const int lane = lane_id();
+  const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (gwarp == 0 && lane == 0) {
+    *w0 += lr * *at(0);
+    if (a.loss_out) {
+      a.loss_out[0] = static_cast<double>(*at(1));
+      a.loss_out[1] = static_cast<double>(*at(2));
+    }
+  }
+  const int64_t v_off = grad_v_off_dev(n);
+  constexpr int R = 4;                             // feature rows in flight per warp (peer loads)
+  for (int64_t j0 = gwarp; j0 < n; j0 += R * nw) {
+    for (int f = lane * 2; f < kp; f += 64) {      // same association as row_norms_kernel / apply_grad_rows_kernel
+      T g0[R], g1[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int64_t j = j0 + r * nw;
+        if (j < n) {
+          const T *g = at(v_off + j * kp + f);     // a pair never straddles a slice boundary (both are even)
+          g0[r] = g[0];
+          g1[r] = g[1];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int64_t j = j0 + r * nw;
+        if (j < n) {
+          V[j * kp + f] += lr * g0[r];
+          V[j * kp + f + 1] += lr * g1[r];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t j = j0 + r * nw;
+      if (j >= n) continue;
+      T s = T(0);
+      for (int f = lane * 2; f < kp; f += 64) {
+        const T v0 = V[j * kp + f], v1 = V[j * kp + f + 1];   // this lane's own writes
+        s += v0 * v0 + v1 * v1;
+      }
+      s = warp_sum(s);
+      if (lane == 0) {
+        vn[j] = s;
+        w[j] += lr * *at(GRAD_W_OFF + j);
+      }
+    }
+  }
+}
+
+}  // namespace
+extern "C" {
+
+int rfm_fm_dp_export(rfm_fm_trainer *t, void *handle_out) {
+  RFM_REQUIRE(t && handle_out, "rfm_fm_dp_export: NULL argument");
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_REQUIRE(!t->xchg, "rfm_fm_dp_export: already exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RFM_DP_HANDLE_BYTES, "IPC handle size");
+  int64_t n = 0;
+  rfm_fm_grad_size(t, &n);
+  t->xchg_grad_bytes = ((size_t)n * dsize(t->m->dtype) + 255) / 256 * 256;
+  const size_t bytes = 2 * t->xchg_grad_bytes + 256;
+  // cudaMalloc, not the stream-ordered pool: pool memory cannot be exported through legacy CUDA IPC
+  RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->xchg), bytes));
+  RFM_CUDA(cudaMemsetAsync(t->xchg, 0, bytes, ctx->stream));
+  RFM_TRY(t->dp_prev_loss.alloc(2));
+  RFM_TRY(t->dp_local.alloc(4));
+  RFM_CUDA(cudaMemsetAsync(t->dp_local.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+  RFM_CUDA(cudaMemsetAsync(t->dp_prev_loss.p, 0, 2 * sizeof(double), ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  RFM_CUDA(cudaIpcGetMemHandle(&h, t->xchg));
+  memcpy(handle_out, &h, sizeof(h));
+  return RFM_OK;
+}
+
+int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world, const void *all_handles) {
+  RFM_REQUIRE(t && all_handles, "rfm_fm_dp_connect: NULL argument");
+  RFM_REQUIRE(t->xchg, "rfm_fm_dp_connect: call rfm_fm_dp_export first");
+  RFM_REQUIRE(world >= 1 && world <= rfm_fm_trainer::DP_MAX_WORLD && rank >= 0 && rank < world,
+              "rfm_fm_dp_connect: rank %d / world %d out of range (at most %d ranks)", rank, world,
+              rfm_fm_trainer::DP_MAX_WORLD);
+  RFM_REQUIRE(t->dp_world == 0, "rfm_fm_dp_connect: already connected");
+  RFM_CUDA(cudaSetDevice(t->m->ctx->device));
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      t->peer_base[q] = t->xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const unsigned char *>(all_handles) + (size_t)q * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RFM_ERR_CUDA, "rfm_fm_dp_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
+    }
+    t->peer_base[q] = static_cast<unsigned char *>(p);
+  }
+  t->dp_rank = rank;
+  t->dp_world = world;
+  return RFM_OK;
+}
+
+int rfm_fm_dp_exchange_apply(rfm_fm_trainer *t, double lr) {
+  RFM_REQUIRE(t && t->dp_world > 0, "rfm_fm_dp_exchange_apply: call rfm_fm_dp_connect first");
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  DpxArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int q = 0; q < t->dp_world; ++q) a.peer[q] = t->peer_base[q];
+  a.grad_off = (size_t)t->dp_parity * t->xchg_grad_bytes;
+  a.flags_off = 2 * t->xchg_grad_bytes;
+  a.rank = t->dp_rank;
+  a.world = t->dp_world;
+  a.seq = ++t->dp_seq;
+  a.total = grad_total(m->n, m->kp);
+  a.slice = (ceil_div(a.total, (int64_t)t->dp_world) + 1) / 2 * 2;
+  a.local = t->dp_local.p;
+  a.loss_in = t->dp_pending_loss ? t->loss_sums.p : nullptr;
+  a.loss_out = t->dp_prev_loss.p;
+  // every CTA must be resident at once (the kernel spins on flags): one wave, four CTAs per SM
+  const int g = (int)std::min<int64_t>(4 * (int64_t)ctx->sm_count, std::max<int64_t>(1, ceil_div(m->n, DPX_THREADS / 32)));
+  if (m->dtype == RFM_F64) {
+    auto fm_dp_exchange_apply = fm_dp_exchange_apply_kernel<double>;
+    RFM_LAUNCH(ctx, fm_dp_exchange_apply, g, DPX_THREADS, 0, a, reinterpret_cast<double *>(m->w0.p),
+               reinterpret_cast<double *>(m->w.p), reinterpret_cast<double *>(m->V.p),
+               reinterpret_cast<double *>(m->vn.p), m->n, m->kp, lr);
+  } else {
+    auto fm_dp_exchange_apply = fm_dp_exchange_apply_kernel<float>;
+    RFM_LAUNCH(ctx, fm_dp_exchange_apply, g, DPX_THREADS, 0, a, reinterpret_cast<float *>(m->w0.p),
+               reinterpret_cast<float *>(m->w.p), reinterpret_cast<float *>(m->V.p),
+               reinterpret_cast<float *>(m->vn.p), m->n, m->kp, (float)lr);
+  }
+  t->dp_parity ^= 1;           // the next gradient goes to the other buffer
+  t->dp_pending_loss = true;   // rfm_fm_loss_sums of this step will ride in the next exchange
+  return RFM_OK;
+}
+
+int rfm_fm_dp_prev_loss_ptr_dev(rfm_fm_trainer *t, void **sums_dev, void **status_dev) {
+  RFM_REQUIRE(t && sums_dev && t->dp_prev_loss.p, "rfm_fm_dp_prev_loss_ptr_dev: not exported");
+  *sums_dev = t->dp_prev_loss.p;
+  if (status_dev) *status_dev = t->dp_local.p + 2;
   return RFM_OK;
 }
 

@@ -56,6 +56,10 @@ _SIGNATURES = {
     "rfm_fm_grad_epoch": ([_P, _P, c_int64], c_int),
     "rfm_fm_grad_epoch_sampled": ([_P, c_uint32, c_uint32, c_int64, c_int64], c_int),
     "rfm_fm_apply_grad": ([_P, c_double], c_int),
+    "rfm_fm_dp_export": ([_P, c_void_p], c_int),
+    "rfm_fm_dp_connect": ([_P, c_int32, c_int32, c_void_p], c_int),
+    "rfm_fm_dp_exchange_apply": ([_P, c_double], c_int),
+    "rfm_fm_dp_prev_loss_ptr_dev": ([_P, POINTER(c_void_p), POINTER(c_void_p)], c_int),
     "rfm_fm_loss_sums_ptr_dev": ([_P, POINTER(_P)], c_int),
     "rfm_fm_loss_sums": ([_P, _P, c_int64, c_int64, c_int64], c_int),
     "rfm_fm_trainer_losses": ([_P, c_int64, c_int64, _P, _P], c_int),

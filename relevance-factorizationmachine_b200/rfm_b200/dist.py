@@ -142,20 +142,65 @@ class DataParallelFM:
         return self.loss_tensor.clone()
 
 
-def make_fm_dp(model, trainer, env: DistEnv, global_batch: int, n_val: int, lr: float, batch_source):
+class NvlinkDataParallelFM(DataParallelFM):
+    """The same step with the exchange done by the library's own kernel over NVLink peer memory
+    (rfm_fm_dp_exchange_apply: barrier, rank-ordered reduce of this rank's slice in place, barrier, apply from
+    the slice owners) instead of {NCCL all-reduce, apply}. torch.distributed only carries the IPC handles."""
+
+    def __init__(self, env, global_batch, n_val, lr, local_grad, exchange_apply, local_loss_sums, loss_tensor,
+                 prev_loss_tensor, status_tensor):
+        super().__init__(env, global_batch, n_val, lr, local_grad, None, None, local_loss_sums, loss_tensor)
+        self.exchange_apply, self.prev_loss_tensor, self.status_tensor = exchange_apply, prev_loss_tensor, status_tensor
+
+    def step(self, epoch: int):
+        self.local_grad(self.begin, self.end, epoch)
+        pending = getattr(self, "_pending", False)
+        self.exchange_apply(self.lr)                 # carries the previous step's local loss sums in the header
+        prev = self.prev_loss_tensor.clone() if pending else None
+        self.local_loss_sums(self.begin, self.end, self.vbegin, self.vend)
+        self._pending = True
+        return prev
+
+    def flush(self):
+        out = super().flush()
+        status = int(self.status_tensor.item())
+        if status:
+            raise RuntimeError("rfm_fm_dp_exchange_apply: a cross-GPU barrier timed out (status %d)" % status)
+        return out
+
+
+def make_fm_dp(model, trainer, env: DistEnv, global_batch: int, n_val: int, lr: float, batch_source,
+               exchange: str = "auto"):
     """Bind DataParallelFM to the C ABI.
 
     batch_source(epoch) -> None | np.ndarray: None selects the device Feistel sampler; an int64
     array is the epoch's GLOBAL batch order (legacy sampler), identical on every rank.
+    exchange: "nvlink" (the library's fused peer-memory kernel; one node, at most 8 ranks), "nccl"
+    (torch.distributed all-reduce + apply), or "auto" (nvlink on an NCCL group of <= 8 ranks unless
+    RFM_DP_EXCHANGE=nccl).
     """
     from . import _capi
     from ._capi import check, lib, ptr
+    if exchange == "auto":
+        exchange = os.environ.get("RFM_DP_EXCHANGE", "nvlink" if env.backend == "nccl" and env.world <= 8 else "nccl")
+    if exchange not in ("nvlink", "nccl"):
+        raise ValueError("exchange must be 'nvlink', 'nccl' or 'auto'")
     n = c_int64()
     check(lib().rfm_fm_grad_size(trainer.handle, byref(n)))
     gp, lp = c_void_p(), c_void_p()
-    check(lib().rfm_fm_grad_ptr_dev(trainer.handle, byref(gp)))
+    if exchange == "nvlink":
+        from ctypes import c_ubyte
+        handle = (c_ubyte * 64)()
+        check(lib().rfm_fm_dp_export(trainer.handle, handle))
+        gathered = [None] * env.world
+        env.dist.all_gather_object(gathered, bytes(handle))
+        every = (c_ubyte * (64 * env.world)).from_buffer_copy(b"".join(gathered))
+        check(lib().rfm_fm_dp_connect(trainer.handle, env.rank, env.world, every))
+        env.barrier()                                   # every rank has mapped every region
+    else:
+        check(lib().rfm_fm_grad_ptr_dev(trainer.handle, byref(gp)))
     check(lib().rfm_fm_loss_sums_ptr_dev(trainer.handle, byref(lp)))
-    grad_tensor = device_tensor(gp.value, n.value, model.dtype, env.device)
+    grad_tensor = device_tensor(gp.value, n.value, model.dtype, env.device) if exchange == "nccl" else None
     loss_tensor = device_tensor(lp.value, 2, "float64", env.device)
     state = {}
 
@@ -174,6 +219,17 @@ def make_fm_dp(model, trainer, env: DistEnv, global_batch: int, n_val: int, lr: 
     def local_loss_sums(begin, end, vbegin, vend):
         check(lib().rfm_fm_loss_sums(trainer.handle, None, end - begin, vbegin, vend))
 
+    if exchange == "nvlink":
+        pp, sp = c_void_p(), c_void_p()
+        check(lib().rfm_fm_dp_prev_loss_ptr_dev(trainer.handle, byref(pp), byref(sp)))
+        import torch
+        status = torch.as_tensor(_DeviceArray(sp.value, 1, "<u4"), device="cuda:%d" % env.device)
+
+        def exchange_apply(step_lr):
+            check(lib().rfm_fm_dp_exchange_apply(trainer.handle, step_lr))
+
+        return NvlinkDataParallelFM(env, global_batch, n_val, lr, local_grad, exchange_apply, local_loss_sums,
+                                    loss_tensor, device_tensor(pp.value, 2, "float64", env.device), status)
     return DataParallelFM(env, global_batch, n_val, lr, local_grad, grad_tensor, apply, local_loss_sums, loss_tensor)
 
 

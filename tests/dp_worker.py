@@ -55,7 +55,7 @@ def main():
     np.testing.assert_array_equal(scores, full_scores)
     assert sc.last_stats["tensor_core_path"]
     if env.rank == 0:
-        print("DP_OK world=%d" % env.world)
+        print("DP_OK world=%d exchange=%s" % (env.world, os.environ.get("RFM_DP_EXCHANGE", "nvlink")))
     env.shutdown()
 
 
