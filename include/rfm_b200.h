@@ -119,6 +119,24 @@ int rfm_fm_train_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t bat
 /* same step, batch drawn on the device by the Feistel sampler (perf mode). */
 int rfm_fm_train_epoch_sampled(rfm_fm_trainer *t, uint32_t seed, uint32_t epoch, int64_t batch,
                                double lr, int64_t slot);
+/* The same epoch with a dense optimizer step instead of the reference's fused SGD (SURVEY.md section 8 row f5;
+ * not in the reference, utils/optimizer.py ends at :64 -- specification: oracle/optimizer_oracle.py). The
+ * batch gradient g of the IPS logloss is formed as in src/fm.py:80-88,135-187, then
+ *   RFM_OPT_SGD:  theta -= lr (g + l2 theta)
+ *   RFM_OPT_ADAM: g += l2 theta; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *                 theta -= lr (m / (1-b1^step)) / (sqrt(v / (1-b2^step)) + eps), step = 1, 2, ...
+ * on w0, w and V; the moments live in the trainer and start at zero. batch_rows == NULL draws the batch on
+ * the device (Feistel sampler, seed/epoch as in rfm_fm_train_epoch_sampled). Losses as rfm_fm_train_epoch. */
+#define RFM_OPT_SGD 0
+#define RFM_OPT_ADAM 1
+typedef struct rfm_optimizer {
+  int32_t kind;
+  int32_t reserved;
+  double lr, l2, beta1, beta2, eps;
+  int64_t step;
+} rfm_optimizer;
+int rfm_fm_train_epoch_opt(rfm_fm_trainer *t, const int64_t *batch_rows /* may be NULL */, uint32_t seed,
+                           uint32_t epoch, int64_t batch, int64_t slot, const rfm_optimizer *opt);
 /* Data-parallel split of the same step: rank-local gradient of a batch
  * slice into a dense buffer [sum_e, 3 pad | dw (n, padded to a multiple of 4) | dV (n x kpad)]
  * (rfm_fm_grad_size scalars of the model dtype), to be all-reduced by the caller, then applied

@@ -795,6 +795,53 @@ apply_grad_rows_kernel(T *__restrict__ w0, T *__restrict__ w, T *__restrict__ V,
   }
 }
 
+// Dense optimizer step on a gradient buffer (rfm_fm_train_epoch_opt). The buffer holds the ASCENT direction d of
+// the reference's closed form (theta += lr d is its SGD step), so the loss gradient is g = -d + l2 theta.
+// ADAM (Kingma & Ba, bias-corrected; c1 = 1 / (1 - beta1^t), c2 = 1 / (1 - beta2^t) computed on the host):
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  theta -= lr (m c1) / (sqrt(v c2) + eps)
+// otherwise SGD with L2: theta -= lr g. Specification: oracle/optimizer_oracle.py.
+template <typename T>
+struct OptArgs {
+  T lr, l2, b1, b2, eps, c1, c2;
+};
+template <typename T, bool ADAM>
+__device__ __forceinline__ T opt_update(T theta, T d, T *__restrict__ m, T *__restrict__ v, const OptArgs<T> &o) {
+  const T g = o.l2 * theta - d;
+  if (!ADAM) return theta - o.lr * g;
+  const T mm = o.b1 * *m + (T(1) - o.b1) * g;
+  const T vv = o.b2 * *v + (T(1) - o.b2) * (g * g);
+  *m = mm;
+  *v = vv;
+  return theta - o.lr * (mm * o.c1) / (sqrt(vv * o.c2) + o.eps);
+}
+template <typename T, bool ADAM>
+__global__ void __launch_bounds__(ROWS_THREADS)
+optimizer_rows_kernel(T *__restrict__ w0, T *__restrict__ w, T *__restrict__ V, T *__restrict__ vn,
+                      const T *__restrict__ grad, T *__restrict__ am, T *__restrict__ av, int64_t n, int k, int kp,
+                      int64_t w_off, int64_t v_off, const OptArgs<T> o) {
+  const int lane = lane_id();
+  const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (gwarp == 0 && lane == 0) *w0 = opt_update<T, ADAM>(*w0, grad[0], am, av, o);
+  for (int64_t j = gwarp; j < n; j += nw) {
+    T s = T(0);
+    for (int f = lane * 2; f < kp; f += 64) {      // same association as row_norms_kernel
+      const int64_t at = v_off + j * kp + f;
+      // padding columns (f >= k) stay exactly zero: no gradient, and Adam's 0 / (0 + eps) is skipped outright
+      const T v0 = f < k ? opt_update<T, ADAM>(V[j * kp + f], grad[at], am + at, av + at, o) : T(0);
+      const T v1 = f + 1 < k ? opt_update<T, ADAM>(V[j * kp + f + 1], grad[at + 1], am + at + 1, av + at + 1, o) : T(0);
+      V[j * kp + f] = v0;
+      V[j * kp + f + 1] = v1;
+      s += v0 * v0 + v1 * v1;
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      vn[j] = s;
+      w[j] = opt_update<T, ADAM>(w[j], grad[w_off + j], am + w_off + j, av + w_off + j, o);
+    }
+  }
+}
+
 // row / column kernels: (threads per row, chunks per lane) for kp = 64 * nch
 #define RFM_DISPATCH_TPR(nch, ...)                                                       \
   switch (nch) {                                                                         \
@@ -894,6 +941,7 @@ struct rfm_fm_trainer {
   int dp_rank = -1, dp_world = 0, dp_parity = 0;
   uint32_t dp_seq = 0;
   bool dp_pending_loss = false;
+  DevBuf<unsigned char> adam_m, adam_v;   // Adam moments, laid out like the gradient buffer
   DevBuf<double> dp_prev_loss;
   DevBuf<uint32_t> dp_local;   // [arrive counter, go flag, error flag]
   unsigned char *grad_ptr() const { return xchg ? xchg + (size_t)dp_parity * xchg_grad_bytes : grad.p; }
@@ -1060,9 +1108,17 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
 }
 
 template <typename T>
+int post_update_losses(rfm_fm_trainer *t, int64_t batch, int64_t slot);
+
+template <typename T>
 int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot, bool sampled, const FeistelKey &fkey) {
   RFM_TRY((step_core<T, false>(t, batch, lr, sampled, fkey, 0)));
-  // post-update batch loss and val loss in ONE launch (the val rows ride along as a second row set)
+  return post_update_losses<T>(t, batch, slot);
+}
+
+// post-update batch loss and val loss in ONE launch (the val rows ride along as a second row set)
+template <typename T>
+int post_update_losses(rfm_fm_trainer *t, int64_t batch, int64_t slot) {
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
   RowsArgs<T> a = rows_args<T>(m, t->train);
@@ -1845,6 +1901,78 @@ int rfm_fm_dp_prev_loss_ptr_dev(rfm_fm_trainer *t, void **sums_dev, void **statu
   *sums_dev = t->dp_prev_loss.p;
   if (status_dev) *status_dev = t->dp_local.p + 2;
   return RFM_OK;
+}
+
+}  // extern "C" (pause)
+namespace {
+template <typename T>
+int opt_epoch_impl(rfm_fm_trainer *t, int64_t batch, int64_t slot, bool sampled, const FeistelKey &key,
+                   const rfm_optimizer &opt) {
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  RFM_TRY((step_core<T, true>(t, batch, 0.0, sampled, key, 0)));       // dense gradient of the whole batch
+  const bool adam = opt.kind == RFM_OPT_ADAM;
+  const size_t total = (size_t)grad_total(m->n, m->kp);
+  if (adam && !t->adam_m.p) {
+    RFM_TRY(t->adam_m.alloc(total * sizeof(T)));
+    RFM_TRY(t->adam_v.alloc(total * sizeof(T)));
+    RFM_CUDA(cudaMemsetAsync(t->adam_m.p, 0, total * sizeof(T), ctx->stream));
+    RFM_CUDA(cudaMemsetAsync(t->adam_v.p, 0, total * sizeof(T), ctx->stream));
+  }
+  OptArgs<T> o;
+  o.lr = (T)opt.lr;
+  o.l2 = (T)opt.l2;
+  o.b1 = (T)opt.beta1;
+  o.b2 = (T)opt.beta2;
+  o.eps = (T)opt.eps;
+  o.c1 = adam ? (T)(1.0 / (1.0 - std::pow(opt.beta1, (double)opt.step))) : T(1);
+  o.c2 = adam ? (T)(1.0 / (1.0 - std::pow(opt.beta2, (double)opt.step))) : T(1);
+  const int g = grid_for(ctx, ceil_div(m->n, ROWS_WARPS), 8);
+  T *gr = reinterpret_cast<T *>(t->grad_ptr());
+  if (adam) {
+    auto fm_adam_step = optimizer_rows_kernel<T, true>;
+    RFM_LAUNCH(ctx, fm_adam_step, g, ROWS_THREADS, 0, reinterpret_cast<T *>(m->w0.p), reinterpret_cast<T *>(m->w.p),
+               reinterpret_cast<T *>(m->V.p), reinterpret_cast<T *>(m->vn.p), gr, reinterpret_cast<T *>(t->adam_m.p),
+               reinterpret_cast<T *>(t->adam_v.p), m->n, m->k, m->kp, GRAD_W_OFF, grad_v_off(m->n), o);
+  } else {
+    auto fm_sgd_l2_step = optimizer_rows_kernel<T, false>;
+    RFM_LAUNCH(ctx, fm_sgd_l2_step, g, ROWS_THREADS, 0, reinterpret_cast<T *>(m->w0.p), reinterpret_cast<T *>(m->w.p),
+               reinterpret_cast<T *>(m->V.p), reinterpret_cast<T *>(m->vn.p), gr, (T *)nullptr, (T *)nullptr, m->n,
+               m->k, m->kp, GRAD_W_OFF, grad_v_off(m->n), o);
+  }
+  return post_update_losses<T>(t, batch, slot);
+}
+}  // namespace
+extern "C" {
+
+int rfm_fm_train_epoch_opt(rfm_fm_trainer *t, const int64_t *batch_rows, uint32_t seed, uint32_t epoch, int64_t batch,
+                           int64_t slot, const rfm_optimizer *opt) {
+  RFM_TRY(check_batch(t, batch, slot, "rfm_fm_train_epoch_opt"));
+  RFM_REQUIRE(opt, "rfm_fm_train_epoch_opt: optimizer is NULL");
+  RFM_REQUIRE(opt->kind == RFM_OPT_SGD || opt->kind == RFM_OPT_ADAM, "rfm_fm_train_epoch_opt: unknown optimizer kind %d",
+              opt->kind);
+  RFM_REQUIRE(opt->l2 >= 0.0, "rfm_fm_train_epoch_opt: l2 must be >= 0");
+  if (opt->kind == RFM_OPT_ADAM)
+    RFM_REQUIRE(opt->step >= 1 && opt->beta1 >= 0.0 && opt->beta1 < 1.0 && opt->beta2 >= 0.0 && opt->beta2 < 1.0 &&
+                    opt->eps > 0.0,
+                "rfm_fm_train_epoch_opt: Adam needs step >= 1, betas in [0, 1), eps > 0");
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  void *g = nullptr;
+  RFM_TRY(rfm_fm_grad_ptr_dev(t, &g));
+  FeistelKey key = make_feistel_key(1, 0, 0);
+  const bool sampled = batch_rows == nullptr;
+  if (sampled) {
+    RFM_REQUIRE(t->train->n_rows <= (1LL << 32), "rfm_fm_train_epoch_opt: at most 2^32 rows");
+    key = make_feistel_key((uint64_t)t->train->n_rows, seed, epoch);
+  } else {
+    for (int64_t q = 0; q < batch; ++q)
+      RFM_REQUIRE(batch_rows[q] >= 0 && batch_rows[q] < t->train->n_rows,
+                  "rfm_fm_train_epoch_opt: row id %lld out of range", (long long)batch_rows[q]);
+    RFM_TRY(stage_batch(t, batch_rows, batch));
+  }
+  return t->m->dtype == RFM_F64 ? opt_epoch_impl<double>(t, batch, slot, sampled, key, *opt)
+                                : opt_epoch_impl<float>(t, batch, slot, sampled, key, *opt);
 }
 
 int rfm_fm_loss_sums_ptr_dev(rfm_fm_trainer *t, void **sums_dev) {

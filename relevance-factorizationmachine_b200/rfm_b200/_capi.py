@@ -56,6 +56,7 @@ _SIGNATURES = {
     "rfm_fm_grad_epoch": ([_P, _P, c_int64], c_int),
     "rfm_fm_grad_epoch_sampled": ([_P, c_uint32, c_uint32, c_int64, c_int64], c_int),
     "rfm_fm_apply_grad": ([_P, c_double], c_int),
+    "rfm_fm_train_epoch_opt": ([_P, c_void_p, c_uint32, c_uint32, c_int64, c_int64, c_void_p], c_int),
     "rfm_fm_dp_export": ([_P, c_void_p], c_int),
     "rfm_fm_dp_connect": ([_P, c_int32, c_int32, c_void_p], c_int),
     "rfm_fm_dp_exchange_apply": ([_P, c_double], c_int),
@@ -235,6 +236,12 @@ class CsrRows(_Handle):
                                    ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
         self.n_rows = X.shape[0]
         self.h2d_bytes = indptr.nbytes + indices.nbytes + data.nbytes + (y.nbytes + ps.nbytes if y is not None else 0)
+
+
+class Optimizer(ctypes.Structure):
+    """``rfm_optimizer`` of include/rfm_b200.h."""
+    _fields_ = [("kind", c_int32), ("reserved", c_int32), ("lr", c_double), ("l2", c_double), ("beta1", c_double),
+                ("beta2", c_double), ("eps", c_double), ("step", c_int64)]
 
 
 def pin_array(a: np.ndarray) -> bool:

@@ -22,7 +22,7 @@ import numpy as np
 from . import _capi
 from ._capi import check, lib, ptr
 from .base import PointwiseBaseRecommender
-from .optimizer import SGD
+from .optimizer import SGD, Adam
 from .sampler import LegacyBatchPrefetcher
 
 
@@ -55,19 +55,35 @@ class FactorizationMachines(PointwiseBaseRecommender):
     device: int = 0
     progress: bool = False        # tqdm bar like the reference's (src/fm.py:71)
     distributed: object = None    # rfm_b200.dist.DistEnv: data-parallel fit over its ranks
+    optimizer: str = "sgd"        # "sgd" = the reference's step; "adam" (spec: oracle/optimizer_oracle.py)
+    l2: float = 0.0               # coupled L2 on w0, w, V (0 = reference behaviour)
+    beta1: float = 0.9
+    beta2: float = 0.999
+    adam_eps: float = 1e-8
     _dev: object = field(default=None, init=False, repr=False, compare=False)
 
     def __post_init__(self) -> None:
         if self.sampler not in ("legacy", "feistel"):
             raise ValueError("sampler must be 'legacy' or 'feistel'")
+        if self.optimizer not in ("sgd", "adam"):
+            raise ValueError("optimizer must be 'sgd' or 'adam'")
+        if self.l2 < 0:
+            raise ValueError("l2 must be >= 0")
+        if self.distributed is not None and (self.optimizer != "sgd" or self.l2 != 0):
+            raise ValueError("the data-parallel fit implements the reference's SGD step only")
         _capi.dtype_code(self.dtype)
+
+        def holder(params):
+            if self.optimizer == "adam":
+                return Adam(params=params, lr=self.lr, beta1=self.beta1, beta2=self.beta2, eps=self.adam_eps, l2=self.l2)
+            return SGD(params=params, lr=self.lr)
+
         np.random.seed(self.seed)                                   # global legacy RNG, like the reference
-        self.w0 = SGD(params=np.array([0.0]), lr=self.lr)
+        self.w0 = holder(np.array([0.0]))
         limit = self.alpha * np.sqrt(6 / self.n_features)
-        self.w = SGD(params=np.random.uniform(low=-limit, high=limit, size=self.n_features), lr=self.lr)
+        self.w = holder(np.random.uniform(low=-limit, high=limit, size=self.n_features))
         limit = self.alpha * np.sqrt(6 / self.n_factors)
-        self.V = SGD(params=np.random.uniform(low=-limit, high=limit, size=(self.n_features, self.n_factors)),
-                     lr=self.lr)
+        self.V = holder(np.random.uniform(low=-limit, high=limit, size=(self.n_features, self.n_factors)))
         if self.evaluator is not None:
             self.val_metrics = []
             self.model_name = "FM"
@@ -158,9 +174,16 @@ class FactorizationMachines(PointwiseBaseRecommender):
             it = tqdm(epochs)
         launches0 = ctx.launch_count()
         t_phase = time.perf_counter()
+        dense_opt = self.optimizer == "adam" or self.l2 != 0          # not the reference's fused SGD step
         try:
             for epoch in it:
-                if prefetch is not None:
+                if dense_opt:
+                    opt = _capi.Optimizer(kind=1 if self.optimizer == "adam" else 0, lr=self.lr, l2=self.l2,
+                                          beta1=self.beta1, beta2=self.beta2, eps=self.adam_eps, step=epoch + 1)
+                    idx = prefetch.next() if prefetch is not None else None
+                    check(lib().rfm_fm_train_epoch_opt(trainer.handle, ptr(idx), self.seed & 0xFFFFFFFF, epoch,
+                                                       self.batch_size, epoch, byref(opt)))
+                elif prefetch is not None:
                     idx = prefetch.next()
                     check(lib().rfm_fm_train_epoch(trainer.handle, ptr(idx), self.batch_size, self.lr, epoch))
                 else:

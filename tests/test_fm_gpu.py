@@ -188,3 +188,40 @@ def test_many_features_three_sort_passes_and_k128():
     np.testing.assert_allclose(vl, rvl, rtol=1e-9)
     np.testing.assert_allclose(m.V(), rV, rtol=1e-9, atol=1e-13)
     np.testing.assert_allclose(m.w(), rw, rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("kind,l2", [("adam", 0.0), ("adam", 0.05), ("sgd", 0.05)])
+@pytest.mark.parametrize("sampler", ["legacy", "feistel"])
+def test_dense_optimizers_match_their_specification(kind, l2, sampler):
+    """Adam / SGD with L2 (rfm_fm_train_epoch_opt) against oracle/optimizer_oracle.py -- the reference has no
+    such optimizer (utils/optimizer.py ends at :64), so the NumPy restatement is the specification."""
+    from oracle import optimizer_oracle
+    g = load_golden("coat_fm_ips_alpha01")
+    train, val = _dicts(g)
+    lr = 0.01 if kind == "adam" else float(g["lr"])
+    from rfm_b200.fm import FactorizationMachines
+    m = FactorizationMachines("IPS", 12, int(g["k"]), lr, int(g["B"]), int(g["seed"]), train["features"].shape[1],
+                              alpha=float(g["alpha"]), optimizer=kind, l2=l2, sampler=sampler)
+    w0, w, V = m.w0().copy(), m.w().copy(), m.V().copy()
+    tl, vl = m.fit(train, val)
+    seed = int(g["seed"])
+    smp = None if sampler == "legacy" else (lambda n, b, e: sampler_oracle.feistel_batch(n, b, e, seed))
+    (rw0, rw, rV), rtl, rvl = optimizer_oracle.fm_fit_opt(train, val, 12, int(g["B"]), lr, w0, w, V, kind=kind, l2=l2,
+                                                         sampler=smp)
+    np.testing.assert_allclose(tl, rtl, rtol=1e-9)
+    np.testing.assert_allclose(vl, rvl, rtol=1e-9)
+    np.testing.assert_allclose(m.w0(), [rw0], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(m.w(), rw, rtol=1e-7, atol=1e-11)
+    np.testing.assert_allclose(m.V(), rV, rtol=1e-7, atol=1e-11)
+    if kind == "adam":          # it actually trained: Adam moves every touched weight by ~lr per step
+        assert np.abs(m.V() - V).max() > 5 * lr
+
+
+def test_l2_zero_dense_sgd_equals_the_reference_step():
+    """The dense path with plain SGD and l2 -> 0 reproduces the fused reference step (same golden trajectory)."""
+    g = load_golden("coat_fm_ips_alpha01")
+    train, val = _dicts(g)
+    m = _model(g, train["features"].shape[1], l2=1e-300)
+    tl, vl = m.fit(train, val)
+    np.testing.assert_allclose(tl, g["train_loss"], rtol=1e-9)
+    np.testing.assert_allclose(m.V(), g["V"], rtol=1e-9, atol=1e-13)
