@@ -1191,7 +1191,9 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     kc = std::max<int64_t>(kc, std::min<int64_t>(item_end - item_begin, 256));
     kc = (kc + 7) / 8 * 8;
     // users are processed in chunks so that the group maxima of a chunk stay within a fixed scratch budget
-    const int64_t scratch_rows = std::max<int64_t>(BM, ((int64_t)1 << 30) / (n_groups * 4) / BM * BM);
+    int64_t scratch_bytes = (int64_t)1 << 30;
+    if (const char *env = getenv("RFM_SCORE_SCRATCH_MB")) scratch_bytes = std::max<int64_t>(1, atoll(env)) << 20;
+    const int64_t scratch_rows = std::max<int64_t>(BM, scratch_bytes / (n_groups * 4) / BM * BM);
     const int chunk_blocks = (int)std::min<int64_t>(n_user_blocks, scratch_rows / BM);
     const size_t chunk_rows = (size_t)chunk_blocks * BM;
     RFM_TRY(t->gmax.ensure(chunk_rows * n_groups));

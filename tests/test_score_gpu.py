@@ -62,6 +62,26 @@ def test_item_terms_alone_rank_the_catalog():
     check(rng.normal(size=(U, k)) * 1e-4, rng.normal(size=(I, k)) * 1e-4, None, beta, 0.0, 9)
 
 
+def test_user_chunking_and_extreme_k(monkeypatch):
+    """Users are processed in chunks when the group maxima would exceed the scratch budget; K = 1 and the
+    largest supported K; a catalog smaller than K (padding with -1 / -inf)."""
+    rng = np.random.default_rng(9)
+    U, I, k = 1500, 9000, 64
+    A, C = rng.normal(size=(U, k)) * 0.4, rng.normal(size=(I, k)) * 0.4
+    beta = rng.normal(size=I) * 0.2
+    monkeypatch.setenv("RFM_SCORE_SCRATCH_MB", "1")            # 1 MiB: a few 128-user blocks per chunk
+    sc = check(A, C, None, beta, 0.0, 9)
+    assert sc.last_stats["users_ranked_exactly"] == 0
+    check(A, C, None, beta, 0.0, 1)
+    check(A[:300], C, None, beta, 0.0, 120)
+    monkeypatch.delenv("RFM_SCORE_SCRATCH_MB")
+    from rfm_b200.score import TopKScorer
+    items, scores = TopKScorer(A[:10], C[:5], None, beta[:5], 0.0).topk(9)
+    assert (items[:, 5:] == -1).all() and np.isneginf(scores[:, 5:]).all()
+    ref_items, ref_scores = numpy_topk(A[:10], C[:5], None, beta[:5], 0.0, 5)
+    np.testing.assert_array_equal(items[:, :5], ref_items)
+
+
 def test_k_wider_than_the_tensor_path_uses_exact_kernel():
     rng = np.random.default_rng(0)
     check(rng.normal(size=(40, 300)), rng.normal(size=(90, 300)), None, None, 0.0, 7, expect_tensor=False)
