@@ -337,6 +337,7 @@ def measure_scoring(device, dist, world, peaks, peak_kind):
     out = {"metric": "scored_user_item_pairs_per_sec", "unit": "pairs/s"}
     rng = np.random.default_rng(11)
     shapes = (("eval_grid_1411x3327", 1411, 3327, 64, 9, 20), ("large_32768x262144", 32768, 262144, 64, 9, 5),
+              ("large_k128_32768x262144", 32768, 262144, 128, 9, 5),
               ("large_k128_top100_16384x131072", 16384, 131072, 128, 100, 5))
     for name, U, I, k, K, reps in shapes:
         A = rng.normal(size=(U, k)) * 0.3
@@ -532,8 +533,8 @@ def run_ours(args):
     scoring = None if args.no_scoring else measure_scoring(local_rank, dist, world, peaks, peak_kind)
     cpu = None
     if not args.no_cpu_baseline:
-        v1, st1, dt1 = cpu_port_run(log, B, 3, 1, budget_s=10.0)
-        v, st, dt, cores = cpu_port_run_parallel(log, B, 16, 1, budget_s=20.0)
+        v1, st1, dt1 = cpu_port_run(log, B, 8, 1, budget_s=8.0)
+        v, st, dt, cores = cpu_port_run_parallel(log, B, 160, 1, budget_s=15.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "host_cores_available": os.cpu_count(),
                "sample": "%d epochs of B=%d on the %d-row train set, reference sampler included, %.1f s on %d "
                          "processes" % (st, B, X.shape[0], dt, cores),
