@@ -26,9 +26,10 @@
 //      first).
 //   6. score_exact_kernel: users whose candidate buffer overflowed (or every user, in exact mode / for k > 128)
 //      are scored in float64 against the whole catalog.
-// The result is therefore always the exact float64 top-K; the tensor-core passes only prune. Both passes are
-// bound by reading the accumulator out of TMEM (128 KB per 128 x 256 step at ~100 B/clk/SM, measured), not by
-// the MMA (640 cycles per step at k = 64) or the epilogue math.
+// The result is therefore always the exact float64 top-K; the tensor-core passes only prune. At k = 64 both
+// passes are bound by the hand-shake chain between the two accumulator stages (commit -> epilogue wake-up ->
+// tcgen05.ld + max tree -> arrive -> issuer wake-up, ~1,100 cycles against a 640-cycle MMA step; DESIGN.md 4.4,
+// tools/ldtm_bw.cu), not by TMEM bandwidth (372 B/clk/SM measured) or the epilogue math.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
