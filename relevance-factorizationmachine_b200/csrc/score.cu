@@ -26,10 +26,10 @@
 //      first).
 //   6. score_exact_kernel: users whose candidate buffer overflowed (or every user, in exact mode / for k > 128)
 //      are scored in float64 against the whole catalog.
-// The result is therefore always the exact float64 top-K; the tensor-core passes only prune. At k = 64 both
-// passes are bound by the hand-shake chain between the two accumulator stages (commit -> epilogue wake-up ->
-// tcgen05.ld + max tree -> arrive -> issuer wake-up, ~1,100 cycles against a 640-cycle MMA step; DESIGN.md 4.4,
-// tools/ldtm_bw.cu), not by TMEM bandwidth (372 B/clk/SM measured) or the epilogue math.
+// The result is therefore always the exact float64 top-K; the tensor-core passes only prune. At k = 64 the passes
+// run at ~1,300-1,800 cycles per 128 x 256 step against a 640-cycle MMA step: pipeline bubbles between MMA and
+// drain, not TMEM bandwidth (372 B/clk/SM measured, tools/ldtm_bw.cu) and not the epilogue math; DESIGN.md 4.4
+// lists the variants measured so far.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
