@@ -61,7 +61,7 @@ constexpr int SCORE_THREADS = 128 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, 
 //    step i + 1 overlaps the whole epilogue of step i; 1: two warp groups, one per accumulator stage
 constexpr int EPI_GROUPS = RFM_EPI_PINGPONG ? 2 : 1;
 constexpr int EPI_PARTS = EPI_WARPS / (4 * EPI_GROUPS);
-static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "8 or 16 epilogue warps");
+static_assert(EPI_WARPS == 16 && EPI_GROUPS == 1, "the drain is written for 16 warps x 64 columns");
 constexpr int MAX_KB = 2;        // k <= 128 on the tensor-core path
 constexpr int MAX_K = 120;
 
@@ -226,11 +226,6 @@ __device__ __forceinline__ void tc_ld_wait_x32(uint32_t (&v)[32]) {
                  "+r"(v[30]), "+r"(v[31])
                :
                : "memory");
-}
-// Scheduling fence: the values listed are complete before anything after this point is issued. Used to finish
-// the math of one slice before the TMEM load that overwrites its registers' twin buffer is issued.
-__device__ __forceinline__ void pin4(float (&m)[4]) {
-  asm volatile("" : "+f"(m[0]), "+f"(m[1]), "+f"(m[2]), "+f"(m[3])::"memory");
 }
 // three-input max (FMNMX3): one instruction per three elements
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -431,63 +426,70 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
     for (int h = 0; h < UB; ++h)
       tau_h[h] = (PASS == 1 && h < nh) ? a.tau[(size_t)(block0 + h) * BM + r] : INFINITY;
-    for (int step = group; step < n_tiles * nh; step += EPI_GROUPS) {
-      const int it = step / nh, h = step - it * nh;
+    // Loop-invariant pieces are hoisted and (tile, user block) advance by counters: the epilogue's instruction
+    // count per step, not its math, is what competes with the MMA issue for the four schedulers.
+    const int c = part * WARP_COLS;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c;
+    const int row0 = block0 * BM + r;                      // row of user block h = row0 + h * BM (inside the chunk)
+    const int kc = a.kc, item_end = a.item_end;
+    uint32_t *const cand_cnt = a.cand_cnt;
+    int2 *const cand = a.cand;
+    float *const gbase = PASS == 0 ? a.gmax + (size_t)row0 * a.n_groups + (int64_t)visit0 * (BN / GCOLS) + c / GCOLS
+                                   : nullptr;
+    const size_t gstride_h = (size_t)BM * a.n_groups;      // gmax: from one user block to the next
+    const int n_steps = n_tiles * nh;
+    int h = 0, item0 = tile_of(0) * BN + c;
+    const int item_step = a.tile_stride * BN;
+    float *gtile = gbase;                                  // gmax slot of (current tile, user block 0)
+    for (int step = 0; step < n_steps; ++step) {
       const int acc = step & 1;
       const uint32_t aph = (step >> 1) & 1;
-      const size_t row = (size_t)(block0 + h) * BM + r;      // row inside this chunk of users
       float tau = tau_h[0];
 #pragma unroll
       for (int hh = 1; hh < UB; ++hh)
         if (h == hh) tau = tau_h[hh];
-      float *grow = PASS == 0 ? a.gmax + row * a.n_groups : nullptr;
+      const int row = row0 + h * BM;
       mbar_wait(tfull + acc, aph);
       tc_fence_after();
-      const int item0 = tile_of(it) * BN;
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      const int c_begin = part * WARP_COLS;
+      const uint32_t tbase = tlane + acc * BN;
+      // Drain first, work later: both of the warp's loads are issued back to back, and the accumulator stage is
+      // handed back to the MMA issuer as soon as they have landed in registers. The max tree, the group-maximum
+      // store (32 scattered sectors per instruction) and above all the cold append path (a global atomic) then
+      // overlap the next MMA instead of sitting between this step's MMA and the next-but-one: every step has
+      // some warp on the cold path, and all 16 must arrive before the stage can be reused.
       uint32_t v0[32], v1[32];
-      float gacc = -INFINITY;
-      tc_ld_issue_x32(tbase + c_begin, v0);
-#pragma unroll 1
-      for (int c = c_begin; c < c_begin + WARP_COLS; c += 64) {
-        // software pipeline over 32-column slices: the next slice's TMEM load is in flight during the math
-        float m0[4], m1[4];
-        tc_ld_wait_x32(v0);
-        tc_ld_issue_x32(tbase + c + 32, v1);
-        slice_max(v0, m0);
-        pin4(m0);
-        if (PASS == 1) {
-          const float mx = fmaxf(max3(m0[0], m0[1], m0[2]), m0[3]);
-          if (__any_sync(FULL, mx >= tau))
-            collect_slice(v0, m0, tau, item0 + c, a.item_end, a.kc, (int)row, a.cand_cnt, a.cand, pend);
-        }
-        tc_ld_wait_x32(v1);
-        if (c + 64 < c_begin + WARP_COLS) tc_ld_issue_x32(tbase + c + 64, v0);
-        slice_max(v1, m1);
-        pin4(m1);
-        if (PASS == 1) {
-          const float mx = fmaxf(max3(m1[0], m1[1], m1[2]), m1[3]);
-          if (__any_sync(FULL, mx >= tau))
-            collect_slice(v1, m1, tau, item0 + c + 32, a.item_end, a.kc, (int)row, a.cand_cnt, a.cand, pend);
-        }
-        if (PASS == 0) {
-          float *dst = grow + (int64_t)(visit0 + it) * (BN / GCOLS) + c / GCOLS;
-          if (GCOLS == 128 && MAX_GCOLS >= 128) {         // a group spans two iterations of this loop
-            const float m = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
-            if ((c & 64) == 0) gacc = m;
-            else *dst = fmaxf(gacc, m);
-          } else if (GCOLS == 64) {
-            *dst = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
-          } else {
-            store_group_max<GCOLS>(dst, m0);
-            store_group_max<GCOLS>(dst + 32 / GCOLS, m1);
-          }
-        }
-      }
+      tc_ld_issue_x32(tbase, v0);
+      tc_ld_issue_x32(tbase + 32, v1);
+      tc_ld_wait_x32(v0);
+      tc_ld_wait_x32(v1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + acc);
+      float m0[4], m1[4];
+      slice_max(v0, m0);
+      slice_max(v1, m1);
+      if (PASS == 1) {
+        const float mx0 = fmaxf(max3(m0[0], m0[1], m0[2]), m0[3]), mx1 = fmaxf(max3(m1[0], m1[1], m1[2]), m1[3]);
+        if (__any_sync(FULL, fmaxf(mx0, mx1) >= tau)) {
+          if (__any_sync(FULL, mx0 >= tau))
+            collect_slice(v0, m0, tau, item0, item_end, kc, row, cand_cnt, cand, pend);
+          if (__any_sync(FULL, mx1 >= tau))
+            collect_slice(v1, m1, tau, item0 + 32, item_end, kc, row, cand_cnt, cand, pend);
+        }
+      } else {
+        float *dst = gtile + h * gstride_h;
+        if (GCOLS == 64) {
+          *dst = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
+        } else {
+          store_group_max<GCOLS>(dst, m0);
+          store_group_max<GCOLS>(dst + 32 / GCOLS, m1);
+        }
+      }
+      if (++h == nh) {        // next tile
+        h = 0;
+        item0 += item_step;
+        gtile += BN / GCOLS;
+      }
     }
     if (PASS == 1) flush_append(pend, a.kc, a.cand);
   }
@@ -982,7 +984,6 @@ int launch_pass_kb(rfm_ctx *ctx, int pass, int gcols, dim3 grid, const CUtensorM
                    const PassArgs &pa) {
   if (pass == 1) return launch_pass_as<KB, 1, 64>(ctx, grid, tmap_a, tmap_c, pa);
   switch (gcols) {
-    case 128: return launch_pass_as<KB, 0, 128>(ctx, grid, tmap_a, tmap_c, pa);
     case 64: return launch_pass_as<KB, 0, 64>(ctx, grid, tmap_a, tmap_c, pa);
     case 32: return launch_pass_as<KB, 0, 32>(ctx, grid, tmap_a, tmap_c, pa);
     case 16: return launch_pass_as<KB, 0, 16>(ctx, grid, tmap_a, tmap_c, pa);
