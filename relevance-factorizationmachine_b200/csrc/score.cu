@@ -27,9 +27,9 @@
 //   6. score_exact_kernel: users whose candidate buffer overflowed (or every user, in exact mode / for k > 128)
 //      are scored in float64 against the whole catalog.
 // The result is therefore always the exact float64 top-K; the tensor-core passes only prune. At k = 64 the passes
-// run at ~1,300-1,800 cycles per 128 x 256 step against a 640-cycle MMA step: pipeline bubbles between MMA and
-// drain, not TMEM bandwidth (372 B/clk/SM measured, tools/ldtm_bw.cu) and not the epilogue math; DESIGN.md 4.4
-// lists the variants measured so far.
+// run at ~1,300-1,450 cycles per 128 x 256 step against a 640-cycle MMA step (tensor pipe ~60 % busy): hand-shake
+// gaps, an MMA slowed by shared-memory contention with the copy engine, and per-CTA prologue -- not TMEM bandwidth
+// (372 B/clk/SM measured) and not the epilogue math; DESIGN.md 4.4, tools/*.cu.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
