@@ -103,6 +103,15 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     __nanosleep(32);
   }
 }
+// one lane of a converged warp; the code around it stays warp-uniform, so the operands of the tcgen05 / TMA
+// instructions it guards are known to be uniform and go to uniform registers directly. Inside an `if (lane == 0)`
+// region the compiler must assume per-thread values and wraps every such operand in a re-execution loop
+// (R2UR + BRA.U.ANY, ~10 instructions each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t leader;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
+  return leader != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -361,54 +370,61 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer =====
+    // ===== TMA producer: uniform control flow, one elected lane issues the copies =====
+    if (elect_one()) {
       mbar_expect_tx(afull, nh * L::A_BLOCK_BYTES);
       for (int h = 0; h < nh; ++h)
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(sA + h * L::A_BLOCK_BYTES + kb * BM * 128, &tmap_a, afull, kb * BK,
                       (a.user_block0 + block0 + h) * BM);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait_relaxed(empty + s, ph ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait_relaxed(empty + s, ph ^ 1);
+      const int tile = tile_of(it);
+      if (elect_one()) {
         mbar_expect_tx(full + s, L::B_STAGE_BYTES);
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sB + s * L::B_STAGE_BYTES + kb * BN * 128, &tmap_c, full + s, kb * BK, tile_of(it) * BN);
-        bulk_load_1d(sB + s * L::B_STAGE_BYTES + L::B_MAIN_BYTES, a.beta16 + (size_t)tile_of(it) * BN * 16,
+          tma_load_2d(sB + s * L::B_STAGE_BYTES + kb * BN * 128, &tmap_c, full + s, kb * BK, tile * BN);
+        bulk_load_1d(sB + s * L::B_STAGE_BYTES + L::B_MAIN_BYTES, a.beta16 + (size_t)tile * BN * 16,
                      L::B_BETA_BYTES, full + s);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer =====
-      mbar_wait(afull, 0);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait_relaxed(full + s, ph);
-        for (int h = 0; h < nh; ++h) {
-          const int step = it * nh + h;
-          const int acc = step & 1;
-          const uint32_t aph = (step >> 1) & 1;
-          mbar_wait_relaxed(tempty + acc, aph ^ 1);
-          tc_fence_after();
+    // ===== MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    mbar_wait(afull, 0);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait_relaxed(full + s, ph);
+      for (int h = 0; h < nh; ++h) {
+        const int step = it * nh + h;
+        const int acc = step & 1;
+        const uint32_t aph = (step >> 1) & 1;
+        mbar_wait_relaxed(tempty + acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        const uint32_t ones = smem_u32(sOnes), bop = smem_u32(sB + s * L::B_STAGE_BYTES + L::B_MAIN_BYTES);
+        const uint32_t a_blk = smem_u32(sA + h * L::A_BLOCK_BYTES), b_blk = smem_u32(sB + s * L::B_STAGE_BYTES);
+        if (elect_one()) {
           // accumulator = 1 * beta (overwrite), then += <A_u, C_i> over the K blocks
-          tc_mma_bf16(tmem_base + acc * BN, umma_desc_interleaved(smem_u32(sOnes), 128, 256),
-                      umma_desc_interleaved(smem_u32(sB + s * L::B_STAGE_BYTES + L::B_MAIN_BYTES), 128, 256),
-                      UMMA_IDESC, 0u);
+          tc_mma_bf16(d, umma_desc_interleaved(ones, 128, 256), umma_desc_interleaved(bop, 128, 256), UMMA_IDESC, 0u);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
-            const uint32_t a_base = smem_u32(sA + h * L::A_BLOCK_BYTES + kb * BM * 128);
-            const uint32_t b_base = smem_u32(sB + s * L::B_STAGE_BYTES + kb * BN * 128);
 #pragma unroll
             for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom
-              tc_mma_bf16(tmem_base + acc * BN, umma_desc_sw128(a_base + k4 * 32), umma_desc_sw128(b_base + k4 * 32),
-                          UMMA_IDESC, 1u);
+              tc_mma_bf16(d, umma_desc_sw128(a_blk + kb * BM * 128 + k4 * 32),
+                          umma_desc_sw128(b_blk + kb * BN * 128 + k4 * 32), UMMA_IDESC, 1u);
             }
           }
-          tc_commit(tfull + acc);    // the accumulator is complete
+          tc_commit(tfull + acc);                    // the accumulator is complete
+          if (h == nh - 1) tc_commit(empty + s);     // the B stage is free once the MMAs of every user block have read it
         }
-        tc_commit(empty + s);        // the B stage is free once the MMAs of every user block have read it
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
