@@ -1,5 +1,5 @@
 import sys, time, json
-sys.path.insert(0, "relevance-factorizationmachine_b200"); sys.path.insert(0, ".")
+sys.path.insert(0, "relevance-factorizationmachine_b200"); sys.path.insert(0, ".")  # run from the repository root
 import numpy as np
 from rfm_b200.score import TopKScorer
 from rfm_b200 import _capi

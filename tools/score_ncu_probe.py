@@ -1,6 +1,6 @@
 """Single large scoring call for ncu captures of score_filter_kernel (not a test)."""
 import sys
-sys.path.insert(0, "relevance-factorizationmachine_b200"); sys.path.insert(0, ".")
+sys.path.insert(0, "relevance-factorizationmachine_b200"); sys.path.insert(0, ".")  # run from the repository root
 import numpy as np
 from rfm_b200.score import TopKScorer
 U, I, k, K = (int(x) for x in (sys.argv[1:5] if len(sys.argv) > 4 else (16384, 131072, 64, 9)))
