@@ -243,6 +243,10 @@ int rfm_topk_set_factors(rfm_topk *t, const double *A, const double *C, const do
                          const double *beta, double bias);
 int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64_t item_end,
                  int32_t *out_items, double *out_scores, int64_t *stats);
+/* The last run's result in the library's own page-locked host buffers (int32 [n_users][K], double
+ * [n_users][K]), valid until the next rfm_topk_run / rfm_topk_result_host / rfm_topk_destroy on this handle:
+ * saves the copy into caller memory when the caller only reads the result (call rfm_topk_run with NULL outputs). */
+int rfm_topk_result_host(rfm_topk *t, int32_t K, const int32_t **items_host, const double **scores_host);
 /* Item-sharded runs: rfm_topk_run with out_items == out_scores == NULL leaves the
  * shard's result on the device; rfm_topk_result_ptr_dev exposes it (int32 [n_users][K], double
  * [n_users][K]) for the caller's all-gather; rfm_topk_merge_dev merges n_lists gathered lists

@@ -1327,6 +1327,23 @@ int rfm_topk_result_ptr_dev(rfm_topk *t, void **items_dev, void **scores_dev) {
   return RFM_OK;
 }
 
+int rfm_topk_result_host(rfm_topk *t, int32_t K, const int32_t **items_host, const double **scores_host) {
+  RFM_REQUIRE(t && items_host && scores_host, "rfm_topk_result_host: NULL argument");
+  RFM_REQUIRE(t->out_items.p && t->out_scores.p, "rfm_topk_result_host: call rfm_topk_run first");
+  RFM_REQUIRE(K >= 1 && (size_t)t->n_users * K <= t->out_items.n, "rfm_topk_result_host: K does not match the last run");
+  rfm_ctx *ctx = t->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  const size_t n_out = (size_t)t->n_users * K;
+  RFM_TRY(t->stage_items.ensure(n_out));
+  RFM_TRY(t->stage_scores.ensure(n_out));
+  RFM_CUDA(cudaMemcpyAsync(t->stage_items.p, t->out_items.p, n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(t->stage_scores.p, t->out_scores.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *items_host = t->stage_items.p;
+  *scores_host = t->stage_scores.p;
+  return RFM_OK;
+}
+
 int rfm_topk_merge_dev(rfm_ctx *ctx, int64_t n_users, int32_t K, int32_t n_lists, const int32_t *items_dev,
                        const double *scores_dev, int32_t *out_items, double *out_scores) {
   RFM_REQUIRE(ctx && items_dev && scores_dev && out_items && out_scores, "rfm_topk_merge_dev: NULL argument");

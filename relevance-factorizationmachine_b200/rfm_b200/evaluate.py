@@ -196,7 +196,7 @@ class FullCatalogEvaluator:
     def evaluate(self, scorer, mode: str = "tensor") -> defaultdict:
         """``scorer`` is a ``TopKScorer`` (see ``rfm_b200.score.fm_factors`` / ``mf_factors``)."""
         k_max = int(max(self.K))
-        items, scores = scorer.topk(k_max, mode=mode)
+        items, scores = scorer.topk(k_max, mode=mode, copy=False)       # consumed before the next call
         self.last_stats = dict(scorer.last_stats)
         # reduced frame: every user's top rows, worst first so that the ranker's tie rule (later row first)
         # reproduces the Cartesian frame's order (larger item id first among exact ties)

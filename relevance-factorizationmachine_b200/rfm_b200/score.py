@@ -9,7 +9,7 @@ equals ``predict`` on the Cartesian-product rows followed by the reference's per
 """
 from __future__ import annotations
 
-from ctypes import byref, c_int64
+from ctypes import byref, c_int64, c_void_p
 
 import numpy as np
 
@@ -63,17 +63,29 @@ class TopKScorer(_capi._Handle):
         check(lib().rfm_topk_set_factors(self.handle, ptr(A), ptr(C), ptr(alpha), ptr(beta), float(bias)))
         self.last_stats = {}
 
-    def topk(self, K: int, mode: str = "tensor", item_range=None):
+    def topk(self, K: int, mode: str = "tensor", item_range=None, copy: bool = True):
         """(items (n_users, K) int32, scores (n_users, K) float64): every user's K best items, best first;
-        -1 / -inf pad when the catalog range holds fewer than K items."""
+        -1 / -inf pad when the catalog range holds fewer than K items. ``copy=False`` returns read-only views
+        of the library's page-locked result buffers, valid until this scorer's next call (saves a host copy)."""
         if mode not in ("tensor", "exact"):
             raise ValueError("mode must be 'tensor' or 'exact'")
         begin, end = (0, self.n_items) if item_range is None else item_range
-        items = np.empty((self.n_users, K), dtype=np.int32)
-        scores = np.empty((self.n_users, K), dtype=np.float64)
         stats = (c_int64 * 4)()
-        check(lib().rfm_topk_run(self.handle, K, 0 if mode == "tensor" else 1, begin, end, ptr(items), ptr(scores),
-                                 stats))
+        if copy:
+            items = np.empty((self.n_users, K), dtype=np.int32)
+            scores = np.empty((self.n_users, K), dtype=np.float64)
+            check(lib().rfm_topk_run(self.handle, K, 0 if mode == "tensor" else 1, begin, end, ptr(items),
+                                     ptr(scores), stats))
+        else:
+            import ctypes
+            check(lib().rfm_topk_run(self.handle, K, 0 if mode == "tensor" else 1, begin, end, None, None, stats))
+            pi, ps = c_void_p(), c_void_p()
+            check(lib().rfm_topk_result_host(self.handle, K, byref(pi), byref(ps)))
+            n = self.n_users * K
+            items = np.ctypeslib.as_array(ctypes.cast(pi, ctypes.POINTER(ctypes.c_int32)), shape=(n,)).reshape(self.n_users, K)
+            scores = np.ctypeslib.as_array(ctypes.cast(ps, ctypes.POINTER(ctypes.c_double)), shape=(n,)).reshape(self.n_users, K)
+            items.flags.writeable = False
+            scores.flags.writeable = False
         self.last_stats = {"tensor_core_path": bool(stats[0]), "users_ranked_exactly": int(stats[1]),
                            "candidates": int(stats[2]), "sample_stride": int(stats[3])}
         return items, scores

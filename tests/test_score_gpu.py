@@ -82,6 +82,17 @@ def test_user_chunking_and_extreme_k(monkeypatch):
     np.testing.assert_array_equal(items[:, :5], ref_items)
 
 
+def test_result_views_equal_copies():
+    from rfm_b200.score import TopKScorer
+    rng = np.random.default_rng(13)
+    sc = TopKScorer(rng.normal(size=(200, 64)), rng.normal(size=(1500, 64)), None, rng.normal(size=1500), 0.0)
+    items, scores = sc.topk(9)
+    vi, vs = sc.topk(9, copy=False)
+    np.testing.assert_array_equal(vi, items)
+    np.testing.assert_array_equal(vs, scores)
+    assert not vi.flags.writeable and not vs.flags.writeable
+
+
 def test_k_wider_than_the_tensor_path_uses_exact_kernel():
     rng = np.random.default_rng(0)
     check(rng.normal(size=(40, 300)), rng.normal(size=(90, 300)), None, None, 0.0, 7, expect_tensor=False)
