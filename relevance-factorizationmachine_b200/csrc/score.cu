@@ -61,7 +61,7 @@ constexpr int SCORE_THREADS = 128 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, 
 //    step i + 1 overlaps the whole epilogue of step i; 1: two warp groups, one per accumulator stage
 constexpr int EPI_GROUPS = RFM_EPI_PINGPONG ? 2 : 1;
 constexpr int EPI_PARTS = EPI_WARPS / (4 * EPI_GROUPS);
-static_assert(EPI_WARPS == 16 && EPI_GROUPS == 1, "the drain is written for 16 warps x 64 columns");
+static_assert((EPI_WARPS == 16 || EPI_WARPS == 8) && EPI_GROUPS == 1, "the drain handles 64 or 128 columns per warp");
 constexpr int MAX_KB = 2;        // k <= 128 on the tensor-core path
 constexpr int MAX_K = 120;
 
@@ -88,6 +88,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+// the same with the 32-bit shared address computed once by the caller: inside the per-step loops the generic ->
+// shared conversion (and the 1 KB alignment of the dynamic shared memory behind it) was re-derived every step
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar_addr, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive_at(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 // same, for the producer / MMA threads: they run far ahead of the epilogue, and a bare spin would steal issue
 // slots from the epilogue warps that share their schedulers (measured: 30 % of all issued instructions)
@@ -179,7 +194,7 @@ struct PassArgs {
 
 constexpr int WARP_COLS = BN / EPI_PARTS;      // columns of an accumulator one epilogue warp filters
 static_assert(WARP_COLS % 64 == 0, "an epilogue warp owns whole groups of 64 columns");
-constexpr int MAX_GCOLS = WARP_COLS >= 128 ? 128 : 64;   // widest pass-1 group one warp can produce alone
+constexpr int MAX_GCOLS = 64;   // widest pass-1 group (the threshold kernel merges adjacent groups on load)
 
 // The item term beta_i is added by the tensor core as well: every step starts with one extra K = 16 MMA of a
 // constant operand [1 1 1 0 ... 0] against [b0 b1 b2 0 ... 0], beta split into three bf16 terms (exact to
@@ -454,6 +469,7 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                    : nullptr;
     const size_t gstride_h = (size_t)BM * a.n_groups;      // gmax: from one user block to the next
     const int n_steps = n_tiles * nh;
+    const uint32_t tfull_at = smem_u32(tfull), tempty_at = smem_u32(tempty);      // + 8 * stage
     int h = 0, item0 = tile_of(0) * BN + c;
     const int item_step = a.tile_stride * BN;
     float *gtile = gbase;                                  // gmax slot of (current tile, user block 0)
@@ -465,7 +481,7 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int hh = 1; hh < UB; ++hh)
         if (h == hh) tau = tau_h[hh];
       const int row = row0 + h * BM;
-      mbar_wait(tfull + acc, aph);
+      mbar_wait_at(tfull_at + acc * 8, aph);
       tc_fence_after();
       const uint32_t tbase = tlane + acc * BN;
       // Drain first, work later: both of the warp's loads are issued back to back, and the accumulator stage is
@@ -473,32 +489,37 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // store (32 scattered sectors per instruction) and above all the cold append path (a global atomic) then
       // overlap the next MMA instead of sitting between this step's MMA and the next-but-one: every step has
       // some warp on the cold path, and all 16 must arrive before the stage can be reused.
-      uint32_t v0[32], v1[32];
-      tc_ld_issue_x32(tbase, v0);
-      tc_ld_issue_x32(tbase + 32, v1);
-      tc_ld_wait_x32(v0);
-      tc_ld_wait_x32(v1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + acc);
-      float m0[4], m1[4];
-      slice_max(v0, m0);
-      slice_max(v1, m1);
-      if (PASS == 1) {
-        const float mx0 = fmaxf(max3(m0[0], m0[1], m0[2]), m0[3]), mx1 = fmaxf(max3(m1[0], m1[1], m1[2]), m1[3]);
-        if (__any_sync(FULL, fmaxf(mx0, mx1) >= tau)) {
-          if (__any_sync(FULL, mx0 >= tau))
-            collect_slice(v0, m0, tau, item0, item_end, kc, row, cand_cnt, cand, pend);
-          if (__any_sync(FULL, mx1 >= tau))
-            collect_slice(v1, m1, tau, item0 + 32, item_end, kc, row, cand_cnt, cand, pend);
+#pragma unroll
+      for (int cc = 0; cc < WARP_COLS; cc += 64) {       // one chunk with 16 warps, two with 8
+        uint32_t v0[32], v1[32];
+        tc_ld_issue_x32(tbase + cc, v0);
+        tc_ld_issue_x32(tbase + cc + 32, v1);
+        tc_ld_wait_x32(v0);
+        tc_ld_wait_x32(v1);
+        if (cc + 64 == WARP_COLS) {                      // everything of this stage is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_at(tempty_at + acc * 8);
         }
-      } else {
-        float *dst = gtile + h * gstride_h;
-        if (GCOLS == 64) {
-          *dst = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
+        float m0[4], m1[4];
+        slice_max(v0, m0);
+        slice_max(v1, m1);
+        if (PASS == 1) {
+          const float mx0 = fmaxf(max3(m0[0], m0[1], m0[2]), m0[3]), mx1 = fmaxf(max3(m1[0], m1[1], m1[2]), m1[3]);
+          if (__any_sync(FULL, fmaxf(mx0, mx1) >= tau)) {
+            if (__any_sync(FULL, mx0 >= tau))
+              collect_slice(v0, m0, tau, item0 + cc, item_end, kc, row, cand_cnt, cand, pend);
+            if (__any_sync(FULL, mx1 >= tau))
+              collect_slice(v1, m1, tau, item0 + cc + 32, item_end, kc, row, cand_cnt, cand, pend);
+          }
         } else {
-          store_group_max<GCOLS>(dst, m0);
-          store_group_max<GCOLS>(dst + 32 / GCOLS, m1);
+          float *dst = gtile + h * gstride_h + cc / GCOLS;
+          if (GCOLS == 64) {
+            *dst = max3(max3(m0[0], m0[1], m0[2]), max3(m0[3], m1[0], m1[1]), fmaxf(m1[2], m1[3]));
+          } else {
+            store_group_max<GCOLS>(dst, m0);
+            store_group_max<GCOLS>(dst + 32 / GCOLS, m1);
+          }
         }
       }
       if (++h == nh) {        // next tile
