@@ -272,3 +272,25 @@ def sharded_topk(scorer, env: DistEnv, K: int, mode: str = "tensor"):
     check(lib().rfm_topk_merge_dev(scorer.ctx.handle, n_users, K, env.world, c_void_p(all_items.data_ptr()),
                                    c_void_p(all_scores.data_ptr()), ptr(items), ptr(scores)))
     return items, scores
+
+
+def sharded_predict(model, X, env: DistEnv) -> np.ndarray:
+    """Row-sharded ``predict`` (independent rows): every rank scores a contiguous slice of
+    the rows of ``X`` with its replica of the parameters and the slices are all-gathered; every rank returns
+    the full vector, equal to the single-process ``model.predict(X)`` bit for bit (a row's score does not
+    depend on which rank computes it)."""
+    torch = env.torch
+    n = X.shape[0]
+    begin, end = slice_bounds(n, env.world, env.rank)
+    mine = model.predict(X=X[begin:end]) if end > begin else np.empty(0)
+    width = -(-n // env.world) if n else 0                 # slices differ by at most one row: pad to the widest
+    dev = "cuda:%d" % env.device if env.backend == "nccl" else "cpu"
+    buf = torch.zeros(max(width, 1), dtype=torch.float64, device=dev)
+    buf[: end - begin] = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64)).to(dev)
+    gathered = [torch.empty_like(buf) for _ in range(env.world)]
+    env.dist.all_gather(gathered, buf)
+    out = np.empty(n)
+    for r, t in enumerate(gathered):
+        b, e = slice_bounds(n, env.world, r)
+        out[b:e] = t[: e - b].cpu().numpy()
+    return out

@@ -44,6 +44,9 @@ def main():
         env.dist.all_reduce(lo, op=env.dist.ReduceOp.MIN)
         env.dist.all_reduce(hi, op=env.dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks diverged"
+    # row-sharded predict == single-process predict, bit for bit
+    test_X = golden_csr(g, "test")
+    np.testing.assert_array_equal(rdist.sharded_predict(m, test_X, env), m.predict(X=test_X))
     # item-sharded full-catalog scoring: merged per-rank lists == one pass over the whole catalog
     from rfm_b200.score import TopKScorer
     rng = np.random.default_rng(21)

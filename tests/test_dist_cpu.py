@@ -106,3 +106,36 @@ def test_slice_bounds_cover_the_batch_exactly():
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             sizes = [e - b for b, e in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeModel:
+    """predict() of a fixed linear model: the gloo test below is about the row split and the gather."""
+
+    def __init__(self, w):
+        self.w = w
+
+    def predict(self, X):
+        return np.asarray(X @ self.w).ravel()
+
+
+def _predict_worker(rank, world, port, out_dir):
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from rfm_b200.dist import DistEnv, sharded_predict
+    rng = np.random.default_rng(0)
+    X, w = rng.normal(size=(101, 7)), rng.normal(size=7)
+    env = DistEnv("gloo")
+    out = sharded_predict(_FakeModel(w), X, env)
+    np.save(os.path.join(out_dir, "pred%d.npy" % rank), out)
+    env.shutdown()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_predict_equals_single_process(tmp_path, world):
+    mp.spawn(_predict_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(0)
+    X, w = rng.normal(size=(101, 7)), rng.normal(size=7)
+    for r in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / ("pred%d.npy" % r)), X @ w)
