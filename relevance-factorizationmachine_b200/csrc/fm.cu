@@ -1723,30 +1723,23 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
     using V2 = typename Vec2<T>::type;
     const int64_t pairs = (hi - lo) / 2;       // total and slice are even
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    constexpr int U = 4;                       // peer loads in flight per thread: NVLink latency is ~2 us
-    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < pairs; i0 += U * stride) {
-      V2 acc[U];
+    constexpr int W = rfm_fm_trainer::DP_MAX_WORLD;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pairs; i += stride) {
+      // the loads from all ranks are issued before the first add: one NVLink round trip (~2-3 us) per element
+      // instead of one per rank; the sum itself stays in rank order (identical bits whoever owns the slice)
+      V2 x[W];
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc[u] = V2{T(0), T(0)};
-      for (int q = 0; q < a.world; ++q) {      // fixed rank order: identical bits whoever owns the slice
-        const V2 *src = reinterpret_cast<const V2 *>(reinterpret_cast<const T *>(a.peer[q] + a.grad_off) + lo);
-        V2 x[U];
+      for (int q = 0; q < W; ++q)
+        if (q < a.world)
+          x[q] = reinterpret_cast<const V2 *>(reinterpret_cast<const T *>(a.peer[q] + a.grad_off) + lo)[i];
+      V2 acc = x[0];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (i0 + u * stride < pairs) x[u] = src[i0 + u * stride];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (q == 0) {
-            acc[u] = x[u];
-          } else {
-            acc[u].x += x[u].x;
-            acc[u].y += x[u].y;
-          }
+      for (int q = 1; q < W; ++q)
+        if (q < a.world) {
+          acc.x += x[q].x;
+          acc.y += x[q].y;
         }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i0 + u * stride < pairs) reinterpret_cast<V2 *>(mine + lo)[i0 + u * stride] = acc[u];
+      reinterpret_cast<V2 *>(mine + lo)[i] = acc;
     }
   }
   dpx_barrier(a, 1);          // every slice is reduced
