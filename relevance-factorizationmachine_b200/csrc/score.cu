@@ -54,14 +54,10 @@ constexpr int UMMA_K = 16;
 #endif
 constexpr int EPI_WARPS = RFM_EPI_WARPS;             // EPI_WARPS/4 per TMEM lane quarter; each owns a slice of a tile's columns
 constexpr int SCORE_THREADS = 128 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue
-#ifndef RFM_EPI_PINGPONG
-#define RFM_EPI_PINGPONG 0
-#endif
-// 0: every epilogue warp filters every accumulator (4 TMEM lane quarters x EPI_PARTS column ranges), so the MMA of
-//    step i + 1 overlaps the whole epilogue of step i; 1: two warp groups, one per accumulator stage
-constexpr int EPI_GROUPS = RFM_EPI_PINGPONG ? 2 : 1;
-constexpr int EPI_PARTS = EPI_WARPS / (4 * EPI_GROUPS);
-static_assert((EPI_WARPS == 16 || EPI_WARPS == 8) && EPI_GROUPS == 1, "the drain handles 64 or 128 columns per warp");
+// every epilogue warp drains every accumulator stage: 4 TMEM lane quarters x EPI_PARTS column ranges, so the MMA of
+// step i + 1 overlaps the whole epilogue of step i (two warp groups ping-ponging the stages were slower)
+constexpr int EPI_PARTS = EPI_WARPS / 4;
+static_assert(EPI_WARPS == 16 || EPI_WARPS == 8, "the drain handles 64 or 128 columns per warp");
 constexpr int MAX_KB = 2;        // k <= 128 on the tensor-core path
 constexpr int MAX_K = 120;
 
@@ -359,7 +355,7 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull + s, 1);
-      mbar_init(tempty + s, EPI_WARPS / EPI_GROUPS);   // one arrival per epilogue warp serving the stage
+      mbar_init(tempty + s, EPI_WARPS);       // one arrival per epilogue warp
     }
     mbar_init(afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -445,8 +441,7 @@ score_pass_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp >= 4) {
     // ===== epilogue: thread r streams the scores of row r of every user block =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int group = EPI_GROUPS == 2 ? ((warp - 4) >> 2) & 1 : 0;        // accumulator stage this warp serves
-    const int part = EPI_GROUPS == 2 ? (warp - 4) >> 3 : (warp - 4) >> 2;  // its range of the accumulator's columns
+    const int part = (warp - 4) >> 2;       // its range of the accumulator's columns
     const int r = q * 32 + lane;
     PendingAppend pend;
     pend.pos = 0u;
@@ -726,7 +721,18 @@ __device__ __forceinline__ double lane_exact_dot(const double *__restrict__ au, 
   for (int f0 = 0; f0 < k; f0 += 32) {
     if (f0 + 32 <= k) {
 #pragma unroll
-      for (int l = 0; l < 32; ++l) x[l] += au[f0 + l] * ci[f0 + l];
+      // the row is read once: keep it out of L1 (ld.global.cg), 16 bytes at a time when rows are 16-byte aligned
+      if ((k & 1) == 0) {
+#pragma unroll
+        for (int l = 0; l < 32; l += 2) {
+          const double2 c2 = __ldcg(reinterpret_cast<const double2 *>(ci + f0 + l));
+          x[l] += au[f0 + l] * c2.x;
+          x[l + 1] += au[f0 + l + 1] * c2.y;
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) x[l] += au[f0 + l] * __ldcg(ci + f0 + l);
+      }
     } else {
 #pragma unroll
       for (int l = 0; l < 32; ++l)
