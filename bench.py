@@ -309,12 +309,12 @@ def run_reference(args):
         return
     log, gen_s = make_data(args.rows, 2024)
     value, steps, dt, cores = cpu_port_run_parallel(log, args.batch, args.steps, max(args.warmup, 1), budget_s=150.0)
-    sample = "%d epochs of B=%d on the %d-row train set (reference sampler included), %.1f s on %d processes" % (
-        steps, args.batch, args.rows, dt, cores)
+    sample = ("%d epochs of B=%d (one GPU's share of the step) on the %d-row train set, reference sampler included, "
+              "%.1f s on %d processes" % (steps, args.batch, args.rows, dt, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
