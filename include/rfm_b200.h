@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RFM_ABI_VERSION 1
+#define RFM_ABI_VERSION 2   /* 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
 
 enum rfm_status {
   RFM_OK = 0,

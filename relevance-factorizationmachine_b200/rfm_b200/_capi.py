@@ -96,6 +96,9 @@ class RfmError(RuntimeError):
     pass
 
 
+ABI_VERSION = 2        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
+
+
 def lib():
     """Load the shared library once; raise loudly when it is not there."""
     global _lib
@@ -109,6 +112,9 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = restype
+        if handle.rfm_abi_version() != ABI_VERSION:
+            raise RuntimeError("rfm_b200: %s has ABI version %d, this shim needs %d -- rebuild the library"
+                               % (LIB_PATH, handle.rfm_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
 
