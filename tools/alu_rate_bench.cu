@@ -32,6 +32,10 @@ __global__ void __launch_bounds__(512, 1) rate_kernel(int iters, float seed, uns
       if (OP == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x80;" : "+r"(u[i]) : "r"(u[j]), "r"(u[k]));
       if (OP == 4) asm volatile("{\n .reg .pred p;\n setp.ge.f32 p, %1, %2;\n @p or.b32 %0, %0, 1;\n}" : "+r"(anyp) : "f"(x[i]), "f"(x[j]));
       if (OP == 5) asm volatile("add.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(x[j]));
+      if (OP == 6) asm volatile("max.bf16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[j]));
+      if (OP == 7) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(x[i]), "f"(x[j]));
+      if (OP == 8) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(u[j]));
+      if (OP == 9) asm volatile("fma.rn.bf16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(u[j]), "r"(u[k]));
     }
   }
   const unsigned long long t1 = clock64();
@@ -66,5 +70,9 @@ int main() {
   run<2>("FADD2 (add.f32x2)", 8);
   run<3>("LOP3", 16);
   run<4>("FSETP + predicated OR", 32);
+  run<6>("HMNMX2 (max.bf16x2)", 16);
+  run<8>("HMNMX2 (max.f16x2)", 16);
+  run<7>("F2FP (cvt.rn.bf16x2.f32)", 16);
+  run<9>("HFMA2 (fma.rn.bf16x2)", 16);
   return 0;
 }
