@@ -1108,7 +1108,14 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
 }
 
 template <typename T>
-int post_update_losses(rfm_fm_trainer *t, int64_t batch, int64_t slot);
+int batch_and_val_losses(rfm_fm_trainer *t, int64_t batch, double scale_b, double *dst_b, int64_t val_begin,
+                         int64_t val_end, double scale_v, double *dst_v);
+template <typename T>
+int post_update_losses(rfm_fm_trainer *t, int64_t batch, int64_t slot) {
+  const int64_t nv = t->val ? t->val->n_rows : 0;
+  return batch_and_val_losses<T>(t, batch, 1.0 / (double)batch, t->losses.p + slot, 0, nv,
+                                 nv > 0 ? 1.0 / (double)nv : 1.0, t->losses.p + t->max_slots + slot);
+}
 
 template <typename T>
 int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot, bool sampled, const FeistelKey &fkey) {
@@ -1116,25 +1123,28 @@ int epoch_impl(rfm_fm_trainer *t, int64_t batch, double lr, int64_t slot, bool s
   return post_update_losses<T>(t, batch, slot);
 }
 
-// post-update batch loss and val loss in ONE launch (the val rows ride along as a second row set)
+// loss of the batch on the device (t->idx) and of val rows [val_begin, val_end) in ONE launch (the val rows ride
+// along as a second row set); each result is scale * sum of the per-row terms
 template <typename T>
-int post_update_losses(rfm_fm_trainer *t, int64_t batch, int64_t slot) {
+int batch_and_val_losses(rfm_fm_trainer *t, int64_t batch, double scale_b, double *dst_b, int64_t val_begin,
+                         int64_t val_end, double scale_v, double *dst_v) {
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
   RowsArgs<T> a = rows_args<T>(m, t->train);
   a.idx = t->idx.p;
   a.n = batch;
-  a.fin = make_finish(1, 1.0 / (double)batch, nullptr, t->losses.p + slot, t->block_partials.p, t->ticket.p);
+  a.fin = make_finish(1, scale_b, nullptr, dst_b, t->block_partials.p, t->ticket.p);
   int64_t n_all = batch;
-  if (t->val && t->val->n_rows > 0) {
-    a.row_ptr2 = t->val->row_ptr.p;
+  if (t->val && val_end > val_begin) {
+    a.row_ptr2 = t->val->row_ptr.p + val_begin;           // row_ptr entries are absolute offsets into col / val
     a.col2 = t->val->col.p;
     a.val2 = reinterpret_cast<const T *>(t->val->val.p);
-    a.yp2 = reinterpret_cast<const T *>(t->val->yp.p);
-    a.n2 = t->val->n_rows;
-    a.fin2 = make_finish(1, 1.0 / (double)t->val->n_rows, nullptr, t->losses.p + t->max_slots + slot,
-                         t->block_partials.p + t->rows_grid, t->ticket.p + 1);
+    a.yp2 = reinterpret_cast<const T *>(t->val->yp.p) + val_begin;
+    a.n2 = val_end - val_begin;
+    a.fin2 = make_finish(1, scale_v, nullptr, dst_v, t->block_partials.p + t->rows_grid, t->ticket.p + 1);
     n_all += a.n2;
+  } else {
+    RFM_CUDA(cudaMemsetAsync(dst_v, 0, sizeof(double), ctx->stream));
   }
   const int grid = grid_for(ctx, ceil_div(n_all, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
   return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid);
@@ -1983,6 +1993,11 @@ int rfm_fm_loss_sums(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch
   const int64_t nv = t->val ? t->val->n_rows : 0;
   RFM_REQUIRE(val_begin >= 0 && val_begin <= val_end && val_end <= nv, "rfm_fm_loss_sums: bad val range");
   if (batch > 0 && batch_rows) RFM_TRY(stage_batch(t, batch_rows, batch));  // NULL: reuse the batch on the device
+  if (batch > 0) {       // one launch for both sums
+    if (t->m->dtype == RFM_F64)
+      return batch_and_val_losses<double>(t, batch, 1.0, t->loss_sums.p, val_begin, val_end, 1.0, t->loss_sums.p + 1);
+    return batch_and_val_losses<float>(t, batch, 1.0, t->loss_sums.p, val_begin, val_end, 1.0, t->loss_sums.p + 1);
+  }
   if (t->m->dtype == RFM_F64) {
     RFM_TRY(loss_pass<double>(t, t->train, t->idx.p, 0, batch, 1.0, t->loss_sums.p));
     RFM_TRY(loss_pass<double>(t, t->val ? t->val : t->train, nullptr, val_begin, val_end - val_begin, 1.0,
