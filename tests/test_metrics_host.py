@@ -35,3 +35,27 @@ def test_optimizer_holder_contract():
     h.update(grad=np.array([2.0, 4.0]), index=(np.array([0, 2]), 1))
     assert p[0, 1] == 0.5 - 1.0 and p[2, 1] == 4.5 - 2.0
     assert h.version == 2
+
+
+def test_merge_topk_follows_the_canonical_order():
+    """Host merge of per-shard top-K lists (item-sharded scoring): score descending, larger item id first among
+    exact ties, -1 / -inf padding last."""
+    from rfm_b200.score import merge_topk
+    rng = np.random.default_rng(3)
+    U, K, n_items = 40, 5, 60
+    scores_full = rng.integers(0, 6, size=(U, n_items)).astype(float)         # many exact ties
+    order = np.argsort(scores_full, axis=1, kind="stable")[:, ::-1]
+    ref_items, ref_scores = order[:, :K], np.take_along_axis(scores_full, order[:, :K], axis=1)
+    parts_i, parts_s = [], []
+    for b, e in ((0, 17), (17, 20), (20, 60)):                                # one shard holds fewer than K items
+        o = np.argsort(scores_full[:, b:e], axis=1, kind="stable")[:, ::-1][:, :K]
+        it = (o + b).astype(np.int32)
+        sc = np.take_along_axis(scores_full[:, b:e], o, axis=1)
+        if it.shape[1] < K:
+            it = np.concatenate([it, np.full((U, K - it.shape[1]), -1, np.int32)], axis=1)
+            sc = np.concatenate([sc, np.full((U, K - sc.shape[1]), -np.inf)], axis=1)
+        parts_i.append(it)
+        parts_s.append(sc)
+    items, scores = merge_topk(parts_i, parts_s, K)
+    np.testing.assert_array_equal(items, ref_items)
+    np.testing.assert_array_equal(scores, ref_scores)
