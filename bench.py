@@ -14,9 +14,15 @@ ours:       value     = K*B*N / device time of K steps (CUDA events), dataset re
             roofline  = dominant kernel's algorithmic bytes / its CUDA-event time (separate profiled
                         pass of the same steps), against MEASURED_PEAKS.json's HBM copy bandwidth.
             cpu_baseline = the CPU oracle (NumPy/SciPy port of the reference step + the reference's
-                        own sampler) on a bounded sample of the same workload, on this box's cores.
-reference:  the CPU oracle port timed alone, same config / metric / unit (the reference is pure
-            Python and cannot travel to the GPU box).
+                        own sampler) on a bounded sample of the same workload, on every host core
+                        (each epoch's batch split over forked workers; single-core figure alongside).
+            scoring   = scored user-item pairs/s of full-catalog top-K (second half of the metric),
+                        with its tensor-core roofline.
+            clocks    = nvidia-smi samples from the warm-up to a run of identical untimed steps.
+reference:  the CPU oracle port on every host core timed alone, same config / metric / unit (the
+            reference is pure Python and cannot travel to the GPU box).
+Under torchrun (N > 1): one rank per GPU, B per GPU (weak scaling), the library's NVLink exchange
+kernel between ranks (RFM_DP_EXCHANGE=nccl for the torch.distributed all-reduce), time = max over ranks.
 """
 import argparse
 import json
