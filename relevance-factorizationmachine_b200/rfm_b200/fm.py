@@ -222,15 +222,21 @@ class FactorizationMachines(PointwiseBaseRecommender):
         env = self.distributed
         ctx = self._context()
         begin, end = rdist.slice_bounds(self.batch_size, env.world, env.rank)
+        phases = {"upload": self._upload_seconds}
+        t_phase = time.perf_counter()
         trainer = _FmTrainer(self._dev, train_rows, val_rows, max(end - begin, 1), 1)
+        phases["trainer_create"] = time.perf_counter() - t_phase
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
         source = (lambda epoch: prefetch.next()) if prefetch is not None else (lambda epoch: None)
+        t_phase = time.perf_counter()
         dp = rdist.make_fm_dp(self, trainer, env, self.batch_size, val_rows.n_rows, self.lr, source)
+        phases["dp_connect"] = time.perf_counter() - t_phase     # exchange region, IPC handles, peer mappings
         torch = env.torch
         hist = torch.zeros((max(self.n_epochs, 1), 2), dtype=torch.float64, device=dp.loss_tensor.device)
         eval_rows = self._rows(self.evaluator.features[self.model_name]) if self.evaluator is not None else None
         launches0 = ctx.launch_count()
+        t_phase = time.perf_counter()
         try:
             for epoch in epochs:
                 prev = dp.step(epoch)                       # global loss sums of the previous epoch
@@ -240,18 +246,27 @@ class FactorizationMachines(PointwiseBaseRecommender):
                     scores = np.empty(eval_rows.n_rows)
                     check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
                     self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
+            phases["enqueue_epochs"] = time.perf_counter() - t_phase
+            t_phase = time.perf_counter()
             last = dp.flush()
             if last is not None:
                 hist[self.n_epochs - 1].copy_(last)
             out = hist.cpu().numpy()
+            phases["drain_and_read_losses"] = time.perf_counter() - t_phase
         finally:
             if prefetch is not None:
                 prefetch.close()
-        self.last_fit_stats = {"gpu_launches": ctx.launch_count() - launches0,
-                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes,
-                               "upload_seconds": self._upload_seconds}
+        launches = ctx.launch_count() - launches0
+        t_phase = time.perf_counter()
         trainer.close()
+        phases["trainer_destroy"] = time.perf_counter() - t_phase   # closes the peer mappings, frees the region
+        t_phase = time.perf_counter()
         self.sync_to_host()
+        phases["download_params"] = time.perf_counter() - t_phase
+        self.last_fit_stats = {"gpu_launches": launches,
+                               "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes,
+                               "upload_seconds": self._upload_seconds,
+                               "phase_seconds": {k: round(v, 5) for k, v in phases.items()}}
         return (out[: self.n_epochs, 0] / self.batch_size).tolist(), (out[: self.n_epochs, 1] / val_rows.n_rows).tolist()
 
     def predict(self, X) -> np.ndarray:
