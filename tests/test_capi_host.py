@@ -76,3 +76,46 @@ def test_no_device_is_an_error_not_a_fallback():
     from scipy.sparse import identity
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.predict(X=identity(5, format="csr"))
+
+
+_NULL_PROBE = r"""
+import ctypes, json, sys
+from rfm_b200 import _capi
+L = _capi.lib()
+out = {}
+for name, (argtypes, _) in _capi._SIGNATURES.items():
+    if name in ("rfm_abi_version", "rfm_last_error", "rfm_device_count", "rfm_legacy_batch", "rfm_feistel_batch",
+                "rfm_host_alloc", "rfm_host_free", "rfm_host_register", "rfm_host_unregister"):
+        continue
+    args = []
+    for t in argtypes:
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents"):
+            args.append(None)
+        elif t is ctypes.c_double:
+            args.append(0.0)
+        else:
+            args.append(0)
+    rc = getattr(L, name)(*args)
+    out[name] = [rc, L.rfm_last_error().decode("utf-8", "replace")]
+print(json.dumps(out))
+"""
+
+
+def test_null_arguments_are_status_codes_never_crashes():
+    """a bad call returns a status and a message naming the entry point; it never
+    takes the interpreter down. Every handle-taking entry point is called with NULL / zero arguments in a
+    child process (so that a segfault would fail this test, not the run). destroy(NULL) is a no-op like free()."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(sys.path))
+    p = subprocess.run([sys.executable, "-c", _NULL_PROBE], capture_output=True, text=True, env=env, timeout=120)
+    assert p.returncode == 0, "the library crashed on NULL arguments:\n" + p.stderr[-2000:]
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert len(res) >= 50
+    for name, (rc, msg) in res.items():
+        if name.endswith("_destroy"):
+            assert rc == 0, name
+        else:
+            assert rc == 1, (name, rc, msg)                       # RFM_ERR_INVALID -> ValueError in the shim
+            assert msg.startswith(name), (name, msg)
