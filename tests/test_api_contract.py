@@ -72,3 +72,20 @@ def test_evaluator_errors_match_the_reference():
     with pytest.raises(ValueError) as e:
         ValEvaluator(frame, {}, 3, "Recall")
     assert str(e.value) == want["message"]
+
+
+def test_reference_import_paths_resolve_to_this_build():
+    """with the package directory first on PYTHONPATH the reference's own import
+    statements (src/fm.py:12-13, main_coat.py) bind to rfm_b200. Child process: clean sys.modules / sys.path."""
+    import subprocess
+    import sys
+    from conftest import PKG
+    code = ("import src.fm, src.mf, src.base, utils.optimizer, utils.metrics, utils.evaluate\n"
+            "mods = [src.fm.FactorizationMachines, src.mf.LogisticMatrixFactorization, utils.optimizer.SGD,\n"
+            "        utils.evaluate.TestEvaluator, utils.evaluate.ValEvaluator, src.base.PointwiseBaseRecommender]\n"
+            "assert all(m.__module__.startswith('rfm_b200.') for m in mods), [m.__module__ for m in mods]\n"
+            "assert utils.metrics.metric_candidates is __import__('rfm_b200.metrics').metrics.metric_candidates\n"
+            "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=PKG)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", p.stderr[-2000:]
