@@ -20,3 +20,27 @@ def test_parallel_cpu_port_equals_scalar_port(monkeypatch):
     np.testing.assert_allclose(vl, rvl[-1], rtol=1e-10)
     np.testing.assert_allclose(V, rV, rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(w, rw, rtol=1e-10, atol=1e-14)
+
+
+def test_roofline_numerator_is_the_survey_formula():
+    """bench.py's roofline.step numerator is SURVEY.md section 8(d)'s bytes per train interaction:
+    [4 + 4 + m(4 + s) + 4 + s] + 2 m (k+1) s + 2 (U_b/B)(k+1) s. Checked on a matrix with exactly m = 16 non-zeros
+    per row against the survey's own worked example (s = 4, k = 64, U_b/B = 0.275 -> about 8.6 KB) and against the
+    per-kernel split DESIGN.md section 4.1 tabulates (the three row/column passes must cover the step's gathers)."""
+    import bench
+    from scipy.sparse import csr_matrix
+    rng = np.random.default_rng(0)
+    n_rows, n_cols, m, B = 4000, 1100, 16, 4000
+    cols = np.stack([rng.choice(n_cols, size=m, replace=False) for _ in range(n_rows)])
+    X = csr_matrix((np.ones(n_rows * m), cols.ravel(), np.arange(0, n_rows * m + 1, m)), shape=(n_rows, n_cols))
+    batch = np.arange(B)
+    for s, k in ((4, 64), (8, 64), (8, 128)):
+        mean_nnz, touched, step, per_kernel = bench.algorithmic_bytes(X, batch, k, s)
+        assert mean_nnz == m and touched == np.unique(cols).size == n_cols      # every column is hit: U_b/B = 0.275
+        want = (4 + 4 + m * (4 + s) + 4 + s) + 2 * m * (k + 1) * s + 2 * (touched / B) * (k + 1) * s
+        assert abs(step - want) < 1e-9
+        # the gathers of the step (2 x m(k+1)s) are split over the train and loss row passes, the touched-row
+        # read/write sits in the column pass; intermediates (S, E, sort triples) come on top, never below
+        assert per_kernel["fm_rows_train"] + per_kernel["fm_cols"] + per_kernel["fm_rows_loss"] >= step
+    _, _, step, _ = bench.algorithmic_bytes(X, batch, 64, 4)
+    assert 8500 < step < 8700                                                   # SURVEY: "about 8.6 KB/interaction"
