@@ -44,3 +44,30 @@ def test_roofline_numerator_is_the_survey_formula():
         assert per_kernel["fm_rows_train"] + per_kernel["fm_cols"] + per_kernel["fm_rows_loss"] >= step
     _, _, step, _ = bench.algorithmic_bytes(X, batch, 64, 4)
     assert 8500 < step < 8700                                                   # SURVEY: "about 8.6 KB/interaction"
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the product arm): one JSON line with the
+    product arm's metric / unit / config keys, impl = reference, a cpu_baseline describing this run and an e2e
+    object that repeats the value with zero copy bytes. Small --rows / --batch so that it runs in seconds."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--rows", "60000", "--batch", "2048"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_interactions_per_sec"
+    assert line["unit"] == "interactions/s" and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["steps"] == 2 and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == line["value"] and 1 <= cb["cores"] <= os.cpu_count()
+    assert "B=2048" in cb["sample"]
+    cfg = line["config"]
+    assert "workload" in cfg and cfg["train_interactions"] == 60000 and cfg["batch_per_gpu"] == 2048
+    assert "model" not in cfg
