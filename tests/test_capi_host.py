@@ -31,14 +31,17 @@ def test_legacy_sampler_matches_numpy_known_answers():
         np.testing.assert_array_equal(_capi.legacy_batch(N, B, ep), g[key], err_msg=key)
 
 
+@pytest.mark.parametrize("path", ["array", "prefix"])
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 16, 17, 255, 256, 257, 1000, 4097, 70000])
-def test_legacy_sampler_matches_numpy_live(N):
+def test_legacy_sampler_matches_numpy_live(N, path, monkeypatch):
+    # the library picks the path by size (prefix = backward tracking of the batch positions, for >= 8 M rows and
+    # small batches); both must give NumPy's answer everywhere, so each is forced in turn
+    monkeypatch.setenv("RFM_LEGACY_SAMPLER_PATH", path)
     for epoch in (0, 1, 2, 499, 123456789):
         ref = np.arange(N)
         np.random.RandomState(epoch).shuffle(ref)
         np.testing.assert_array_equal(_capi.legacy_batch(N, N, epoch), ref)
-        # batch <= N/16 takes the backward-tracking path (only the batch positions are followed), larger batches the
-        # index-array path: both sides of the boundary, the extremes, with and without a caller-provided scratch
+        # the extremes and a spread of batch sizes, with and without a caller-provided scratch
         scratch = np.empty(N, dtype=np.int32)
         for B in sorted({0, 1, 2, max(1, N // 3), N // 16, N // 16 + 1, N // 50, N - 1}):
             if 0 <= B <= N:
@@ -46,15 +49,29 @@ def test_legacy_sampler_matches_numpy_live(N):
                 np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch, scratch), ref[:B], err_msg="B=%d" % B)
 
 
-def test_legacy_sampler_large_matches_sklearn_resample():
-    """The call the reference makes (src/fm.py:72-79), at a size where the row-pointer bound crosses several
-    powers of two and the tracking path sees tens of thousands of hits."""
+@pytest.mark.parametrize("path", ["array", "prefix", ""])
+def test_legacy_sampler_large_matches_sklearn_resample(path, monkeypatch):
+    """The call the reference makes (src/fm.py:72-79), at a size where the rejection bound crosses several
+    powers of two and the tracking path sees tens of thousands of hits; "" = the library's own choice."""
     from sklearn.utils import resample
+    if path:
+        monkeypatch.setenv("RFM_LEGACY_SAMPLER_PATH", path)
+    else:
+        monkeypatch.delenv("RFM_LEGACY_SAMPLER_PATH", raising=False)
     N = 1_000_003
     ids = np.arange(N)
     for epoch, B in ((0, 500), (7, 2000), (31, 62500), (499, 65536)):
         want = resample(ids, replace=False, n_samples=B, random_state=epoch)
         np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch), want)
+
+
+def test_legacy_sampler_bench_shape_takes_the_prefix_path_and_matches_numpy(monkeypatch):
+    """12 M rows, batch 65,536 (the bench shape): the size rule selects backward tracking; one epoch against NumPy."""
+    monkeypatch.delenv("RFM_LEGACY_SAMPLER_PATH", raising=False)
+    N, B = 12_000_000, 65536
+    ref = np.arange(N)
+    np.random.RandomState(5).shuffle(ref)
+    np.testing.assert_array_equal(_capi.legacy_batch(N, B, 5), ref[:B])
 
 
 def test_legacy_sampler_rejects_oversized_batch_like_sklearn():
