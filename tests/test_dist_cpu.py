@@ -139,3 +139,49 @@ def test_row_sharded_predict_equals_single_process(tmp_path, world):
     X, w = rng.normal(size=(101, 7)), rng.normal(size=7)
     for r in range(world):
         np.testing.assert_array_equal(np.load(tmp_path / ("pred%d.npy" % r)), X @ w)
+
+
+def test_fit_data_parallel_host_flow_with_stub_device(monkeypatch):
+    """The Python flow of FactorizationMachines._fit_data_parallel (loss history assembly from the one-step-late
+    loss sums, the final flush, normalisation, phase timings) with the device pieces stubbed: no GPU, no C calls."""
+    import types
+    import torch
+    from rfm_b200 import dist as rdist, fm as fmmod
+
+    class StubTrainer:
+        def __init__(self, *a):
+            self.closed = False
+
+        def close(self):
+            self.closed = True
+
+    class StubDP:
+        loss_tensor = torch.zeros(2, dtype=torch.float64)
+
+        def __init__(self):
+            self.steps = []
+
+        def step(self, epoch):                 # returns the PREVIOUS epoch's global [batch, val] loss sums
+            self.steps.append(epoch)
+            return None if epoch == 0 else torch.tensor([10.0 * epoch, 4.0 * epoch], dtype=torch.float64)
+
+        def flush(self):
+            return torch.tensor([10.0 * len(self.steps), 4.0 * len(self.steps)], dtype=torch.float64)
+
+    dp = StubDP()
+    monkeypatch.setattr(fmmod, "_FmTrainer", StubTrainer)
+    monkeypatch.setattr(rdist, "make_fm_dp", lambda *a, **k: dp)
+    m = object.__new__(fmmod.FactorizationMachines)
+    m.distributed = types.SimpleNamespace(world=2, rank=1, torch=torch)
+    m._context = lambda: types.SimpleNamespace(launch_count=lambda: 7)
+    m.batch_size, m.n_epochs, m.sampler, m.lr, m.evaluator, m._dev = 10, 3, "feistel", 0.1, None, None
+    m._upload_seconds = 0.25
+    m.sync_to_host = lambda: None
+    rows = types.SimpleNamespace(h2d_bytes=5, n_rows=4)
+    train_loss, val_loss = m._fit_data_parallel(rows, rows, 100)
+    assert dp.steps == [0, 1, 2]
+    assert train_loss == [1.0, 2.0, 3.0] and val_loss == [1.0, 2.0, 3.0]       # sums / batch_size, sums / n_val
+    st = m.last_fit_stats
+    assert st["h2d_bytes_rows"] == 10 and st["upload_seconds"] == 0.25 and st["gpu_launches"] == 0
+    assert set(st["phase_seconds"]) == {"upload", "trainer_create", "dp_connect", "enqueue_epochs",
+                                        "drain_and_read_losses", "trainer_destroy", "download_params"}
