@@ -59,3 +59,32 @@ def test_merge_topk_follows_the_canonical_order():
     items, scores = merge_topk(parts_i, parts_s, K)
     np.testing.assert_array_equal(items, ref_items)
     np.testing.assert_array_equal(scores, ref_scores)
+
+
+def test_fm_grid_decomposition_equals_predict_on_cartesian_rows():
+    """SURVEY.md Appendix A.4, the bridge from FM rows to the scoring GEMM: for rows x = [user features | item
+    features], sigma(w0 + alpha_u + beta_i + <A_u, C_i>) with (A, C, alpha, beta, w0) = fm_factors(model, ...)
+    equals FM predict (src/fm.py:114-133, here the pinned oracle) on the Cartesian-product rows. Host NumPy only."""
+    import scipy.sparse as sp
+    from oracle import fm_oracle
+    from rfm_b200.fm import FactorizationMachines
+    from rfm_b200.score import fm_factors
+    rng = np.random.default_rng(11)
+    n_users, n_items, n_uf, n_if, k = 13, 17, 20, 31, 8
+    n = n_uf + n_if
+
+    def side(rows, lo, width):          # a few real-valued entries per entity inside its side's column range
+        cols = np.stack([rng.choice(width, size=4, replace=False) + lo for _ in range(rows)])
+        vals = rng.normal(size=cols.shape)
+        ptr_ = np.arange(0, rows * 4 + 1, 4)
+        return sp.csr_matrix((vals.ravel(), cols.ravel(), ptr_), shape=(rows, n))
+
+    user_table, item_table = side(n_users, 0, n_uf), side(n_items, n_uf, n_if)
+    model = FactorizationMachines("IPS", 1, k, 0.1, 4, 12345, n)
+    model.w0.params[:] = 0.3                                   # a non-zero global bias as well
+    A, C, alpha, beta, bias = fm_factors(model, user_table, item_table)
+    logits = bias + alpha[:, None] + beta[None, :] + A @ C.T
+    u, i = np.divmod(np.arange(n_users * n_items), n_items)
+    X = (user_table[u] + item_table[i]).tocsr()
+    want = fm_oracle.fm_predict(X, model.w0(), model.w(), model.V()).reshape(n_users, n_items)
+    np.testing.assert_allclose(1.0 / (1.0 + np.exp(-logits)), want, rtol=1e-12, atol=1e-15)
