@@ -936,6 +936,7 @@ struct rfm_fm_trainer {
   // through CUDA IPC: [gradient buffer, parity 0 | gradient buffer, parity 1 | flags]
   static constexpr int DP_MAX_WORLD = 8;
   unsigned char *xchg = nullptr;
+  bool xchg_borrowed = false;   // xchg and peer_base[] belong to the context's DpRegion cache
   size_t xchg_grad_bytes = 0;
   unsigned char *peer_base[DP_MAX_WORLD] = {nullptr};
   int dp_rank = -1, dp_world = 0, dp_parity = 0;
@@ -1545,9 +1546,13 @@ int rfm_fm_trainer_destroy(rfm_fm_trainer *t) {
     cudaStreamSynchronize(t->m->ctx->stream);
     for (int r = 0; r < rfm_fm_trainer::RING; ++r)
       if (t->stage_ev[r]) cudaEventDestroy(t->stage_ev[r]);
-    for (int q = 0; q < t->dp_world; ++q)
-      if (q != t->dp_rank && t->peer_base[q]) cudaIpcCloseMemHandle(t->peer_base[q]);
-    if (t->xchg) cudaFree(t->xchg);
+    if (t->xchg_borrowed) {
+      t->m->ctx->dp.borrowers = 0;
+    } else {
+      for (int q = 0; q < t->dp_world; ++q)
+        if (q != t->dp_rank && t->peer_base[q]) cudaIpcCloseMemHandle(t->peer_base[q]);
+      if (t->xchg) cudaFree(t->xchg);
+    }
     delete t;
   }
   return RFM_OK;
@@ -1835,15 +1840,37 @@ int rfm_fm_dp_export(rfm_fm_trainer *t, void *handle_out) {
   t->xchg_grad_bytes = ((size_t)n * dsize(t->m->dtype) + 255) / 256 * 256;
   const size_t bytes = 2 * t->xchg_grad_bytes + 256;
   // cudaMalloc, not the stream-ordered pool: pool memory cannot be exported through legacy CUDA IPC
-  RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->xchg), bytes));
+  cudaIpcMemHandle_t h;
+  if (ctx->dp_cache && ctx->dp.borrowers == 0) {
+    // Reuse is safe: the previous borrower's last exchange kernel has finished on EVERY rank before any rank
+    // could read its final losses (they come out of a collective ordered after it), and no rank starts stepping
+    // before the post-connect barrier, i.e. after every rank has re-zeroed its region here.
+    rfm_ctx::DpRegion &c = ctx->dp;
+    if (c.base && c.bytes < bytes) {   // outgrown: peers may still map it, so it is retired, not freed
+      c.retired.push_back(c.base);
+      c.base = nullptr;
+      c.bytes = 0;
+    }
+    if (!c.base) {
+      RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&c.base), bytes));
+      c.bytes = bytes;
+      RFM_CUDA(cudaIpcGetMemHandle(&h, c.base));
+      memcpy(c.own_handle, &h, sizeof(h));
+    }
+    memcpy(&h, c.own_handle, sizeof(h));
+    t->xchg = c.base;
+    t->xchg_borrowed = true;
+    c.borrowers = 1;
+  } else {
+    RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->xchg), bytes));
+    RFM_CUDA(cudaIpcGetMemHandle(&h, t->xchg));
+  }
   RFM_CUDA(cudaMemsetAsync(t->xchg, 0, bytes, ctx->stream));
   RFM_TRY(t->dp_prev_loss.alloc(2));
   RFM_TRY(t->dp_local.alloc(4));
   RFM_CUDA(cudaMemsetAsync(t->dp_local.p, 0, 4 * sizeof(uint32_t), ctx->stream));
   RFM_CUDA(cudaMemsetAsync(t->dp_prev_loss.p, 0, 2 * sizeof(double), ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaIpcMemHandle_t h;
-  RFM_CUDA(cudaIpcGetMemHandle(&h, t->xchg));
   memcpy(handle_out, &h, sizeof(h));
   return RFM_OK;
 }
@@ -1856,13 +1883,34 @@ int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world, const void
               rfm_fm_trainer::DP_MAX_WORLD);
   RFM_REQUIRE(t->dp_world == 0, "rfm_fm_dp_connect: already connected");
   RFM_CUDA(cudaSetDevice(t->m->ctx->device));
+  rfm_ctx::DpRegion &c = t->m->ctx->dp;
+  if (t->xchg_borrowed && (c.world != world || c.rank != rank)) {   // another group layout: drop every mapping
+    for (int q = 0; q < rfm_ctx::DpRegion::MAX_WORLD; ++q) {
+      if (q != c.rank && c.peer[q]) cudaIpcCloseMemHandle(c.peer[q]);
+      c.peer[q] = nullptr;
+    }
+    cudaGetLastError();
+    c.world = world;
+    c.rank = rank;
+  }
   for (int q = 0; q < world; ++q) {
     if (q == rank) {
       t->peer_base[q] = t->xchg;
+      if (t->xchg_borrowed) c.peer[q] = t->xchg;
       continue;
     }
+    const unsigned char *hq = static_cast<const unsigned char *>(all_handles) + (size_t)q * sizeof(cudaIpcMemHandle_t);
+    if (t->xchg_borrowed && c.peer[q]) {
+      if (memcmp(hq, c.peer_handle[q], sizeof(cudaIpcMemHandle_t)) == 0) {   // same region as last time: stay mapped
+        t->peer_base[q] = c.peer[q];
+        continue;
+      }
+      cudaIpcCloseMemHandle(c.peer[q]);                                       // the peer re-allocated
+      cudaGetLastError();
+      c.peer[q] = nullptr;
+    }
     cudaIpcMemHandle_t h;
-    memcpy(&h, static_cast<const unsigned char *>(all_handles) + (size_t)q * sizeof(h), sizeof(h));
+    memcpy(&h, hq, sizeof(h));
     void *p = nullptr;
     const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
@@ -1870,6 +1918,10 @@ int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world, const void
       return fail(RFM_ERR_CUDA, "rfm_fm_dp_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
     }
     t->peer_base[q] = static_cast<unsigned char *>(p);
+    if (t->xchg_borrowed) {
+      c.peer[q] = t->peer_base[q];
+      memcpy(c.peer_handle[q], hq, sizeof(cudaIpcMemHandle_t));
+    }
   }
   t->dp_rank = rank;
   t->dp_world = world;
