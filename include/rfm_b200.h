@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RFM_ABI_VERSION 2   /* 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
+#define RFM_ABI_VERSION 3   /* 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
 
 enum rfm_status {
   RFM_OK = 0,
@@ -93,6 +93,17 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
                    const int64_t *labels,  /* may be NULL (predict-only rows)            */
                    const double *pscores,  /* may be NULL                                */
                    int dtype, rfm_csr **out);
+/* Data-parallel upload (no reference counterpart; SURVEY section 8e "train CSR replicated"): the object has the
+ * full shape and every row pointer, but only rows [row_begin, row_end) are copied from the host, so G ranks move
+ * 1/G of the train set over PCIe each. The caller fills the other ranges of col / val / targets through the
+ * device pointers (rfm_b200.dist.sharded_csr_rows: NCCL broadcasts over NVLink) before the rows are used.
+ * val elements have the object's dtype; targets are y/pscore in that dtype, one per row. */
+int rfm_csr_create_range(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
+                         const void *indptr, int indptr_is_int64, const int32_t *indices, const double *data,
+                         const int64_t *labels, const double *pscores, int dtype,
+                         int64_t row_begin, int64_t row_end, rfm_csr **out);
+int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev /* int64[n_rows+1] */, void **col_dev /* int32[nnz] */,
+                        void **val_dev, void **targets_dev);
 int rfm_csr_destroy(rfm_csr *rows);
 
 /* ---- FM model: w0, w, V (src/fm.py:31-53); parameter holders of utils/optimizer.py:10-64 */

@@ -40,6 +40,9 @@ _SIGNATURES = {
     "rfm_legacy_batch": ([c_int64, c_int64, c_uint32, _P, _P], c_int),
     "rfm_feistel_batch": ([c_int64, c_int64, c_uint32, c_uint32, _P], c_int),
     "rfm_csr_create": ([_P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P, c_int, POINTER(_P)], c_int),
+    "rfm_csr_create_range": ([_P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P, c_int, c_int64, c_int64, POINTER(_P)],
+                             c_int),
+    "rfm_csr_device_ptrs": ([_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)], c_int),
     "rfm_csr_destroy": ([_P], c_int),
     "rfm_fm_create": ([_P, c_int64, c_int32, c_int, POINTER(_P)], c_int),
     "rfm_fm_destroy": ([_P], c_int),
@@ -96,7 +99,7 @@ class RfmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 2        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
+ABI_VERSION = 3        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
 
 
 def lib():
@@ -222,7 +225,9 @@ class CsrRows(_Handle):
 
     _destroy = "rfm_csr_destroy"
 
-    def __init__(self, ctx: Context, X, labels=None, pscores=None, dtype="float64"):
+    def __init__(self, ctx: Context, X, labels=None, pscores=None, dtype="float64", row_range=None):
+        """row_range=(begin, end): copy only those rows from the host (the object keeps the full shape; the
+        caller fills the rest on the device, see rfm_b200.dist.sharded_csr_rows)."""
         super().__init__()
         X = X.tocsr()
         if not X.has_canonical_format:
@@ -239,10 +244,26 @@ class CsrRows(_Handle):
         ps = None if pscores is None else as_array(pscores, np.float64)
         if y is not None and (y.shape[0] != X.shape[0] or ps is None or ps.shape[0] != X.shape[0]):
             raise ValueError("labels/pscores must have one entry per row")
-        check(lib().rfm_csr_create(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
-                                   ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
         self.n_rows = X.shape[0]
-        self.h2d_bytes = indptr.nbytes + indices.nbytes + data.nbytes + (y.nbytes + ps.nbytes if y is not None else 0)
+        if row_range is None:
+            check(lib().rfm_csr_create(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
+                                       ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
+            self.h2d_bytes = (indptr.nbytes + indices.nbytes + data.nbytes
+                              + (y.nbytes + ps.nbytes if y is not None else 0))
+        else:
+            begin, end = row_range
+            check(lib().rfm_csr_create_range(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
+                                             ptr(data), ptr(y), ptr(ps), dtype_code(dtype), begin, end,
+                                             byref(self.handle)))
+            nz = int(indptr[end]) - int(indptr[begin])
+            self.h2d_bytes = indptr.nbytes + nz * 12 + ((end - begin) * 16 if y is not None else 0)
+        self.indptr_host = indptr          # kept for range arithmetic (a view of the caller's array when possible)
+
+    def device_ptrs(self):
+        """(row_ptr, col, val, targets) device addresses."""
+        out = [c_void_p() for _ in range(4)]
+        check(lib().rfm_csr_device_ptrs(self.handle, *[byref(p) for p in out]))
+        return tuple(p.value for p in out)
 
 
 class Optimizer(ctypes.Structure):
