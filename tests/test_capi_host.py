@@ -37,8 +37,24 @@ def test_legacy_sampler_matches_numpy_live(N):
         ref = np.arange(N)
         np.random.RandomState(epoch).shuffle(ref)
         np.testing.assert_array_equal(_capi.legacy_batch(N, N, epoch), ref)
-        B = max(1, N // 3)
-        np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch), ref[:B])
+        # batch <= N/16 takes the backward-tracking path (only the batch positions are followed), larger batches the
+        # index-array path: both sides of the boundary, the extremes, with and without a caller-provided scratch
+        scratch = np.empty(N, dtype=np.int32)
+        for B in sorted({0, 1, 2, max(1, N // 3), N // 16, N // 16 + 1, N // 50, N - 1}):
+            if 0 <= B <= N:
+                np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch), ref[:B], err_msg="B=%d" % B)
+                np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch, scratch), ref[:B], err_msg="B=%d" % B)
+
+
+def test_legacy_sampler_large_matches_sklearn_resample():
+    """The call the reference makes (src/fm.py:72-79), at a size where the row-pointer bound crosses several
+    powers of two and the tracking path sees tens of thousands of hits."""
+    from sklearn.utils import resample
+    N = 1_000_003
+    ids = np.arange(N)
+    for epoch, B in ((0, 500), (7, 2000), (31, 62500), (499, 65536)):
+        want = resample(ids, replace=False, n_samples=B, random_state=epoch)
+        np.testing.assert_array_equal(_capi.legacy_batch(N, B, epoch), want)
 
 
 def test_legacy_sampler_rejects_oversized_batch_like_sklearn():
