@@ -84,6 +84,17 @@ int rfm_host_unregister(void *p);
  *   a keyed bijection of [0,N). Host statement of what the device kernel computes. */
 int rfm_legacy_batch(int64_t n_rows, int64_t batch, uint32_t epoch, int64_t *out_rows, int32_t *scratch);
 int rfm_feistel_batch(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epoch, int64_t *out_rows);
+/* Host helpers of the "upload only what the fit samples" mode (no reference counterpart). rfm_feistel_batches:
+ * positions [begin, begin+count) of the batches of epochs epoch0 .. epoch0+n_epochs-1, epoch-major, on
+ * n_threads host threads (0 = all). rfm_csr_gather_rows: the CSR made of the listed rows, in that order
+ * (scipy's X[rows]); called with out_indices == NULL it only fills out_indptr[n_sel+1] so that the caller can
+ * size the other outputs (out_indptr[n_sel] non-zeros). Pure host code: both run without a GPU. */
+int rfm_feistel_batches(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epoch0, int32_t n_epochs,
+                        int64_t begin, int64_t count, int64_t *out_rows, int32_t n_threads);
+int rfm_csr_gather_rows(int64_t n_rows, const void *indptr, int indptr_is_int64, const int32_t *indices,
+                        const double *data, const int64_t *labels, const double *pscores, const int64_t *rows,
+                        int64_t n_sel, int64_t *out_indptr, int32_t *out_indices, double *out_data,
+                        int64_t *out_labels, double *out_pscores, int32_t n_threads);
 
 /* ---- FM rows: scipy.sparse.csr_matrix + labels + pscores (the train/val dicts of
  * src/fm.py:55-70; layout from utils/dataloader/coat/_preparer.py:154-170) --------------- */
