@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RFM_ABI_VERSION 2   /* 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
+#define RFM_ABI_VERSION 3   /* 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
 
 enum rfm_status {
   RFM_OK = 0,
@@ -84,6 +84,17 @@ int rfm_host_unregister(void *p);
  *   a keyed bijection of [0,N). Host statement of what the device kernel computes. */
 int rfm_legacy_batch(int64_t n_rows, int64_t batch, uint32_t epoch, int64_t *out_rows, int32_t *scratch);
 int rfm_feistel_batch(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epoch, int64_t *out_rows);
+/* Host helpers of the "upload only what the fit samples" mode (no reference counterpart). rfm_feistel_batches:
+ * positions [begin, begin+count) of the batches of epochs epoch0 .. epoch0+n_epochs-1, epoch-major, on
+ * n_threads host threads (0 = all). rfm_csr_gather_rows: the CSR made of the listed rows, in that order
+ * (scipy's X[rows]); called with out_indices == NULL it only fills out_indptr[n_sel+1] so that the caller can
+ * size the other outputs (out_indptr[n_sel] non-zeros). Pure host code: both run without a GPU. */
+int rfm_feistel_batches(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epoch0, int32_t n_epochs,
+                        int64_t begin, int64_t count, int64_t *out_rows, int32_t n_threads);
+int rfm_csr_gather_rows(int64_t n_rows, const void *indptr, int indptr_is_int64, const int32_t *indices,
+                        const double *data, const int64_t *labels, const double *pscores, const int64_t *rows,
+                        int64_t n_sel, int64_t *out_indptr, int32_t *out_indices, double *out_data,
+                        int64_t *out_labels, double *out_pscores, int32_t n_threads);
 
 /* ---- FM rows: scipy.sparse.csr_matrix + labels + pscores (the train/val dicts of
  * src/fm.py:55-70; layout from utils/dataloader/coat/_preparer.py:154-170) --------------- */
@@ -93,6 +104,17 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
                    const int64_t *labels,  /* may be NULL (predict-only rows)            */
                    const double *pscores,  /* may be NULL                                */
                    int dtype, rfm_csr **out);
+/* Data-parallel upload (no reference counterpart; SURVEY section 8e "train CSR replicated"): the object has the
+ * full shape and every row pointer, but only rows [row_begin, row_end) are copied from the host, so G ranks move
+ * 1/G of the train set over PCIe each. The caller fills the other ranges of col / val / targets through the
+ * device pointers (rfm_b200.dist.sharded_csr_rows: NCCL broadcasts over NVLink) before the rows are used.
+ * val elements have the object's dtype; targets are y/pscore in that dtype, one per row. */
+int rfm_csr_create_range(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
+                         const void *indptr, int indptr_is_int64, const int32_t *indices, const double *data,
+                         const int64_t *labels, const double *pscores, int dtype,
+                         int64_t row_begin, int64_t row_end, rfm_csr **out);
+int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev /* int64[n_rows+1] */, void **col_dev /* int32[nnz] */,
+                        void **val_dev, void **targets_dev);
 int rfm_csr_destroy(rfm_csr *rows);
 
 /* ---- FM model: w0, w, V (src/fm.py:31-53); parameter holders of utils/optimizer.py:10-64 */

@@ -116,6 +116,23 @@ struct rfm_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // staging ring for small host->device / device->host transfers
   rfm::PinnedBuf<unsigned char> stage;
+  // Data-parallel exchange region and the CUDA-IPC mappings of the peers' regions (rfm_fm_dp_*). They belong
+  // to the context, not to a trainer: cudaMalloc / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree cost
+  // tens of milliseconds per fit, more than the epochs of a short fit. A trainer borrows the region; a later
+  // trainer of the same (or a smaller) gradient size re-zeroes and reuses it, and peers whose handle did not
+  // change stay mapped. RFM_DP_CACHE=0 restores one region per trainer.
+  struct DpRegion {
+    static constexpr int MAX_WORLD = 8;
+    unsigned char *base = nullptr;
+    size_t bytes = 0;
+    unsigned char own_handle[64] = {0};
+    int world = 0, rank = -1;
+    int borrowers = 0;                      // a second live trainer gets a region of its own
+    unsigned char *peer[MAX_WORLD] = {nullptr};
+    unsigned char peer_handle[MAX_WORLD][64] = {{0}};
+    std::vector<unsigned char *> retired;   // outgrown regions: peers may still map them, freed with the context
+  } dp;
+  bool dp_cache = true;
 };
 
 namespace rfm {

@@ -936,6 +936,7 @@ struct rfm_fm_trainer {
   // through CUDA IPC: [gradient buffer, parity 0 | gradient buffer, parity 1 | flags]
   static constexpr int DP_MAX_WORLD = 8;
   unsigned char *xchg = nullptr;
+  bool xchg_borrowed = false;   // xchg and peer_base[] belong to the context's DpRegion cache
   size_t xchg_grad_bytes = 0;
   unsigned char *peer_base[DP_MAX_WORLD] = {nullptr};
   int dp_rank = -1, dp_world = 0, dp_parity = 0;
@@ -1181,26 +1182,34 @@ int check_batch(const rfm_fm_trainer *t, int64_t batch, int64_t slot, const char
 // ---- C ABI ------------------------------------------------------------------------------------
 extern "C" {
 
-int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *indptr, int indptr_is_int64,
-                   const int32_t *indices, const double *data, const int64_t *labels, const double *pscores,
-                   int dtype, rfm_csr **out) {
-  RFM_REQUIRE(ctx && out, "rfm_csr_create: NULL ctx/out");
+// Rows [row_begin, row_end) are copied from the host; the object always has the full shape (every row pointer is
+// uploaded). rfm_csr_create passes the whole range; rfm_csr_create_range leaves the rest for the caller to fill.
+static int csr_create_impl(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *indptr, int indptr_is_int64,
+                           const int32_t *indices, const double *data, const int64_t *labels,
+                           const double *pscores, int dtype, int64_t row_begin, int64_t row_end, rfm_csr **out,
+                           const char *who) {
+  RFM_REQUIRE(ctx && out, "%s: NULL ctx/out", who);
   *out = nullptr;
-  RFM_REQUIRE(n_rows >= 0 && n_cols >= 1, "rfm_csr_create: bad shape (%lld, %lld)", (long long)n_rows,
+  RFM_REQUIRE(n_rows >= 0 && n_cols >= 1, "%s: bad shape (%lld, %lld)", who, (long long)n_rows,
               (long long)n_cols);
-  RFM_REQUIRE(n_cols < 0xFFFFFFFFLL, "rfm_csr_create: too many columns");
-  RFM_REQUIRE(indptr != nullptr, "rfm_csr_create: indptr is NULL");
-  RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "rfm_csr_create: bad dtype %d", dtype);
-  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "rfm_csr_create: labels and pscores go together");
+  RFM_REQUIRE(n_cols < 0xFFFFFFFFLL, "%s: too many columns", who);
+  RFM_REQUIRE(indptr != nullptr, "%s: indptr is NULL", who);
+  RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "%s: bad dtype %d", who, dtype);
+  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "%s: labels and pscores go together", who);
   RFM_CUDA(cudaSetDevice(ctx->device));
   const int64_t *p64 = static_cast<const int64_t *>(indptr);
   const int32_t *p32 = static_cast<const int32_t *>(indptr);
   auto ptr_at = [&](int64_t i) -> int64_t { return indptr_is_int64 ? p64[i] : (int64_t)p32[i]; };
   const int64_t nnz = ptr_at(n_rows) - ptr_at(0);
-  RFM_REQUIRE(ptr_at(0) == 0 && nnz >= 0, "rfm_csr_create: indptr must start at 0 and be non-decreasing");
-  RFM_REQUIRE(nnz == 0 || (indices && data), "rfm_csr_create: indices/data are NULL");
+  RFM_REQUIRE(ptr_at(0) == 0 && nnz >= 0, "%s: indptr must start at 0 and be non-decreasing", who);
+  RFM_REQUIRE(nnz == 0 || (indices && data), "%s: indices/data are NULL", who);
+  RFM_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_rows,
+              "%s: row range [%lld, %lld) outside [0, %lld)", who, (long long)row_begin,
+              (long long)row_end, (long long)n_rows);
+  const int64_t z0 = ptr_at(row_begin), z1 = ptr_at(row_end), nz = z1 - z0, nr = row_end - row_begin;
+  RFM_REQUIRE(z0 >= 0 && nz >= 0 && z1 <= nnz, "%s: indptr must be non-decreasing", who);
   rfm_csr *r = new (std::nothrow) rfm_csr();
-  if (!r) return fail(RFM_ERR_NOMEM, "rfm_csr_create: out of host memory");
+  if (!r) return fail(RFM_ERR_NOMEM, "%s: out of host memory", who);
   r->ctx = ctx;
   r->dtype = dtype;
   r->n_rows = n_rows;
@@ -1223,37 +1232,37 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *ind
       RFM_LAUNCH(ctx, widen_i32_kernel, grid_for(ctx, ceil_div(n_rows + 1, 256), 8), 256, 0,
                  reinterpret_cast<const int32_t *>(tmp.p), r->row_ptr.p, n_rows + 1);
     }
-    RFM_TRY(upload(ctx, r->col.p, indices, (size_t)nnz * 4));
+    RFM_TRY(upload(ctx, r->col.p + z0, indices + z0, (size_t)nz * 4));
     DevBuf<int> bad;
     RFM_TRY(bad.alloc(1));
     RFM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
-    if (nnz > 0)
-      RFM_LAUNCH(ctx, check_columns_kernel, grid_for(ctx, ceil_div(nnz, 256), 8), 256, 0, r->col.p, nnz, n_cols,
+    if (nz > 0)
+      RFM_LAUNCH(ctx, check_columns_kernel, grid_for(ctx, ceil_div(nz, 256), 8), 256, 0, r->col.p + z0, nz, n_cols,
                  bad.p);
     if (dtype == RFM_F64) {
-      RFM_TRY(upload(ctx, r->val.p, data, (size_t)nnz * 8));
-    } else if (nnz > 0) {
-      RFM_TRY(tmp2.alloc((size_t)nnz * 8));
-      RFM_TRY(upload(ctx, tmp2.p, data, (size_t)nnz * 8));
-      RFM_LAUNCH(ctx, convert_f64_kernel<float>, grid_for(ctx, ceil_div(nnz, 256), 8), 256, 0,
-                 reinterpret_cast<const double *>(tmp2.p), reinterpret_cast<float *>(r->val.p), nnz);
+      RFM_TRY(upload(ctx, r->val.p + (size_t)z0 * 8, data + z0, (size_t)nz * 8));
+    } else if (nz > 0) {
+      RFM_TRY(tmp2.alloc((size_t)nz * 8));
+      RFM_TRY(upload(ctx, tmp2.p, data + z0, (size_t)nz * 8));
+      RFM_LAUNCH(ctx, convert_f64_kernel<float>, grid_for(ctx, ceil_div(nz, 256), 8), 256, 0,
+                 reinterpret_cast<const double *>(tmp2.p), reinterpret_cast<float *>(r->val.p) + z0, nz);
     }
     DevBuf<int64_t> ytmp;
     DevBuf<double> pstmp;
-    if (labels && n_rows > 0) {
-      RFM_TRY(ytmp.alloc(n_rows));
-      RFM_TRY(pstmp.alloc(n_rows));
-      RFM_TRY(upload(ctx, ytmp.p, labels, (size_t)n_rows * 8));
-      RFM_TRY(upload(ctx, pstmp.p, pscores, (size_t)n_rows * 8));
-      const int g = grid_for(ctx, ceil_div(n_rows, 256), 8);
+    if (labels && nr > 0) {
+      RFM_TRY(ytmp.alloc(nr));
+      RFM_TRY(pstmp.alloc(nr));
+      RFM_TRY(upload(ctx, ytmp.p, labels + row_begin, (size_t)nr * 8));
+      RFM_TRY(upload(ctx, pstmp.p, pscores + row_begin, (size_t)nr * 8));
+      const int g = grid_for(ctx, ceil_div(nr, 256), 8);
       if (dtype == RFM_F64) {
-        RFM_LAUNCH(ctx, targets_kernel<double>, g, 256, 0, ytmp.p, pstmp.p, reinterpret_cast<double *>(r->yp.p),
-                   n_rows);
+        RFM_LAUNCH(ctx, targets_kernel<double>, g, 256, 0, ytmp.p, pstmp.p,
+                   reinterpret_cast<double *>(r->yp.p) + row_begin, nr);
       } else {
-        RFM_LAUNCH(ctx, targets_kernel<float>, g, 256, 0, ytmp.p, pstmp.p, reinterpret_cast<float *>(r->yp.p),
-                   n_rows);
+        RFM_LAUNCH(ctx, targets_kernel<float>, g, 256, 0, ytmp.p, pstmp.p,
+                   reinterpret_cast<float *>(r->yp.p) + row_begin, nr);
       }
-    } else {
+    } else if (!labels || n_rows == 0) {
       RFM_CUDA(cudaMemsetAsync(r->yp.p, 0, (size_t)(n_rows ? n_rows : 1) * es, ctx->stream));
     }
     // The host scan of the row pointers (monotonic? longest row?) runs while the copies enqueued above are
@@ -1278,8 +1287,8 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *ind
     int bad_host = 0;
     RFM_CUDA(cudaMemcpyAsync(&bad_host, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RFM_CUDA(cudaStreamSynchronize(ctx->stream));  // temporaries are freed on return
-    RFM_REQUIRE(bad_row < 0, "rfm_csr_create: indptr decreases at row %lld", (long long)bad_row);
-    RFM_REQUIRE(bad_host == 0, "rfm_csr_create: CSR column index out of range [0, %lld)", (long long)n_cols);
+    RFM_REQUIRE(bad_row < 0, "%s: indptr decreases at row %lld", who, (long long)bad_row);
+    RFM_REQUIRE(bad_host == 0, "%s: CSR column index out of range [0, %lld)", who, (long long)n_cols);
     return RFM_OK;
   };
   rc = body();
@@ -1288,6 +1297,29 @@ int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *ind
     return rc;
   }
   *out = r;
+  return RFM_OK;
+}
+
+int rfm_csr_create(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *indptr, int indptr_is_int64,
+                   const int32_t *indices, const double *data, const int64_t *labels, const double *pscores,
+                   int dtype, rfm_csr **out) {
+  return csr_create_impl(ctx, n_rows, n_cols, indptr, indptr_is_int64, indices, data, labels, pscores, dtype, 0,
+                         n_rows, out, "rfm_csr_create");
+}
+
+int rfm_csr_create_range(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const void *indptr, int indptr_is_int64,
+                         const int32_t *indices, const double *data, const int64_t *labels, const double *pscores,
+                         int dtype, int64_t row_begin, int64_t row_end, rfm_csr **out) {
+  return csr_create_impl(ctx, n_rows, n_cols, indptr, indptr_is_int64, indices, data, labels, pscores, dtype,
+                         row_begin, row_end, out, "rfm_csr_create_range");
+}
+
+int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev, void **col_dev, void **val_dev, void **targets_dev) {
+  RFM_REQUIRE(rows, "rfm_csr_device_ptrs: rows is NULL");
+  if (row_ptr_dev) *row_ptr_dev = rows->row_ptr.p;
+  if (col_dev) *col_dev = rows->col.p;
+  if (val_dev) *val_dev = rows->val.p;
+  if (targets_dev) *targets_dev = rows->yp.p;
   return RFM_OK;
 }
 
@@ -1545,9 +1577,13 @@ int rfm_fm_trainer_destroy(rfm_fm_trainer *t) {
     cudaStreamSynchronize(t->m->ctx->stream);
     for (int r = 0; r < rfm_fm_trainer::RING; ++r)
       if (t->stage_ev[r]) cudaEventDestroy(t->stage_ev[r]);
-    for (int q = 0; q < t->dp_world; ++q)
-      if (q != t->dp_rank && t->peer_base[q]) cudaIpcCloseMemHandle(t->peer_base[q]);
-    if (t->xchg) cudaFree(t->xchg);
+    if (t->xchg_borrowed) {
+      t->m->ctx->dp.borrowers = 0;
+    } else {
+      for (int q = 0; q < t->dp_world; ++q)
+        if (q != t->dp_rank && t->peer_base[q]) cudaIpcCloseMemHandle(t->peer_base[q]);
+      if (t->xchg) cudaFree(t->xchg);
+    }
     delete t;
   }
   return RFM_OK;
@@ -1835,15 +1871,37 @@ int rfm_fm_dp_export(rfm_fm_trainer *t, void *handle_out) {
   t->xchg_grad_bytes = ((size_t)n * dsize(t->m->dtype) + 255) / 256 * 256;
   const size_t bytes = 2 * t->xchg_grad_bytes + 256;
   // cudaMalloc, not the stream-ordered pool: pool memory cannot be exported through legacy CUDA IPC
-  RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->xchg), bytes));
+  cudaIpcMemHandle_t h;
+  if (ctx->dp_cache && ctx->dp.borrowers == 0) {
+    // Reuse is safe: the previous borrower's last exchange kernel has finished on EVERY rank before any rank
+    // could read its final losses (they come out of a collective ordered after it), and no rank starts stepping
+    // before the post-connect barrier, i.e. after every rank has re-zeroed its region here.
+    rfm_ctx::DpRegion &c = ctx->dp;
+    if (c.base && c.bytes < bytes) {   // outgrown: peers may still map it, so it is retired, not freed
+      c.retired.push_back(c.base);
+      c.base = nullptr;
+      c.bytes = 0;
+    }
+    if (!c.base) {
+      RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&c.base), bytes));
+      c.bytes = bytes;
+      RFM_CUDA(cudaIpcGetMemHandle(&h, c.base));
+      memcpy(c.own_handle, &h, sizeof(h));
+    }
+    memcpy(&h, c.own_handle, sizeof(h));
+    t->xchg = c.base;
+    t->xchg_borrowed = true;
+    c.borrowers = 1;
+  } else {
+    RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->xchg), bytes));
+    RFM_CUDA(cudaIpcGetMemHandle(&h, t->xchg));
+  }
   RFM_CUDA(cudaMemsetAsync(t->xchg, 0, bytes, ctx->stream));
   RFM_TRY(t->dp_prev_loss.alloc(2));
   RFM_TRY(t->dp_local.alloc(4));
   RFM_CUDA(cudaMemsetAsync(t->dp_local.p, 0, 4 * sizeof(uint32_t), ctx->stream));
   RFM_CUDA(cudaMemsetAsync(t->dp_prev_loss.p, 0, 2 * sizeof(double), ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaIpcMemHandle_t h;
-  RFM_CUDA(cudaIpcGetMemHandle(&h, t->xchg));
   memcpy(handle_out, &h, sizeof(h));
   return RFM_OK;
 }
@@ -1856,13 +1914,34 @@ int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world, const void
               rfm_fm_trainer::DP_MAX_WORLD);
   RFM_REQUIRE(t->dp_world == 0, "rfm_fm_dp_connect: already connected");
   RFM_CUDA(cudaSetDevice(t->m->ctx->device));
+  rfm_ctx::DpRegion &c = t->m->ctx->dp;
+  if (t->xchg_borrowed && (c.world != world || c.rank != rank)) {   // another group layout: drop every mapping
+    for (int q = 0; q < rfm_ctx::DpRegion::MAX_WORLD; ++q) {
+      if (q != c.rank && c.peer[q]) cudaIpcCloseMemHandle(c.peer[q]);
+      c.peer[q] = nullptr;
+    }
+    cudaGetLastError();
+    c.world = world;
+    c.rank = rank;
+  }
   for (int q = 0; q < world; ++q) {
     if (q == rank) {
       t->peer_base[q] = t->xchg;
+      if (t->xchg_borrowed) c.peer[q] = t->xchg;
       continue;
     }
+    const unsigned char *hq = static_cast<const unsigned char *>(all_handles) + (size_t)q * sizeof(cudaIpcMemHandle_t);
+    if (t->xchg_borrowed && c.peer[q]) {
+      if (memcmp(hq, c.peer_handle[q], sizeof(cudaIpcMemHandle_t)) == 0) {   // same region as last time: stay mapped
+        t->peer_base[q] = c.peer[q];
+        continue;
+      }
+      cudaIpcCloseMemHandle(c.peer[q]);                                       // the peer re-allocated
+      cudaGetLastError();
+      c.peer[q] = nullptr;
+    }
     cudaIpcMemHandle_t h;
-    memcpy(&h, static_cast<const unsigned char *>(all_handles) + (size_t)q * sizeof(h), sizeof(h));
+    memcpy(&h, hq, sizeof(h));
     void *p = nullptr;
     const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
@@ -1870,6 +1949,10 @@ int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world, const void
       return fail(RFM_ERR_CUDA, "rfm_fm_dp_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
     }
     t->peer_base[q] = static_cast<unsigned char *>(p);
+    if (t->xchg_borrowed) {
+      c.peer[q] = t->peer_base[q];
+      memcpy(c.peer_handle[q], hq, sizeof(cudaIpcMemHandle_t));
+    }
   }
   t->dp_rank = rank;
   t->dp_world = world;

@@ -180,6 +180,8 @@ int rfm_ctx_create(int device, void *cuda_stream, rfm_ctx **out) {
     }
     cudaGetLastError();
   }
+  const char *dc = getenv("RFM_DP_CACHE");
+  ctx->dp_cache = !(dc && dc[0] == '0');
   const char *sl = getenv("RFM_SYNC_LAUNCHES");
   ctx->sync_launches = sl && sl[0] == '1';
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
@@ -194,6 +196,11 @@ int rfm_ctx_destroy(rfm_ctx *ctx) {
   if (!ctx) return RFM_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int q = 0; q < rfm_ctx::DpRegion::MAX_WORLD; ++q)
+    if (q != ctx->dp.rank && ctx->dp.peer[q]) cudaIpcCloseMemHandle(ctx->dp.peer[q]);
+  if (ctx->dp.base) cudaFree(ctx->dp.base);
+  for (unsigned char *p : ctx->dp.retired) cudaFree(p);
+  cudaGetLastError();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   delete ctx;

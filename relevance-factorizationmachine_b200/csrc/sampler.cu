@@ -8,7 +8,9 @@
 // where rk_interval draws 32-bit outputs masked to the smallest 2^b-1 >= i and rejects
 // values > i. The algorithm is NumPy's published one (numpy/random/mtrand.pyx `shuffle`,
 // `_legacy_seeding`; src/distributions `random_interval`); tests check it against NumPy.
+#include <algorithm>
 #include <cstdlib>
+#include <thread>
 
 #include "common.cuh"
 #include "sampler.cuh"
@@ -217,6 +219,25 @@ void shuffle_prefix(int64_t n_rows, int64_t batch, uint32_t epoch, int64_t *out_
     if (slot_of.key[s] != PosMap::EMPTY) out_rows[slot_of.val[s]] = (int64_t)slot_of.key[s];
 }
 
+// fn(begin, end) over [0, n) on up to n_threads host threads (contiguous ranges; the caller's thread takes one)
+template <typename F>
+void parallel_ranges(int64_t n, int n_threads, F fn) {
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n / 4096));
+  if (n_threads <= 1) {
+    fn((int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 1; t < n_threads; ++t) {
+    const int64_t b = std::min(n, t * per), e = std::min(n, (t + 1) * per);
+    if (b < e) pool.emplace_back([=] { fn(b, e); });
+  }
+  fn((int64_t)0, std::min(n, per));
+  for (auto &th : pool) th.join();
+}
+
 }  // namespace
 
 using namespace rfm;
@@ -255,6 +276,77 @@ int rfm_feistel_batch(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epo
   RFM_REQUIRE(n_rows <= (1LL << 32), "rfm_feistel_batch: at most 2^32 rows");
   const FeistelKey key = make_feistel_key((uint64_t)n_rows, seed, epoch);
   for (int64_t q = 0; q < batch; ++q) out_rows[q] = (int64_t)feistel_permute((uint64_t)q, key);
+  return RFM_OK;
+}
+
+
+int rfm_feistel_batches(int64_t n_rows, int64_t batch, uint32_t seed, uint32_t epoch0, int32_t n_epochs,
+                        int64_t begin, int64_t count, int64_t *out_rows, int32_t n_threads) {
+  RFM_REQUIRE(n_rows >= 0 && batch >= 0 && n_epochs >= 0 && out_rows != nullptr, "rfm_feistel_batches: bad argument");
+  RFM_REQUIRE(batch <= n_rows,
+              "Cannot sample %lld out of arrays with dim %lld when replace is False",
+              (long long)batch, (long long)n_rows);
+  RFM_REQUIRE(begin >= 0 && count >= 0 && begin + count <= batch,
+              "rfm_feistel_batches: slice [%lld, %lld) outside the batch of %lld", (long long)begin,
+              (long long)(begin + count), (long long)batch);
+  RFM_REQUIRE(n_rows <= (1LL << 32), "rfm_feistel_batches: at most 2^32 rows");
+  const int64_t total = (int64_t)n_epochs * count;
+  parallel_ranges(total, n_threads, [=](int64_t b, int64_t e) {
+    int64_t cur_epoch = -1;
+    FeistelKey key = make_feistel_key((uint64_t)n_rows, seed, epoch0);
+    for (int64_t q = b; q < e; ++q) {
+      const int64_t ep = q / count, pos = q - ep * count;
+      if (ep != cur_epoch) {
+        key = make_feistel_key((uint64_t)n_rows, seed, epoch0 + (uint32_t)ep);
+        cur_epoch = ep;
+      }
+      out_rows[q] = (int64_t)feistel_permute((uint64_t)(begin + pos), key);
+    }
+  });
+  return RFM_OK;
+}
+
+int rfm_csr_gather_rows(int64_t n_rows, const void *indptr, int indptr_is_int64, const int32_t *indices,
+                        const double *data, const int64_t *labels, const double *pscores, const int64_t *rows,
+                        int64_t n_sel, int64_t *out_indptr, int32_t *out_indices, double *out_data,
+                        int64_t *out_labels, double *out_pscores, int32_t n_threads) {
+  RFM_REQUIRE(n_rows >= 0 && n_sel >= 0 && indptr && out_indptr && (rows || n_sel == 0),
+              "rfm_csr_gather_rows: bad argument");
+  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "rfm_csr_gather_rows: labels and pscores go together");
+  const int64_t *p64 = static_cast<const int64_t *>(indptr);
+  const int32_t *p32 = static_cast<const int32_t *>(indptr);
+  auto ptr_at = [=](int64_t i) -> int64_t { return indptr_is_int64 ? p64[i] : (int64_t)p32[i]; };
+  // pass 1 (always): row lengths -> out_indptr (exclusive prefix sum, serial: n_sel adds)
+  out_indptr[0] = 0;
+  for (int64_t q = 0; q < n_sel; ++q) {
+    const int64_t r = rows[q];
+    RFM_REQUIRE(r >= 0 && r < n_rows, "rfm_csr_gather_rows: row id %lld outside [0, %lld)", (long long)r,
+                (long long)n_rows);
+    const int64_t len = ptr_at(r + 1) - ptr_at(r);
+    RFM_REQUIRE(len >= 0, "rfm_csr_gather_rows: indptr decreases at row %lld", (long long)r);
+    out_indptr[q + 1] = out_indptr[q] + len;
+  }
+  if (!out_indices) return RFM_OK;   // sizing call: the caller allocates out_indptr[n_sel] entries and calls again
+  RFM_REQUIRE(out_data && (out_indptr[n_sel] == 0 || (indices && data)), "rfm_csr_gather_rows: NULL data arrays");
+  RFM_REQUIRE(!labels || (out_labels && out_pscores), "rfm_csr_gather_rows: NULL label outputs");
+  parallel_ranges(n_sel, n_threads, [=](int64_t b, int64_t e) {
+    constexpr int AHEAD = 8;        // the rows are random: request the source lines a few rows early
+    for (int64_t q = b; q < e; ++q) {
+      if (q + AHEAD < e) {
+        const int64_t z = ptr_at(rows[q + AHEAD]);
+        __builtin_prefetch(indices + z, 0, 0);
+        __builtin_prefetch(data + z, 0, 0);
+        __builtin_prefetch(data + z + 8, 0, 0);
+      }
+      const int64_t r = rows[q], z0 = ptr_at(r), len = ptr_at(r + 1) - z0, o = out_indptr[q];
+      memcpy(out_indices + o, indices + z0, (size_t)len * sizeof(int32_t));
+      memcpy(out_data + o, data + z0, (size_t)len * sizeof(double));
+      if (labels) {
+        out_labels[q] = labels[r];
+        out_pscores[q] = pscores[r];
+      }
+    }
+  });
   return RFM_OK;
 }
 

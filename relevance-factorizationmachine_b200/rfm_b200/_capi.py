@@ -39,7 +39,12 @@ _SIGNATURES = {
     "rfm_host_free": ([_P], c_int),
     "rfm_legacy_batch": ([c_int64, c_int64, c_uint32, _P, _P], c_int),
     "rfm_feistel_batch": ([c_int64, c_int64, c_uint32, c_uint32, _P], c_int),
+    "rfm_feistel_batches": ([c_int64, c_int64, c_uint32, c_uint32, c_int32, c_int64, c_int64, _P, c_int32], c_int),
+    "rfm_csr_gather_rows": ([c_int64, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int32], c_int),
     "rfm_csr_create": ([_P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P, c_int, POINTER(_P)], c_int),
+    "rfm_csr_create_range": ([_P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P, c_int, c_int64, c_int64, POINTER(_P)],
+                             c_int),
+    "rfm_csr_device_ptrs": ([_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)], c_int),
     "rfm_csr_destroy": ([_P], c_int),
     "rfm_fm_create": ([_P, c_int64, c_int32, c_int, POINTER(_P)], c_int),
     "rfm_fm_destroy": ([_P], c_int),
@@ -96,7 +101,7 @@ class RfmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 2        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
+ABI_VERSION = 3        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
 
 
 def lib():
@@ -222,7 +227,9 @@ class CsrRows(_Handle):
 
     _destroy = "rfm_csr_destroy"
 
-    def __init__(self, ctx: Context, X, labels=None, pscores=None, dtype="float64"):
+    def __init__(self, ctx: Context, X, labels=None, pscores=None, dtype="float64", row_range=None):
+        """row_range=(begin, end): copy only those rows from the host (the object keeps the full shape; the
+        caller fills the rest on the device, see rfm_b200.dist.sharded_csr_rows)."""
         super().__init__()
         X = X.tocsr()
         if not X.has_canonical_format:
@@ -239,10 +246,26 @@ class CsrRows(_Handle):
         ps = None if pscores is None else as_array(pscores, np.float64)
         if y is not None and (y.shape[0] != X.shape[0] or ps is None or ps.shape[0] != X.shape[0]):
             raise ValueError("labels/pscores must have one entry per row")
-        check(lib().rfm_csr_create(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
-                                   ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
         self.n_rows = X.shape[0]
-        self.h2d_bytes = indptr.nbytes + indices.nbytes + data.nbytes + (y.nbytes + ps.nbytes if y is not None else 0)
+        if row_range is None:
+            check(lib().rfm_csr_create(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
+                                       ptr(data), ptr(y), ptr(ps), dtype_code(dtype), byref(self.handle)))
+            self.h2d_bytes = (indptr.nbytes + indices.nbytes + data.nbytes
+                              + (y.nbytes + ps.nbytes if y is not None else 0))
+        else:
+            begin, end = row_range
+            check(lib().rfm_csr_create_range(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
+                                             ptr(data), ptr(y), ptr(ps), dtype_code(dtype), begin, end,
+                                             byref(self.handle)))
+            nz = int(indptr[end]) - int(indptr[begin])
+            self.h2d_bytes = indptr.nbytes + nz * 12 + ((end - begin) * 16 if y is not None else 0)
+        self.indptr_host = indptr          # kept for range arithmetic (a view of the caller's array when possible)
+
+    def device_ptrs(self):
+        """(row_ptr, col, val, targets) device addresses."""
+        out = [c_void_p() for _ in range(4)]
+        check(lib().rfm_csr_device_ptrs(self.handle, *[byref(p) for p in out]))
+        return tuple(p.value for p in out)
 
 
 class Optimizer(ctypes.Structure):
@@ -269,6 +292,44 @@ def legacy_batch(n_rows: int, batch: int, epoch: int, scratch=None) -> np.ndarra
     out = np.empty(batch, dtype=np.int64)
     check(lib().rfm_legacy_batch(n_rows, batch, epoch & 0xFFFFFFFF, ptr(out), ptr(scratch)))
     return out
+
+
+def feistel_batches(n_rows: int, batch: int, seed: int, epoch0: int, n_epochs: int, begin: int = 0, count=None,
+                    n_threads: int = 0) -> np.ndarray:
+    """(n_epochs, count) row ids: positions [begin, begin+count) of each epoch's Feistel batch (host threads)."""
+    count = batch - begin if count is None else count
+    out = np.empty((n_epochs, count), dtype=np.int64)
+    check(lib().rfm_feistel_batches(n_rows, batch, seed & 0xFFFFFFFF, epoch0 & 0xFFFFFFFF, n_epochs, begin, count,
+                                    ptr(out), n_threads))
+    return out
+
+
+def gather_rows(X, labels, pscores, rows: np.ndarray, n_threads: int = 0):
+    """scipy's ``X[rows]`` (+ labels[rows], pscores[rows]) on host threads; returns a csr_matrix flagged canonical
+    (rows of a canonical matrix are canonical) and the two target arrays."""
+    from scipy.sparse import csr_matrix
+    indptr = np.ascontiguousarray(X.indptr)
+    is64 = indptr.dtype == np.int64
+    if not is64:
+        indptr = as_array(indptr, np.int32)
+    indices, data = as_array(X.indices, np.int32), as_array(X.data, np.float64)
+    y = None if labels is None else as_array(labels, np.int64)
+    ps = None if pscores is None else as_array(pscores, np.float64)
+    rows = as_array(rows, np.int64).reshape(-1)
+    n_sel = rows.shape[0]
+    out_ptr = np.empty(n_sel + 1, dtype=np.int64)
+    args = (X.shape[0], ptr(indptr), int(is64), ptr(indices), ptr(data), ptr(y), ptr(ps), ptr(rows), n_sel)
+    check(lib().rfm_csr_gather_rows(*args, ptr(out_ptr), None, None, None, None, n_threads))
+    nnz = int(out_ptr[-1])
+    out_idx, out_val = np.empty(nnz, dtype=np.int32), np.empty(nnz, dtype=np.float64)
+    out_y = None if y is None else np.empty(n_sel, dtype=np.int64)
+    out_ps = None if ps is None else np.empty(n_sel, dtype=np.float64)
+    check(lib().rfm_csr_gather_rows(*args, ptr(out_ptr), ptr(out_idx), ptr(out_val), ptr(out_y), ptr(out_ps),
+                                    n_threads))
+    sub = csr_matrix((out_val, out_idx, out_ptr), shape=(n_sel, X.shape[1]), copy=False)
+    if X.has_canonical_format:
+        sub.has_canonical_format = True
+    return sub, out_y, out_ps
 
 
 def feistel_batch(n_rows: int, batch: int, epoch: int, seed: int = 0) -> np.ndarray:

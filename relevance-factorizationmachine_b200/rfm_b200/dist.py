@@ -98,6 +98,49 @@ def device_tensor(ptr: int, n: int, dtype: str, device: int):
     return torch.as_tensor(_DeviceArray(ptr, n, typestr), device="cuda:%d" % device)
 
 
+def csr_ranges(indptr, n_rows: int, world: int, es: int):
+    """Per rank: the byte ranges (offset, length) of its row slice inside the device arrays col (int32 per
+    non-zero), val (es bytes per non-zero) and targets (es bytes per row). Pure host arithmetic."""
+    out = []
+    for r in range(world):
+        rb, re = slice_bounds(n_rows, world, r)
+        z0, z1 = int(indptr[rb]), int(indptr[re])
+        out.append(((z0 * 4, (z1 - z0) * 4), (z0 * es, (z1 - z0) * es), (rb * es, (re - rb) * es)))
+    return out
+
+
+def sharded_csr_rows(ctx, X, labels, pscores, dtype: str, env: DistEnv):
+    """The replicated device CSR every rank trains on, built with 1/G of the PCIe traffic: rank r copies only rows
+    ``slice_bounds(N, G, r)`` from the host (``rfm_csr_create_range``), then every slice is broadcast from its
+    owner into the same offsets on all ranks over NVLink (3 NCCL broadcasts per rank: col, val, targets). The
+    result is byte-identical to ``CsrRows(ctx, X, labels, pscores, dtype)`` on every rank, so the sampler, the
+    kernels and the results do not change. All ranks must call this with the same matrix."""
+    from . import _capi
+    if env.backend != "nccl":
+        raise RuntimeError("sharded_csr_rows needs the NCCL backend (the slices are exchanged on the device)")
+    torch = env.torch
+    n = X.shape[0]
+    begin, end = slice_bounds(n, env.world, env.rank)
+    err = None
+    try:
+        rows = _capi.CsrRows(ctx, X, labels, pscores, dtype, row_range=(begin, end))
+    except Exception as e:                      # noqa: BLE001 -- every rank must learn about it before the collectives
+        rows, err = None, e
+    if env.max_over_ranks(0.0 if err is None else 1.0) > 0:
+        raise err if err is not None else RuntimeError("sharded_csr_rows: the upload failed on another rank")
+    ctx.synchronize()
+    _, col, val, targets = rows.device_ptrs()
+    es = 8 if dtype == "float64" else 4
+    dev = "cuda:%d" % env.device
+    for src, ranges in enumerate(csr_ranges(rows.indptr_host, n, env.world, es)):
+        for base, (off, nbytes) in zip((col, val, targets), ranges):
+            if nbytes:
+                t = torch.as_tensor(_DeviceArray(base + off, nbytes, "|u1"), device=dev)
+                env.dist.broadcast(t, src=src)
+    torch.cuda.synchronize(env.device)
+    return rows
+
+
 class DataParallelFM:
     """The DP step, independent of where the arithmetic runs.
 

@@ -11,6 +11,7 @@ and the lazy host mirrors of the parameters.
 """
 from __future__ import annotations
 
+import os
 import time
 import weakref
 from ctypes import byref, c_double, c_void_p
@@ -136,7 +137,15 @@ class FactorizationMachines(PointwiseBaseRecommender):
         hit = self._rows_cache.get(key)
         if hit is not None and hit[0]() is X:
             return hit[1]
-        rows = _capi.CsrRows(self._context(), X, labels, pscores, self.dtype)
+        env = self.distributed
+        if (env is not None and labels is not None and env.backend == "nccl" and env.world > 1
+                and X.shape[0] >= int(os.environ.get("RFM_DP_UPLOAD_MIN_ROWS", "1000000"))
+                and os.environ.get("RFM_DP_UPLOAD", "sharded") == "sharded"):
+            # data-parallel fit on a large train set: each rank uploads 1/G of the rows, NVLink carries the rest
+            from .dist import sharded_csr_rows
+            rows = sharded_csr_rows(self._context(), X, labels, pscores, self.dtype, env)
+        else:
+            rows = _capi.CsrRows(self._context(), X, labels, pscores, self.dtype)
         try:
             self._rows_cache[key] = (weakref.ref(X), rows)
         except TypeError:

@@ -44,6 +44,28 @@ def main():
         env.dist.all_reduce(lo, op=env.dist.ReduceOp.MIN)
         env.dist.all_reduce(hi, op=env.dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks diverged"
+    # sharded upload (1/G of the rows over PCIe per rank, the rest over NVLink) == the replicated upload, byte for byte
+    from rfm_b200 import _capi
+    from rfm_b200.dist import _DeviceArray, sharded_csr_rows
+    import torch
+    X = train["features"]
+    ctx = m._context()
+    for dtype in ("float64", "float32"):
+        full = _capi.CsrRows(ctx, X, train["labels"], train["pscores"], dtype)
+        part = sharded_csr_rows(ctx, X, train["labels"], train["pscores"], dtype, env)
+        es = 8 if dtype == "float64" else 4
+        sizes = ((X.shape[0] + 1) * 8, X.nnz * 4, X.nnz * es, X.shape[0] * es)
+        for pa, pb, nbytes in zip(full.device_ptrs(), part.device_ptrs(), sizes):
+            if nbytes:
+                ta = torch.as_tensor(_DeviceArray(pa, nbytes, "|u1"), device="cuda:%d" % local_rank)
+                tb = torch.as_tensor(_DeviceArray(pb, nbytes, "|u1"), device="cuda:%d" % local_rank)
+                assert torch.equal(ta, tb), "sharded upload differs from the replicated one (%s)" % dtype
+    os.environ["RFM_DP_UPLOAD_MIN_ROWS"] = "0"                # and a whole fit through it gives the same bits
+    m2 = FactorizationMachines(distributed=env, **kw)
+    tl2, vl2 = m2.fit(train, val)
+    np.testing.assert_array_equal(tl2, tl)
+    np.testing.assert_array_equal(m2.V(), m.V())
+    os.environ["RFM_DP_UPLOAD_MIN_ROWS"] = "1000000"
     # row-sharded predict == single-process predict, bit for bit
     test_X = golden_csr(g, "test")
     np.testing.assert_array_equal(rdist.sharded_predict(m, test_X, env), m.predict(X=test_X))

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(handle, s)]
     assert not missing, "declared in include/rfm_b200.h but not exported: %s" % missing
     assert set(_capi.DECLARED_SYMBOLS) == declared, set(_capi.DECLARED_SYMBOLS) ^ declared
-    assert _capi.lib().rfm_abi_version() == 2
+    assert _capi.lib().rfm_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_legacy_sampler_matches_numpy_known_answers():
@@ -152,3 +152,33 @@ def test_null_arguments_are_status_codes_never_crashes():
         else:
             assert rc == 1, (name, rc, msg)                       # RFM_ERR_INVALID -> ValueError in the shim
             assert msg.startswith(name), (name, msg)
+
+
+def test_feistel_batches_and_row_gather_match_their_serial_counterparts():
+    """Host helpers of the "upload only what the fit samples" idea (round2-prework): the threaded multi-epoch
+    Feistel batches equal rfm_feistel_batch epoch by epoch (any slice), and the threaded CSR gather equals scipy's
+    X[rows] with labels[rows] / pscores[rows] (repeated rows, empty rows, int64 row pointers)."""
+    import scipy.sparse as sp
+    N, B = 50_000, 2048
+    a = _capi.feistel_batches(N, B, 12345, 3, 4, n_threads=3)
+    for e in range(4):
+        np.testing.assert_array_equal(a[e], _capi.feistel_batch(N, B, 3 + e, 12345))
+    np.testing.assert_array_equal(_capi.feistel_batches(N, B, 12345, 3, 4, begin=100, count=700, n_threads=2),
+                                  a[:, 100:800])
+    rng = np.random.default_rng(0)
+    X = sp.random(N, 300, density=0.01, format="csr", random_state=1, dtype=np.float64)
+    X.sum_duplicates()
+    y, ps = rng.integers(0, 2, N), rng.uniform(0.1, 1.0, N)
+    rows = np.concatenate([a.reshape(-1), a[0, :50]])                       # repeats across "epochs"
+    for indptr_dtype in (np.int32, np.int64):
+        X.indptr = X.indptr.astype(indptr_dtype)
+        for nt in (1, 4):
+            sub, sy, sps = _capi.gather_rows(X, y, ps, rows, n_threads=nt)
+            ref = X[rows]
+            np.testing.assert_array_equal(sub.indptr, ref.indptr)
+            np.testing.assert_array_equal(sub.indices, ref.indices)
+            np.testing.assert_array_equal(sub.data, ref.data)
+            np.testing.assert_array_equal(sy, y[rows])
+            np.testing.assert_array_equal(sps, ps[rows])
+    with pytest.raises(ValueError, match="outside"):
+        _capi.gather_rows(X, y, ps, np.array([0, N]))

@@ -185,3 +185,22 @@ def test_fit_data_parallel_host_flow_with_stub_device(monkeypatch):
     assert st["h2d_bytes_rows"] == 10 and st["upload_seconds"] == 0.25 and st["gpu_launches"] == 0
     assert set(st["phase_seconds"]) == {"upload", "trainer_create", "dp_connect", "enqueue_epochs",
                                         "drain_and_read_losses", "trainer_destroy", "download_params"}
+
+
+def test_csr_ranges_tile_the_device_arrays():
+    """Host arithmetic of the sharded upload: the ranks' byte ranges partition col / val / targets exactly."""
+    from rfm_b200.dist import csr_ranges
+    rng = np.random.default_rng(5)
+    for n_rows, world, es in ((0, 2, 8), (1, 3, 8), (10, 4, 4), (1000, 8, 8), (7, 8, 4)):
+        lens = rng.integers(0, 6, size=n_rows)
+        indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(indptr[-1])
+        ranges = csr_ranges(indptr, n_rows, world, es)
+        assert len(ranges) == world
+        for which, (unit, total) in enumerate(((4, nnz), (es, nnz), (es, n_rows))):
+            cursor = 0
+            for r in range(world):
+                off, nbytes = ranges[r][which]
+                assert off == cursor and nbytes >= 0 and nbytes % unit == 0
+                cursor += nbytes
+            assert cursor == total * unit
