@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RFM_ABI_VERSION 3   /* 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
+#define RFM_ABI_VERSION 4   /* 4: rfm_*_set_targets; factored rows, device-chained evaluation, sharded top-K exchange (round 2). 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
 
 enum rfm_status {
   RFM_OK = 0,
@@ -115,6 +115,9 @@ int rfm_csr_create_range(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
                          int64_t row_begin, int64_t row_end, rfm_csr **out);
 int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev /* int64[n_rows+1] */, void **col_dev /* int32[nnz] */,
                         void **val_dev, void **targets_dev);
+/* Replace the per-row targets y/pscore with values the caller computed in float64 (fractional labels: the
+ * reference divides whatever `labels` holds, src/fm.py:80; rfm_csr_create takes integer labels). */
+int rfm_csr_set_targets(rfm_csr *rows, const double *targets /* [n_rows] */);
 int rfm_csr_destroy(rfm_csr *rows);
 
 /* ---- FM model: w0, w, V (src/fm.py:31-53); parameter holders of utils/optimizer.py:10-64 */
@@ -198,6 +201,7 @@ int rfm_fm_trainer_losses(rfm_fm_trainer *t, int64_t first_slot, int64_t n_slots
 /* ---- MF rows and model (src/mf.py) ---------------------------------------------------- */
 int rfm_pairs_create(rfm_ctx *ctx, int64_t n_rows, const int64_t *user_item /* (n_rows,2) */,
                      const int64_t *labels, const double *pscores, int dtype, rfm_pairs **out);
+int rfm_pairs_set_targets(rfm_pairs *rows, const double *targets /* [n_rows]: y/pscore, src/mf.py:99 */);
 int rfm_pairs_destroy(rfm_pairs *rows);
 int rfm_mf_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, int32_t n_factors, int dtype,
                   rfm_mf **out);

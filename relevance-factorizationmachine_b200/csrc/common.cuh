@@ -160,7 +160,7 @@ void prof_end(rfm_ctx *ctx);
                          cudaGetErrorString(err__), __FILE__, __LINE__);                    \
   } while (0)
 
-inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers -------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;

@@ -1323,6 +1323,27 @@ int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev, void **col_dev, void 
   return RFM_OK;
 }
 
+// Overwrite the per-row targets with y/pscore computed by the caller in float64 (fractional labels: the reference
+// divides whatever `labels` holds, src/fm.py:80, while rfm_csr_create takes integer labels).
+int rfm_csr_set_targets(rfm_csr *rows, const double *targets) {
+  RFM_REQUIRE(rows && targets, "rfm_csr_set_targets: NULL argument");
+  rfm_ctx *ctx = rows->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  if (rows->n_rows == 0) return RFM_OK;
+  if (rows->dtype == RFM_F64) {
+    RFM_TRY(upload(ctx, rows->yp.p, targets, (size_t)rows->n_rows * 8));
+  } else {
+    DevBuf<double> tmp;
+    RFM_TRY(tmp.alloc(rows->n_rows));
+    RFM_TRY(upload(ctx, tmp.p, targets, (size_t)rows->n_rows * 8));
+    RFM_LAUNCH(ctx, convert_f64_kernel<float>, grid_for(ctx, ceil_div(rows->n_rows, 256), 8), 256, 0, tmp.p,
+               reinterpret_cast<float *>(rows->yp.p), rows->n_rows);
+  }
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  rows->has_targets = true;
+  return RFM_OK;
+}
+
 int rfm_csr_destroy(rfm_csr *rows) {
   if (rows) {
     cudaSetDevice(rows->ctx->device);
@@ -1731,8 +1752,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 }
 
 // all CTAs of this rank and all ranks: CTA 0 collects the local arrivals, exchanges flags with the peers, then
-// releases the local CTAs. go values are 2 * seq + phase, so they only ever grow.
-__device__ void dpx_barrier(const DpxArgs &a, int phase) {
+// releases the local CTAs. go values are 2 * seq + phase, so they only ever grow. Returns false (to every thread of
+// every CTA of this rank) when a wait ran out of patience or an earlier barrier did: the status word local[2] is
+// sticky, the caller skips its reduce / apply, and the host raises when it reads the word. The leader's waits are
+// bounded by DPX_SPIN_LIMIT polls; the followers wait for the leader's release, which always comes (with the
+// status set if need be), so their own, much larger bound only guards against a leader that never ran.
+__device__ bool dpx_barrier(const DpxArgs &a, int phase) {
   __syncthreads();
   const uint32_t go = 2u * a.seq + (uint32_t)phase;
   if (blockIdx.x == 0) {     // block-uniform branch
@@ -1742,7 +1767,7 @@ __device__ void dpx_barrier(const DpxArgs &a, int phase) {
       uint32_t spins = 0;
       const uint32_t want = gridDim.x * (2u * (a.seq - 1u) + (uint32_t)phase + 1u);   // the counter never resets
       while (ld_acquire_gpu(a.local) < want)
-        if (++spins > DPX_SPIN_LIMIT) { a.local[2] = 1u; break; }
+        if (++spins > DPX_SPIN_LIMIT) { atomicCAS(a.local + 2, 0u, 1u); break; }
       __threadfence_system();
     }
     __syncthreads();
@@ -1753,18 +1778,22 @@ __device__ void dpx_barrier(const DpxArgs &a, int phase) {
       const uint32_t *mine = reinterpret_cast<const uint32_t *>(a.peer[a.rank] + a.flags_off);
       uint32_t spins = 0;
       while (ld_acquire_sys(mine + phase * rfm_fm_trainer::DP_MAX_WORLD + q) < a.seq)
-        if (++spins > DPX_SPIN_LIMIT) { a.local[2] = 2u + (uint32_t)q; break; }
+        if (++spins > DPX_SPIN_LIMIT) { atomicCAS(a.local + 2, 0u, 2u + (uint32_t)q); break; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(a.local + 1, go);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_release_sys(a.local + 1, go);
+    }
   } else if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(a.local, 1u);
-    uint32_t spins = 0;
+    uint64_t spins = 0;
     while (ld_acquire_gpu(a.local + 1) < go)
-      if (++spins > DPX_SPIN_LIMIT) break;
+      if (++spins > 64ull * DPX_SPIN_LIMIT) { atomicCAS(a.local + 2, 0u, 100u); break; }
   }
-  __syncthreads();
+  const uint32_t status = threadIdx.x == 0 ? ld_acquire_gpu(a.local + 2) : 0u;
+  return __syncthreads_or(status != 0u) == 0;
 }
 
 template <typename T>
@@ -1776,7 +1805,7 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
     mine[1] = static_cast<T>(a.loss_in[0]);
     mine[2] = static_cast<T>(a.loss_in[1]);
   }
-  dpx_barrier(a, 0);          // every rank's gradient is complete
+  if (!dpx_barrier(a, 0)) return;   // every rank's gradient is complete (or the exchange is abandoned: status set)
   {
     const int64_t lo = min(a.total, (int64_t)a.rank * a.slice), hi = min(a.total, lo + a.slice);
     using V2 = typename Vec2<T>::type;
@@ -1801,7 +1830,7 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
       reinterpret_cast<V2 *>(mine + lo)[i] = acc;
     }
   }
-  dpx_barrier(a, 1);          // every slice is reduced
+  if (!dpx_barrier(a, 1)) return;   // every slice is reduced
   auto at = [&](int64_t i) -> const T * {      // element i of the reduced gradient, in its owner's buffer
     const int64_t owner = min((int64_t)a.world - 1, i / a.slice);
     return reinterpret_cast<const T *>(a.peer[owner] + a.grad_off) + i;

@@ -198,6 +198,12 @@ __global__ void mf_targets_kernel(const int64_t *__restrict__ y, const double *_
     yp[i] = static_cast<T>(static_cast<double>(y[i]) / ps[i]);
 }
 
+template <typename T>
+__global__ void mf_convert_targets_kernel(const double *__restrict__ in, T *__restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = static_cast<T>(in[i]);
+}
+
 #define MF_DISPATCH_NCH(nch, ...)                                  \
   switch (nch) {                                                   \
     case 1: { constexpr int NCH = 1; __VA_ARGS__; } break;         \
@@ -398,6 +404,28 @@ int rfm_pairs_create(rfm_ctx *ctx, int64_t n_rows, const int64_t *user_item, con
     return rc;
   }
   *out = r;
+  return RFM_OK;
+}
+
+// Overwrite the per-row targets with y/pscore computed by the caller in float64 (fractional labels, src/mf.py:99).
+int rfm_pairs_set_targets(rfm_pairs *rows, const double *targets) {
+  RFM_REQUIRE(rows && targets, "rfm_pairs_set_targets: NULL argument");
+  rfm_ctx *ctx = rows->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  if (rows->n_rows == 0) return RFM_OK;
+  DevBuf<double> tmp;
+  RFM_TRY(tmp.alloc(rows->n_rows));
+  RFM_CUDA(cudaMemcpyAsync(tmp.p, targets, (size_t)rows->n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int g = grid_for(ctx, ceil_div(rows->n_rows, 256), 8);
+  if (rows->dtype == RFM_F64) {
+    RFM_LAUNCH(ctx, mf_convert_targets_kernel<double>, g, 256, 0, tmp.p, reinterpret_cast<double *>(rows->yp.p),
+               rows->n_rows);
+  } else {
+    RFM_LAUNCH(ctx, mf_convert_targets_kernel<float>, g, 256, 0, tmp.p, reinterpret_cast<float *>(rows->yp.p),
+               rows->n_rows);
+  }
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  rows->has_targets = true;
   return RFM_OK;
 }
 

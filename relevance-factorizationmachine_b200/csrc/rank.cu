@@ -11,8 +11,8 @@
 //   Recall@k     utils/metrics.py:32-50     MAP@k      utils/metrics.py:9-29
 //   coverage     utils/metrics.py:152-166   |union of kept users' top-k items| (integer, exact)
 //
-// One CTA per user selects the top max(K) candidates by repeated block-wide arg-max over the
-// user's list (keys are unique because the in-list position breaks ties), then one thread walks
+// One CTA per user sorts the user's list in shared memory (bitonic; order-preserving 64-bit score keys with NaN
+// first, the in-list position breaks ties, so the order is total), then one thread per K walks
 // the ranked prefix and emits the per-user metric terms. A second kernel sums the per-user terms
 // in a fixed order, so the aggregates are bit-reproducible. Item hit counts use integer atomics.
 #include <algorithm>
@@ -45,37 +45,62 @@ constexpr int RK_THREADS = 128;
 constexpr int RK_MAX_K = 128;     // largest supported ranking position
 constexpr int RK_MAX_NK = 16;     // how many K values per call
 constexpr int NTERMS = 7;         // dcg, ipsdcg, me, me_valid, recall, map, kept
+constexpr int RK_SORT_CAP = 2048; // longest candidate list that is sorted whole in shared memory
 
-struct Key {
-  double score;
-  int pos;   // position inside the user's list; -1 = none
-};
-
-__device__ __forceinline__ bool better(const Key &a, const Key &b) {
-  // true when a ranks before b
-  if (a.pos < 0) return false;
-  if (b.pos < 0) return true;
-  return a.score > b.score || (a.score == b.score && a.pos > b.pos);
+// Total order on scores, as an order-preserving 64-bit key (larger key ranks first). The reference ranks with
+// scores.argsort()[::-1] (utils/evaluate.py:93,197): NumPy sorts NaN behind every number, so the reversal puts NaN
+// FIRST; -0.0 and +0.0 compare equal. Key 0 is never produced (it would be the bit pattern of a NaN), so it
+// serves as the padding value that sorts last.
+__device__ __forceinline__ uint64_t score_key(double s) {
+  if (s != s) return ~0ull;
+  if (s == 0.0) s = 0.0;                                  // -0.0 -> +0.0
+  const uint64_t b = static_cast<uint64_t>(__double_as_longlong(s));
+  return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
 }
 
-__device__ __forceinline__ Key block_best(Key mine, Key *smem) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Key other;
-    other.score = __shfl_xor_sync(FULL, mine.score, o);
-    other.pos = __shfl_xor_sync(FULL, mine.pos, o);
-    if (better(other, mine)) mine = other;
+// (key, pos) ranks before (key2, pos2): larger key first, later row first among equal keys
+__device__ __forceinline__ bool before(uint64_t ka, int pa, uint64_t kb, int pb) {
+  return ka > kb || (ka == kb && pa > pb);
+}
+
+// descending bitonic sort of n (a power of two) (key, pos) pairs in shared memory by the whole CTA
+__device__ __forceinline__ void block_bitonic_sort(uint64_t *key, int *pos, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n >> 1); t += RK_THREADS) {
+        const int lo = ((t / stride) * stride << 1) + (t % stride), hi = lo + stride;
+        const bool descending = (lo & size) == 0;
+        const uint64_t ka = key[lo], kb = key[hi];
+        const int pa = pos[lo], pb = pos[hi];
+        if (before(kb, pb, ka, pa) == descending) {
+          key[lo] = kb; key[hi] = ka;
+          pos[lo] = pb; pos[hi] = pa;
+        }
+      }
+    }
   }
-  if (lane == 0) smem[wid] = mine;
   __syncthreads();
-  Key best = smem[0];
-  for (int w = 1; w < RK_THREADS / 32; ++w)
-    if (better(smem[w], best)) best = smem[w];
-  __syncthreads();
-  return best;
 }
 
+// CTA-wide sum of a per-thread count (every thread gets the total)
+__device__ __forceinline__ int block_count(int c, int *wcnt) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < RK_THREADS / 32; ++w) t += wcnt[w];
+  return t;
+}
+
+// One CTA per user. The user's top max(K) candidates in the canonical order are found by a bitonic sort of the
+// whole list in shared memory (lists up to RK_SORT_CAP rows: every list of the reference's own workloads), or,
+// for longer lists, by a two-level bisection (on the score key, then on the row position among exact ties) that
+// selects exactly max(K) rows, which are then sorted. O(L log^2 L / threads) resp. O(96 L / threads) per user
+// instead of max(K) passes over the list.
 __global__ void __launch_bounds__(RK_THREADS)
 rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restrict__ order,
                   const int32_t *__restrict__ item, const double *__restrict__ label,
@@ -83,9 +108,11 @@ rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restric
                   const double *__restrict__ user_totals, int64_t n_users,
                   const int32_t *__restrict__ K, int n_k, int k_max, int64_t n_items,
                   double *__restrict__ per_user, int32_t *__restrict__ hits, int64_t *__restrict__ top_rows) {
-  __shared__ Key wbest[RK_THREADS / 32];
+  __shared__ uint64_t skey[RK_SORT_CAP];
+  __shared__ int spos[RK_SORT_CAP];
   __shared__ double wsum[RK_THREADS / 32];
-  __shared__ int top_pos[RK_MAX_K];
+  __shared__ int wcnt[RK_THREADS / 32];
+  __shared__ int n_sel;
   __shared__ double total_y_s;
   for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x) {
     const int64_t beg = user_ptr[u];
@@ -100,34 +127,64 @@ rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restric
       double t = 0.0;
       for (int w = 0; w < RK_THREADS / 32; ++w) t += wsum[w];
       total_y_s = t;
+      n_sel = 0;
     }
     __syncthreads();
     // label total that decides the skip rule and Recall's denominator: over the rows given, or the
     // caller's total when the rows are only a prefix of the user's candidates (full-catalog evaluation)
     const double total_y = user_totals ? user_totals[u] : total_y_s;
     const int n_top = L < k_max ? L : k_max;
-    // top-n_top by repeated arg-max below the previously selected key
-    Key last;
-    last.score = 0.0;
-    last.pos = -2;   // -2: nothing selected yet
-    for (int r = 0; r < n_top; ++r) {
-      Key mine;
-      mine.score = 0.0;
-      mine.pos = -1;
-      for (int j = threadIdx.x; j < L; j += RK_THREADS) {
-        Key c;
-        c.score = scores[order[beg + j]];
-        c.pos = j;
-        const bool below = last.pos == -2 || better(last, c);
-        if (below && better(c, mine)) mine = c;
+    int n_sort = 1;
+    if (L <= RK_SORT_CAP) {
+      while (n_sort < L) n_sort <<= 1;
+      for (int j = threadIdx.x; j < n_sort; j += RK_THREADS) {
+        skey[j] = j < L ? score_key(scores[order[beg + j]]) : 0ull;
+        spos[j] = j < L ? j : -1;
       }
-      last = block_best(mine, wbest);
-      if (threadIdx.x == 0) top_pos[r] = last.pos;
+    } else {
+      // n_top-th largest key: bisection on the key bits
+      uint64_t thr = 0ull;
+      for (int bit = 63; bit >= 0; --bit) {
+        const uint64_t cand = thr | (1ull << bit);
+        int c = 0;
+        for (int j = threadIdx.x; j < L; j += RK_THREADS) c += score_key(scores[order[beg + j]]) >= cand;
+        if (block_count(c, wcnt) >= n_top) thr = cand;
+      }
+      int above = 0;
+      for (int j = threadIdx.x; j < L; j += RK_THREADS) above += score_key(scores[order[beg + j]]) > thr;
+      above = block_count(above, wcnt);
+      // among the rows that tie with it, the n_top - above latest ones: bisection on the position
+      const int need = n_top - above;
+      int pthr = 0;
+      for (int bit = 30; bit >= 0; --bit) {
+        const int cand = pthr | (1 << bit);
+        int c = 0;
+        for (int j = threadIdx.x; j < L; j += RK_THREADS)
+          c += (j >= cand) && score_key(scores[order[beg + j]]) == thr;
+        if (block_count(c, wcnt) >= need) pthr = cand;
+      }
+      while (n_sort < n_top) n_sort <<= 1;
+      for (int j = threadIdx.x; j < n_sort; j += RK_THREADS) {
+        skey[j] = 0ull;
+        spos[j] = -1;
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < L; j += RK_THREADS) {
+        const uint64_t kj = score_key(scores[order[beg + j]]);
+        if (kj > thr || (kj == thr && j >= pthr)) {
+          const int at = atomicAdd(&n_sel, 1);
+          if (at < n_sort) {
+            skey[at] = kj;
+            spos[at] = j;
+          }
+        }
+      }
     }
-    __syncthreads();
+    block_bitonic_sort(skey, spos, n_sort);
+    const int *top_pos = spos;             // positions inside the user's list, best first; -1 = padding
     if (top_rows) {
       for (int r = threadIdx.x; r < k_max; r += RK_THREADS)
-        top_rows[u * k_max + r] = r < n_top ? static_cast<int64_t>(order[beg + top_pos[r]]) : -1;
+        top_rows[u * k_max + r] = (r < n_top && top_pos[r] >= 0) ? static_cast<int64_t>(order[beg + top_pos[r]]) : -1;
     }
     if (threadIdx.x < n_k) {
       const int kk = threadIdx.x;
@@ -139,7 +196,9 @@ rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restric
         const int n = L < k ? L : k;
         double dcg = 0.0, ips = 0.0, hit = 0.0, ap = 0.0;
         for (int j = 0; j < n; ++j) {
-          const double y = label[beg + top_pos[j]], ps = pscore[beg + top_pos[j]];
+          const int tp = top_pos[j];
+          if (tp < 0) break;
+          const double y = label[beg + tp], ps = pscore[beg + tp];
           if (j == 0) {
             dcg += y;
             ips += y / ps;
@@ -150,11 +209,11 @@ rank_users_kernel(const int64_t *__restrict__ user_ptr, const int32_t *__restric
           }
           hit += y;
           if (y >= 1.0) ap += hit / static_cast<double>(j + 1);
-          if (hits) atomicAdd(hits + (size_t)kk * n_items + item[beg + top_pos[j]], 1);
+          if (hits) atomicAdd(hits + (size_t)kk * n_items + item[beg + tp], 1);
         }
         out[0] = dcg;
         out[1] = ips;
-        out[2] = L >= k ? pscore[beg + top_pos[k - 1]] : 0.0;
+        out[2] = (L >= k && top_pos[k - 1] >= 0) ? pscore[beg + top_pos[k - 1]] : 0.0;
         out[3] = L >= k ? 1.0 : 0.0;
         out[4] = hit / total_y;
         out[5] = ap;

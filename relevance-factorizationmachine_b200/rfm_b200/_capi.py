@@ -45,6 +45,7 @@ _SIGNATURES = {
     "rfm_csr_create_range": ([_P, c_int64, c_int64, _P, c_int, _P, _P, _P, _P, c_int, c_int64, c_int64, POINTER(_P)],
                              c_int),
     "rfm_csr_device_ptrs": ([_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)], c_int),
+    "rfm_csr_set_targets": ([_P, _P], c_int),
     "rfm_csr_destroy": ([_P], c_int),
     "rfm_fm_create": ([_P, c_int64, c_int32, c_int, POINTER(_P)], c_int),
     "rfm_fm_destroy": ([_P], c_int),
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "rfm_fm_loss_sums": ([_P, _P, c_int64, c_int64, c_int64], c_int),
     "rfm_fm_trainer_losses": ([_P, c_int64, c_int64, _P, _P], c_int),
     "rfm_pairs_create": ([_P, c_int64, _P, _P, _P, c_int, POINTER(_P)], c_int),
+    "rfm_pairs_set_targets": ([_P, _P], c_int),
     "rfm_pairs_destroy": ([_P], c_int),
     "rfm_mf_create": ([_P, c_int64, c_int64, c_int32, c_int, POINTER(_P)], c_int),
     "rfm_mf_destroy": ([_P], c_int),
@@ -101,7 +103,7 @@ class RfmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 3        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
+ABI_VERSION = 4        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
 
 
 def lib():
@@ -222,6 +224,34 @@ class _Handle:
             pass
 
 
+def weak_refs(*objs):
+    """Weak references to every non-None object, or None when one of them cannot be weakly referenced (the caller
+    then skips its cache: an id() alone can be reused after garbage collection)."""
+    import weakref
+    try:
+        return tuple(None if o is None else weakref.ref(o) for o in objs)
+    except TypeError:
+        return None
+
+
+def refs_match(refs, *objs) -> bool:
+    return refs is not None and all((r is None and o is None) or (r is not None and r() is o) for r, o in zip(refs, objs))
+
+
+def integer_labels(labels, pscores):
+    """(labels as int64, float64 targets or None): the C ABI takes integer labels and divides on the device exactly
+    as NumPy would (``y / pscore``, src/fm.py:80); labels with a fractional part keep the reference's semantics by
+    sending ``labels / pscores`` computed here in float64 (``rfm_*_set_targets``) instead of being truncated."""
+    y = np.asarray(labels)
+    if y.dtype.kind in "iub":
+        return as_array(y, np.int64), None
+    yf = as_array(y, np.float64)
+    yi = yf.astype(np.int64)
+    if np.array_equal(yi, yf):
+        return yi, None
+    return np.zeros(yf.shape, dtype=np.int64), np.ascontiguousarray(yf / as_array(pscores, np.float64))
+
+
 class CsrRows(_Handle):
     """Device copy of a scipy CSR matrix (+ labels / pscores)."""
 
@@ -242,10 +272,10 @@ class CsrRows(_Handle):
             indptr = as_array(indptr, np.int32)
         indices = as_array(X.indices, np.int32)
         data = as_array(X.data, np.float64)
-        y = None if labels is None else as_array(labels, np.int64)
         ps = None if pscores is None else as_array(pscores, np.float64)
-        if y is not None and (y.shape[0] != X.shape[0] or ps is None or ps.shape[0] != X.shape[0]):
+        if labels is not None and (len(labels) != X.shape[0] or ps is None or ps.shape[0] != X.shape[0]):
             raise ValueError("labels/pscores must have one entry per row")
+        y, targets = (None, None) if labels is None else integer_labels(labels, ps)
         self.n_rows = X.shape[0]
         if row_range is None:
             check(lib().rfm_csr_create(ctx.handle, X.shape[0], X.shape[1], ptr(indptr), int(is64), ptr(indices),
@@ -260,6 +290,8 @@ class CsrRows(_Handle):
             nz = int(indptr[end]) - int(indptr[begin])
             self.h2d_bytes = indptr.nbytes + nz * 12 + ((end - begin) * 16 if y is not None else 0)
         self.indptr_host = indptr          # kept for range arithmetic (a view of the caller's array when possible)
+        if targets is not None:
+            check(lib().rfm_csr_set_targets(self.handle, ptr(targets)))
 
     def device_ptrs(self):
         """(row_ptr, col, val, targets) device addresses."""

@@ -195,6 +195,14 @@ class NvlinkDataParallelFM(DataParallelFM):
         super().__init__(env, global_batch, n_val, lr, local_grad, None, None, local_loss_sums, loss_tensor)
         self.exchange_apply, self.prev_loss_tensor, self.status_tensor = exchange_apply, prev_loss_tensor, status_tensor
 
+    STATUS_EVERY = 64      # steps between reads of the exchange kernel's status word (a read drains the stream)
+
+    def _check_status(self):
+        status = int(self.status_tensor.item())
+        if status:
+            raise RuntimeError("rfm_fm_dp_exchange_apply: a cross-GPU barrier timed out (status %d); the parameters "
+                               "of this fit are not trustworthy from that step on" % status)
+
     def step(self, epoch: int):
         self.local_grad(self.begin, self.end, epoch)
         pending = getattr(self, "_pending", False)
@@ -202,13 +210,15 @@ class NvlinkDataParallelFM(DataParallelFM):
         prev = self.prev_loss_tensor.clone() if pending else None
         self.local_loss_sums(self.begin, self.end, self.vbegin, self.vend)
         self._pending = True
+        self._steps = getattr(self, "_steps", 0) + 1
+        if self._steps % self.STATUS_EVERY == 0:     # a timed-out barrier skips its reduce/apply: stop here, not after the fit
+            self._check_status()
         return prev
 
     def flush(self):
+        self._check_status()
         out = super().flush()
-        status = int(self.status_tensor.item())
-        if status:
-            raise RuntimeError("rfm_fm_dp_exchange_apply: a cross-GPU barrier timed out (status %d)" % status)
+        self._check_status()
         return out
 
 

@@ -70,16 +70,43 @@ class _BaseEvaluator(ABC):
         ...
 
     def _ranker(self, pscore_name="pscore", n_items=None, device=0):
+        """Device copy of the frame grouped by user, rebuilt when the frame's columns are replaced or n_items
+        changes (the reference regroups on every call, ``utils/evaluate.py:141-156``). The cache keys on the identity
+        of the column arrays: replacing a column is seen, editing one IN PLACE is not -- call ``reset_cache()``."""
         cache = self.__dict__.setdefault("_rankers", {})
-        key = (pscore_name, len(_column(self.interaction_df, "user")))
-        if key not in cache:
-            items = _column(self.interaction_df, "item")
-            if n_items is None:
-                n_items = int(items.max()) + 1 if items.size else 1
-            cache[key] = _Ranker(_capi.Context.default(device), _column(self.interaction_df, "user"), items,
-                                 _column(self.interaction_df, "label"), _column(self.interaction_df, pscore_name),
-                                 n_items)
-        return cache[key]
+        cols = [np.asarray(_column(self.interaction_df, name)) for name in ("user", "item", "label", pscore_name)]
+        items = cols[1]
+        if n_items is None:
+            n_items = int(items.max()) + 1 if items.size else 1
+        stamp = tuple((c.__array_interface__["data"][0], c.shape[0], c.dtype.str) for c in cols) + (int(n_items),)
+        hit = cache.get(pscore_name)
+        if hit is None or hit[0] != stamp:
+            if hit is not None:
+                hit[1].close()
+            cache[pscore_name] = (stamp, _Ranker(_capi.Context.default(device), cols[0], items, cols[2], cols[3],
+                                                 n_items), cols)     # cols kept alive: the stamp holds their addresses
+        return cache[pscore_name][1]
+
+    def reset_cache(self):
+        """Drop the device copies (after editing a column of ``interaction_df`` in place)."""
+        for _, ranker, _cols in self.__dict__.pop("_rankers", {}).values():
+            ranker.close()
+
+    def _grouped(self, y_scores, pscore_name):
+        """``{user: {"items", "labels", "y_scores", "pscores"}}`` -- what the reference's pandas group-by returns
+        (``utils/evaluate.py:141-156, 223-239``): users ascending, a user's rows in frame order."""
+        self._record_scores(y_scores)
+        users = np.asarray(_column(self.interaction_df, "user"))
+        order = np.argsort(users, kind="stable")
+        su = users[order]
+        starts = np.flatnonzero(np.r_[True, su[1:] != su[:-1]]) if len(su) else np.zeros(0, dtype=np.int64)
+        ends = np.r_[starts[1:], len(order)]
+        cols = {"items": "item", "labels": "label", "pscores": pscore_name}
+        data = {k: np.asarray(_column(self.interaction_df, v))[order] for k, v in cols.items()}
+        data["y_scores"] = np.asarray(y_scores)[order]
+        return {su[b].item(): {"items": data["items"][b:e], "labels": data["labels"][b:e],
+                               "y_scores": data["y_scores"][b:e], "pscores": data["pscores"][b:e]}
+                for b, e in zip(starts, ends)}
 
     def _record_scores(self, y_scores):
         # the reference mutates interaction_df["y_score"] (evaluate.py:141, 223); keep that visible
@@ -132,8 +159,9 @@ class TestEvaluator(_BaseEvaluator):
         _, _, top = self._ranker(n_items=self.n_items).evaluate(y_scores, [k], want_top=True)
         return top
 
-    def _group_by_user_data(self, *args, **kwargs):  # kept for API fidelity; grouping is done once on creation
-        raise NotImplementedError("grouping happens inside the device ranker")
+    def _group_by_user_data(self, y_scores: np.ndarray) -> Dict[str, Dict[str, np.ndarray]]:
+        """``utils/evaluate.py:129-156`` (host helper; ``evaluate`` itself groups once on the device)."""
+        return self._grouped(y_scores, "pscore")
 
 
 @dataclass
@@ -154,8 +182,9 @@ class ValEvaluator(_BaseEvaluator):
         kept = metrics[0, RANK_COLS["USERS"]]
         return metrics[0, RANK_COLS["IPSDCG_SUM"]] / kept if kept else np.nan
 
-    def _group_by_user_data(self, *args, **kwargs):
-        raise NotImplementedError("grouping happens inside the device ranker")
+    def _group_by_user_data(self, y_scores: np.ndarray, estimator: str) -> Dict[str, Dict[str, np.ndarray]]:
+        """``utils/evaluate.py:209-239`` (host helper; ``evaluate`` itself groups once on the device)."""
+        return self._grouped(y_scores, "pscore" if estimator == "IPS" else "ones_pscore")
 
 
 @dataclass

@@ -132,27 +132,32 @@ class FactorizationMachines(PointwiseBaseRecommender):
 
     def _rows(self, X, labels=None, pscores=None):
         """Device copy of a CSR matrix, cached per Python object so that the evaluator's features
-        and the val set are uploaded once, not every epoch."""
+        and the val set are uploaded once, not every epoch. The cache holds weak references to X, labels and
+        pscores: a replaced object is seen, an array edited IN PLACE is not -- call ``reset_rows_cache()``."""
         key = (id(X), id(labels), id(pscores))
         hit = self._rows_cache.get(key)
-        if hit is not None and hit[0]() is X:
+        if hit is not None and _capi.refs_match(hit[0], X, labels, pscores):
             return hit[1]
+        rows = self._make_rows(X, labels, pscores)
+        refs = _capi.weak_refs(X, labels, pscores)
+        if refs is not None:
+            self._rows_cache[key] = (refs, rows)
+            if len(self._rows_cache) > 8:
+                self._rows_cache.pop(next(iter(self._rows_cache)))
+        return rows
+
+    def _make_rows(self, X, labels, pscores):
         env = self.distributed
         if (env is not None and labels is not None and env.backend == "nccl" and env.world > 1
                 and X.shape[0] >= int(os.environ.get("RFM_DP_UPLOAD_MIN_ROWS", "1000000"))
                 and os.environ.get("RFM_DP_UPLOAD", "sharded") == "sharded"):
             # data-parallel fit on a large train set: each rank uploads 1/G of the rows, NVLink carries the rest
             from .dist import sharded_csr_rows
-            rows = sharded_csr_rows(self._context(), X, labels, pscores, self.dtype, env)
-        else:
-            rows = _capi.CsrRows(self._context(), X, labels, pscores, self.dtype)
-        try:
-            self._rows_cache[key] = (weakref.ref(X), rows)
-        except TypeError:
-            pass
-        if len(self._rows_cache) > 8:
-            self._rows_cache.pop(next(iter(self._rows_cache)))
-        return rows
+            return sharded_csr_rows(self._context(), X, labels, pscores, self.dtype, env)
+        return _capi.CsrRows(self._context(), X, labels, pscores, self.dtype)
+
+    def reset_rows_cache(self) -> None:
+        self._rows_cache.clear()
 
     # ---- reference API -----------------------------------------------------------------------
     def fit(self, train, val) -> tuple:

@@ -42,12 +42,14 @@ class PairRows(_capi._Handle):
         if pairs.ndim != 2 or pairs.shape[1] != 2:
             raise ValueError("MF features must have shape (N, 2): [user, item]")
         pairs = _capi.as_array(pairs, np.int64)
-        y = None if labels is None else _capi.as_array(labels, np.int64)
         ps = None if pscores is None else _capi.as_array(pscores, np.float64)
-        if y is not None and (y.shape[0] != pairs.shape[0] or ps is None or ps.shape[0] != pairs.shape[0]):
+        if labels is not None and (len(labels) != pairs.shape[0] or ps is None or ps.shape[0] != pairs.shape[0]):
             raise ValueError("labels/pscores must have one entry per row")
+        y, targets = (None, None) if labels is None else _capi.integer_labels(labels, ps)
         check(lib().rfm_pairs_create(ctx.handle, pairs.shape[0], ptr(pairs), ptr(y), ptr(ps),
                                      _capi.dtype_code(dtype), byref(self.handle)))
+        if targets is not None:
+            check(lib().rfm_pairs_set_targets(self.handle, ptr(targets)))
         self.n_rows = pairs.shape[0]
 
 
@@ -119,16 +121,22 @@ class LogisticMatrixFactorization(PointwiseBaseRecommender):
         self._synced = self._host_state()
 
     def _rows(self, X, labels=None, pscores=None):
+        """Device copy of (N, 2) rows, cached on weak references to X, labels and pscores (in-place edits are not
+        seen: ``reset_rows_cache()``)."""
         key = (id(X), id(labels), id(pscores))
         hit = self._rows_cache.get(key)
-        if hit is not None and hit[0]() is X:
+        if hit is not None and _capi.refs_match(hit[0], X, labels, pscores):
             return hit[1]
         rows = PairRows(self._context(), X, labels, pscores, self.dtype)
-        if isinstance(X, np.ndarray):
-            self._rows_cache[key] = (weakref.ref(X), rows)
+        refs = _capi.weak_refs(X, labels, pscores) if isinstance(X, np.ndarray) else None
+        if refs is not None:
+            self._rows_cache[key] = (refs, rows)
             if len(self._rows_cache) > 8:
                 self._rows_cache.pop(next(iter(self._rows_cache)))
         return rows
+
+    def reset_rows_cache(self) -> None:
+        self._rows_cache.clear()
 
     # ---- reference API -----------------------------------------------------------------------
     def fit(self, train, val) -> tuple:

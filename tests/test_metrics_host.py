@@ -88,3 +88,41 @@ def test_fm_grid_decomposition_equals_predict_on_cartesian_rows():
     X = (user_table[u] + item_table[i]).tocsr()
     want = fm_oracle.fm_predict(X, model.w0(), model.w(), model.V()).reshape(n_users, n_items)
     np.testing.assert_allclose(1.0 / (1.0 + np.exp(-logits)), want, rtol=1e-12, atol=1e-15)
+
+
+def test_group_by_user_data_matches_the_pandas_group_by():
+    """TestEvaluator/ValEvaluator._group_by_user_data return what the reference's pandas expression returns
+    (utils/evaluate.py:141-156, 223-239): users ascending, rows in frame order, the four keys, y_score recorded."""
+    import pandas as pd
+    from rfm_b200.evaluate import TestEvaluator, ValEvaluator
+    rng = np.random.default_rng(2)
+    n = 300
+    df = pd.DataFrame({"user": rng.integers(0, 17, n), "item": rng.integers(0, 40, n), "label": rng.integers(0, 2, n),
+                       "pscore": rng.uniform(0.1, 1, n), "ones_pscore": np.ones(n)})
+    scores = rng.random(n)
+    ref = df.assign(y_score=scores).groupby("user").agg(list).map(np.array)
+    te = TestEvaluator(interaction_df=df.copy(), features={}, K=[1, 3], used_metrics={"DCG"}, n_items=40)
+    ve = ValEvaluator(interaction_df=df.copy(), features={}, k=3, metric_name="DCG")
+    for got, ps_name in ((te._group_by_user_data(scores), "pscore"), (ve._group_by_user_data(scores, "IPS"), "pscore"),
+                         (ve._group_by_user_data(scores, "Naive"), "ones_pscore")):
+        assert list(got) == list(ref.index)
+        for user, data in got.items():
+            assert set(data) == {"items", "labels", "y_scores", "pscores"}
+            np.testing.assert_array_equal(data["items"], ref.loc[user, "item"])
+            np.testing.assert_array_equal(data["labels"], ref.loc[user, "label"])
+            np.testing.assert_array_equal(data["y_scores"], ref.loc[user, "y_score"])
+            np.testing.assert_array_equal(data["pscores"], ref.loc[user, ps_name])
+    np.testing.assert_array_equal(te.interaction_df["y_score"].to_numpy(), scores)
+
+
+def test_fractional_labels_are_not_truncated():
+    """The reference divides whatever `labels` holds (src/fm.py:80); the shim sends integer labels to the device and
+    falls back to host-computed float64 targets when a label has a fractional part."""
+    from rfm_b200 import _capi
+    ps = np.array([0.5, 0.25, 1.0])
+    y, t = _capi.integer_labels(np.array([1, 0, 1]), ps)
+    assert y.dtype == np.int64 and t is None
+    y, t = _capi.integer_labels(np.array([1.0, 0.0, 2.0]), ps)
+    assert y.tolist() == [1, 0, 2] and t is None
+    y, t = _capi.integer_labels(np.array([0.5, 0.0, 1.0]), ps)
+    np.testing.assert_array_equal(t, np.array([0.5, 0.0, 1.0]) / ps)

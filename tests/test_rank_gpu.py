@@ -98,3 +98,66 @@ def test_pandas_frame_is_accepted_and_mutated_like_the_reference():
     ve = ValEvaluator(interaction_df=df, features={}, k=5, metric_name="DCG")
     np.testing.assert_allclose(ve.evaluate(g["scores"], "IPS"), g["val_IPS_5"], rtol=1e-12)
     np.testing.assert_array_equal(df["y_score"].to_numpy(), g["scores"])
+
+
+def test_nan_and_signed_zero_scores_rank_like_numpy():
+    """A diverged fit hands over NaN scores. NumPy's argsort puts NaN behind every number, so the reference's
+    argsort()[::-1] ranks NaN FIRST; -0.0 ties with +0.0. The device order is total and equal to the oracle's."""
+    from rfm_b200.evaluate import TestEvaluator
+    rng = np.random.default_rng(5)
+    n_users, per_user, n_items = 60, 23, 90
+    users = np.repeat(np.arange(n_users), per_user)
+    frame = {"user": users, "item": rng.integers(0, n_items, users.size),
+             "label": rng.integers(0, 2, users.size), "pscore": rng.uniform(0.1, 1, users.size),
+             "ones_pscore": np.ones(users.size)}
+    scores = rng.normal(size=users.size)
+    scores[rng.random(users.size) < 0.2] = np.nan
+    scores[rng.random(users.size) < 0.1] = 0.0
+    scores[rng.random(users.size) < 0.1] = -0.0
+    scores[rng.random(users.size) < 0.05] = np.inf
+    scores[rng.random(users.size) < 0.05] = -np.inf
+    scores[:per_user] = np.nan                                   # a user whose every score is NaN
+    te = TestEvaluator(interaction_df=frame, features={}, K=[1, 5, 9], used_metrics=USED, n_items=n_items)
+    res = te.evaluate(scores)
+    ref = metrics_oracle.test_evaluate(frame, scores, [1, 5, 9], USED, n_items)
+    for m in ["ME"] + sorted(USED):
+        np.testing.assert_allclose(res[m], ref[m], rtol=1e-12, err_msg=m)
+    top = te.top_rows(scores, 9)
+    for row, (user, rows) in zip(top, metrics_oracle.ranked_lists(frame, scores)):
+        np.testing.assert_array_equal(row, rows[:9])
+
+
+def test_long_tie_heavy_lists_use_the_selection_path():
+    """Lists longer than the shared-memory sort (2,048 rows) with a handful of distinct scores: the two-level
+    bisection (score key, then row position among ties) must pick exactly the canonical top-K."""
+    from rfm_b200.evaluate import TestEvaluator
+    rng = np.random.default_rng(8)
+    n_users, per_user, n_items = 12, 5000, 6000
+    users = np.repeat(np.arange(n_users), per_user)
+    frame = {"user": users, "item": np.concatenate([rng.permutation(n_items)[:per_user] for _ in range(n_users)]),
+             "label": (rng.random(users.size) < 0.01).astype(np.int64), "pscore": rng.uniform(0.1, 1, users.size),
+             "ones_pscore": np.ones(users.size)}
+    scores = rng.integers(0, 4, users.size) / 3.0
+    scores[per_user: 2 * per_user] = 0.5                          # one user: every score equal
+    K = [1, 10, 100, 128]
+    te = TestEvaluator(interaction_df=frame, features={}, K=K, used_metrics=USED, n_items=n_items)
+    res = te.evaluate(scores)
+    ref = metrics_oracle.test_evaluate(frame, scores, K, USED, n_items)
+    for m in ["ME"] + sorted(USED):
+        np.testing.assert_allclose(res[m], ref[m], rtol=1e-12, err_msg=m)
+    top = te.top_rows(scores, 128)
+    for row, (user, rows) in zip(top, metrics_oracle.ranked_lists(frame, scores)):
+        np.testing.assert_array_equal(row, rows[:128])
+
+
+def test_replaced_frame_columns_rebuild_the_device_ranker():
+    """The reference regroups interaction_df on every call; the device copy must follow a replaced column."""
+    from rfm_b200.evaluate import ValEvaluator
+    g = load_golden("coat_eval_tiefree")
+    frame = dict(golden_frame(g))
+    ve = ValEvaluator(interaction_df=frame, features={}, k=5, metric_name="DCG")
+    first = ve.evaluate(g["scores"], "IPS")
+    np.testing.assert_allclose(first, g["val_IPS_5"], rtol=1e-12)
+    frame["label"] = 1 - frame["label"]                           # same length, other content
+    ref = metrics_oracle.val_evaluate(frame, g["scores"], 5, "IPS")
+    np.testing.assert_allclose(ve.evaluate(g["scores"], "IPS"), ref, rtol=1e-12)
