@@ -278,6 +278,22 @@ int rfm_topk_result_host(rfm_topk *t, int32_t K, const int32_t **items_host, con
  * [n_users][K]) for the caller's all-gather; rfm_topk_merge_dev merges n_lists gathered lists
  * ([n_lists][n_users][K], device pointers) into the global top-K (host outputs), canonical order. */
 int rfm_topk_result_ptr_dev(rfm_topk *t, void **items_dev, void **scores_dev);
+/* The same exchange over NVLink peer memory instead of an all-gather ("all-to-all by user
+ * range ... then K-way merge"). One process per GPU of one node, at most 8 ranks. rfm_topk_dp_export allocates the
+ * scorer's exchange region (per-rank lists and per-rank group maxima for up to k_cap entries per user) and returns
+ * its CUDA-IPC handle; the caller gathers the handles of all ranks and passes them, in rank order, to
+ * rfm_topk_dp_connect. rfm_topk_run_sharded is then a COLLECTIVE call (same K and mode on every rank): rank r
+ * ranks catalog tiles slice(r) for every user -- the collect threshold is GLOBAL: the K-th largest of the union of
+ * all ranks' sampled group maxima, read from the peers' regions, so re-scoring work shrinks with the number of
+ * ranks too -- and merges the sorted per-rank lists of the users it owns, users [r U/G, (r+1) U/G) with the
+ * remainder spread over the first ranks, reading the peers' lists directly. out_items / out_scores (host,
+ * [owned users][K], may be NULL: the result stays on the device, rfm_topk_result_ptr_dev) receive the owned users'
+ * global top-K; user_range[2] (may be NULL) their [begin, end). Cross-GPU barriers are bounded: a rank that does
+ * not arrive within 20 s fails the call with RFM_ERR_CUDA instead of hanging. stats as rfm_topk_run. */
+int rfm_topk_dp_export(rfm_topk *t, int32_t k_cap, void *handle_out /* RFM_DP_HANDLE_BYTES */);
+int rfm_topk_dp_connect(rfm_topk *t, int32_t rank, int32_t world, const void *all_handles);
+int rfm_topk_run_sharded(rfm_topk *t, int32_t K, int32_t mode, int32_t *out_items, double *out_scores,
+                         int64_t *user_range, int64_t *stats);
 int rfm_topk_merge_dev(rfm_ctx *ctx, int64_t n_users, int32_t K, int32_t n_lists, const int32_t *items_dev,
                        const double *scores_dev, int32_t *out_items, double *out_scores);
 

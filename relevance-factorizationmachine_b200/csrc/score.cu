@@ -548,6 +548,14 @@ __device__ __forceinline__ double score_error_bound(double a_norm, double a_res,
   return (operands + accumulation + ldexp(beta_abs_max, -23)) * (1.0 + 0x1p-20) + 1e-300;
 }
 
+__device__ __forceinline__ uint32_t thr_keep(float x) {    // order-preserving uint key of a float
+  const uint32_t bits = __float_as_uint(x);
+  return bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t key) {
+  return __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
+}
+
 // One warp per user: the K-th largest group maximum of the sample is a lower bound on the user's K-th best
 // approximate score (K different items reach it). tau = that bound - 2 eps: every item whose EXACT score can
 // reach the exact K-th best has an approximate score >= tau (eps bounds |approximate - exact|).
@@ -560,7 +568,7 @@ score_threshold_kernel(const float *__restrict__ gmax, int64_t n_groups, int fol
                        const double *__restrict__ a_norm, const double *__restrict__ a_res,
                        const double *__restrict__ c_norm_max, const double *__restrict__ c_res_max,
                        const double *__restrict__ beta_abs_max, int kpad, float *__restrict__ tau,
-                       float *__restrict__ eps_out, uint32_t *__restrict__ cand_cnt) {
+                       float *__restrict__ eps_out, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ gtop) {
   extern __shared__ __align__(16) unsigned char th_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t *skey = reinterpret_cast<uint32_t *>(th_smem) + (size_t)wid * (NJ > 0 ? 0 : n_groups);
@@ -611,6 +619,40 @@ score_threshold_kernel(const float *__restrict__ gmax, int64_t n_groups, int fol
       t0 = __uint_as_float(bits);
     }
     __syncwarp();
+    if (gtop) {
+      // item-sharded runs: this rank's K largest group maxima (as keys, any order) go to the exchange region; the
+      // K-th largest of the union over all ranks is the global bound (score_global_threshold_kernel)
+      uint32_t *out = gtop + u * (int64_t)K;
+      const uint32_t none = 0x007FFFFFu;                       // key of -inf
+      if (n_groups >= K) {
+        int base = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        if (NJ > 0) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const bool up = key[j] > thr_keep(t0);
+            const uint32_t m = __ballot_sync(FULL, up);
+            if (up) out[base + __popc(m & lt)] = key[j];
+            base += __popc(m);
+          }
+        } else {
+          for (int64_t i0 = 0; i0 < n_groups; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const bool up = i < n_groups && skey[i] > thr_keep(t0);
+            const uint32_t m = __ballot_sync(FULL, up);
+            if (up) out[base + __popc(m & lt)] = skey[i];
+            base += __popc(m);
+          }
+        }
+        for (int r = base + lane; r < K; r += 32) out[r] = thr_keep(t0);     // the ties at the K-th value
+      } else {
+        for (int r = lane; r < K; r += 32) {
+          uint32_t v = none;
+          if (r < n_groups) v = to_key(group_max(r));
+          out[r] = v;
+        }
+      }
+    }
     if (lane == 0) {
       const double eps = score_error_bound(a_norm[u], a_res[u], *c_norm_max, *c_res_max, *beta_abs_max, kpad);
       tau[u] = t0 > -INFINITY ? __double2float_rd((double)t0 - 2.0 * eps) : -INFINITY;
@@ -958,6 +1000,158 @@ topk_merge_kernel(const int32_t *__restrict__ items, const double *__restrict__ 
   }
 }
 
+
+// ---- item-sharded runs: exchange over NVLink peer memory ---------------------------------
+// Every rank ranks a slice of the catalog for ALL users. Two things cross the GPUs, both through a cudaMalloc'ed
+// region that every rank maps with CUDA IPC (no NCCL, no staging):
+//   (1) after the sampled pass, each rank's K largest group maxima per user. The K-th largest of their union is a
+//       bound on the user's K-th best score over the WHOLE catalog, so every rank collects against the global
+//       threshold: the candidates of a user add up to ~K x stride over all ranks instead of per rank, and the
+//       exact re-scoring shrinks with the number of ranks like the tensor passes do;
+//   (2) the per-rank exact top-K lists, which the owner of a user range (rank r owns users [r U/G, (r+1) U/G))
+//       merges with a K-way merge by rank counting.
+// A barrier is its own tiny kernel in stream order: one thread per peer stores this rank's step number into the
+// peer's flag word (st.release.sys) and polls its own copy of the peer's (ld.acquire.sys). Step numbers only grow,
+// waits are bounded by a wall-clock limit and raise a sticky status word instead of hanging.
+constexpr int XCH_MAX_WORLD = 8;
+constexpr unsigned long long XCH_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct XchPeers {
+  const unsigned char *base[XCH_MAX_WORLD];
+};
+struct ListPtrs {           // the sorted (item, score) lists to merge, [n_users][K] each
+  const int32_t *items[XCH_MAX_WORLD];
+  const double *scores[XCH_MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void topk_xch_barrier_kernel(const XchPeers peers, size_t flags_off, int rank, int world, uint32_t seq,
+                                        uint32_t *__restrict__ status) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  __threadfence_system();
+  uint32_t *theirs = reinterpret_cast<uint32_t *>(const_cast<unsigned char *>(peers.base[q]) + flags_off) + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
+  const uint32_t *mine = reinterpret_cast<const uint32_t *>(peers.base[rank] + flags_off) + q;
+  const unsigned long long t0 = global_ns();
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v >= seq) break;
+    if (global_ns() - t0 > XCH_TIMEOUT_NS) {
+      atomicCAS(status, 0u, 1u + (uint32_t)q);
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
+// One warp per user: K-th largest of the world x K group-maximum keys the ranks exported -> collect threshold
+__global__ void __launch_bounds__(SELECT_WARPS * 32)
+score_global_threshold_kernel(const XchPeers peers, size_t gtop_off, int world, int K, int64_t user0,
+                              int64_t n_users_chunk, const float *__restrict__ eps, float *__restrict__ tau) {
+  extern __shared__ __align__(16) unsigned char gt_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = world * K;
+  uint32_t *skey = reinterpret_cast<uint32_t *>(gt_smem) + (size_t)wid * n;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = gw; row < n_users_chunk; row += nw) {
+    const int64_t u = user0 + row;
+    for (int i = lane; i < n; i += 32) {
+      const int q = i / K, j = i - q * K;
+      skey[i] = __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + gtop_off) + u * K + j);
+    }
+    __syncwarp();
+    uint32_t thr = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand_thr = thr | (1u << bit);
+      int cnt = 0;
+      for (int i = lane; i < n; i += 32) cnt += skey[i] >= cand_thr;
+      cnt = __reduce_add_sync(FULL, cnt);
+      if (cnt >= K) thr = cand_thr;
+    }
+    const float t0 = key_to_float(thr);
+    if (lane == 0) tau[row] = t0 > -INFINITY ? __double2float_rd((double)t0 - 2.0 * (double)eps[row]) : -INFINITY;
+    __syncwarp();
+  }
+}
+
+// K-way merge of the ranks' sorted top-K lists for the users this rank owns. One warp per user: the world x K
+// (item, score) pairs are staged in shared memory (coalesced peer loads), then every pair finds its global
+// position = its position in its own list + the number of pairs of every other list that rank before it (binary
+// search; the canonical order is strict because items are distinct). Positions below K are the answer.
+constexpr int MERGE_WARPS = 8;
+__global__ void __launch_bounds__(MERGE_WARPS * 32)
+topk_xch_merge_kernel(const ListPtrs lists, int world, int K, int64_t user_begin,
+                      int64_t user_end, int32_t *__restrict__ out_items, double *__restrict__ out_scores) {
+  extern __shared__ __align__(16) unsigned char mg_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = world * K;
+  double *ss = reinterpret_cast<double *>(mg_smem) + (size_t)wid * n;
+  int32_t *si = reinterpret_cast<int32_t *>(mg_smem + (size_t)MERGE_WARPS * n * 8) + (size_t)wid * n;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = user_begin + gw; u < user_end; u += nw) {
+    int valid = 0;
+    for (int i = lane; i < n; i += 32) {
+      const int q = i / K, j = i - q * K;
+      const int32_t it = __ldcg(lists.items[q] + u * K + j);
+      si[i] = it;
+      ss[i] = __ldcg(lists.scores[q] + u * K + j);
+      valid += it >= 0;
+    }
+    valid = __reduce_add_sync(FULL, valid);
+    __syncwarp();
+    int32_t *oi = out_items + (u - user_begin) * K;
+    double *os = out_scores + (u - user_begin) * K;
+    for (int i = lane; i < n; i += 32) {
+      Best mine;
+      mine.item = si[i];
+      mine.s = ss[i];
+      if (mine.item < 0) continue;
+      const int q = i / K;
+      int rank = i - q * K;
+      for (int l = 0; l < world; ++l) {
+        if (l == q) continue;
+        int lo = 0, hi = K;                   // first position of list l that does NOT rank before mine
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          Best other;
+          other.item = si[l * K + mid];
+          other.s = ss[l * K + mid];
+          if (ranks_before(other, mine)) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < K) {
+        oi[rank] = mine.item;
+        os[rank] = mine.s;
+      }
+    }
+    for (int r = valid + lane; r < K; r += 32) {
+      oi[r] = -1;
+      os[r] = -INFINITY;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void fill_lists_kernel(int32_t *__restrict__ items, double *__restrict__ scores, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    items[i] = -1;
+    scores[i] = -INFINITY;
+  }
+}
+__global__ void fill_u32_kernel(uint32_t *__restrict__ p, uint32_t v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1043,12 +1237,12 @@ template <int NJ>
 int launch_threshold_as(rfm_ctx *ctx, int grid, const float *gmax, int64_t n_groups, int fold, int64_t n_rows,
                         int64_t n_users_chunk, int K, const double *a_norm, const double *a_res, const double *c_norm_max,
                         const double *c_res_max, const double *beta_abs_max, int kpad, float *tau, float *eps_out,
-                        uint32_t *cand_cnt) {
+                        uint32_t *cand_cnt, uint32_t *gtop) {
   auto score_threshold = score_threshold_kernel<NJ>;
   const size_t smem = NJ > 0 ? 0 : (size_t)SELECT_WARPS * n_groups * 4;
   if (smem) RFM_CUDA(cudaFuncSetAttribute(score_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RFM_LAUNCH(ctx, score_threshold, grid, SELECT_WARPS * 32, smem, gmax, n_groups, fold, n_rows, n_users_chunk, K, a_norm,
-             a_res, c_norm_max, c_res_max, beta_abs_max, kpad, tau, eps_out, cand_cnt);
+             a_res, c_norm_max, c_res_max, beta_abs_max, kpad, tau, eps_out, cand_cnt, gtop);
   return RFM_OK;
 }
 template <typename... Args>
@@ -1080,6 +1274,16 @@ struct rfm_topk {
   DevBuf<uint32_t> n_fail, cand_cnt;
   DevBuf<unsigned long long> n_cand;
   CUtensorMap tmap_a, tmap_c;
+  // item-sharded exchange (rfm_topk_dp_*): [items int32 [U][k_cap] | scores f64 [U][k_cap] | gtop u32 [U][k_cap] | flags]
+  unsigned char *xchg = nullptr;
+  size_t x_items_off = 0, x_scores_off = 0, x_gtop_off = 0, x_flags_off = 0, x_bytes = 0;
+  int x_kcap = 0, x_rank = -1, x_world = 0;
+  uint32_t x_seq = 0;
+  unsigned char *x_peer[XCH_MAX_WORLD] = {nullptr};
+  DevBuf<uint32_t> x_status;
+  int64_t own_begin = 0, own_end = 0;       // users whose merged lists the last sharded run left in out_items/out_scores
+  int64_t result_rows = 0;                  // rows of out_items / out_scores that hold the last result
+  PinnedBuf<unsigned long long> counters;   // [users ranked exactly (low 32 bits), candidates collected] of the last run
 };
 
 extern "C" {
@@ -1134,6 +1338,10 @@ int rfm_topk_destroy(rfm_topk *t) {
   if (t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
+    for (int q = 0; q < t->x_world; ++q)
+      if (q != t->x_rank && t->x_peer[q]) cudaIpcCloseMemHandle(t->x_peer[q]);
+    if (t->xchg) cudaFree(t->xchg);
+    cudaGetLastError();
     delete t;
   }
   return RFM_OK;
@@ -1171,25 +1379,42 @@ int rfm_topk_set_factors(rfm_topk *t, const double *A, const double *C, const do
   return RFM_OK;
 }
 
-int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64_t item_end, int32_t *out_items,
-                 double *out_scores, int64_t *stats) {
-  RFM_REQUIRE(t, "rfm_topk_run: NULL argument");
-  RFM_REQUIRE((out_items == nullptr) == (out_scores == nullptr), "rfm_topk_run: out_items and out_scores go together");
-  RFM_REQUIRE(t->ready, "rfm_topk_run: call rfm_topk_set_factors first");
-  RFM_REQUIRE(K >= 1 && K <= MAX_K, "rfm_topk_run: K=%d outside [1, %d]", K, MAX_K);
-  RFM_REQUIRE(mode == 0 || mode == 1, "rfm_topk_run: mode must be 0 (tensor-core prune + exact) or 1 (exact only)");
-  if (item_end <= 0) item_end = t->n_items;
-  RFM_REQUIRE(item_begin >= 0 && item_begin < item_end && item_end <= t->n_items, "rfm_topk_run: bad item range");
+}  // extern "C" (pause)
+namespace {
+
+struct ShardPlan {          // how the item-sharded run differs from the single-GPU one
+  bool on = false;
+  int tiles_max = 0;        // item tiles of the largest shard: every rank cuts the users into the same chunks
+};
+
+XchPeers xch_peers(const rfm_topk *t) {
+  XchPeers p;
+  for (int q = 0; q < XCH_MAX_WORLD; ++q) p.base[q] = q < t->x_world ? t->x_peer[q] : nullptr;
+  return p;
+}
+
+int xch_barrier(rfm_topk *t) {
   rfm_ctx *ctx = t->ctx;
-  const bool timing = getenv("RFM_SCORE_TIMING") != nullptr;
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-    return std::chrono::duration<double, std::milli>(b - a).count();
-  };
-  const auto t_start = now();
-  RFM_CUDA(cudaSetDevice(ctx->device));
-  RFM_TRY(t->out_items.ensure((size_t)t->n_users * K));
-  RFM_TRY(t->out_scores.ensure((size_t)t->n_users * K));
+  ++t->x_seq;
+  RFM_LAUNCH(ctx, topk_xch_barrier_kernel, 1, 32, 0, xch_peers(t), t->x_flags_off, t->x_rank, t->x_world, t->x_seq,
+             t->x_status.p);
+  return RFM_OK;
+}
+
+// tile range [begin, end) of a rank's slice of the catalog (the rule of rfm_b200.dist.item_shard)
+void shard_tiles(int64_t n_items, int world, int rank, int64_t *begin, int64_t *end) {
+  const int64_t n_tiles = (n_items + BN - 1) / BN, base = n_tiles / world, extra = n_tiles % world;
+  *begin = rank * base + std::min<int64_t>(rank, extra);
+  *end = *begin + base + (rank < extra ? 1 : 0);
+}
+
+// The pipeline of one call over the catalog range [item_begin, item_end); the per-user lists go to
+// dst_items / dst_scores ([n_users][K], device). plan.on: thresholds are global (exchange (1) above) and the range
+// may be empty (a rank beyond the last tile still takes part in every barrier).
+int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item_end, const ShardPlan &plan,
+                  int32_t *dst_items, double *dst_scores, bool *tensor_path_out, int64_t *n_failed_out,
+                  int64_t *n_candidates_out, int64_t *stride_out) {
+  rfm_ctx *ctx = t->ctx;
   ExactArgs e;
   e.A = t->A.p;
   e.C = t->C.p;
@@ -1202,46 +1427,52 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
   e.item_begin = (int)item_begin;
   e.item_end = (int)item_end;
   int64_t n_failed = 0, n_candidates = 0, sample_stride = 0;
+  const bool empty = item_end <= item_begin;
   // the tensor-core path needs a tile-aligned range (item shards are cut at multiples of 256; the catalog's own
   // end is padded with beta = -inf) and k <= 128
-  const bool tensor_path = mode == 0 && t->kb <= MAX_KB && item_begin % BN == 0 &&
-                           (item_end % BN == 0 || item_end == t->n_items);
+  const bool tensor_path = mode == 0 && t->kb <= MAX_KB && (empty || (item_begin % BN == 0 &&
+                           (item_end % BN == 0 || item_end == t->n_items)));
   if (tensor_path) {
     const int tile_begin = (int)(item_begin / BN);
-    const int n_item_tiles = (int)((item_end + BN - 1) / BN) - tile_begin;
+    const int n_item_tiles = empty ? 0 : (int)((item_end + BN - 1) / BN) - tile_begin;
+    const int plan_tiles = plan.on ? plan.tiles_max : n_item_tiles;       // identical on every rank
     const int n_user_blocks = (int)(t->n_users_pad / BM);
     // Pass 1 scores a sample of the catalog, every stride-th tile. A sparser sample is cheaper but gives a
     // lower threshold: about K * stride items per user reach it (negative binomial, sd stride * sqrt(K (1 - 1/stride))).
     int stride = K <= 16 ? 4 : (K <= 64 ? 2 : 1);
     if (const char *env = getenv("RFM_SCORE_STRIDE")) stride = std::max(1, atoi(env));
     // The threshold is the K-th largest group maximum, so the sample must hold many more groups than K: small
-    // catalogs are sampled densely and in narrower groups (128 -> 8 items).
+    // catalogs are sampled densely and in narrower groups (128 -> 8 items). Sharded runs size the sample from the
+    // largest shard so that every rank samples alike (the union over the ranks then holds world x as many groups).
     int gcols = MAX_GCOLS;
-    auto groups_of = [&](int st, int g) { return (int64_t)((n_item_tiles + st - 1) / st) * (BN / g); };
-    const int64_t want_groups = 8 * (int64_t)K + 64;
-    while (stride > 1 && groups_of(stride, gcols) < want_groups) stride /= 2;
-    while (gcols > 8 && groups_of(stride, gcols) < want_groups) gcols /= 2;
-    while (groups_of(stride, gcols) > MAX_GROUPS) ++stride;
+    auto groups_of = [&](int tiles, int st, int g) { return (int64_t)((tiles + st - 1) / st) * (BN / g); };
+    // (a sharded run's threshold comes from the union of the ranks' samples: each needs 1 / world of the groups)
+    const int64_t want_groups = plan.on ? std::max<int64_t>(64, (8 * (int64_t)K + 64 + t->x_world - 1) / t->x_world)
+                                        : 8 * (int64_t)K + 64;
+    while (stride > 1 && groups_of(plan_tiles, stride, gcols) < want_groups) stride /= 2;
+    while (gcols > 8 && groups_of(plan_tiles, stride, gcols) < want_groups) gcols /= 2;
+    while (groups_of(plan_tiles, stride, gcols) > MAX_GROUPS) ++stride;
     const int n_sample = (n_item_tiles + stride - 1) / stride;
-    const int64_t n_groups = groups_of(stride, gcols);
+    const int64_t n_groups = groups_of(n_item_tiles, stride, gcols);
+    const int64_t plan_groups = std::max<int64_t>(1, groups_of(plan_tiles, stride, gcols));
     // About c K stride items per user reach the threshold (negative binomial in the sampling, sd
     // stride sqrt(K (1 - 1/stride)); c = -ln(1 - f) / f corrects for top items sharing a group, f = K / groups).
-    const int fold = (n_groups % 2 == 0 && n_groups / 2 >= want_groups) ? 2 : 1;   // threshold over pairs of groups
-    const double f = std::min(0.5, (double)K * fold / (double)n_groups);
+    const int fold = (!plan.on && n_groups % 2 == 0 && n_groups / 2 >= want_groups) ? 2 : 1;   // threshold over pairs of groups
+    const double f = std::min(0.5, (double)K * fold / (double)plan_groups);
     const double cf = -std::log1p(-f) / f;
     const double sd = stride * std::sqrt((double)K * (1.0 - 1.0 / stride));
     // The 2 eps safety margin lowers the threshold further (how much depends on the score distribution), so the
     // buffer is four times the expected count: an overflow costs an exact re-rank of that user.
     int kc = (int)std::ceil(cf * (4.0 * K * stride + 6.0 * sd)) + 32;
-    kc = std::max<int64_t>(kc, std::min<int64_t>(item_end - item_begin, 256));
+    kc = std::max<int64_t>(kc, std::min<int64_t>((int64_t)plan_tiles * BN, 256));
     kc = (kc + 7) / 8 * 8;
     // users are processed in chunks so that the group maxima of a chunk stay within a fixed scratch budget
     int64_t scratch_bytes = (int64_t)1 << 30;
     if (const char *env = getenv("RFM_SCORE_SCRATCH_MB")) scratch_bytes = std::max<int64_t>(1, atoll(env)) << 20;
-    const int64_t scratch_rows = std::max<int64_t>(BM, scratch_bytes / (n_groups * 4) / BM * BM);
+    const int64_t scratch_rows = std::max<int64_t>(BM, scratch_bytes / (plan_groups * 4) / BM * BM);
     const int chunk_blocks = (int)std::min<int64_t>(n_user_blocks, scratch_rows / BM);
     const size_t chunk_rows = (size_t)chunk_blocks * BM;
-    RFM_TRY(t->gmax.ensure(chunk_rows * n_groups));
+    RFM_TRY(t->gmax.ensure(chunk_rows * std::max<int64_t>(1, n_groups)));
     RFM_TRY(t->tau.ensure(chunk_rows));
     RFM_TRY(t->cand_cnt.ensure(chunk_rows));
     RFM_TRY(t->cand.ensure(chunk_rows * kc));
@@ -1252,10 +1483,19 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     const size_t rs_smem = (size_t)RESCORE_WARPS * ((size_t)kc * 16 + (size_t)t->k * 8);
     RFM_REQUIRE(rs_smem <= 200 * 1024, "rfm_topk_run: %d candidates per user do not fit the re-scoring kernel", kc);
     RFM_CUDA(cudaFuncSetAttribute(score_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    uint32_t *gtop = plan.on ? reinterpret_cast<uint32_t *>(t->xchg + t->x_gtop_off) : nullptr;
+    if (plan.on && empty) {     // nothing to rank here: no group maxima, empty lists
+      RFM_LAUNCH(ctx, fill_u32_kernel, ctx->sm_count * 4, 256, 0, gtop, 0x007FFFFFu, (int64_t)t->n_users * K);
+      RFM_LAUNCH(ctx, fill_lists_kernel, ctx->sm_count * 4, 256, 0, dst_items, dst_scores, (int64_t)t->n_users * K);
+    }
     for (int ub0 = 0; ub0 < n_user_blocks; ub0 += chunk_blocks) {
       const int nb = std::min(chunk_blocks, n_user_blocks - ub0);
       const int64_t user0 = (int64_t)ub0 * BM;
       const int64_t users_here = std::min<int64_t>((int64_t)nb * BM, t->n_users - user0);
+      if (empty) {
+        RFM_TRY(xch_barrier(t));      // the peers' thresholds wait for this rank's (empty) export
+        continue;
+      }
       PassArgs pa;
       pa.beta16 = t->beta16.p;
       pa.tile_begin = tile_begin;
@@ -1284,7 +1524,15 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
                                                (int64_t)ctx->sm_count * 8);
       RFM_TRY(launch_threshold(ctx, tgrid, t->gmax.p, n_groups / fold, fold, (int64_t)nb * BM, users_here, (int)K,
                                t->a_norm.p + user0, t->a_res.p + user0, t->c_norm_max.p, t->c_res_max.p,
-                               t->beta_abs_max.p, t->kpad, t->tau.p, t->eps.p, t->cand_cnt.p));
+                               t->beta_abs_max.p, t->kpad, t->tau.p, t->eps.p, t->cand_cnt.p,
+                               gtop ? gtop + user0 * K : (uint32_t *)nullptr));
+      if (plan.on) {
+        // every rank's K largest group maxima are in place -> the global K-th largest replaces the local bound
+        RFM_TRY(xch_barrier(t));
+        const size_t gsmem = (size_t)SELECT_WARPS * t->x_world * K * 4;
+        RFM_LAUNCH(ctx, score_global_threshold_kernel, tgrid, SELECT_WARPS * 32, gsmem, xch_peers(t), t->x_gtop_off,
+                   t->x_world, (int)K, user0, users_here, t->eps.p, t->tau.p);
+      }
       // pass 2: collect every item that reaches the threshold
       pa.tile_stride = 1;
       pa.n_visit = n_item_tiles;
@@ -1295,45 +1543,83 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
       const int rgrid = (int)std::min<int64_t>((users_here + RESCORE_WARPS - 1) / RESCORE_WARPS,
                                                (int64_t)ctx->sm_count * 8);
       RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
-                 t->cand.p, t->eps.p, kc, (int)K, t->out_items.p, t->out_scores.p, t->fail_list.p, t->n_fail.p,
-                 t->n_cand.p);
+                 t->cand.p, t->eps.p, kc, (int)K, dst_items, dst_scores, t->fail_list.p, t->n_fail.p, t->n_cand.p);
     }
-    // users whose candidate buffer overflowed are ranked exactly against the whole catalog range
-    const int fgrid = exact_grid(ctx, t->n_users, item_end - item_begin);
-    RFM_TRY(t->exact_scratch.ensure((size_t)fgrid * (item_end - item_begin)));
-    RFM_LAUNCH(ctx, score_exact_kernel, fgrid, EXACT_THREADS, 0, e, t->fail_list.p, t->n_fail.p, (int64_t)0, (int)K,
-               t->exact_scratch.p, t->out_items.p, t->out_scores.p);
-    uint32_t nf = 0;
-    unsigned long long nc = 0;
-    RFM_CUDA(cudaMemcpyAsync(&nf, t->n_fail.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    RFM_CUDA(cudaMemcpyAsync(&nc, t->n_cand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
-    n_failed = nf;
-    n_candidates = (int64_t)nc;
+    if (!empty) {
+      // users whose candidate buffer overflowed are ranked exactly against the whole catalog range
+      const int fgrid = exact_grid(ctx, t->n_users, item_end - item_begin);
+      RFM_TRY(t->exact_scratch.ensure((size_t)fgrid * (item_end - item_begin)));
+      RFM_LAUNCH(ctx, score_exact_kernel, fgrid, EXACT_THREADS, 0, e, t->fail_list.p, t->n_fail.p, (int64_t)0, (int)K,
+                 t->exact_scratch.p, dst_items, dst_scores);
+    }
+    // the two counters come back through page-locked memory (a copy into pageable memory would block the host
+    // until the stream drains); sharded runs read them after the merge, single-GPU runs right here
+    RFM_TRY(t->counters.ensure(2));
+    RFM_CUDA(cudaMemcpyAsync(t->counters.p, t->n_fail.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(t->counters.p + 1, t->n_cand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    if (!plan.on) {
+      RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+      n_failed = (int64_t)(uint32_t)t->counters.p[0];
+      n_candidates = (int64_t)t->counters.p[1];
+    }
     sample_stride = stride;
+  } else if (empty) {
+    RFM_LAUNCH(ctx, fill_lists_kernel, ctx->sm_count * 4, 256, 0, dst_items, dst_scores, (int64_t)t->n_users * K);
   } else {
     const int fgrid = exact_grid(ctx, t->n_users, item_end - item_begin);
     RFM_TRY(t->exact_scratch.ensure((size_t)fgrid * (item_end - item_begin)));
     RFM_LAUNCH(ctx, score_exact_kernel, fgrid, EXACT_THREADS, 0, e, (const int32_t *)nullptr, (const uint32_t *)nullptr,
-               t->n_users, (int)K, t->exact_scratch.p, t->out_items.p, t->out_scores.p);
+               t->n_users, (int)K, t->exact_scratch.p, dst_items, dst_scores);
   }
-  const auto t_launched = now();
-  if (timing) RFM_CUDA(cudaStreamSynchronize(ctx->stream));
-  const auto t_computed = now();
-  if (out_items) {   // NULL: the caller reads the result on the device (rfm_topk_result_ptr_dev)
-    // through page-locked staging: a device-to-host copy into pageable memory runs at a fraction of the link rate
-    const size_t n_out = (size_t)t->n_users * K;
-    RFM_TRY(t->stage_items.ensure(n_out));
-    RFM_TRY(t->stage_scores.ensure(n_out));
-    RFM_CUDA(cudaMemcpyAsync(t->stage_items.p, t->out_items.p, n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    RFM_CUDA(cudaMemcpyAsync(t->stage_scores.p, t->out_scores.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
-    const auto t_d2h = now();
+  *tensor_path_out = tensor_path;
+  *n_failed_out = n_failed;
+  *n_candidates_out = n_candidates;
+  *stride_out = sample_stride;
+  return RFM_OK;
+}
+
+// result rows [0, n_rows) of t->out_items / out_scores -> caller memory through the page-locked staging buffers
+int topk_result_to_host(rfm_topk *t, int64_t n_rows, int K, int32_t *out_items, double *out_scores) {
+  rfm_ctx *ctx = t->ctx;
+  const size_t n_out = (size_t)n_rows * K;
+  RFM_TRY(t->stage_items.ensure(n_out ? n_out : 1));
+  RFM_TRY(t->stage_scores.ensure(n_out ? n_out : 1));
+  RFM_CUDA(cudaMemcpyAsync(t->stage_items.p, t->out_items.p, n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(t->stage_scores.p, t->out_scores.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (out_items) {
     memcpy(out_items, t->stage_items.p, n_out * 4);
     memcpy(out_scores, t->stage_scores.p, n_out * 8);
-    if (timing)
-      fprintf(stderr, "rfm_topk_run: launch %.3f ms, device %.3f ms, d2h %.3f ms, host copy %.3f ms\n",
-              ms(t_start, t_launched), ms(t_launched, t_computed), ms(t_computed, t_d2h), ms(t_d2h, now()));
+  }
+  return RFM_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64_t item_end, int32_t *out_items,
+                 double *out_scores, int64_t *stats) {
+  RFM_REQUIRE(t, "rfm_topk_run: NULL argument");
+  RFM_REQUIRE((out_items == nullptr) == (out_scores == nullptr), "rfm_topk_run: out_items and out_scores go together");
+  RFM_REQUIRE(t->ready, "rfm_topk_run: call rfm_topk_set_factors first");
+  RFM_REQUIRE(K >= 1 && K <= MAX_K, "rfm_topk_run: K=%d outside [1, %d]", K, MAX_K);
+  RFM_REQUIRE(mode == 0 || mode == 1, "rfm_topk_run: mode must be 0 (tensor-core prune + exact) or 1 (exact only)");
+  if (item_end <= 0) item_end = t->n_items;
+  RFM_REQUIRE(item_begin >= 0 && item_begin < item_end && item_end <= t->n_items, "rfm_topk_run: bad item range");
+  rfm_ctx *ctx = t->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_TRY(t->out_items.ensure((size_t)t->n_users * K));
+  RFM_TRY(t->out_scores.ensure((size_t)t->n_users * K));
+  bool tensor_path = false;
+  int64_t n_failed = 0, n_candidates = 0, sample_stride = 0;
+  RFM_TRY(topk_run_core(t, K, mode, item_begin, item_end, ShardPlan(), t->out_items.p, t->out_scores.p, &tensor_path,
+                        &n_failed, &n_candidates, &sample_stride));
+  t->result_rows = t->n_users;
+  t->own_begin = 0;
+  t->own_end = t->n_users;
+  if (out_items) {   // NULL: the caller reads the result on the device (rfm_topk_result_ptr_dev)
+    RFM_TRY(topk_result_to_host(t, t->n_users, K, out_items, out_scores));
   } else {
     RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -1341,6 +1627,134 @@ int rfm_topk_run(rfm_topk *t, int32_t K, int32_t mode, int64_t item_begin, int64
     stats[0] = tensor_path ? 1 : 0;
     stats[1] = n_failed;
     stats[2] = n_candidates;
+    stats[3] = sample_stride;
+  }
+  return RFM_OK;
+}
+
+int rfm_topk_dp_export(rfm_topk *t, int32_t k_cap, void *handle_out) {
+  RFM_REQUIRE(t && handle_out, "rfm_topk_dp_export: NULL argument");
+  RFM_REQUIRE(k_cap >= 1 && k_cap <= MAX_K, "rfm_topk_dp_export: k_cap=%d outside [1, %d]", k_cap, MAX_K);
+  RFM_REQUIRE(!t->xchg, "rfm_topk_dp_export: already exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RFM_DP_HANDLE_BYTES, "IPC handle size");
+  rfm_ctx *ctx = t->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t n = (size_t)t->n_users * k_cap;
+  t->x_items_off = 0;
+  t->x_scores_off = up(n * 4);
+  t->x_gtop_off = t->x_scores_off + up(n * 8);
+  t->x_flags_off = t->x_gtop_off + up(n * 4);
+  t->x_bytes = t->x_flags_off + 256;
+  t->x_kcap = k_cap;
+  // cudaMalloc, not the stream-ordered pool: pool memory cannot be exported through legacy CUDA IPC
+  RFM_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->xchg), t->x_bytes));
+  RFM_CUDA(cudaMemsetAsync(t->xchg, 0, t->x_bytes, ctx->stream));
+  RFM_TRY(t->x_status.alloc(1));
+  RFM_CUDA(cudaMemsetAsync(t->x_status.p, 0, sizeof(uint32_t), ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  RFM_CUDA(cudaIpcGetMemHandle(&h, t->xchg));
+  memcpy(handle_out, &h, sizeof(h));
+  return RFM_OK;
+}
+
+int rfm_topk_dp_connect(rfm_topk *t, int32_t rank, int32_t world, const void *all_handles) {
+  RFM_REQUIRE(t && all_handles, "rfm_topk_dp_connect: NULL argument");
+  RFM_REQUIRE(t->xchg, "rfm_topk_dp_connect: call rfm_topk_dp_export first");
+  RFM_REQUIRE(world >= 1 && world <= XCH_MAX_WORLD && rank >= 0 && rank < world,
+              "rfm_topk_dp_connect: rank %d / world %d out of range (at most %d ranks)", rank, world, XCH_MAX_WORLD);
+  RFM_REQUIRE(t->x_world == 0, "rfm_topk_dp_connect: already connected");
+  RFM_CUDA(cudaSetDevice(t->ctx->device));
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      t->x_peer[q] = t->xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const unsigned char *>(all_handles) + (size_t)q * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    const cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RFM_ERR_CUDA, "rfm_topk_dp_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(err));
+    }
+    t->x_peer[q] = static_cast<unsigned char *>(p);
+  }
+  t->x_rank = rank;
+  t->x_world = world;
+  return RFM_OK;
+}
+
+int rfm_topk_run_sharded(rfm_topk *t, int32_t K, int32_t mode, int32_t *out_items, double *out_scores,
+                         int64_t *user_range, int64_t *stats) {
+  RFM_REQUIRE(t, "rfm_topk_run_sharded: NULL argument");
+  RFM_REQUIRE((out_items == nullptr) == (out_scores == nullptr), "rfm_topk_run_sharded: out_items and out_scores go together");
+  RFM_REQUIRE(t->ready, "rfm_topk_run_sharded: call rfm_topk_set_factors first");
+  RFM_REQUIRE(t->x_world >= 1, "rfm_topk_run_sharded: call rfm_topk_dp_export / rfm_topk_dp_connect first");
+  RFM_REQUIRE(K >= 1 && K <= t->x_kcap, "rfm_topk_run_sharded: K=%d outside [1, %d] (the exchange region's capacity)", K,
+              t->x_kcap);
+  RFM_REQUIRE(mode == 0 || mode == 1, "rfm_topk_run_sharded: mode must be 0 or 1");
+  rfm_ctx *ctx = t->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  const int world = t->x_world, rank = t->x_rank;
+  int64_t tb = 0, te = 0, tiles_max = 0;
+  for (int q = 0; q < world; ++q) {
+    int64_t b, e2;
+    shard_tiles(t->n_items, world, q, &b, &e2);
+    tiles_max = std::max(tiles_max, e2 - b);
+    if (q == rank) {
+      tb = b;
+      te = e2;
+    }
+  }
+  const int64_t item_begin = std::min<int64_t>(tb * BN, t->n_items), item_end = std::min<int64_t>(te * BN, t->n_items);
+  // users this rank owns after the merge (the rule of rfm_b200.dist.slice_bounds)
+  const int64_t ubase = t->n_users / world, uextra = t->n_users % world;
+  const int64_t own_begin = rank * ubase + std::min<int64_t>(rank, uextra);
+  const int64_t own_end = own_begin + ubase + (rank < uextra ? 1 : 0);
+  const int64_t n_own = own_end - own_begin;
+  RFM_TRY(t->out_items.ensure((size_t)std::max<int64_t>(1, n_own) * K));
+  RFM_TRY(t->out_scores.ensure((size_t)std::max<int64_t>(1, n_own) * K));
+  ShardPlan plan;
+  plan.on = true;
+  plan.tiles_max = (int)tiles_max;
+  bool tensor_path = false;
+  int64_t n_failed = 0, n_candidates = 0, sample_stride = 0;
+  int32_t *lists_i = reinterpret_cast<int32_t *>(t->xchg + t->x_items_off);
+  double *lists_s = reinterpret_cast<double *>(t->xchg + t->x_scores_off);
+  RFM_TRY(topk_run_core(t, K, mode, item_begin, item_end, plan, lists_i, lists_s, &tensor_path, &n_failed, &n_candidates,
+                        &sample_stride));
+  RFM_TRY(xch_barrier(t));      // every rank's lists are complete
+  if (n_own > 0) {
+    const size_t msmem = (size_t)MERGE_WARPS * world * K * 12;
+    RFM_CUDA(cudaFuncSetAttribute(topk_xch_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    const int mgrid = (int)std::min<int64_t>((n_own + MERGE_WARPS - 1) / MERGE_WARPS, (int64_t)ctx->sm_count * 2);
+    ListPtrs lp;
+    for (int q = 0; q < XCH_MAX_WORLD; ++q) {
+      lp.items[q] = q < world ? reinterpret_cast<const int32_t *>(t->x_peer[q] + t->x_items_off) : nullptr;
+      lp.scores[q] = q < world ? reinterpret_cast<const double *>(t->x_peer[q] + t->x_scores_off) : nullptr;
+    }
+    RFM_LAUNCH(ctx, topk_xch_merge_kernel, mgrid, MERGE_WARPS * 32, msmem, lp, world, (int)K, own_begin, own_end,
+               t->out_items.p, t->out_scores.p);
+  }
+  uint32_t status = 0;
+  RFM_CUDA(cudaMemcpyAsync(&status, t->x_status.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  t->result_rows = n_own;
+  t->own_begin = own_begin;
+  t->own_end = own_end;
+  RFM_TRY(topk_result_to_host(t, out_items ? n_own : 0, K, out_items, out_scores));   // synchronises the stream
+  if (status != 0)
+    return fail(RFM_ERR_CUDA, "rfm_topk_run_sharded: rank %u did not reach a cross-GPU barrier within %.0f s",
+                status - 1u, (double)XCH_TIMEOUT_NS * 1e-9);
+  if (user_range) {
+    user_range[0] = own_begin;
+    user_range[1] = own_end;
+  }
+  if (stats) {
+    stats[0] = tensor_path ? 1 : 0;
+    stats[1] = tensor_path ? (int64_t)(uint32_t)t->counters.p[0] : 0;
+    stats[2] = tensor_path ? (int64_t)t->counters.p[1] : 0;
     stats[3] = sample_stride;
   }
   return RFM_OK;
@@ -1357,10 +1771,10 @@ int rfm_topk_result_ptr_dev(rfm_topk *t, void **items_dev, void **scores_dev) {
 int rfm_topk_result_host(rfm_topk *t, int32_t K, const int32_t **items_host, const double **scores_host) {
   RFM_REQUIRE(t && items_host && scores_host, "rfm_topk_result_host: NULL argument");
   RFM_REQUIRE(t->out_items.p && t->out_scores.p, "rfm_topk_result_host: call rfm_topk_run first");
-  RFM_REQUIRE(K >= 1 && (size_t)t->n_users * K <= t->out_items.n, "rfm_topk_result_host: K does not match the last run");
+  RFM_REQUIRE(K >= 1 && (size_t)t->result_rows * K <= t->out_items.n, "rfm_topk_result_host: K does not match the last run");
   rfm_ctx *ctx = t->ctx;
   RFM_CUDA(cudaSetDevice(ctx->device));
-  const size_t n_out = (size_t)t->n_users * K;
+  const size_t n_out = (size_t)t->result_rows * K;
   RFM_TRY(t->stage_items.ensure(n_out));
   RFM_TRY(t->stage_scores.ensure(n_out));
   RFM_CUDA(cudaMemcpyAsync(t->stage_items.p, t->out_items.p, n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1380,8 +1794,21 @@ int rfm_topk_merge_dev(rfm_ctx *ctx, int64_t n_users, int32_t K, int32_t n_lists
   DevBuf<double> os;
   RFM_TRY(oi.alloc((size_t)n_users * K));
   RFM_TRY(os.alloc((size_t)n_users * K));
-  const int grid = (int)std::min<int64_t>((n_users + 7) / 8, (int64_t)ctx->sm_count * 8);
-  RFM_LAUNCH(ctx, topk_merge_kernel, grid, 256, 0, items_dev, scores_dev, n_users, (int)K, (int)n_lists, oi.p, os.p);
+  const size_t msmem = (size_t)MERGE_WARPS * n_lists * K * 12;
+  if (n_lists <= XCH_MAX_WORLD && msmem <= 200 * 1024) {      // K-way merge by rank counting (lists are sorted)
+    ListPtrs lp;
+    for (int q = 0; q < XCH_MAX_WORLD; ++q) {
+      lp.items[q] = q < n_lists ? items_dev + (size_t)q * n_users * K : nullptr;
+      lp.scores[q] = q < n_lists ? scores_dev + (size_t)q * n_users * K : nullptr;
+    }
+    RFM_CUDA(cudaFuncSetAttribute(topk_xch_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    const int mgrid = (int)std::min<int64_t>((n_users + MERGE_WARPS - 1) / MERGE_WARPS, (int64_t)ctx->sm_count * 2);
+    RFM_LAUNCH(ctx, topk_xch_merge_kernel, mgrid, MERGE_WARPS * 32, msmem, lp, (int)n_lists, (int)K, (int64_t)0, n_users,
+               oi.p, os.p);
+  } else {
+    const int grid = (int)std::min<int64_t>((n_users + 7) / 8, (int64_t)ctx->sm_count * 8);
+    RFM_LAUNCH(ctx, topk_merge_kernel, grid, 256, 0, items_dev, scores_dev, n_users, (int)K, (int)n_lists, oi.p, os.p);
+  }
   RFM_CUDA(cudaMemcpyAsync(out_items, oi.p, (size_t)n_users * K * 4, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaMemcpyAsync(out_scores, os.p, (size_t)n_users * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -87,6 +87,9 @@ _SIGNATURES = {
     "rfm_topk_run": ([_P, c_int32, c_int32, c_int64, c_int64, _P, _P, _P], c_int),
     "rfm_topk_result_ptr_dev": ([_P, POINTER(_P), POINTER(_P)], c_int),
     "rfm_topk_result_host": ([_P, c_int32, POINTER(_P), POINTER(_P)], c_int),
+    "rfm_topk_dp_export": ([_P, c_int32, c_void_p], c_int),
+    "rfm_topk_dp_connect": ([_P, c_int32, c_int32, c_void_p], c_int),
+    "rfm_topk_run_sharded": ([_P, c_int32, c_int32, _P, _P, _P, _P], c_int),
     "rfm_topk_merge_dev": ([_P, c_int64, c_int32, c_int32, _P, _P, _P, _P], c_int),
     "rfm_ranker_create": ([_P, c_int64, _P, _P, _P, _P, c_int64, POINTER(_P)], c_int),
     "rfm_ranker_destroy": ([_P], c_int),

@@ -293,19 +293,94 @@ def item_shard(n_items: int, world: int, rank: int, tile: int = 256):
     return min(begin * tile, n_items), min(end * tile, n_items)
 
 
-def sharded_topk(scorer, env: DistEnv, K: int, mode: str = "tensor"):
-    """Item-sharded full-catalog top-K: every rank holds all users' factors, ranks
-    its own slice of the catalog on its GPU, the per-rank (item, score) lists are all-gathered on the
-    device (the one exchange step, n_users x K x 12 bytes per rank) and merged by a kernel with the
-    canonical order. Every rank returns the same global top-K."""
+def connect_scorer(scorer, env: DistEnv, k_cap: int = 120):
+    """One-time set-up of a scorer's NVLink exchange (collective): allocate the exchange region, gather the CUDA-IPC
+    handles through torch.distributed, map every peer's region."""
+    from ._capi import check, lib
+    from ctypes import c_ubyte
+    if getattr(scorer, "_xchg", None) is not None:
+        if scorer._xchg[0] != env.world or scorer._xchg[1] < k_cap:
+            raise ValueError("scorer is already connected to %d ranks with k_cap %d" % scorer._xchg)
+        return
+    if env.world > 8:
+        raise ValueError("the peer-memory exchange serves one node (at most 8 ranks)")
+    handle = (c_ubyte * 64)()
+    check(lib().rfm_topk_dp_export(scorer.handle, k_cap, handle))
+    gathered = [None] * env.world
+    env.dist.all_gather_object(gathered, bytes(handle))
+    every = (c_ubyte * (64 * env.world)).from_buffer_copy(b"".join(gathered))
+    check(lib().rfm_topk_dp_connect(scorer.handle, env.rank, env.world, every))
+    env.barrier()                                       # every rank has mapped every region
+    scorer._xchg = (env.world, k_cap)
+    scorer._xchg_env = env
+
+
+def sharded_topk(scorer, env: DistEnv, K: int, mode: str = "tensor", gather: bool = True, exchange: str = "auto",
+                 copy: bool = True):
+    """Item-sharded full-catalog top-K: every rank holds all users' factors and ranks its own
+    slice of the catalog on its GPU.
+
+    exchange="nvlink" (default on an NCCL group of <= 8 ranks): the library's own peer-memory exchange -- global
+    collect thresholds from the union of the ranks' sampled group maxima, then rank r merges the sorted per-rank
+    lists of the users it owns, ``slice_bounds(n_users, world, rank)``, reading the peers' lists directly
+    (``rfm_topk_run_sharded``). exchange="nccl": two all-gathers of the per-rank lists and a merge of every user on
+    every rank (the round-1 path, kept for comparison).
+
+    gather=True: every rank returns the same global ``(items, scores)`` for all users (the owned ranges are
+    all-gathered). gather=False (nvlink only): returns ``(user_begin, user_end, items, scores)`` for the users this
+    rank owns -- what the metric reductions downstream need."""
     from . import _capi
     from ._capi import check, lib, ptr
     if env.backend != "nccl":
         raise RuntimeError("sharded_topk needs the NCCL backend (results stay on the device)")
+    if exchange == "auto":
+        exchange = os.environ.get("RFM_TOPK_EXCHANGE", "nvlink" if env.world <= 8 else "nccl")
+    if exchange not in ("nvlink", "nccl"):
+        raise ValueError("exchange must be 'nvlink', 'nccl' or 'auto'")
     torch = env.torch
     n_users = scorer.n_users
-    begin, end = item_shard(scorer.n_items, env.world, env.rank)
     dev = "cuda:%d" % env.device
+    if exchange == "nvlink":
+        connect_scorer(scorer, env, max(K, 1))
+        ub, ue = slice_bounds(n_users, env.world, env.rank)
+        rng = (c_int64 * 2)()
+        stats = (c_int64 * 4)()
+        if copy:
+            items = np.empty((ue - ub, K), dtype=np.int32)
+            scores = np.empty((ue - ub, K), dtype=np.float64)
+            check(lib().rfm_topk_run_sharded(scorer.handle, K, 0 if mode == "tensor" else 1, ptr(items), ptr(scores),
+                                             rng, stats))
+        else:
+            import ctypes
+            check(lib().rfm_topk_run_sharded(scorer.handle, K, 0 if mode == "tensor" else 1, None, None, rng, stats))
+            pi, ps = c_void_p(), c_void_p()
+            check(lib().rfm_topk_result_host(scorer.handle, K, byref(pi), byref(ps)))
+            n = (ue - ub) * K
+            items = np.ctypeslib.as_array(ctypes.cast(pi, ctypes.POINTER(ctypes.c_int32)), shape=(n,)).reshape(ue - ub, K)
+            scores = np.ctypeslib.as_array(ctypes.cast(ps, ctypes.POINTER(ctypes.c_double)), shape=(n,)).reshape(ue - ub, K)
+        assert (rng[0], rng[1]) == (ub, ue)
+        scorer.last_stats = {"tensor_core_path": bool(stats[0]), "users_ranked_exactly": int(stats[1]),
+                             "candidates": int(stats[2]), "sample_stride": int(stats[3])}
+        if not gather:
+            return ub, ue, items, scores
+        width = -(-n_users // env.world)
+        mine_i = torch.full((width, K), -1, dtype=torch.int32, device=dev)
+        mine_s = torch.full((width, K), float("-inf"), dtype=torch.float64, device=dev)
+        mine_i[: ue - ub] = torch.from_numpy(np.ascontiguousarray(items)).to(dev)
+        mine_s[: ue - ub] = torch.from_numpy(np.ascontiguousarray(scores)).to(dev)
+        all_i = torch.empty((env.world, width, K), dtype=torch.int32, device=dev)
+        all_s = torch.empty((env.world, width, K), dtype=torch.float64, device=dev)
+        env.dist.all_gather_into_tensor(all_i, mine_i)
+        env.dist.all_gather_into_tensor(all_s, mine_s)
+        out_i = np.empty((n_users, K), dtype=np.int32)
+        out_s = np.empty((n_users, K), dtype=np.float64)
+        hi, hs = all_i.cpu().numpy(), all_s.cpu().numpy()
+        for r in range(env.world):
+            b, e = slice_bounds(n_users, env.world, r)
+            out_i[b:e] = hi[r, : e - b]
+            out_s[b:e] = hs[r, : e - b]
+        return out_i, out_s
+    begin, end = item_shard(scorer.n_items, env.world, env.rank)
     if end > begin:
         check(lib().rfm_topk_run(scorer.handle, K, 0 if mode == "tensor" else 1, begin, end, None, None, None))
         ip, sp = c_void_p(), c_void_p()

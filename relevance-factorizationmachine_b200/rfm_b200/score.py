@@ -62,6 +62,23 @@ class TopKScorer(_capi._Handle):
         check(lib().rfm_topk_create(self.ctx.handle, self.n_users, self.n_items, self.k, byref(self.handle)))
         check(lib().rfm_topk_set_factors(self.handle, ptr(A), ptr(C), ptr(alpha), ptr(beta), float(bias)))
         self.last_stats = {}
+        self._xchg = None           # (world, k_cap) once rfm_b200.dist.connect_scorer has mapped the peers' regions
+        self._xchg_env = None
+
+    def close(self):
+        """Collective when the scorer is connected to peers: no rank may unmap / free its exchange region while
+        another still merges from it."""
+        if self._xchg_env is not None and self.handle:
+            env, self._xchg_env = self._xchg_env, None
+            try:
+                env.barrier()
+            except Exception:
+                pass
+        super().close()
+
+    def __del__(self):              # garbage collection is not a collective moment: no barrier here
+        self._xchg_env = None
+        super().__del__()
 
     def topk(self, K: int, mode: str = "tensor", item_range=None, copy: bool = True):
         """(items (n_users, K) int32, scores (n_users, K) float64): every user's K best items, best first;

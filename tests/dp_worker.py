@@ -69,16 +69,32 @@ def main():
     # row-sharded predict == single-process predict, bit for bit
     test_X = golden_csr(g, "test")
     np.testing.assert_array_equal(rdist.sharded_predict(m, test_X, env), m.predict(X=test_X))
-    # item-sharded full-catalog scoring: merged per-rank lists == one pass over the whole catalog
+    # item-sharded full-catalog scoring: merged per-rank lists == one pass over the whole catalog, bit for bit,
+    # through the library's NVLink exchange (global thresholds + user-partitioned K-way merge) and through NCCL
     from rfm_b200.score import TopKScorer
+    from rfm_b200.dist import slice_bounds
     rng = np.random.default_rng(21)
-    A, C, beta = rng.normal(size=(500, 64)) * 0.4, rng.normal(size=(3000, 64)) * 0.4, rng.normal(size=3000) * 0.2
-    sc = TopKScorer(A, C, None, beta, 0.0, device=local_rank)
-    full_items, full_scores = sc.topk(9)
-    items, scores = rdist.sharded_topk(sc, env, 9)
-    np.testing.assert_array_equal(items, full_items)
-    np.testing.assert_array_equal(scores, full_scores)
-    assert sc.last_stats["tensor_core_path"]
+    cases = [(500, 3000, 64, 9, "normal"), (300, 5000, 128, 100, "normal"), (257, 700, 64, 20, "ties"),
+             (130, 300, 32, 9, "normal"), (64, 2600, 200, 9, "normal")]       # last: k > 128 -> exact path per shard
+    for n_u, n_i, k, K, kind in cases:
+        A, C, beta = rng.normal(size=(n_u, k)) * 0.4, rng.normal(size=(n_i, k)) * 0.4, rng.normal(size=n_i) * 0.2
+        if kind == "ties":                                       # few distinct scores: exact ties across shards
+            A, C, beta = np.round(A), np.round(C), np.round(beta)
+        sc = TopKScorer(A, C, None, beta, 0.0, device=local_rank)
+        full_items, full_scores = sc.topk(K)
+        for exchange in ("nvlink", "nccl"):
+            items, scores = rdist.sharded_topk(sc, env, K, exchange=exchange)
+            np.testing.assert_array_equal(items, full_items, err_msg="%s %s" % (exchange, (n_u, n_i, k, K)))
+            np.testing.assert_array_equal(scores, full_scores)
+        ub, ue, own_items, own_scores = rdist.sharded_topk(sc, env, K, gather=False, copy=False)
+        assert (ub, ue) == slice_bounds(n_u, env.world, env.rank)
+        np.testing.assert_array_equal(own_items, full_items[ub:ue])
+        np.testing.assert_array_equal(own_scores, full_scores[ub:ue])
+        items, scores = rdist.sharded_topk(sc, env, K, mode="exact")
+        np.testing.assert_array_equal(items, full_items)
+        if k <= 128:
+            assert sc.last_stats["tensor_core_path"] is False    # the exact-mode call above
+        sc.close()
     if env.rank == 0:
         print("DP_OK world=%d exchange=%s" % (env.world, os.environ.get("RFM_DP_EXCHANGE", "nvlink")))
     env.shutdown()
