@@ -115,6 +115,38 @@ int rfm_csr_create_range(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols,
                          int64_t row_begin, int64_t row_end, rfm_csr **out);
 int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev /* int64[n_rows+1] */, void **col_dev /* int32[nnz] */,
                         void **val_dev, void **targets_dev);
+/* Factored rows: what the reference's data layer holds BEFORE scipy.sparse.hstack --
+ * utils/dataloader/coat/_preparer.py:154-170 stacks [onehot_user_ids[u] | user_features[u] | onehot_item_ids[i] |
+ * item_features[i]], utils/dataloader/kuairec/_feature.py:169-209 stacks [I_user | I_item | interaction columns |
+ * user table | video table]. The rows object is described by those blocks, in column order, plus one
+ * (user, item) pair per interaction; the row kernels assemble x_t on the fly, in the hstacked matrix's column
+ * order, so every entry point that takes an rfm_csr gives the same bits for both representations while an
+ * interaction costs ~40 bytes of PCIe / HBM instead of 12 m + 16.
+ *   RFM_BLOCK_ID:    one-hot of the row's user / item id, n_cols ids wide (value 1.0)
+ *   RFM_BLOCK_TABLE: row `id` of a CSR table with n_entities rows and n_cols columns (indices local to the block,
+ *                    ascending inside a row, as scipy's canonical CSR)
+ *   RFM_BLOCK_CTX:   n_cols dense per-interaction values, row-major [n_rows][n_cols] (at most 32 context columns
+ *                    over all blocks); a zero contributes no entry, as in scipy's csr_matrix(dense)
+ * users / items: int32 or int64 ids, one per row; labels: int8, int32 or int64 (label_bytes). At most 6 blocks. */
+#define RFM_BLOCK_ID 0
+#define RFM_BLOCK_TABLE 1
+#define RFM_BLOCK_CTX 2
+#define RFM_KEY_USER 0
+#define RFM_KEY_ITEM 1
+typedef struct rfm_rows_block {
+  int32_t kind, key;
+  int64_t n_cols;
+  int64_t n_entities;          /* TABLE: rows of the table (ID: n_cols is used) */
+  const void *indptr;          /* TABLE */
+  int32_t indptr_is_int64, reserved;
+  const int32_t *indices;      /* TABLE */
+  const double *data;          /* TABLE */
+  const double *values;        /* CTX */
+} rfm_rows_block;
+int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64, const void *items,
+                        int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks,
+                        const void *labels /* may be NULL */, int32_t label_bytes, const double *pscores, int dtype,
+                        rfm_csr **out);
 /* Replace the per-row targets y/pscore with values the caller computed in float64 (fractional labels: the
  * reference divides whatever `labels` holds, src/fm.py:80; rfm_csr_create takes integer labels). */
 int rfm_csr_set_targets(rfm_csr *rows, const double *targets /* [n_rows] */);

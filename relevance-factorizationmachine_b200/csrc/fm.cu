@@ -28,6 +28,30 @@
 using namespace rfm;
 
 // ---- handles ----------------------------------------------------------------------------------
+// Factored rows: what the reference's data layer holds BEFORE scipy.sparse.hstack
+// (utils/dataloader/coat/_preparer.py:154-170, kuairec/_feature.py:169-209) -- per-entity feature tables plus one
+// (user, item[, context]) record per interaction. A row is the concatenation, in column order, of up to FAC_MAX_SEG
+// blocks: the one-hot of an id, the table row of an id, or dense per-row context values. The row kernels assemble
+// x_t on the fly, so an interaction costs 8 + 8 n_ctx + 8 bytes of HBM instead of 12 m + 16.
+constexpr int FAC_MAX_SEG = 6;
+enum FacKind { SEG_ID = 0, SEG_TABLE = 1, SEG_CTX = 2 };
+struct FacSegDev {
+  int kind, key;            // key: 0 = the row's user id, 1 = its item id (SEG_ID, SEG_TABLE)
+  uint32_t col0;            // first global column of the block
+  int width;                // SEG_CTX: number of columns
+  const int32_t *ptr;       // SEG_TABLE: CSR of the table, columns local to the block
+  const int32_t *col;
+  const void *val;          // T
+  int ctx0;                 // SEG_CTX: first column of the block inside a row's context record
+  int pad;
+};
+struct FacDev {
+  int n_seg, n_ctx, es, pad;  // es: bytes per value (4 or 8)
+  const int32_t *user, *item;
+  const void *ctx;          // T [n_rows][n_ctx]
+  FacSegDev seg[FAC_MAX_SEG];
+};
+
 struct rfm_csr {
   rfm_ctx *ctx = nullptr;
   int dtype = RFM_F64;
@@ -36,6 +60,38 @@ struct rfm_csr {
   DevBuf<int64_t> row_ptr;
   DevBuf<int32_t> col;
   DevBuf<unsigned char> val, yp;
+  // factored rows (rfm_factored_create): the CSR buffers above stay empty
+  bool factored = false;
+  int n_seg = 0, n_ctx = 0;
+  DevBuf<int32_t> f_user, f_item;
+  DevBuf<unsigned char> f_ctx;
+  struct Seg {
+    int kind = 0, key = 0, width = 0, ctx0 = 0;
+    uint32_t col0 = 0;
+    DevBuf<int32_t> ptr, col;
+    DevBuf<unsigned char> val;
+  } seg[FAC_MAX_SEG];
+  FacDev fac_dev(int64_t row_offset = 0) const {
+    FacDev f;
+    memset(&f, 0, sizeof(f));
+    f.n_seg = n_seg;
+    f.n_ctx = n_ctx;
+    f.es = dtype == RFM_F64 ? 8 : 4;
+    f.user = f_user.p + row_offset;
+    f.item = f_item.p + row_offset;
+    f.ctx = f_ctx.p ? f_ctx.p + (size_t)row_offset * n_ctx * (dtype == RFM_F64 ? 8 : 4) : nullptr;
+    for (int s = 0; s < n_seg; ++s) {
+      f.seg[s].kind = seg[s].kind;
+      f.seg[s].key = seg[s].key;
+      f.seg[s].col0 = seg[s].col0;
+      f.seg[s].width = seg[s].width;
+      f.seg[s].ptr = seg[s].ptr.p;
+      f.seg[s].col = seg[s].col.p;
+      f.seg[s].val = seg[s].val.p;
+      f.seg[s].ctx0 = seg[s].ctx0;
+    }
+    return f;
+  }
 };
 
 struct rfm_fm {
@@ -192,7 +248,159 @@ struct RowsArgs {
   const T *yp2;
   int64_t n2;
   Finish fin2;
+  // FAC kernels: the rows (and the optional second row set) are factored; row_ptr / col / val are unused
+  FacDev fac, fac2;
 };
+
+// ---- factored rows: per-row block layout --------------------------------------------------------------------
+// cum[s] = entries of blocks 0..s of the row; base[s] + (position inside the row) = index into block s's own
+// arrays (table entry, context column) -- for an id block base[s] is the id itself.
+struct FacRow {
+  int cum[FAC_MAX_SEG];
+  int base[FAC_MAX_SEG];
+  int len;
+};
+// Bit j: context column j of row t holds a non-zero. scipy's csr_matrix(dense) stores no zeros, so the stacked
+// matrix the reference builds has no entry there; rows are assembled without them to keep the entry positions
+// (and with them the association of every per-row sum) identical to the CSR path.
+__device__ __forceinline__ unsigned fac_ctx_mask(const FacDev &f, int64_t t) {
+  unsigned m = 0u;
+  if (f.es == 8) {
+    const double *c = static_cast<const double *>(f.ctx) + t * f.n_ctx;
+    for (int j = 0; j < f.n_ctx; ++j) m |= (c[j] != 0.0 ? 1u : 0u) << j;
+  } else {
+    const float *c = static_cast<const float *>(f.ctx) + t * f.n_ctx;
+    for (int j = 0; j < f.n_ctx; ++j) m |= (c[j] != 0.f ? 1u : 0u) << j;
+  }
+  return m;
+}
+__device__ __forceinline__ unsigned seg_ctx_mask(const FacSegDev &g, unsigned mask) {
+  return (mask >> g.ctx0) & (g.width >= 32 ? 0xFFFFFFFFu : ((1u << g.width) - 1u));
+}
+__device__ __forceinline__ FacRow fac_row(const FacDev &f, int u, int i, unsigned mask) {
+  FacRow r;
+  int at = 0;
+#pragma unroll
+  for (int s = 0; s < FAC_MAX_SEG; ++s) {
+    int n = 0, b = 0;
+    if (s < f.n_seg) {
+      const FacSegDev &g = f.seg[s];
+      const int key = g.key == 0 ? u : i;
+      if (g.kind == SEG_ID) {
+        n = 1;
+        b = key;
+      } else if (g.kind == SEG_TABLE) {
+        const int e0 = __ldg(g.ptr + key);
+        n = __ldg(g.ptr + key + 1) - e0;
+        b = e0 - at;
+      } else {
+        const unsigned m = seg_ctx_mask(g, mask);
+        n = __popc(m);
+        b = static_cast<int>(m);        // the block's non-zero columns; its first entry sits at cum[s - 1]
+      }
+    }
+    at += n;
+    r.cum[s] = at;
+    r.base[s] = b;
+  }
+  r.len = at;
+  return r;
+}
+__device__ __forceinline__ int fac_row_len(const FacDev &f, int u, int i, unsigned mask) {
+  int at = 0;
+  for (int s = 0; s < f.n_seg; ++s) {
+    const FacSegDev &g = f.seg[s];
+    const int key = g.key == 0 ? u : i;
+    at += g.kind == SEG_ID ? 1 : g.kind == SEG_TABLE ? __ldg(g.ptr + key + 1) - __ldg(g.ptr + key)
+                                                     : __popc(seg_ctx_mask(g, mask));
+  }
+  return at;
+}
+// entry `off` (< r.len) of row t: global column and value
+template <typename T>
+__device__ __forceinline__ void fac_entry(const FacDev &f, const FacRow &r, int64_t t, int off, int &c, T &x) {
+  int s = 0, b = r.base[0], start = 0;
+#pragma unroll
+  for (int j = 1; j < FAC_MAX_SEG; ++j)
+    if (off >= r.cum[j - 1]) {        // cum is non-decreasing and off < len: the last block that starts at or before off
+      s = j;
+      b = r.base[j];
+      start = r.cum[j - 1];
+    }
+  const FacSegDev &g = f.seg[s];
+  if (g.kind == SEG_ID) {
+    c = static_cast<int>(g.col0) + b;
+    x = T(1);
+  } else if (g.kind == SEG_TABLE) {
+    c = static_cast<int>(g.col0) + __ldg(g.col + b + off);
+    x = __ldg(static_cast<const T *>(g.val) + b + off);
+  } else {
+    const int j = __fns(static_cast<unsigned>(b), 0u, off - start + 1);     // the (off - start)-th non-zero column
+    c = static_cast<int>(g.col0) + j;
+    x = __ldg(static_cast<const T *>(f.ctx) + t * f.n_ctx + g.ctx0 + j);
+  }
+}
+
+// ---- factored rows: upload helpers ---------------------------------------------------------------------------
+template <typename S>
+__global__ void narrow_ids_kernel(const S *in, int32_t *out, int64_t n, int64_t limit,   // in may alias out
+                                  int *__restrict__ bad) {
+  bool mine = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = static_cast<int64_t>(in[i]);
+    mine |= (v < 0 || v >= limit);
+    out[i] = static_cast<int32_t>(v);
+  }
+  if (mine) atomicOr(bad, 1);
+}
+
+// labels of 1, 4 or 8 bytes (signed integers) -> y / pscore as NumPy computes it (src/fm.py:80)
+template <typename T, typename Y>
+__global__ void targets_any_kernel(const Y *__restrict__ y, const double *__restrict__ ps, T *__restrict__ yp, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    yp[i] = static_cast<T>(static_cast<double>(y[i]) / ps[i]);
+}
+
+// one context block's columns into the per-row context record
+template <typename T>
+__global__ void ctx_pack_kernel(const double *__restrict__ in, int64_t n_rows, int width, T *__restrict__ out,
+                                int n_ctx, int ctx0) {
+  const int64_t total = n_rows * width;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / width;
+    const int c = static_cast<int>(i - r * width);
+    out[r * n_ctx + ctx0 + c] = static_cast<T>(in[i]);
+  }
+}
+
+// non-zeros of the whole row set and the longest row (what the CSR path reads off the row pointers)
+__global__ void fac_stats_kernel(const FacDev f, int64_t n_rows, unsigned long long *__restrict__ nnz,
+                                 int *__restrict__ max_len) {
+  unsigned long long s = 0;
+  int m = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_rows; t += (int64_t)gridDim.x * blockDim.x) {
+    const int len = fac_row_len(f, f.user[t], f.item[t], fac_ctx_mask(f, t));
+    s += (unsigned long long)len;
+    m = max(m, len);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(FULL, s, o);
+    m = max(m, __shfl_xor_sync(FULL, m, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(nnz, s);
+    atomicMax(max_len, m);
+  }
+}
+
+__global__ void fac_row_len_kernel(const FacDev f, const int64_t *__restrict__ idx, int64_t batch,
+                                   uint32_t *__restrict__ len) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < batch; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx[q];
+    len[q] = static_cast<uint32_t>(fac_row_len(f, f.user[t], f.item[t], fac_ctx_mask(f, t)));
+  }
+}
 
 __device__ __forceinline__ double sigmoid_ref(double z) {
   // src/base.py:63-66
@@ -250,7 +458,7 @@ __device__ __forceinline__ T group_sum(T v, unsigned mask) {
 // 2-element chunks {(ch*TPR + g)*2, +1}, so each load instruction of a group reads TPR*2 contiguous
 // elements of a V row. The per-non-zero bookkeeping (broadcast of (column, x), address arithmetic,
 // loop control) and the scalar epilogue are shared by all rows of the warp.
-template <typename T, int TPR, int NCV, int MODE, bool SAMPLED>
+template <typename T, int TPR, int NCV, int MODE, bool SAMPLED, bool FAC>
 __global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? RFM_ROWS_MIN_BLOCKS : 1)
 fm_rows_kernel(const RowsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
@@ -274,21 +482,29 @@ fm_rows_kernel(const RowsArgs<T> a) {
   // on the critical path of every row. (A second stage that also prefetched the next row's first column
   // entries was measured and did not pay: 59 -> 61-65 us.)
   struct RowMeta {
-    int64_t t, beg, end;
+    int64_t t, beg, end;      // FAC: beg = the row's user id, end = its item id
     T ypv;
+    unsigned mask;            // FAC: non-zero context columns of the row
     bool active, second;
   };
   auto fetch = [&](int64_t qq) {
     RowMeta r;
     r.t = r.beg = r.end = 0;
     r.ypv = T(0);
+    r.mask = 0u;
     r.active = qq < n_total;
     r.second = MODE == MODE_LOSS && qq >= a.n;
     if (r.active) {
       if (r.second) {
         r.t = qq - a.n;
-        r.beg = a.row_ptr2[r.t];
-        r.end = a.row_ptr2[r.t + 1];
+        if (FAC) {
+          r.beg = a.fac2.user[r.t];
+          r.end = a.fac2.item[r.t];
+          r.mask = fac_ctx_mask(a.fac2, r.t);
+        } else {
+          r.beg = a.row_ptr2[r.t];
+          r.end = a.row_ptr2[r.t + 1];
+        }
         r.ypv = a.yp2[r.t];
       } else {
         if (SAMPLED) {
@@ -297,8 +513,14 @@ fm_rows_kernel(const RowsArgs<T> a) {
         } else {
           r.t = a.idx ? a.idx[qq] : a.row0 + qq;
         }
-        r.beg = a.row_ptr[r.t];
-        r.end = a.row_ptr[r.t + 1];
+        if (FAC) {
+          r.beg = a.fac.user[r.t];
+          r.end = a.fac.item[r.t];
+          r.mask = fac_ctx_mask(a.fac, r.t);
+        } else {
+          r.beg = a.row_ptr[r.t];
+          r.end = a.row_ptr[r.t + 1];
+        }
         if (MODE != MODE_PREDICT) r.ypv = a.yp[r.t];
       }
     }
@@ -313,7 +535,12 @@ fm_rows_kernel(const RowsArgs<T> a) {
     const int32_t *colp = second ? a.col2 : a.col;
     const T *valp = second ? a.val2 : a.val;
     const int64_t t = cur.t, beg = cur.beg, end = cur.end;
-    const int len = static_cast<int>(end - beg);
+    FacRow fr;
+    if (FAC) {
+      if (MODE == MODE_LOSS && second) fr = fac_row(a.fac2, static_cast<int>(beg), static_cast<int>(end), cur.mask);
+      else fr = fac_row(a.fac, static_cast<int>(beg), static_cast<int>(end), cur.mask);
+    }
+    const int len = FAC ? (active ? fr.len : 0) : static_cast<int>(end - beg);
     const int maxlen = __reduce_max_sync(FULL, len);
     V2 acc[NCV];
 #pragma unroll
@@ -327,8 +554,13 @@ fm_rows_kernel(const RowsArgs<T> a) {
       int c = 0;
       T x = T(0);
       if (off < len) {
-        c = colp[beg + off];
-        x = valp[beg + off];
+        if (FAC) {
+          if (MODE == MODE_LOSS && second) fac_entry<T>(a.fac2, fr, t, off, c, x);
+          else fac_entry<T>(a.fac, fr, t, off, c, x);
+        } else {
+          c = colp[beg + off];
+          x = valp[beg + off];
+        }
         sl += x * __ldg(a.w + c) - T(0.5) * (x * x) * __ldg(a.vn + c);
         if (MODE == MODE_TRAIN) {
           const uint32_t o = out_base + static_cast<uint32_t>(off);
@@ -882,31 +1114,32 @@ int upload(rfm_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
   return RFM_OK;
 }
 
-template <typename T>
-int launch_rows(rfm_ctx *ctx, int nch, int mode, bool sampled, const RowsArgs<T> &args, int grid) {
+template <typename T, bool FAC>
+int launch_rows_as(rfm_ctx *ctx, int nch, int mode, bool sampled, const RowsArgs<T> &args, int grid) {
   RFM_DISPATCH_TPR(nch, {
     if (mode == MODE_TRAIN) {
       if (sampled) {
-        auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, true>;
+        auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, true, FAC>;
         RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
       } else {
-        auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, false>;
+        auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, false, FAC>;
         RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
       }
     } else if (mode == MODE_LOSS) {
-      if (args.idx) {  // post-update loss of the batch vs. loss over a plain row range (val)
-        auto fm_rows_loss = fm_rows_kernel<T, TPR, NCV, MODE_LOSS, false>;
-        RFM_LAUNCH(ctx, fm_rows_loss, grid, ROWS_THREADS, 0, args);
-      } else {
-        auto fm_rows_loss_range = fm_rows_kernel<T, TPR, NCV, MODE_LOSS, false>;
-        RFM_LAUNCH(ctx, fm_rows_loss_range, grid, ROWS_THREADS, 0, args);
-      }
+      auto fm_rows_loss = fm_rows_kernel<T, TPR, NCV, MODE_LOSS, false, FAC>;
+      RFM_LAUNCH(ctx, fm_rows_loss, grid, ROWS_THREADS, 0, args);
     } else {
-      auto fm_rows_predict = fm_rows_kernel<T, TPR, NCV, MODE_PREDICT, false>;
+      auto fm_rows_predict = fm_rows_kernel<T, TPR, NCV, MODE_PREDICT, false, FAC>;
       RFM_LAUNCH(ctx, fm_rows_predict, grid, ROWS_THREADS, 0, args);
     }
   });
   return RFM_OK;
+}
+// fac: the rows (both sets of a loss launch) are factored
+template <typename T>
+int launch_rows(rfm_ctx *ctx, int nch, int mode, bool sampled, const RowsArgs<T> &args, int grid, bool fac = false) {
+  return fac ? launch_rows_as<T, true>(ctx, nch, mode, sampled, args, grid)
+             : launch_rows_as<T, false>(ctx, nch, mode, sampled, args, grid);
 }
 
 // rows (or 32-entry chunks) a CTA of ROWS_THREADS handles per pass of its loop
@@ -978,6 +1211,7 @@ RowsArgs<T> rows_args(const rfm_fm *m, const rfm_csr *rows) {
   a.V = reinterpret_cast<const T *>(m->V.p);
   a.vn = reinterpret_cast<const T *>(m->vn.p);
   a.kp = m->kp;
+  if (rows->factored) a.fac = rows->fac_dev();
   return a;
 }
 
@@ -1008,7 +1242,7 @@ int loss_pass(rfm_fm_trainer *t, const rfm_csr *rows, const int64_t *idx_dev, in
   a.n = n;
   a.fin = make_finish(1, scale, nullptr, dst_dev, t->block_partials.p, t->ticket.p);
   const int grid = grid_for(ctx, ceil_div(n, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
-  return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid);
+  return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid, rows->factored);
 }
 
 // forward + residual + triples + sort + column pass (+ fix-up). DP=false applies SGD in place.
@@ -1025,7 +1259,11 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
                t->idx.p);
   if (t->stride == 0) {
     const int small_grid = grid_for(ctx, ceil_div(batch, 256), 4);
-    RFM_LAUNCH(ctx, row_len_kernel, small_grid, 256, 0, tr->row_ptr.p, t->idx.p, batch, t->row_len.p);
+    if (tr->factored) {
+      RFM_LAUNCH(ctx, fac_row_len_kernel, small_grid, 256, 0, tr->fac_dev(), t->idx.p, batch, t->row_len.p);
+    } else {
+      RFM_LAUNCH(ctx, row_len_kernel, small_grid, 256, 0, tr->row_ptr.p, t->idx.p, batch, t->row_len.p);
+    }
     RFM_TRY(exclusive_scan_u32(ctx, t->row_len.p, t->bptr.p, batch, t->scan_tmp.p, t->count.p));
   } else {
     const uint32_t cnt = (uint32_t)batch * t->stride;
@@ -1061,7 +1299,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
     a.fin = make_finish(0, lr, m->w0.p, nullptr, t->block_partials.p, t->ticket.p);
   }
   const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, fused_draw, a, grid));
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, fused_draw, a, grid, tr->factored));
   int sorted = 0;
   RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true));
 
@@ -1137,7 +1375,11 @@ int batch_and_val_losses(rfm_fm_trainer *t, int64_t batch, double scale_b, doubl
   a.fin = make_finish(1, scale_b, nullptr, dst_b, t->block_partials.p, t->ticket.p);
   int64_t n_all = batch;
   if (t->val && val_end > val_begin) {
-    a.row_ptr2 = t->val->row_ptr.p + val_begin;           // row_ptr entries are absolute offsets into col / val
+    if (t->val->factored) {
+      a.fac2 = t->val->fac_dev(val_begin);
+    } else {
+      a.row_ptr2 = t->val->row_ptr.p + val_begin;         // row_ptr entries are absolute offsets into col / val
+    }
     a.col2 = t->val->col.p;
     a.val2 = reinterpret_cast<const T *>(t->val->val.p);
     a.yp2 = reinterpret_cast<const T *>(t->val->yp.p) + val_begin;
@@ -1148,7 +1390,7 @@ int batch_and_val_losses(rfm_fm_trainer *t, int64_t batch, double scale_b, doubl
     RFM_CUDA(cudaMemsetAsync(dst_v, 0, sizeof(double), ctx->stream));
   }
   const int grid = grid_for(ctx, ceil_div(n_all, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
-  return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid);
+  return launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid, t->train->factored);
 }
 
 int stage_batch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
@@ -1316,10 +1558,196 @@ int rfm_csr_create_range(rfm_ctx *ctx, int64_t n_rows, int64_t n_cols, const voi
 
 int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev, void **col_dev, void **val_dev, void **targets_dev) {
   RFM_REQUIRE(rows, "rfm_csr_device_ptrs: rows is NULL");
+  RFM_REQUIRE(!rows->factored, "rfm_csr_device_ptrs: factored rows have no CSR arrays");
   if (row_ptr_dev) *row_ptr_dev = rows->row_ptr.p;
   if (col_dev) *col_dev = rows->col.p;
   if (val_dev) *val_dev = rows->val.p;
   if (targets_dev) *targets_dev = rows->yp.p;
+  return RFM_OK;
+}
+
+int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64, const void *items,
+                        int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks, const void *labels,
+                        int32_t label_bytes, const double *pscores, int dtype, rfm_csr **out) {
+  RFM_REQUIRE(ctx && out, "rfm_factored_create: NULL ctx/out");
+  *out = nullptr;
+  RFM_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffffLL, "rfm_factored_create: bad row count %lld", (long long)n_rows);
+  RFM_REQUIRE(blocks && n_blocks >= 1 && n_blocks <= FAC_MAX_SEG, "rfm_factored_create: between 1 and %d blocks",
+              FAC_MAX_SEG);
+  RFM_REQUIRE(n_rows == 0 || (users && items), "rfm_factored_create: users/items are NULL");
+  RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "rfm_factored_create: bad dtype %d", dtype);
+  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "rfm_factored_create: labels and pscores go together");
+  RFM_REQUIRE(!labels || label_bytes == 1 || label_bytes == 4 || label_bytes == 8,
+              "rfm_factored_create: labels must be int8, int32 or int64 (label_bytes = %d)", label_bytes);
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  // column layout and the id ranges the blocks agree on
+  int64_t n_cols = 0, n_ctx = 0, limit[2] = {INT64_MAX, INT64_MAX};
+  for (int b = 0; b < n_blocks; ++b) {
+    const rfm_rows_block &k = blocks[b];
+    RFM_REQUIRE(k.kind == RFM_BLOCK_ID || k.kind == RFM_BLOCK_TABLE || k.kind == RFM_BLOCK_CTX,
+                "rfm_factored_create: block %d has unknown kind %d", b, k.kind);
+    RFM_REQUIRE(k.n_cols >= 1, "rfm_factored_create: block %d has no columns", b);
+    if (k.kind == RFM_BLOCK_CTX) {
+      RFM_REQUIRE(k.values || n_rows == 0, "rfm_factored_create: context block %d has no values", b);
+      n_ctx += k.n_cols;
+      RFM_REQUIRE(n_ctx <= 32, "rfm_factored_create: more than 32 context columns in total");
+    } else {
+      RFM_REQUIRE(k.key == RFM_KEY_USER || k.key == RFM_KEY_ITEM, "rfm_factored_create: block %d has unknown key %d", b, k.key);
+      const int64_t ne = k.kind == RFM_BLOCK_ID ? k.n_cols : k.n_entities;
+      RFM_REQUIRE(ne >= 1 && ne < 0x7fffffffLL, "rfm_factored_create: block %d is indexed by %lld ids", b, (long long)ne);
+      limit[k.key] = std::min(limit[k.key], ne);
+      if (k.kind == RFM_BLOCK_TABLE) RFM_REQUIRE(k.indptr, "rfm_factored_create: table block %d has no indptr", b);
+    }
+    n_cols += k.n_cols;
+  }
+  RFM_REQUIRE(n_cols < 0xFFFFFFFFLL, "rfm_factored_create: too many columns");
+  rfm_csr *r = new (std::nothrow) rfm_csr();
+  if (!r) return fail(RFM_ERR_NOMEM, "rfm_factored_create: out of host memory");
+  r->ctx = ctx;
+  r->dtype = dtype;
+  r->n_rows = n_rows;
+  r->n_cols = n_cols;
+  r->has_targets = labels != nullptr;
+  r->factored = true;
+  r->n_seg = n_blocks;
+  r->n_ctx = (int)n_ctx;
+  const size_t es = dsize(dtype);
+  auto body = [&]() -> int {
+    const int64_t nr = n_rows ? n_rows : 1;
+    RFM_TRY(r->f_user.alloc(nr));
+    RFM_TRY(r->f_item.alloc(nr));
+    RFM_TRY(r->yp.alloc((size_t)nr * es));
+    if (n_ctx) RFM_TRY(r->f_ctx.alloc((size_t)nr * n_ctx * es));
+    DevBuf<int> bad;
+    RFM_TRY(bad.alloc(4));
+    RFM_CUDA(cudaMemsetAsync(bad.p, 0, 4 * sizeof(int), ctx->stream));
+    std::vector<DevBuf<unsigned char>> tmp(2 * n_blocks + 4);      // staging, freed (stream-ordered) on return
+    int n_tmp = 0;
+    const int g = grid_for(ctx, ceil_div(nr, 256), 8);
+    // ids: 4 or 8 bytes per row over PCIe as the caller holds them, narrowed (and range-checked) on the device
+    for (int side = 0; side < 2 && n_rows > 0; ++side) {
+      const void *src = side == 0 ? users : items;
+      const bool is64 = (side == 0 ? users_is_int64 : items_is_int64) != 0;
+      int32_t *dst = side == 0 ? r->f_user.p : r->f_item.p;
+      const int64_t lim = limit[side] == INT64_MAX ? 0x7fffffffLL : limit[side];
+      if (is64) {
+        DevBuf<unsigned char> &st = tmp[n_tmp++];
+        RFM_TRY(st.alloc((size_t)n_rows * 8));
+        RFM_TRY(upload(ctx, st.p, src, (size_t)n_rows * 8));
+        RFM_LAUNCH(ctx, narrow_ids_kernel<int64_t>, g, 256, 0, reinterpret_cast<const int64_t *>(st.p), dst, n_rows, lim,
+                   bad.p + side);
+      } else {
+        RFM_TRY(upload(ctx, dst, src, (size_t)n_rows * 4));
+        RFM_LAUNCH(ctx, narrow_ids_kernel<int32_t>, g, 256, 0, dst, dst, n_rows, lim, bad.p + side);
+      }
+    }
+    // blocks
+    uint32_t col0 = 0;
+    int ctx0 = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+      const rfm_rows_block &k = blocks[b];
+      rfm_csr::Seg &sg = r->seg[b];
+      sg.kind = k.kind == RFM_BLOCK_ID ? SEG_ID : k.kind == RFM_BLOCK_TABLE ? SEG_TABLE : SEG_CTX;
+      sg.key = k.key;
+      sg.col0 = col0;
+      sg.width = (int)k.n_cols;
+      sg.ctx0 = ctx0;
+      if (sg.kind == SEG_TABLE) {
+        const int64_t ne = k.n_entities;
+        const int64_t *p64 = static_cast<const int64_t *>(k.indptr);
+        const int32_t *p32 = static_cast<const int32_t *>(k.indptr);
+        std::vector<int32_t> ptr((size_t)ne + 1);
+        for (int64_t i = 0; i <= ne; ++i) {
+          const int64_t v = k.indptr_is_int64 ? p64[i] : (int64_t)p32[i];
+          RFM_REQUIRE(v >= 0 && v < 0x7fffffffLL && (i == 0 ? v == 0 : v >= ptr[(size_t)i - 1]),
+                      "rfm_factored_create: indptr of table block %d is not a valid row-pointer array (row %lld)", b,
+                      (long long)i);
+          ptr[(size_t)i] = (int32_t)v;
+        }
+        const int64_t tnz = ptr[(size_t)ne];
+        RFM_REQUIRE(tnz == 0 || (k.indices && k.data), "rfm_factored_create: table block %d has no indices/data", b);
+        for (int64_t z = 0; z < tnz; ++z)
+          RFM_REQUIRE(k.indices[z] >= 0 && k.indices[z] < k.n_cols,
+                      "rfm_factored_create: table block %d has a column index outside [0, %lld)", b, (long long)k.n_cols);
+        RFM_TRY(sg.ptr.alloc((size_t)ne + 1));
+        RFM_TRY(sg.col.alloc((size_t)tnz));
+        RFM_TRY(sg.val.alloc((size_t)(tnz ? tnz : 1) * es));
+        RFM_CUDA(cudaMemcpyAsync(sg.ptr.p, ptr.data(), ((size_t)ne + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        RFM_CUDA(cudaStreamSynchronize(ctx->stream));       // ptr is a host temporary
+        if (tnz > 0) {
+          RFM_TRY(upload(ctx, sg.col.p, k.indices, (size_t)tnz * 4));
+          if (dtype == RFM_F64) {
+            RFM_TRY(upload(ctx, sg.val.p, k.data, (size_t)tnz * 8));
+          } else {
+            DevBuf<unsigned char> &st = tmp[n_tmp++];
+            RFM_TRY(st.alloc((size_t)tnz * 8));
+            RFM_TRY(upload(ctx, st.p, k.data, (size_t)tnz * 8));
+            RFM_LAUNCH(ctx, convert_f64_kernel<float>, grid_for(ctx, ceil_div(tnz, 256), 8), 256, 0,
+                       reinterpret_cast<const double *>(st.p), reinterpret_cast<float *>(sg.val.p), tnz);
+          }
+        }
+      } else if (sg.kind == SEG_CTX && n_rows > 0) {
+        if (dtype == RFM_F64 && n_ctx == k.n_cols) {      // the only context block, already in the record's layout
+          RFM_TRY(upload(ctx, r->f_ctx.p, k.values, (size_t)n_rows * n_ctx * 8));
+        } else {
+          DevBuf<unsigned char> &st = tmp[n_tmp++];
+          RFM_TRY(st.alloc((size_t)n_rows * k.n_cols * 8));
+          RFM_TRY(upload(ctx, st.p, k.values, (size_t)n_rows * k.n_cols * 8));
+          const int gg = grid_for(ctx, ceil_div(n_rows * k.n_cols, 256), 8);
+          if (dtype == RFM_F64) {
+            RFM_LAUNCH(ctx, ctx_pack_kernel<double>, gg, 256, 0, reinterpret_cast<const double *>(st.p), n_rows,
+                       (int)k.n_cols, reinterpret_cast<double *>(r->f_ctx.p), (int)n_ctx, ctx0);
+          } else {
+            RFM_LAUNCH(ctx, ctx_pack_kernel<float>, gg, 256, 0, reinterpret_cast<const double *>(st.p), n_rows,
+                       (int)k.n_cols, reinterpret_cast<float *>(r->f_ctx.p), (int)n_ctx, ctx0);
+          }
+        }
+      }
+      if (sg.kind == SEG_CTX) ctx0 += (int)k.n_cols;
+      col0 += (uint32_t)k.n_cols;
+    }
+    // targets
+    if (labels && n_rows > 0) {
+      DevBuf<unsigned char> &ys = tmp[n_tmp++];
+      DevBuf<unsigned char> &ps = tmp[n_tmp++];
+      RFM_TRY(ys.alloc((size_t)n_rows * label_bytes));
+      RFM_TRY(ps.alloc((size_t)n_rows * 8));
+      RFM_TRY(upload(ctx, ys.p, labels, (size_t)n_rows * label_bytes));
+      RFM_TRY(upload(ctx, ps.p, pscores, (size_t)n_rows * 8));
+      const double *psd = reinterpret_cast<const double *>(ps.p);
+#define RFM_TARGETS(T, Y) \
+  RFM_LAUNCH(ctx, (targets_any_kernel<T, Y>), g, 256, 0, reinterpret_cast<const Y *>(ys.p), psd, reinterpret_cast<T *>(r->yp.p), n_rows)
+      if (dtype == RFM_F64) {
+        if (label_bytes == 8) RFM_TARGETS(double, int64_t); else if (label_bytes == 4) RFM_TARGETS(double, int32_t); else RFM_TARGETS(double, int8_t);
+      } else {
+        if (label_bytes == 8) RFM_TARGETS(float, int64_t); else if (label_bytes == 4) RFM_TARGETS(float, int32_t); else RFM_TARGETS(float, int8_t);
+      }
+#undef RFM_TARGETS
+    } else {
+      RFM_CUDA(cudaMemsetAsync(r->yp.p, 0, (size_t)nr * es, ctx->stream));
+    }
+    // row statistics (what the CSR path reads off the row pointers): total non-zeros, longest row
+    DevBuf<unsigned long long> nnz_dev;
+    RFM_TRY(nnz_dev.alloc(1));
+    RFM_CUDA(cudaMemsetAsync(nnz_dev.p, 0, 8, ctx->stream));
+    if (n_rows > 0) RFM_LAUNCH(ctx, fac_stats_kernel, g, 256, 0, r->fac_dev(), n_rows, nnz_dev.p, bad.p + 2);
+    unsigned long long nnz_host = 0;
+    int bad_host[4] = {0, 0, 0, 0};
+    RFM_CUDA(cudaMemcpyAsync(&nnz_host, nnz_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(bad_host, bad.p, sizeof(bad_host), cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    RFM_REQUIRE(bad_host[0] == 0, "rfm_factored_create: a user id is outside [0, %lld)", (long long)limit[0]);
+    RFM_REQUIRE(bad_host[1] == 0, "rfm_factored_create: an item id is outside [0, %lld)", (long long)limit[1]);
+    r->nnz = (int64_t)nnz_host;
+    r->max_row_len = bad_host[2];
+    return RFM_OK;
+  };
+  const int rc = body();
+  if (rc != RFM_OK) {
+    delete r;
+    return rc;
+  }
+  *out = r;
   return RFM_OK;
 }
 
@@ -1482,7 +1910,7 @@ int predict_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
   RowsArgs<T> a = rows_args<T>(m, rows);
   a.n = rows->n_rows;
   a.out = out.p;
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_PREDICT, false, a, grid_for(ctx, ceil_div(rows->n_rows, units_per_block(m->nch)), 6)));
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_PREDICT, false, a, grid_for(ctx, ceil_div(rows->n_rows, units_per_block(m->nch)), 6), rows->factored));
   RFM_CUDA(cudaMemcpyAsync(out_host, out.p, (size_t)rows->n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
@@ -1501,7 +1929,7 @@ int logloss_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
   RowsArgs<T> a = rows_args<T>(m, rows);
   a.n = rows->n_rows;
   a.fin = make_finish(1, 1.0 / (double)rows->n_rows, nullptr, res.p, partials.p, ticket.p);
-  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid));
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid, rows->factored));
   RFM_CUDA(cudaMemcpyAsync(out_host, res.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
@@ -1532,6 +1960,8 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
   RFM_TRY(check_rows(m, train, "rfm_fm_trainer_create(train)"));
   if (val) RFM_TRY(check_rows(m, val, "rfm_fm_trainer_create(val)"));
   RFM_REQUIRE(train->has_targets && (!val || val->has_targets), "rfm_fm_trainer_create: rows need labels/pscores");
+  RFM_REQUIRE(!val || val->factored == train->factored,
+              "rfm_fm_trainer_create: train and val rows must both be CSR or both be factored");
   RFM_REQUIRE(max_batch >= 1 && max_slots >= 1, "rfm_fm_trainer_create: bad max_batch/max_slots");
   RFM_REQUIRE(max_batch <= 0x7fffffffLL, "rfm_fm_trainer_create: max_batch too large");
   rfm_ctx *ctx = m->ctx;

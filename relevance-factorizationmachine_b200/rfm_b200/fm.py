@@ -147,6 +147,9 @@ class FactorizationMachines(PointwiseBaseRecommender):
         return rows
 
     def _make_rows(self, X, labels, pscores):
+        from .factored import FactoredFeatures, FactoredRows
+        if isinstance(X, FactoredFeatures):     # user table + item table + (user, item, ctx) records: assembled on the device
+            return FactoredRows(self._context(), X, labels, pscores, self.dtype)
         env = self.distributed
         if (env is not None and labels is not None and env.backend == "nccl" and env.world > 1
                 and X.shape[0] >= int(os.environ.get("RFM_DP_UPLOAD_MIN_ROWS", "1000000"))

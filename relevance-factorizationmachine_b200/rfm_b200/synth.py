@@ -23,7 +23,7 @@ from typing import Dict, Optional
 import numpy as np
 from scipy.sparse import csr_matrix
 
-__all__ = ["SyntheticLog", "make_coat_shaped", "make_kuairec_shaped", "csr_from_tables"]
+__all__ = ["SyntheticLog", "make_coat_shaped", "make_kuairec_shaped", "csr_from_tables", "factored_from_tables"]
 
 
 def _sigmoid(x):
@@ -109,6 +109,33 @@ def csr_from_tables(users, items, tables, ctx=None) -> csr_matrix:
     return X
 
 
+def factored_from_tables(tables, users, items, ctx=None):
+    """The same rows as ``csr_from_tables`` (after its column sort) in the factored form (SURVEY.md section 8 f3,
+    ``rfm_b200.factored.FactoredFeatures``): the blocks the reference's preparers stack -- Coat
+    ``[I_user | user_feat | I_item | item_feat]`` (``coat/_preparer.py:154-170``), KuaiRec
+    ``[I_user | I_item | ctx | user_feat | item_feat]`` (``kuairec/_feature.py:201-207``) -- plus the id pairs."""
+    from .factored import FactoredFeatures
+    n_users, n_items = tables["n_users"], tables["n_items"]
+
+    def side_table(ptr, col, val, base, width):
+        # every table row starts with the entity's one-hot id entry; the rest are its side features (global columns)
+        n = ptr.shape[0] - 1
+        keep = np.ones(col.shape[0], dtype=bool)
+        keep[ptr[:-1]] = False
+        new_ptr = ptr - np.arange(n + 1)
+        return csr_matrix((val[keep], (col[keep] - base).astype(np.int32), new_ptr), shape=(n, width))
+
+    ut = side_table(tables["u_ptr"], tables["u_col"], tables["u_val"], tables["uf_base"], tables["n_uf"])
+    it = side_table(tables["i_ptr"], tables["i_col"], tables["i_val"], tables["if_base"], tables["n_if"])
+    if tables.get("ctx_col") is None:
+        blocks = [("id", "user", n_users), ("table", "user", ut), ("id", "item", n_items), ("table", "item", it)]
+    else:
+        c = np.zeros(len(users)) if ctx is None else np.asarray(ctx, dtype=np.float64)
+        blocks = [("id", "user", n_users), ("id", "item", n_items), ("ctx", c), ("table", "user", ut),
+                  ("table", "item", it)]
+    return FactoredFeatures(blocks, np.asarray(users), np.asarray(items))
+
+
 def _ragged(rows_cols, rows_vals):
     ptr = np.zeros(len(rows_cols) + 1, dtype=np.int64)
     np.cumsum([len(c) for c in rows_cols], out=ptr[1:])
@@ -161,7 +188,8 @@ def make_coat_shaped(seed: int = 2024, n_users: int = 290, n_items: int = 300,
     u_ptr, u_col, u_val = _ragged(u_cols, [np.ones(len(c)) for c in u_cols])
     i_ptr, i_col, i_val = _ragged(i_cols, [np.ones(len(c)) for c in i_cols])
     tables = dict(u_ptr=u_ptr, u_col=u_col, u_val=u_val, i_ptr=i_ptr, i_col=i_col, i_val=i_val,
-                  ctx_col=None, order=("user", "item"), n_features=n_features)
+                  ctx_col=None, order=("user", "item"), n_features=n_features, n_users=n_users, n_items=n_items,
+                  uf_base=uf_base, n_uf=n_uf, if_base=if_base, n_if=n_if)
 
     pop = _popularity(n_items, rng)
     hidden_p = rng.normal(size=(n_users, 8)) * 0.6
@@ -187,7 +215,8 @@ def make_coat_shaped(seed: int = 2024, n_users: int = 290, n_items: int = 300,
 
     def dicts(sel):
         X = csr_from_tables(users[sel], items[sel], tables)
-        fm = {"features": X, "labels": labels[sel].copy(), "pscores": pscores[sel].copy()}
+        fm = {"features": X, "labels": labels[sel].copy(), "pscores": pscores[sel].copy(),
+              "users": users[sel].copy(), "items": items[sel].copy(), "ctx": None}
         mf = {"features": np.stack([users[sel], items[sel]], axis=1).astype(np.int64),
               "labels": labels[sel].copy(), "pscores": pscores[sel].copy()}
         return fm, mf
@@ -259,7 +288,8 @@ def make_kuairec_shaped(seed: int = 2024, n_users: int = 7176, n_items: int = 10
     # The item table's first entry (the one-hot id) sorts before ctx, the rest after, so the
     # item side is split into two blocks to keep indices ascending.
     tables = dict(u_ptr=u_ptr, u_col=u_col, u_val=u_val, i_ptr=i_ptr, i_col=i_col, i_val=i_val,
-                  ctx_col=ctx_col, n_features=n_features, order=("user", "item", "ctx"))
+                  ctx_col=ctx_col, n_features=n_features, order=("user", "item", "ctx"), n_users=n_users,
+                  n_items=n_items, uf_base=uf_base, n_uf=n_uf, if_base=if_base, n_if=n_real + n_cat)
 
     pop = _popularity(n_items, rng)
     z = rng.normal(size=n_items)
@@ -295,7 +325,7 @@ def make_kuairec_shaped(seed: int = 2024, n_users: int = 7176, n_items: int = 10
         y = (r & o).astype(np.int64)
         ps = theta[i] ** pow_used
         ctx = rng.normal(size=n_rows)
-        fm = {"features": sorted_rows(u, i, ctx), "labels": y, "pscores": ps}
+        fm = {"features": sorted_rows(u, i, ctx), "labels": y, "pscores": ps, "users": u, "items": i, "ctx": ctx}
         mf = ({"features": np.stack([u, i], axis=1), "labels": y.copy(), "pscores": ps.copy()}
               if build_mf else None)
         return fm, mf
