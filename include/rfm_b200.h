@@ -160,6 +160,9 @@ int rfm_fm_set_params(rfm_fm *m, const double *w0, const double *w, const double
 int rfm_fm_get_params(rfm_fm *m, double *w0, double *w, double *V);
 /* FactorizationMachines.predict, src/fm.py:114-133 (+ _sigmoid, src/base.py:63-66). */
 int rfm_fm_predict(rfm_fm *m, const rfm_csr *rows, double *out_scores);
+/* The same scores left in DEVICE memory (double [n_rows]), asynchronously on the context's stream: what
+ * fit(evaluator=...) chains into rfm_ranker_evaluate_dev every epoch (src/fm.py:104-110) without a host round trip. */
+int rfm_fm_predict_dev(rfm_fm *m, const rfm_csr *rows, double *out_scores_dev);
 /* _cross_entropy_loss(labels, predict(rows), pscores), src/base.py:37-61. */
 int rfm_fm_logloss(rfm_fm *m, const rfm_csr *rows, double *out_loss);
 
@@ -243,6 +246,7 @@ int rfm_mf_set_params(rfm_mf *m, const double *P, const double *Q, const double 
 int rfm_mf_get_params(rfm_mf *m, double *P, double *Q, double *b_u, double *b_i);
 /* LogisticMatrixFactorization.predict, src/mf.py:136-170. */
 int rfm_mf_predict(rfm_mf *m, const rfm_pairs *rows, double *out_scores);
+int rfm_mf_predict_dev(rfm_mf *m, const rfm_pairs *rows, double *out_scores_dev);
 int rfm_mf_logloss(rfm_mf *m, const rfm_pairs *rows, double *out_loss);
 /* one reference epoch, src/mf.py:97-124: strictly sequential per-sample SGD semantics
  * (P then Q-with-new-P then b_u, b_i; residual taken first) executed as a wavefront
@@ -278,6 +282,32 @@ enum rfm_rank_col {
 int rfm_ranker_set_user_totals(rfm_ranker *r, const double *totals);
 int rfm_ranker_evaluate(rfm_ranker *r, const double *scores, const int32_t *K, int32_t n_k,
                         double *out_metrics, int32_t *out_item_hits, int64_t *out_top_rows);
+
+/* Device-chained evaluation (the epoch search, utils/search_params.py:79-152, calls
+ * ValEvaluator.evaluate after every epoch, src/fm.py:104-110). rfm_ranker_scores_ptr_dev exposes the ranker's own
+ * score buffer (double [n_rows], original row order) so that rfm_fm_predict_dev / rfm_mf_predict_dev can write
+ * into it; rfm_ranker_evaluate_dev ranks them (scores_dev == NULL or that buffer: in place) and stores the metric
+ * rows of up to 4 ranking positions in history slot `slot` ON THE DEVICE -- no synchronisation, no copy;
+ * rfm_ranker_read_slots returns double[n_slots][n_k][RFM_RANK_NCOLS] after one synchronisation per fit. The
+ * covered-items column is not filled on this path. */
+int rfm_ranker_scores_ptr_dev(rfm_ranker *r, void **scores_dev);
+int rfm_ranker_evaluate_dev(rfm_ranker *r, const double *scores_dev, const int32_t *K, int32_t n_k, int64_t slot,
+                            int64_t max_slots);
+int rfm_ranker_read_slots(rfm_ranker *r, int64_t first_slot, int64_t n_slots, int32_t n_k, double *out_metrics);
+
+/* Full-catalog evaluation on the device (utils/evaluate.py:80-127 on the Cartesian-product frame: every item is a
+ * candidate, the label is the held-out label where one exists and 0 elsewhere, the pscore the item's exposure).
+ * The held-out labels come as a CSR by user (items strictly ascending inside a user). rfm_catalog_eval_run takes
+ * ranked lists as rfm_topk_run / rfm_topk_run_sharded leave them on the device (int32 [n_rows][k_list], best
+ * first, -1 padded; row r is user user_begin + r), looks the labels up, and returns the same metric rows and
+ * per-item hit counts as rfm_ranker_evaluate (sums over the given users: ranks all-reduce them). */
+typedef struct rfm_catalog_eval rfm_catalog_eval;
+int rfm_catalog_eval_create(rfm_ctx *ctx, int64_t n_users, int64_t n_items, const int64_t *label_indptr,
+                            const int32_t *label_items, const double *label_values, const double *item_pscores,
+                            rfm_catalog_eval **out);
+int rfm_catalog_eval_destroy(rfm_catalog_eval *e);
+int rfm_catalog_eval_run(rfm_catalog_eval *e, const int32_t *lists_dev, int32_t k_list, int64_t user_begin,
+                         int64_t n_rows, const int32_t *K, int32_t n_k, double *out_metrics, int32_t *out_item_hits);
 
 /* ---- full-catalog scoring + exact top-K (new capability) ------------
  * score(u, i) = bias + alpha[u] + beta[i] + <A_u, C_i>: MF with A = P, C = Q, alpha = b_u, beta = b_i,

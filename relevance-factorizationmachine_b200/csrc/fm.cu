@@ -1901,6 +1901,17 @@ int check_rows(const rfm_fm *m, const rfm_csr *rows, const char *who) {
   return RFM_OK;
 }
 
+// scores of every row into device memory (asynchronous): the evaluation chain of fit(evaluator=...) never leaves the GPU
+template <typename T>
+int predict_dev_impl(rfm_fm *m, const rfm_csr *rows, double *out_dev) {
+  rfm_ctx *ctx = m->ctx;
+  if (rows->n_rows == 0) return RFM_OK;
+  RowsArgs<T> a = rows_args<T>(m, rows);
+  a.n = rows->n_rows;
+  a.out = out_dev;
+  return launch_rows<T>(ctx, m->nch, MODE_PREDICT, false, a, grid_for(ctx, ceil_div(rows->n_rows, units_per_block(m->nch)), 6), rows->factored);
+}
+
 template <typename T>
 int predict_impl(rfm_fm *m, const rfm_csr *rows, double *out_host) {
   rfm_ctx *ctx = m->ctx;
@@ -1942,6 +1953,14 @@ int rfm_fm_predict(rfm_fm *m, const rfm_csr *rows, double *out_scores) {
   RFM_REQUIRE(out_scores || rows->n_rows == 0, "rfm_fm_predict: out_scores is NULL");
   RFM_CUDA(cudaSetDevice(m->ctx->device));
   return m->dtype == RFM_F64 ? predict_impl<double>(m, rows, out_scores) : predict_impl<float>(m, rows, out_scores);
+}
+
+int rfm_fm_predict_dev(rfm_fm *m, const rfm_csr *rows, double *out_scores_dev) {
+  RFM_TRY(check_rows(m, rows, "rfm_fm_predict_dev"));
+  RFM_REQUIRE(out_scores_dev || rows->n_rows == 0, "rfm_fm_predict_dev: out_scores_dev is NULL");
+  RFM_CUDA(cudaSetDevice(m->ctx->device));
+  return m->dtype == RFM_F64 ? predict_dev_impl<double>(m, rows, out_scores_dev)
+                             : predict_dev_impl<float>(m, rows, out_scores_dev);
 }
 
 int rfm_fm_logloss(rfm_fm *m, const rfm_csr *rows, double *out_loss) {

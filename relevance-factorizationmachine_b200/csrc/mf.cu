@@ -539,6 +539,29 @@ int rfm_mf_get_params(rfm_mf *m, double *P, double *Q, double *b_u, double *b_i)
   return RFM_OK;
 }
 
+static int mf_predict_to(rfm_mf *m, const rfm_pairs *rows, double *out_dev) {
+  rfm_ctx *ctx = m->ctx;
+  const int grid = grid_for(ctx, ceil_div(rows->n_rows, MF_WARPS), 6);
+  if (m->dtype == RFM_F64) {
+    MfArgs<double> a = mf_args<double>(m, rows);
+    a.n = rows->n_rows;
+    a.out = out_dev;
+    MF_DISPATCH_NCH(m->nch, {
+      auto mf_rows_predict = mf_rows_kernel<double, NCH, 0>;
+      RFM_LAUNCH(ctx, mf_rows_predict, grid, MF_THREADS, 0, a);
+    });
+  } else {
+    MfArgs<float> a = mf_args<float>(m, rows);
+    a.n = rows->n_rows;
+    a.out = out_dev;
+    MF_DISPATCH_NCH(m->nch, {
+      auto mf_rows_predict = mf_rows_kernel<float, NCH, 0>;
+      RFM_LAUNCH(ctx, mf_rows_predict, grid, MF_THREADS, 0, a);
+    });
+  }
+  return RFM_OK;
+}
+
 int rfm_mf_predict(rfm_mf *m, const rfm_pairs *rows, double *out_scores) {
   RFM_TRY(check_pairs(m, rows, "rfm_mf_predict"));
   if (rows->n_rows == 0) return RFM_OK;
@@ -547,27 +570,19 @@ int rfm_mf_predict(rfm_mf *m, const rfm_pairs *rows, double *out_scores) {
   RFM_CUDA(cudaSetDevice(ctx->device));
   DevBuf<double> out;
   RFM_TRY(out.alloc(rows->n_rows));
-  const int grid = grid_for(ctx, ceil_div(rows->n_rows, MF_WARPS), 6);
-  if (m->dtype == RFM_F64) {
-    MfArgs<double> a = mf_args<double>(m, rows);
-    a.n = rows->n_rows;
-    a.out = out.p;
-    MF_DISPATCH_NCH(m->nch, {
-      auto mf_rows_predict = mf_rows_kernel<double, NCH, 0>;
-      RFM_LAUNCH(ctx, mf_rows_predict, grid, MF_THREADS, 0, a);
-    });
-  } else {
-    MfArgs<float> a = mf_args<float>(m, rows);
-    a.n = rows->n_rows;
-    a.out = out.p;
-    MF_DISPATCH_NCH(m->nch, {
-      auto mf_rows_predict = mf_rows_kernel<float, NCH, 0>;
-      RFM_LAUNCH(ctx, mf_rows_predict, grid, MF_THREADS, 0, a);
-    });
-  }
+  RFM_TRY(mf_predict_to(m, rows, out.p));
   RFM_CUDA(cudaMemcpyAsync(out_scores, out.p, (size_t)rows->n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
+}
+
+// the same scores left in device memory, asynchronously (the evaluation chain of fit(evaluator=...))
+int rfm_mf_predict_dev(rfm_mf *m, const rfm_pairs *rows, double *out_scores_dev) {
+  RFM_TRY(check_pairs(m, rows, "rfm_mf_predict_dev"));
+  if (rows->n_rows == 0) return RFM_OK;
+  RFM_REQUIRE(out_scores_dev, "rfm_mf_predict_dev: out_scores_dev is NULL");
+  RFM_CUDA(cudaSetDevice(m->ctx->device));
+  return mf_predict_to(m, rows, out_scores_dev);
 }
 
 int rfm_mf_logloss(rfm_mf *m, const rfm_pairs *rows, double *out_loss) {

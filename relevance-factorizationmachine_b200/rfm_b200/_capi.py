@@ -54,6 +54,7 @@ _SIGNATURES = {
     "rfm_fm_set_params": ([_P, _P, _P, _P], c_int),
     "rfm_fm_get_params": ([_P, _P, _P, _P], c_int),
     "rfm_fm_predict": ([_P, _P, _P], c_int),
+    "rfm_fm_predict_dev": ([_P, _P, _P], c_int),
     "rfm_fm_logloss": ([_P, _P, POINTER(c_double)], c_int),
     "rfm_fm_trainer_create": ([_P, _P, _P, c_int64, c_int64, POINTER(_P)], c_int),
     "rfm_fm_trainer_destroy": ([_P], c_int),
@@ -80,6 +81,7 @@ _SIGNATURES = {
     "rfm_mf_set_params": ([_P, _P, _P, _P, _P, c_double], c_int),
     "rfm_mf_get_params": ([_P, _P, _P, _P, _P], c_int),
     "rfm_mf_predict": ([_P, _P, _P], c_int),
+    "rfm_mf_predict_dev": ([_P, _P, _P], c_int),
     "rfm_mf_logloss": ([_P, _P, POINTER(c_double)], c_int),
     "rfm_mf_train_epoch": ([_P, _P, _P, _P, c_int64, c_double, c_double, POINTER(c_double), POINTER(c_double)],
                            c_int),
@@ -98,6 +100,12 @@ _SIGNATURES = {
     "rfm_ranker_num_users": ([_P, POINTER(c_int64)], c_int),
     "rfm_ranker_set_user_totals": ([_P, _P], c_int),
     "rfm_ranker_evaluate": ([_P, _P, _P, c_int32, _P, _P, _P], c_int),
+    "rfm_ranker_scores_ptr_dev": ([_P, POINTER(_P)], c_int),
+    "rfm_ranker_evaluate_dev": ([_P, _P, _P, c_int32, c_int64, c_int64], c_int),
+    "rfm_ranker_read_slots": ([_P, c_int64, c_int64, c_int32, _P], c_int),
+    "rfm_catalog_eval_create": ([_P, c_int64, c_int64, _P, _P, _P, _P, POINTER(_P)], c_int),
+    "rfm_catalog_eval_destroy": ([_P], c_int),
+    "rfm_catalog_eval_run": ([_P, _P, c_int32, c_int64, c_int64, _P, c_int32, _P, _P], c_int),
 }
 
 # every symbol include/rfm_b200.h declares (tests check the library exports all of them)

@@ -43,6 +43,24 @@ class _Ranker(_capi._Handle):
         check(lib().rfm_ranker_num_users(self.handle, byref(n)))
         self.n_users = n.value
 
+    def scores_ptr(self) -> int:
+        """Device address of the ranker's score buffer (double [n_rows], frame order)."""
+        from ctypes import c_void_p
+        p = c_void_p()
+        check(lib().rfm_ranker_scores_ptr_dev(self.handle, byref(p)))
+        return p.value
+
+    def evaluate_dev(self, K, slot: int, max_slots: int):
+        """Rank the scores already in the device buffer; metric rows go to history slot ``slot`` on the device
+        (asynchronous: no copy, no synchronisation)."""
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        check(lib().rfm_ranker_evaluate_dev(self.handle, None, ptr(K), len(K), slot, max_slots))
+
+    def read_slots(self, first: int, n: int, n_k: int) -> np.ndarray:
+        out = np.zeros((n, n_k, RANK_NCOLS))
+        check(lib().rfm_ranker_read_slots(self.handle, first, n, n_k, ptr(out)))
+        return out
+
     def evaluate(self, scores, K, want_hits=False, want_top=False):
         scores = _capi.as_array(scores, np.float64)
         if scores.shape[0] != self.n_rows:
@@ -182,6 +200,20 @@ class ValEvaluator(_BaseEvaluator):
         kept = metrics[0, RANK_COLS["USERS"]]
         return metrics[0, RANK_COLS["IPSDCG_SUM"]] / kept if kept else np.nan
 
+    # ---- device-chained use inside fit(evaluator=...) ------------------------------
+    def device_chain(self, estimator: str, device: int = 0):
+        """The ranker a model's ``fit`` writes its per-epoch scores into (``rfm_*_predict_dev`` ->
+        ``rfm_ranker_evaluate_dev``): the epoch loop of ``src/fm.py:104-110`` without a host round trip."""
+        return self._ranker("pscore" if estimator == "IPS" else "ones_pscore", device=device)
+
+    def chain_results(self, ranker, n_epochs: int) -> list:
+        """IPS-DCG@k of every epoch (``np.mean`` over the kept users, ``utils/evaluate.py:207``) read back once."""
+        rows = ranker.read_slots(0, n_epochs, 1)[:, 0, :]
+        kept = rows[:, RANK_COLS["USERS"]]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            vals = np.where(kept > 0, rows[:, RANK_COLS["IPSDCG_SUM"]] / kept, np.nan)
+        return [float(v) for v in vals]
+
     def _group_by_user_data(self, y_scores: np.ndarray, estimator: str) -> Dict[str, Dict[str, np.ndarray]]:
         """``utils/evaluate.py:209-239`` (host helper; ``evaluate`` itself groups once on the device)."""
         return self._grouped(y_scores, "pscore" if estimator == "IPS" else "ones_pscore")
@@ -218,30 +250,21 @@ class FullCatalogEvaluator:
         items = _column(self.interaction_df, "item").astype(np.int64)
         labels = _column(self.interaction_df, "label").astype(np.float64)
         self._labels = csr_matrix((labels, (users, items)), shape=(self.n_users, self.n_items))
+        self._labels.sum_duplicates()
+        self._labels.sort_indices()
         self._totals = np.asarray(self._labels.sum(axis=1)).ravel().astype(np.float64)
         self.item_pscores = _capi.as_array(self.item_pscores, np.float64)
         self.last_stats = {}
+        self._dev = {}
 
-    def evaluate(self, scorer, mode: str = "tensor") -> defaultdict:
-        """``scorer`` is a ``TopKScorer`` (see ``rfm_b200.score.fm_factors`` / ``mf_factors``)."""
-        k_max = int(max(self.K))
-        items, scores = scorer.topk(k_max, mode=mode, copy=False)       # consumed before the next call
-        self.last_stats = dict(scorer.last_stats)
-        # reduced frame: every user's top rows, worst first so that the ranker's tie rule (later row first)
-        # reproduces the Cartesian frame's order (larger item id first among exact ties)
-        items = items[:, ::-1]
-        scores = scores[:, ::-1]
-        valid = (items >= 0).ravel()
-        u = np.repeat(np.arange(self.n_users, dtype=np.int64), k_max)[valid]
-        it = items.ravel()[valid].astype(np.int64)
-        lab = np.asarray(self._labels[u, it]).ravel()
-        ranker = _Ranker(scorer.ctx, u, it, lab, self.item_pscores[it], self.n_items)
-        present = np.unique(u)                                      # users in ascending order, as the ranker groups them
-        totals = np.ascontiguousarray(self._totals[present])
-        check(lib().rfm_ranker_set_user_totals(ranker.handle, ptr(totals)))
-        need_hits = any(m in self.metric_names for m in ("CatalogCoverage", "Gini"))
-        metrics, hits, _ = ranker.evaluate(scores.ravel()[valid], list(self.K), want_hits=need_hits)
-        ranker.close()
+    def _device_state(self, ctx):
+        """Held-out labels (CSR by user) and item exposures, uploaded once per context."""
+        key = id(ctx)
+        if key not in self._dev:
+            self._dev[key] = _CatalogEval(ctx, self.n_users, self.n_items, self._labels, self.item_pscores)
+        return self._dev[key]
+
+    def _results(self, metrics, hits) -> defaultdict:
         results = defaultdict(list)
         for j, _k in enumerate(self.K):
             row = metrics[j]
@@ -258,3 +281,64 @@ class FullCatalogEvaluator:
                     col = {"DCG": "DCG_SUM", "Recall": "RECALL_SUM", "MAP": "MAP_SUM"}[name]
                     results[name].append(row[RANK_COLS[col]] / kept if kept else np.nan)
         return results
+
+    def evaluate(self, scorer, mode: str = "tensor", env=None) -> defaultdict:
+        """``scorer`` is a ``TopKScorer`` (see ``rfm_b200.score.fm_factors`` / ``mf_factors``). The ranked lists
+        never leave the device: top-K -> label look-up -> metric reductions -> one small read-back
+        (``rfm_catalog_eval_run``). With ``env`` (a ``rfm_b200.dist.DistEnv``) the catalog is item-sharded over
+        the ranks, every rank reduces the users it owns after the merge, and the partial sums and per-item hit
+        counts are all-reduced; every rank returns the same metrics."""
+        from ctypes import c_int64, c_void_p
+        k_max = int(max(self.K))
+        if k_max > scorer.n_items:
+            k_max = scorer.n_items
+        state = self._device_state(scorer.ctx)
+        K = np.ascontiguousarray([int(k) for k in self.K], dtype=np.int32)     # lists shorter than k: ME@k is nan
+        need_hits = any(m in self.metric_names for m in ("CatalogCoverage", "Gini"))
+        sharded = env is not None and env.world > 1
+        if sharded:
+            from . import dist as rdist
+            rdist.connect_scorer(scorer, env, k_max)
+            rng, stats = (c_int64 * 2)(), (c_int64 * 4)()
+            check(lib().rfm_topk_run_sharded(scorer.handle, k_max, 0 if mode == "tensor" else 1, None, None, rng, stats))
+            user_begin, n_rows = rng[0], rng[1] - rng[0]
+        else:
+            stats = (c_int64 * 4)()
+            check(lib().rfm_topk_run(scorer.handle, k_max, 0 if mode == "tensor" else 1, 0, scorer.n_items, None, None,
+                                     stats))
+            user_begin, n_rows = 0, self.n_users
+        scorer.last_stats = {"tensor_core_path": bool(stats[0]), "users_ranked_exactly": int(stats[1]),
+                             "candidates": int(stats[2]), "sample_stride": int(stats[3])}
+        self.last_stats = dict(scorer.last_stats)
+        ip, sp = c_void_p(), c_void_p()
+        check(lib().rfm_topk_result_ptr_dev(scorer.handle, byref(ip), byref(sp)))
+        metrics = np.zeros((len(K), RANK_NCOLS))
+        hits = np.zeros((len(K), self.n_items), dtype=np.int32) if (need_hits or sharded) else None
+        check(lib().rfm_catalog_eval_run(state.handle, ip, k_max, user_begin, n_rows, ptr(K), len(K), ptr(metrics),
+                                         ptr(hits)))
+        if sharded:
+            torch = env.torch
+            dev = "cuda:%d" % env.device
+            tm = torch.from_numpy(metrics).to(dev)
+            th = torch.from_numpy(hits.astype(np.int64)).to(dev)
+            env.dist.all_reduce(tm)                      # sums of per-user terms and user counts
+            env.dist.all_reduce(th)                      # per-item hit counts (coverage = non-zeros, Gini)
+            metrics = tm.cpu().numpy()
+            hits = th.cpu().numpy()
+            metrics[:, RANK_COLS["COVERED"]] = (hits != 0).sum(axis=1)
+        return self._results(metrics, hits)
+
+
+class _CatalogEval(_capi._Handle):
+    _destroy = "rfm_catalog_eval_destroy"
+
+    def __init__(self, ctx, n_users, n_items, labels_csr, item_pscores):
+        super().__init__()
+        indptr = _capi.as_array(labels_csr.indptr, np.int64)
+        items = _capi.as_array(labels_csr.indices, np.int32)
+        vals = _capi.as_array(labels_csr.data, np.float64)
+        ps = _capi.as_array(item_pscores, np.float64)
+        if ps.shape != (n_items,):
+            raise ValueError("item_pscores must have one entry per item")
+        check(lib().rfm_catalog_eval_create(ctx.handle, n_users, n_items, ptr(indptr), ptr(items), ptr(vals), ptr(ps),
+                                            byref(self.handle)))

@@ -22,7 +22,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import check, lib, ptr
-from .base import PointwiseBaseRecommender
+from .base import EvalChain, PointwiseBaseRecommender
 from .optimizer import SGD, Adam
 from .sampler import LegacyBatchPrefetcher
 
@@ -182,9 +182,11 @@ class FactorizationMachines(PointwiseBaseRecommender):
         phases = {"upload": self._upload_seconds, "trainer_create": time.perf_counter() - t_phase}
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
-        eval_rows = None
+        eval_rows, chain = None, None
         if self.evaluator is not None:
             eval_rows = self._rows(self.evaluator.features[self.model_name])
+            if EvalChain.supported(self.evaluator):
+                chain = EvalChain(self.evaluator, self.estimator, eval_rows.n_rows, self.n_epochs, self.device)
         it = epochs
         if self.progress:
             from tqdm import tqdm
@@ -206,12 +208,17 @@ class FactorizationMachines(PointwiseBaseRecommender):
                 else:
                     check(lib().rfm_fm_train_epoch_sampled(trainer.handle, self.seed & 0xFFFFFFFF, epoch,
                                                            self.batch_size, self.lr, epoch))
-                if eval_rows is not None:
+                if chain is not None:           # predict -> rank -> metric slot, all on the device, no synchronisation
+                    check(lib().rfm_fm_predict_dev(self._dev.handle, eval_rows.handle, c_void_p(chain.scores_ptr)))
+                    chain.after_epoch(epoch)
+                elif eval_rows is not None:
                     scores = np.empty(eval_rows.n_rows)
                     check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
                     self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
             phases["enqueue_epochs"] = time.perf_counter() - t_phase
             t_phase = time.perf_counter()
+            if chain is not None:
+                self.val_metrics.extend(chain.finish(self.n_epochs))
             train_loss = np.empty(self.n_epochs)
             val_loss = np.empty(self.n_epochs)
             check(lib().rfm_fm_trainer_losses(trainer.handle, 0, self.n_epochs, ptr(train_loss), ptr(val_loss)))
@@ -252,6 +259,9 @@ class FactorizationMachines(PointwiseBaseRecommender):
         torch = env.torch
         hist = torch.zeros((max(self.n_epochs, 1), 2), dtype=torch.float64, device=dp.loss_tensor.device)
         eval_rows = self._rows(self.evaluator.features[self.model_name]) if self.evaluator is not None else None
+        chain = None
+        if eval_rows is not None and EvalChain.supported(self.evaluator):
+            chain = EvalChain(self.evaluator, self.estimator, eval_rows.n_rows, self.n_epochs, self.device)
         launches0 = ctx.launch_count()
         t_phase = time.perf_counter()
         try:
@@ -259,12 +269,17 @@ class FactorizationMachines(PointwiseBaseRecommender):
                 prev = dp.step(epoch)                       # global loss sums of the previous epoch
                 if prev is not None:
                     hist[epoch - 1].copy_(prev)
-                if eval_rows is not None:
+                if chain is not None:
+                    check(lib().rfm_fm_predict_dev(self._dev.handle, eval_rows.handle, c_void_p(chain.scores_ptr)))
+                    chain.after_epoch(epoch)
+                elif eval_rows is not None:
                     scores = np.empty(eval_rows.n_rows)
                     check(lib().rfm_fm_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
                     self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
             phases["enqueue_epochs"] = time.perf_counter() - t_phase
             t_phase = time.perf_counter()
+            if chain is not None:
+                self.val_metrics.extend(chain.finish(self.n_epochs))
             last = dp.flush()
             if last is not None:
                 hist[self.n_epochs - 1].copy_(last)

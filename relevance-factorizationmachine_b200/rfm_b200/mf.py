@@ -9,7 +9,7 @@ sequential SGD of ``src/mf.py:97-108`` runs on the device as a wavefront schedul
 from __future__ import annotations
 
 import weakref
-from ctypes import byref, c_double
+from ctypes import byref, c_double, c_void_p
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import check, lib, ptr
-from .base import PointwiseBaseRecommender
+from .base import EvalChain, PointwiseBaseRecommender
 from .optimizer import SGD
 from .sampler import LegacyBatchPrefetcher
 
@@ -150,6 +150,9 @@ class LogisticMatrixFactorization(PointwiseBaseRecommender):
         val_rows = self._rows(val["features"], val["labels"], val["pscores"])
         self.sync_to_device()
         eval_rows = self._rows(self.evaluator.features[self.model_name]) if self.evaluator is not None else None
+        chain = None
+        if eval_rows is not None and EvalChain.supported(self.evaluator):
+            chain = EvalChain(self.evaluator, self.estimator, eval_rows.n_rows, self.n_epochs, self.device)
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs)
         it = epochs
@@ -160,16 +163,21 @@ class LogisticMatrixFactorization(PointwiseBaseRecommender):
         tl, vl = c_double(), c_double()
         launches0 = ctx.launch_count()
         try:
-            for _ in it:
+            for epoch in it:
                 idx = prefetch.next()
                 check(lib().rfm_mf_train_epoch(self._dev.handle, train_rows.handle, val_rows.handle, ptr(idx),
                                                self.batch_size, self.lr, self.reg, byref(tl), byref(vl)))
                 train_loss.append(tl.value)
                 val_loss.append(vl.value)
-                if eval_rows is not None:
+                if chain is not None:           # predict -> rank -> metric slot on the device (no read-back per epoch)
+                    check(lib().rfm_mf_predict_dev(self._dev.handle, eval_rows.handle, c_void_p(chain.scores_ptr)))
+                    chain.after_epoch(epoch)
+                elif eval_rows is not None:
                     scores = np.empty(eval_rows.n_rows)
                     check(lib().rfm_mf_predict(self._dev.handle, eval_rows.handle, ptr(scores)))
                     self.val_metrics.append(self.evaluator.evaluate(y_scores=scores, estimator=self.estimator))
+            if chain is not None:
+                self.val_metrics.extend(chain.finish(self.n_epochs))
         finally:
             prefetch.close()
         self.last_fit_stats = {"gpu_launches": ctx.launch_count() - launches0}

@@ -7,7 +7,7 @@ the float32 perf mode is checked at the north-star tolerance where the arithmeti
 import numpy as np
 import pytest
 
-from conftest import load_golden, golden_csr
+from conftest import load_golden, golden_csr, golden_frame
 from oracle import fm_oracle, sampler_oracle
 
 pytestmark = pytest.mark.gpu
@@ -225,3 +225,69 @@ def test_l2_zero_dense_sgd_equals_the_reference_step():
     tl, vl = m.fit(train, val)
     np.testing.assert_allclose(tl, g["train_loss"], rtol=1e-9)
     np.testing.assert_allclose(m.V(), g["V"], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["coat_fm_ips_alpha2", "coat_fm_ips_alpha01", "kuairec_small_fm_ips",
+                                  "kuairec_small_fm_ips_alpha01"])
+def test_val_metrics_every_epoch_match_reference(name):
+    """The evaluator hook inside fit (src/fm.py:104-110): every FM golden carries the reference's per-epoch IPS-DCG@5.
+    With this package's ValEvaluator the chain predict -> rank -> metric slot stays on the device; an evaluator object
+    the chain does not know (here: a thin wrapper, standing in for the reference's own class) takes the host flow.
+    Both must reproduce the reference."""
+    from rfm_b200.evaluate import ValEvaluator
+    from rfm_b200.fm import FactorizationMachines
+    g = load_golden(name)
+    train = {"features": golden_csr(g, "train"), "labels": g["train_labels"], "pscores": g["train_pscores"]}
+    val = {"features": golden_csr(g, "val"), "labels": g["val_labels"], "pscores": g["val_pscores"]}
+
+    class Foreign:                       # no device_chain attribute: fit falls back to the reference's host flow
+        def __init__(self, inner):
+            self.inner, self.features, self.calls = inner, inner.features, 0
+
+        def evaluate(self, y_scores, estimator):
+            self.calls += 1
+            return self.inner.evaluate(y_scores=y_scores, estimator=estimator)
+
+    results = []
+    for wrap in (False, True):
+        ev = ValEvaluator(interaction_df=golden_frame(g), features={"FM": golden_csr(g, "test")}, k=5,
+                          metric_name="DCG")
+        ev = Foreign(ev) if wrap else ev
+        m = FactorizationMachines(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]),
+                                  lr=float(g["lr"]), batch_size=int(g["B"]), seed=int(g["seed"]),
+                                  n_features=train["features"].shape[1], alpha=float(g["alpha"]), evaluator=ev)
+        tl, _ = m.fit(train, val)
+        assert m.model_name == "FM" and len(m.val_metrics) == int(g["n_epochs"])
+        np.testing.assert_allclose(tl, g["train_loss"], rtol=1e-9)
+        if wrap:
+            assert ev.calls == int(g["n_epochs"])
+        results.append(np.array(m.val_metrics))
+    np.testing.assert_array_equal(results[0], results[1])          # device chain == host flow, bit for bit
+    frame = golden_frame(g)
+    pairs = np.stack([frame["user"], frame["item"]], axis=1)
+    if np.unique(pairs, axis=0).shape[0] == pairs.shape[0]:
+        np.testing.assert_allclose(results[0], g["val_metrics"], rtol=1e-9)
+        return
+    # The KuaiRec-shaped frame holds some (user, item) pairs twice: identical rows, identical scores, different labels.
+    # The reference orders such exact ties by NumPy's unstable default sort (build dependent, SURVEY.md F10); this
+    # build orders them canonically. What can be pinned: (1) the canonical value equals the oracle's on the final
+    # scores; (2) the reference's value lies between the worst and the best tie-breaking of the same scores.
+    from oracle import metrics_oracle
+    scores = m.predict(X=golden_csr(g, "test"))
+    np.testing.assert_allclose(results[0][-1], metrics_oracle.val_evaluate(frame, scores, 5, "IPS"), rtol=1e-12)
+    lo_hi = []
+    for sign in (1.0, -1.0):                 # ties ordered by label ascending / descending
+        vals = []
+        uniq, order, ptr = metrics_oracle.group_by_user(frame["user"])
+        for gi in range(len(uniq)):
+            rows = order[ptr[gi]: ptr[gi + 1]]
+            y = frame["label"][rows]
+            if y.sum() == 0:
+                continue
+            rank = np.lexsort((sign * y / frame["pscore"][rows], -scores[rows]))
+            vals.append(metrics_oracle.ips_dcg_at_k(y[rank], 5, frame["pscore"][rows][rank]))
+        lo_hi.append(float(np.mean(vals)))
+    lo, hi = min(lo_hi), max(lo_hi)
+    assert lo < hi                                                   # the ties do matter here
+    assert lo - 1e-9 <= g["val_metrics"][-1] <= hi + 1e-9
+    assert lo - 1e-9 <= results[0][-1] <= hi + 1e-9

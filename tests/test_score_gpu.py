@@ -190,3 +190,38 @@ def test_full_catalog_evaluator_equals_test_evaluator_on_cartesian_frame():
     for m in ["ME"] + sorted(used):
         np.testing.assert_allclose(res[m], ref[m], rtol=1e-12, err_msg=m)
     np.testing.assert_array_equal(np.array(res["CatalogCoverage"]), np.array(ref["CatalogCoverage"]))
+
+
+def test_full_catalog_evaluator_large_k_and_short_catalog():
+    """K up to 100 (the stress configuration's top-100), a catalog shorter than max(K) (ME@k is nan there), users
+    without any held-out positive, duplicate held-out pairs (summed like scipy's csr_matrix)."""
+    from oracle import metrics_oracle
+    from rfm_b200.evaluate import FullCatalogEvaluator
+    from rfm_b200.score import TopKScorer
+    rng = np.random.default_rng(18)
+    for U, I, K in ((70, 600, [1, 10, 50, 100]), (40, 30, [1, 9, 50])):
+        k = 32
+        A, C = rng.normal(size=(U, k)) * 0.4, rng.normal(size=(I, k)) * 0.4
+        beta = rng.normal(size=I) * 0.2
+        hu = np.repeat(np.arange(U), 8)
+        hi = rng.integers(0, I, hu.size)                         # duplicates happen
+        hl = (rng.random(hu.size) < 0.5).astype(np.int64)
+        hl[hu % 5 == 0] = 0
+        theta = rng.uniform(0.1, 1.0, size=I)
+        used = {"DCG", "CatalogCoverage", "Recall", "MAP", "Gini"}
+        ev = FullCatalogEvaluator({"user": hu, "item": hi, "label": hl}, theta, K, used, U, I)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = ev.evaluate(TopKScorer(A, C, None, beta, 0.0))
+        uu, ii = np.meshgrid(np.arange(U), np.arange(I), indexing="ij")
+        lab = np.zeros((U, I))
+        np.add.at(lab, (hu, hi), hl)
+        frame = {"user": uu.ravel(), "item": ii.ravel(), "label": lab.ravel(), "pscore": theta[ii.ravel()],
+                 "ones_pscore": np.ones(U * I)}
+        S = (A @ C.T) + beta[None, :]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = metrics_oracle.test_evaluate(frame, S.ravel(), K, used, I)
+        for m in ["ME"] + sorted(used):
+            np.testing.assert_allclose(res[m], ref[m], rtol=1e-12, equal_nan=True, err_msg="%s U=%d I=%d" % (m, U, I))
