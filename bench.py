@@ -1,28 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- train interactions/s of the fused IPS-FM epoch on synthetic KuaiRec-big-shaped data.
+"""bench.py -- train interactions/s of the fused IPS-FM epoch on synthetic KuaiRec-big-shaped data, and the rest of
+BASELINE.json's metric (scored user-item pairs/s) next to it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one reference epoch (src/fm.py:71-102): one minibatch of B interactions through
-forward, IPS residual, the simultaneous w0/w/V update, the post-update batch loss and the val loss.
+A "step" is one reference epoch (src/fm.py:71-102): one minibatch of B interactions through forward, IPS residual,
+the simultaneous w0/w/V update, the post-update batch loss and the val loss.
 
-ours:       value     = K*B*N / device time of K steps (CUDA events), dataset resident in HBM,
-                        batches drawn on the device (Feistel sampler, perf mode), float64.
-            e2e       = the same metric through the public API, FactorizationMachines.fit(train, val)
-                        on HOST (pinned) arrays: dataset upload, K epochs, loss read-back, parameter
-                        download, wall clock around the call.
-            roofline  = dominant kernel's algorithmic bytes / its CUDA-event time (separate profiled
-                        pass of the same steps), against MEASURED_PEAKS.json's HBM copy bandwidth.
-            cpu_baseline = the CPU oracle (NumPy/SciPy port of the reference step + the reference's
-                        own sampler) on a bounded sample of the same workload, on every host core
-                        (each epoch's batch split over forked workers; single-core figure alongside).
-            scoring   = scored user-item pairs/s of full-catalog top-K (second half of the metric),
-                        with its tensor-core roofline.
-            clocks    = nvidia-smi samples from the warm-up to a run of identical untimed steps.
-reference:  the CPU oracle port on every host core timed alone, same config / metric / unit (the
-            reference is pure Python and cannot travel to the GPU box).
-Under torchrun (N > 1): one rank per GPU, B per GPU (weak scaling), the library's NVLink exchange
-kernel between ranks (RFM_DP_EXCHANGE=nccl for the torch.distributed all-reduce), time = max over ranks.
+ours:
+  value        K*B*N / device time of K steps (CUDA events), rows resident in HBM in the factored form (SURVEY 8 f3;
+               config.input_format), batches drawn on the device (Feistel sampler, perf mode), float64.
+  e2e          the same metric through the public API on HOST (pinned) arrays, FactorizationMachines.fit(train, val):
+               row upload, K epochs, loss read-back, parameter download, wall clock around the call. Headline:
+               factored input + device sampler; e2e.hstacked_csr = the reference's own stacked-CSR input;
+               e2e.legacy_sampler = the reference's batch order (RandomState(epoch) shuffle, host-bound by design);
+               e2e.scoring / e2e.mf = the same for full-catalog ranking and for MF.
+  roofline     frac = SURVEY 8(d) whole-step algorithmic bytes / step time / measured HBM copy peak, l2_assisted says
+               whether the gathers are served by L2 at this shape (they are at configs[2]); roofline.stress = the same
+               fraction on the configs[4]-shaped stress rows where nothing fits L2 (the HBM claim);
+               roofline.scoring = tensor-core fractions of the scoring passes; per-kernel CUDA-event times alongside.
+  cpu_baseline the CPU oracle (NumPy/SciPy port of the reference step + the reference's own sampler) on a bounded
+               sample of the same workload, on every host core; cpu_baseline.scoring / .mf likewise.
+  clocks       nvidia-smi samples from the warm-up to a run of identical untimed steps.
+reference:     the CPU oracle port on every host core timed alone, same config / metric / unit (the reference is pure
+               Python and cannot travel to the GPU box).
+Under torchrun (N > 1): one rank per GPU, B per GPU (weak scaling), the library's NVLink exchange kernel between
+ranks; before anything is timed the kuairec_small golden is fitted data-parallel with both samplers and checked
+(dp_parity; a mismatch fails the run); time = max over ranks; scoring is item-sharded over the ranks.
 """
 import argparse
 import json
@@ -57,69 +61,74 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="interactions per step per GPU")
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--rows", type=int, default=N_TRAIN, help="train interactions in the job")
+    ap.add_argument("--input", default="csr", choices=["factored", "csr"],
+                    help="row format RESIDENT IN HBM for the device-timed steps (value): csr = the reference's stacked "
+                         "matrix, factored = user table + item table + (user, item, ctx) records (SURVEY 8 f3); the "
+                         "other one is timed next to it (roofline.other_input_format)")
+    ap.add_argument("--e2e-input", default="factored", choices=["factored", "csr"],
+                    help="row format the headline e2e uploads from host memory; the other one is e2e.hstacked_csr / "
+                         "e2e.factored")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-stress", action="store_true")
+    ap.add_argument("--no-mf", action="store_true")
+    ap.add_argument("--stress-rows", type=int, default=20_000_000)
     ap.add_argument("--workload", default="kuairec_big", choices=["kuairec_big", "stress"],
-                    help="kuairec_big = BASELINE configs[2] (the headline); stress = configs[4]-shaped: 1M users x 1M "
-                         "items, k=128, 8 non-zeros per row, parameter table far larger than L2")
+                    help="kuairec_big = BASELINE configs[2] (the headline; the stress shape runs as a section of it); "
+                         "stress = only the configs[4]-shaped section: 1M users x 1M items, k=128, 8 non-zeros per row")
     return ap.parse_args()
 
 
 def workload_config(args, world):
     return {
-        "workload": ("IPS-FM, synthetic KuaiRec big_matrix shape (BASELINE.json configs[2])" if WORKLOAD == "kuairec_big"
-                     else "IPS-FM stress, BASELINE.json configs[4] shape on one GPU's share: 1M users x 1M items, "
-                          "k=128, 8 non-zeros per row"),
+        "workload": "IPS-FM, synthetic KuaiRec big_matrix shape (BASELINE.json configs[2])",
         "n_users": N_USERS, "n_items": N_ITEMS, "train_interactions": args.rows, "val_rows": N_VAL,
         "n_factors": K_FACTORS, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
         "lr": LR, "parallelism": "dp%d" % world if world > 1 else "single",
         "l2": "inputs larger than L2: each step gathers a fresh random batch from the resident "
-              "train CSR; the parameter table V is legitimately L2-resident across steps",
+              "train rows; the parameter table V is legitimately L2-resident across steps",
     }
 
 
+STRESS_USERS = STRESS_ITEMS = 1_000_000
+STRESS_K = 128
+STRESS_GROUPS = (4, 8, 12, 6, 10, 20)
+
+
 def make_stress_data(rows, seed):
-    """configs[4]-shaped rows: [user id | 3 user-side one-hots | item id | 3 item-side one-hots], m = 8,
-    n = 2,000,000 + 60 columns. Sorted columns per row, float64 values, vectorised."""
+    """configs[4]-shaped rows, [user id | 3 user-side one-hots | item id | 3 item-side one-hots] (m = 8,
+    n = 2,000,000 + 60 columns), in the factored form: two 1 M-row side tables and one (user, item) pair per row."""
     from scipy.sparse import csr_matrix
-    from rfm_b200.synth import SyntheticLog
+    from rfm_b200.factored import FactoredFeatures
     rng = np.random.default_rng(seed)
-    U = I = 1_000_000
-    groups = (4, 8, 12, 6, 10, 20)
+    U, I = STRESS_USERS, STRESS_ITEMS
     t0 = time.perf_counter()
 
-    def rows_of(n_rows):
-        u = rng.integers(0, U, n_rows)
-        i = rng.integers(0, I, n_rows)
-        cols = np.empty((n_rows, 8), dtype=np.int32)
-        cols[:, 0] = u
-        off = U
-        for g_idx in range(3):                       # user-side one-hots are a function of the user
-            cols[:, 1 + g_idx] = off + (u * (g_idx + 3) + g_idx) % groups[g_idx]
-            off += groups[g_idx]
-        cols[:, 4] = off + i
-        off += I
-        for g_idx in range(3, 6):
-            cols[:, 1 + g_idx + 1] = off + (i * (g_idx + 2) + g_idx) % groups[g_idx]
-            off += groups[g_idx]
-        X = csr_matrix((np.ones(n_rows * 8), cols.ravel(), np.arange(0, 8 * n_rows + 1, 8, dtype=np.int64)
-                        if n_rows * 8 >= 2**31 else np.arange(0, 8 * n_rows + 1, 8, dtype=np.int32)),
-                       shape=(n_rows, off))
-        X.has_sorted_indices = True
-        y = (rng.random(n_rows) < 0.3).astype(np.int64)
-        ps = rng.uniform(0.3, 1.0, n_rows)
-        return {"features": X, "labels": y, "pscores": ps}, off
+    def side(n, groups, mult0):
+        cols = np.empty((n, 3), dtype=np.int32)
+        ids = np.arange(n, dtype=np.int64)
+        off = 0
+        for j, g in enumerate(groups):
+            cols[:, j] = off + (ids * (j + mult0) + j) % g
+            off += g
+        return csr_matrix((np.ones(n * 3), cols.ravel(), np.arange(0, 3 * n + 1, 3, dtype=np.int32)), shape=(n, off))
 
-    train, n = rows_of(rows)
-    val, _ = rows_of(N_VAL)
-    log = SyntheticLog(U, I, n, train, val, None, None, {}, None, np.zeros((0, 2), np.int64), {})
-    return log, time.perf_counter() - t0
+    ut, it = side(U, STRESS_GROUPS[:3], 3), side(I, STRESS_GROUPS[3:], 5)
+    blocks = [("id", "user", U), ("table", "user", ut), ("id", "item", I), ("table", "item", it)]
+
+    def rows_of(n_rows):
+        u = rng.integers(0, U, n_rows).astype(np.int32)
+        i = rng.integers(0, I, n_rows).astype(np.int32)
+        y = (rng.random(n_rows) < 0.3).astype(np.int8)
+        ps = rng.uniform(0.3, 1.0, n_rows)
+        return {"features": FactoredFeatures(blocks, u, i), "labels": y, "pscores": ps}
+
+    train, val = rows_of(rows), rows_of(N_VAL)
+    return train, val, train["features"].shape[1], time.perf_counter() - t0
 
 
 def make_data(rows, seed, rank=0):
-    if WORKLOAD == "stress":
-        return make_stress_data(rows, seed)
     from rfm_b200.synth import make_kuairec_shaped
     t0 = time.perf_counter()
     log = make_kuairec_shaped(seed=seed + rank, n_users=N_USERS, n_items=N_ITEMS, n_train=rows, n_val=N_VAL,
@@ -127,12 +136,33 @@ def make_data(rows, seed, rank=0):
     return log, time.perf_counter() - t0
 
 
+def factored_dicts(log):
+    """The train / val dicts with the rows in the factored form (what the reference's preparer holds before hstack),
+    in the compact dtypes the format allows: int32 ids, float64 context, int8 labels, float64 pscores = 25 bytes per
+    interaction (0.30 GB at 12 M rows, against 2.6 GB of stacked CSR)."""
+    from rfm_b200.synth import factored_from_tables
+    out = []
+    for d in (log.fm_train, log.fm_val):
+        out.append({"features": factored_from_tables(log.tables, d["users"].astype(np.int32), d["items"].astype(np.int32),
+                                                     d["ctx"]),
+                    "labels": d["labels"].astype(np.int8), "pscores": d["pscores"]})
+    return out
+
+
+def pin_host_arrays(arrays):
+    from rfm_b200 import _capi
+    return [a for a in arrays if isinstance(a, np.ndarray) and a.nbytes >= (1 << 20) and _capi.pin_array(a)]
+
+
 def algorithmic_bytes(X, batch_rows, k, s):
     """bytes one interaction must move, per pass of the hot path."""
     m = X.nnz / X.shape[0]
     sub = X[batch_rows]
     touched = np.unique(sub.indices).size
-    B = len(batch_rows)
+    return (m, touched) + algorithmic_bytes_of(m, touched, len(batch_rows), k, s)
+
+
+def algorithmic_bytes_of(m, touched, B, k, s):
     stream = 4 + 4 + m * (4 + s) + 4 + s
     step = stream + 2 * m * (k + 1) * s + 2 * (touched / B) * (k + 1) * s
     per_kernel = {
@@ -143,7 +173,7 @@ def algorithmic_bytes(X, batch_rows, k, s):
         # loss pass: batch stream + gather of V rows and w
         "fm_rows_loss": 8 + 16 + m * (4 + s) + s + m * (k + 1) * s,
     }
-    return m, touched, step, per_kernel
+    return step, per_kernel
 
 
 class ClockSampler:
@@ -334,42 +364,52 @@ def run_reference(args):
 
 
 # ---- full-catalog scoring (second half of BASELINE.json's metric) ------------------------------------
+SCORING_SHAPES = (("eval_grid_1411x3327", 1411, 3327, 64, 9, 20), ("large_32768x262144", 32768, 262144, 64, 9, 5),
+                  ("large_k128_32768x262144", 32768, 262144, 128, 9, 5),
+                  ("large_k128_top100_16384x131072", 16384, 131072, 128, 100, 5))
+
+
 def measure_scoring(device, dist, world, peaks, peak_kind):
     """Scored user-item pairs/s of rank-all-items-for-all-users: bf16 tcgen05 GEMM prune + exact float64
-    top-K (csrc/score.cu). Two shapes: BASELINE configs[3]'s evaluation grid (1,411 x 3,327, k=64, top-9;
-    latency-bound: 0.6 GFLOP) and a grid large enough for the tensor pipe to matter. With N GPUs the
-    catalog is item-sharded and the per-rank lists are all-gathered and merged."""
+    top-K (csrc/score.cu). Shapes: BASELINE configs[3]'s evaluation grid (1,411 x 3,327, k=64, top-9;
+    latency-bound: 0.6 GFLOP) and grids large enough for the tensor pipe to matter. With N GPUs the catalog is
+    item-sharded: global thresholds and the user-partitioned K-way merge run over NVLink peer memory and every rank
+    ends with the lists of the users it owns in host memory. The same call on one GPU is timed next to it
+    (single_gpu_ms), so the line carries its own speed-up and scaling efficiency."""
     from rfm_b200.score import TopKScorer
     out = {"metric": "scored_user_item_pairs_per_sec", "unit": "pairs/s"}
     rng = np.random.default_rng(11)
-    shapes = (("eval_grid_1411x3327", 1411, 3327, 64, 9, 20), ("large_32768x262144", 32768, 262144, 64, 9, 5),
-              ("large_k128_32768x262144", 32768, 262144, 128, 9, 5),
-              ("large_k128_top100_16384x131072", 16384, 131072, 128, 100, 5))
-    for name, U, I, k, K, reps in shapes:
+    for name, U, I, k, K, reps in SCORING_SHAPES:
         A = rng.normal(size=(U, k)) * 0.3
         C = rng.normal(size=(I, k)) * 0.3
         beta = rng.normal(size=I) * 0.2
         sc = TopKScorer(A, C, None, beta, 0.0, device=device)
         ctx = sc.ctx
 
+        def single():
+            return sc.topk(K, copy=False)      # views of the library's page-locked result buffers
+
         def call():
             if dist is not None:
                 from rfm_b200 import dist as rdist
-                return rdist.sharded_topk(sc, dist, K)
-            return sc.topk(K, copy=False)      # views of the library's page-locked result buffers
+                return rdist.sharded_topk(sc, dist, K, gather=False, copy=False)
+            return single()
 
-        for _ in range(3):
-            call()
-        if dist is not None:
-            dist.barrier()
-        ctx.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            call()
-        ctx.synchronize()
-        dt = (time.perf_counter() - t0) / reps
-        if dist is not None:
-            dt = dist.max_over_ranks(dt)
+        def timed(fn, sync_ranks):
+            for _ in range(3):
+                fn()
+            if sync_ranks:
+                dist.barrier()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            ctx.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            return dist.max_over_ranks(dt) if sync_ranks else dt
+
+        single_dt = timed(single, False) if dist is not None else None
+        dt = timed(call, dist is not None)
         ctx.profile_begin()
         call()
         prof = ctx.profile_end()
@@ -379,11 +419,15 @@ def measure_scoring(device, dist, world, peaks, peak_kind):
         entry = {"users": U, "items": I, "n_factors": k, "top_k": K, "value": U * I / dt, "ms_per_call": dt * 1e3,
                  "includes": "operands resident; per call: sampled threshold pass, collect pass, exact re-score, "
                              "D2H of (items, scores)"
-                             + ("; all-gather + merge across ranks" if world > 1 else ""),
+                             + ("; item-sharded: threshold exchange + user-partitioned K-way merge over NVLink peer "
+                                "memory, every rank reads back the users it owns" if world > 1 else ""),
                  "users_ranked_exactly": sc.last_stats.get("users_ranked_exactly"),
                  "candidates_per_user": round(sc.last_stats.get("candidates", 0) / U, 2),
                  "sample_stride": sc.last_stats.get("sample_stride"),
                  "kernels_ms": {k2: [v[0], round(v[1], 4)] for k2, v in prof.items()}}
+        if single_dt is not None:
+            entry.update(single_gpu_ms=single_dt * 1e3, speedup_vs_1gpu=single_dt / dt,
+                         scoring_efficiency=single_dt / dt / world)
         if fk > 0:
             tf = 2.0 * upad * ipad * 64 * -(-k // 64) / (fk * 1e-3) / 1e12     # one pass over the grid is algorithmic
             entry["roofline"] = {"bound": "tensor", "kernel": "score_pass_kernel (sample + collect)", "achieved": tf,
@@ -397,63 +441,200 @@ def measure_scoring(device, dist, world, peaks, peak_kind):
     return out
 
 
+def eval_grid_inputs(log_small=None):
+    """BASELINE configs[3]'s evaluation grid: 1,411 users x 3,327 items of the KuaiRec-shaped catalog, an FM at its
+    reference initialisation, ~46 held-out rows per user (labels), item exposures."""
+    from rfm_b200.synth import make_kuairec_shaped
+    from oracle import fm_oracle
+    log = make_kuairec_shaped(seed=2024, n_users=N_USERS, n_items=N_ITEMS, n_train=50_000, n_val=100)
+    w0, w, V = fm_oracle.fm_init(12345, log.n_features, K_FACTORS, alpha=0.1)
+    frame = log.test_frame
+    users = np.unique(frame["user"])
+    items = np.unique(frame["item"])
+    return log, (w0, w, V), frame, users, items
+
+
+def scoring_cpu_and_e2e(device, budget_s=12.0):
+    """The reference's way of ranking a full grid -- FactorizationMachines.predict on the Cartesian-product rows
+    (src/fm.py:114-133) + TestEvaluator.evaluate (utils/evaluate.py:80-127), restated by the oracle -- timed on a
+    bounded sample of users; and this build's end-to-end path on the same grid from HOST arrays: per-side FM
+    factors -> upload + bf16 conversion -> tensor-core top-K -> device metric reductions -> metrics on the host."""
+    from oracle import fm_oracle, metrics_oracle
+    from rfm_b200.evaluate import FullCatalogEvaluator
+    from rfm_b200.score import TopKScorer, fm_side
+    from rfm_b200.synth import csr_from_tables
+    log, (w0, w, V), frame, users, items = eval_grid_inputs()
+    U, I = users.size, items.size
+    K = [1, 3, 5, 7, 9]
+    used = {"DCG", "CatalogCoverage"}
+    u_of = {int(u): j for j, u in enumerate(users)}
+    i_of = {int(i): j for j, i in enumerate(items)}
+    lab_u = np.array([u_of[int(u)] for u in frame["user"]])
+    lab_i = np.array([i_of[int(i)] for i in frame["item"]])
+    theta = np.zeros(I)
+    theta[lab_i] = frame["pscore"]
+    theta[theta == 0] = 0.5
+    # ---- CPU: Cartesian rows of a sample of users, oracle predict + oracle TestEvaluator
+    n_sample = 120
+    t0 = time.perf_counter()
+    su = np.arange(n_sample)
+    uu = np.repeat(users[su], I)
+    ii = np.tile(items, n_sample)
+    X = csr_from_tables(uu, ii, log.tables, np.zeros(uu.size))
+    X.has_sorted_indices = False
+    X.sort_indices()
+    build_s = time.perf_counter() - t0
+    lab = np.zeros((n_sample, I), dtype=np.int64)
+    sel = lab_u < n_sample
+    lab[lab_u[sel], lab_i[sel]] = frame["label"][sel]
+    cart = {"user": np.repeat(su, I), "item": np.tile(np.arange(I), n_sample), "label": lab.ravel(),
+            "pscore": np.tile(theta, n_sample), "ones_pscore": np.ones(n_sample * I)}
+    t0 = time.perf_counter()
+    scores = fm_oracle.fm_predict(X, w0, w, V)
+    t_pred = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = metrics_oracle.test_evaluate(cart, scores, K, used, I)
+    t_eval = time.perf_counter() - t0
+    cpu = {"value": n_sample * I / (t_pred + t_eval), "unit": "pairs/s", "cores": 1, "kind": "port",
+           "sample": "%d of %d users x %d items: oracle fm_predict on the Cartesian CSR (%.2f s) + oracle TestEvaluator "
+                     "(%.2f s); building the Cartesian rows (%.2f s) not counted" % (n_sample, U, I, t_pred, t_eval, build_s)}
+    # ---- ours, end to end from host arrays, whole grid
+    # per-side tables: the user side holds the user's id and side features (+ the context column at its fixed value),
+    # the item side the item's id and side features; both as rows over the global columns
+    from scipy.sparse import csr_matrix
+    t = log.tables
+
+    def side_rows(ptr, col, val, ids):
+        lens = (ptr[ids + 1] - ptr[ids]).astype(np.int64)
+        indptr = np.zeros(ids.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=indptr[1:])
+        take = np.concatenate([np.arange(ptr[e], ptr[e + 1]) for e in ids])
+        return csr_matrix((val[take], col[take], indptr), shape=(ids.size, t["n_features"]))
+
+    ut = side_rows(t["u_ptr"], t["u_col"], t["u_val"], users)
+    it = side_rows(t["i_ptr"], t["i_col"], t["i_val"], items)
+    ev = FullCatalogEvaluator({"user": lab_u, "item": lab_i, "label": frame["label"]}, theta, K, used, U, I)
+
+    def ours():
+        A, alpha = fm_side(ut, w, V)
+        C, beta = fm_side(it, w, V)
+        sc = TopKScorer(A, C, alpha, beta, float(w0[0]), device=device)
+        res = ev.evaluate(sc)
+        sc.close()
+        return res
+
+    res = ours()
+    # parity of the sampled users' share is not comparable (coverage is global); DCG of the sample is checked in tests
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = ours()
+    dt = (time.perf_counter() - t0) / reps
+    e2e = {"value": U * I / dt, "unit": "pairs/s", "ms_per_call": dt * 1e3, "grid": "%d x %d, k=%d, K=%s" % (U, I, K_FACTORS, K),
+           "h2d_bytes_per_step": (U + I) * (K_FACTORS + 1) * 8, "d2h_bytes_per_step": len(K) * 12 * 8 + len(K) * I * 4,
+           "api": "fm_side (host, per-side FM factors) -> TopKScorer (upload, bf16 operands) -> "
+                  "FullCatalogEvaluator.evaluate (tcgen05 top-K, device label look-up + DCG/ME/coverage reductions) "
+                  "-> metrics dict on the host",
+           "dcg_at_9": float(res["DCG"][-1]), "coverage_at_9": float(res["CatalogCoverage"][-1])}
+    return cpu, e2e
+
+
+# ---- MF (src/mf.py:68-134) -----------------------------------------------------------------------------
+def measure_mf(device, with_cpu, budget_s=8.0):
+    """IPS-MF at the KuaiRec big_matrix shape (7,176 x 10,728, 2 M train pairs, k = 64, B = 65,536): the reference's
+    strictly sequential per-sample SGD executed as a wavefront schedule (csrc/mf.cu), reference batch order.
+    End to end through LogisticMatrixFactorization.fit (upload, epochs, both losses, parameter download)."""
+    from rfm_b200.mf import LogisticMatrixFactorization
+    from rfm_b200.synth import make_kuairec_shaped
+    log = make_kuairec_shaped(seed=2024, n_users=N_USERS, n_items=N_ITEMS, n_train=2_000_000, n_val=N_VAL,
+                              build_eval=False)
+    B, epochs, k, lr, reg = 65536, 10, K_FACTORS, 9e-6, 1e-4
+    LogisticMatrixFactorization("IPS", 2, k, lr, B, 12345, log.n_users, log.n_items, reg, device=device).fit(
+        log.mf_train, log.mf_val)
+    m = LogisticMatrixFactorization("IPS", epochs, k, lr, B, 12345, log.n_users, log.n_items, reg, device=device)
+    t0 = time.perf_counter()
+    tl, vl = m.fit(log.mf_train, log.mf_val)
+    dt = time.perf_counter() - t0
+    assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl))
+    out = {"value": epochs * B / dt, "unit": UNIT, "epochs": epochs, "batch": B, "seconds": dt, "n_factors": k,
+           "train_pairs": int(log.mf_train["features"].shape[0]), "sampler": "legacy (reference batch order)",
+           "gpu_launches": m.last_fit_stats.get("gpu_launches"),
+           "h2d_bytes_per_step": log.mf_train["features"].nbytes * 2 / epochs + B * 8,
+           "d2h_bytes_per_step": 16 + (log.n_users + log.n_items) * (k + 1) * 8 / epochs,
+           "api": "LogisticMatrixFactorization.fit(train, val) on host arrays (replicas only: MF does not shard)"}
+    cpu = None
+    if with_cpu:
+        from oracle import mf_oracle
+        P, Q, bu, bi = mf_oracle.mf_init(12345, log.n_users, log.n_items, k)
+        t0 = time.perf_counter()
+        mf_oracle.mf_fit(log.mf_train, log.mf_val, 1, B, lr, reg, P, Q, bu, bi)
+        one = time.perf_counter() - t0
+        n_ep = max(1, min(4, int(budget_s / max(one, 1e-3))))
+        t0 = time.perf_counter()
+        mf_oracle.mf_fit(log.mf_train, log.mf_val, n_ep, B, lr, reg, P, Q, bu, bi)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": n_ep * B / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d epochs of B=%d, oracle/mf_oracle.py (C inner loop) incl. the reference sampler and both "
+                         "losses, %.1f s" % (n_ep, B, dtc)}
+    return out, cpu
+
+
+# ---- data-parallel parity, where the driver can see it ---------------------------------------------------------------
+def dp_parity(dist, device):
+    """Before anything is timed on N > 1 GPUs: the kuairec_small golden (the unmodified reference's trajectory) fitted
+    data-parallel over this process group with the reference sampler, and the device sampler against the single-GPU
+    fit; every rank must hold the same bits afterwards. A mismatch fails the run."""
+    from scipy.sparse import csr_matrix
+    from rfm_b200.fm import FactorizationMachines
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kuairec_small_fm_ips.npz"))
+
+    def csr(prefix):
+        return csr_matrix((g[prefix + "_data"], g[prefix + "_indices"], g[prefix + "_indptr"]),
+                          shape=tuple(int(v) for v in g[prefix + "_shape"]))
+
+    train = {"features": csr("train"), "labels": g["train_labels"], "pscores": g["train_pscores"]}
+    val = {"features": csr("val"), "labels": g["val_labels"], "pscores": g["val_pscores"]}
+    kw = dict(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]), lr=float(g["lr"]),
+              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=train["features"].shape[1],
+              alpha=float(g["alpha"]), device=device)
+    torch = dist.torch
+    worst, identical = 0.0, True
+    for sampler in ("legacy", "feistel"):
+        m = FactorizationMachines(distributed=dist, sampler=sampler, **kw)
+        tl, vl = m.fit(train, val)
+        if sampler == "legacy":
+            ref = (g["train_loss"], g["val_loss"], g["V"], g["w"])
+        else:
+            one = FactorizationMachines(sampler=sampler, **kw)
+            rtl, rvl = one.fit(train, val)
+            ref = (np.array(rtl), np.array(rvl), one.V(), one.w())
+        for mine, want in zip((np.array(tl), np.array(vl), m.V(), m.w()), ref):
+            err = np.max(np.abs(mine - want) / np.maximum(np.abs(want), 1e-13))
+            worst = max(worst, float(err))
+        mine = torch.from_numpy(m.V().copy()).to("cuda:%d" % device)
+        lo, hi = mine.clone(), mine.clone()
+        dist.dist.all_reduce(lo, op=dist.dist.ReduceOp.MIN)
+        dist.dist.all_reduce(hi, op=dist.dist.ReduceOp.MAX)
+        identical = identical and bool(torch.equal(lo, hi))
+    worst = dist.max_over_ranks(worst)
+    out = {"max_rel_err": worst, "ranks_bit_identical": identical, "tolerance": 1e-9, "world": dist.world,
+           "what": "kuairec_small golden (unmodified reference) fitted data-parallel: legacy sampler vs the golden, "
+                   "device sampler vs the single-GPU fit; losses, w, V"}
+    if not (worst <= 1e-9 and identical):
+        raise SystemExit("dp_parity FAILED: %s" % json.dumps(out))
+    return out
+
+
 # ---- our arm ----------------------------------------------------------------------------------------
-def run_ours(args):
-    from ctypes import byref
-    from rfm_b200 import _capi
-    from rfm_b200._capi import check, lib, ptr
-    from rfm_b200.fm import FactorizationMachines, _FmTrainer
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d ...)"
-                             % (args.gpus, args.gpus))
-    dist = None
-    if world > 1:
-        from rfm_b200 import dist as rdist
-        dist = rdist.init(local_rank)
-
-    # data-parallel runs replicate the train set on every GPU (2.6 GB of 180 GB): same seed everywhere
-    log, gen_s = make_data(args.rows, 2024)
-    X = log.fm_train["features"]
-    pinned = []
-    host_arrays = (X.indptr, X.indices, X.data, log.fm_train["labels"], log.fm_train["pscores"])
-    for a in host_arrays:
-        if _capi.pin_array(a):
-            pinned.append(a)
-    log.pinned_note = "%d of %d train arrays page-locked (cudaHostRegister)" % (len(pinned), len(host_arrays))
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    s = 8 if args.dtype == "float64" else 4
-    dtype_tag = "f64" if args.dtype == "float64" else "f32"
-
-    model = FactorizationMachines("IPS", K, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
-                                  sampler="feistel", device=local_rank)
-    ctx = model._context()
-    train_rows = model._rows(X, log.fm_train["labels"], log.fm_train["pscores"])
-    val_rows = model._rows(log.fm_val["features"], log.fm_val["labels"], log.fm_val["pscores"])
-    model.sync_to_device()
-    trainer = _FmTrainer(model._dev, train_rows, val_rows, B, W + 2 * K + 8)
-
-    if dist is not None:
-        from rfm_b200 import dist as rdist
-        model.batch_size = B * world                       # weak scaling: B per GPU, global batch B*world
-        dp = rdist.make_fm_dp(model, trainer, dist, B * world, N_VAL, LR, lambda epoch: None)
-
-        def stepper(epoch, slot):
-            dp.step(epoch)
-    else:
-        def stepper(epoch, slot):
-            check(lib().rfm_fm_train_epoch_sampled(trainer.handle, 12345, epoch, B, LR, slot))
-
+def timed_steps(ctx, dist, stepper, W, K, device):
+    """W warm-up steps, K timed steps (CUDA events on the launching stream, barrier + synchronize on both sides, max
+    over ranks), nvidia-smi clocks sampled around a run of identical untimed steps, then a profiled pass of K steps."""
     def barrier():
         if dist is not None:
             dist.barrier()
         ctx.synchronize()
 
-    clocks = ClockSampler(local_rank)                      # nvidia-smi -lms 100 from before the warm-up on
+    clocks = ClockSampler(device)                      # nvidia-smi -lms 100 from before the warm-up on
     for e in range(W):
         stepper(e, e)
     barrier()
@@ -480,86 +661,222 @@ def run_ours(args):
     if dist is not None:
         ms = dist.max_over_ranks(ms)
         launches = int(dist.sum_over_ranks(launches))
-    value = K * B * world / (ms * 1e-3)
-
-    # per-kernel share of the step: CUDA events around every launch, separate pass of the same steps
-    ctx.profile_begin()
+    ctx.profile_begin()                                # per-kernel share of the step: CUDA events around every launch
     for e in range(K):
         stepper(W + K + e, W + K + e)
     prof = ctx.profile_end()
-    tl = np.empty(W + 2 * K)
-    vl = np.empty(W + 2 * K)
-    if dist is None:
-        check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + 2 * K, ptr(tl), ptr(vl)))
-    else:
-        last = dp.flush().cpu().numpy()
-        tl[:] = last[0] / (B * world)
-        vl[:] = last[1] / N_VAL
-    assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl)), "non-finite loss in the timed region"
+    return ms, launches, clk, prof
+
+
+def step_roofline(prof, K, ms, B, world, m, touched, k, s, peaks, peak_kind, l2_assisted, note, traffic_key):
+    step_bytes, per_kernel = algorithmic_bytes_of(m, touched, B, k, s)
+    total_prof_ms = sum(v[1] for v in prof.values())
+    top = max((kk for kk in prof if kk in per_kernel), key=lambda kk: prof[kk][1])
+    top_ms = prof[top][1] / prof[top][0]
+    achieved = step_bytes * B / (ms / K * 1e-3) / 1e9
+    traffic, kernel_traffic = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:     # DRAM bytes per launch from the committed ncu --set full captures of this workload
+            tj = json.load(f).get(traffic_key, {})
+        per = {kk: v.get("dram_bytes") for kk, v in tj.items() if isinstance(v, dict) and v.get("dram_bytes")}
+        if per:
+            kernel_traffic = per
+            traffic = float(sum(v * max(1, round(prof[kk][0] / K)) if kk in prof else v for kk, v in per.items()))
+    return {
+        "bound": "hbm", "scope": "whole step: SURVEY.md section 8(d) algorithmic bytes per interaction x B / step time",
+        "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        "traffic": traffic, "traffic_per_kernel": kernel_traffic, "l2_assisted": l2_assisted,
+        "algorithmic_bytes_per_interaction": step_bytes, "peak_kind": peak_kind + " (HBM copy, burst)", "note": note,
+        "dominant_kernel": {"kernel": top, "avg_launch_ms": top_ms, "share_of_step": prof[top][1] / total_prof_ms,
+                            "algorithmic_bytes_per_interaction": per_kernel[top],
+                            "achieved": per_kernel[top] * B / (top_ms * 1e-3) / 1e9},
+        "kernels_ms_per_step": {kk: round(v[1] / K, 5) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        "timing": "step: cudaEvent pair around %d steps; kernels: cudaEvent pair around each launch, separate pass" % K,
+    }
+
+
+def measure_stress(args, device, peaks, peak_kind):
+    """The HBM-bound shape (BASELINE configs[4] on one GPU's share): n = 2 M features, k = 128, B = 2^20, 8 non-zeros
+    per row -- a 2 GB parameter table and 1 GB of per-batch s_t rows, nothing L2-resident."""
+    from rfm_b200._capi import check, lib
+    from rfm_b200.fm import FactorizationMachines, _FmTrainer
+    train, val, n_features, gen_s = make_stress_data(args.stress_rows, 2024)
+    B, K, W = 1 << 20, max(3, min(args.steps, 10)), 3
+    model = FactorizationMachines("IPS", K, STRESS_K, LR, B, 12345, n_features, dtype=args.dtype, sampler="feistel",
+                                  device=device)
+    ctx = model._context()
+    train_rows = model._rows(train["features"], train["labels"], train["pscores"])
+    val_rows = model._rows(val["features"], val["labels"], val["pscores"])
+    model.sync_to_device()
+    trainer = _FmTrainer(model._dev, train_rows, val_rows, B, W + 2 * K + 8)
+
+    def stepper(epoch, slot):
+        check(lib().rfm_fm_train_epoch_sampled(trainer.handle, 12345, epoch, B, LR, slot))
+
+    ms, launches, clk, prof = timed_steps(ctx, None, stepper, W, K, device)
+    s = 8 if args.dtype == "float64" else 4
+    u = train["features"].users[:B].astype(np.int64)
+    i = train["features"].items[:B].astype(np.int64)
+    touched = np.unique(u).size + np.unique(i).size + sum(STRESS_GROUPS)
+    roof = step_roofline(prof, K, ms, B, 1, 8.0, touched, STRESS_K, s, peaks, peak_kind, False,
+                         "V (%.1f GB) and S (%.1f GB) exceed L2: id-column gathers and the s_t gather are HBM traffic"
+                         % (n_features * STRESS_K * s / 1e9, B * STRESS_K * s / 1e9), "stress")
+    roof.update(value=K * B / (ms * 1e-3), unit=UNIT, ms_per_step=ms / K, steps=K, warmup=W, batch=B,
+                n_factors=STRESS_K, n_features=n_features, train_interactions=args.stress_rows,
+                input_format="factored", data_gen_s=round(gen_s, 1), clocks=clk,
+                workload="IPS-FM stress, BASELINE.json configs[4] shape on one GPU's share: 1M users x 1M items, "
+                         "k=128, 8 non-zeros per row")
+    trainer.close()
+    return roof
+
+
+def run_ours(args):
+    from ctypes import byref
+    from rfm_b200 import _capi
+    from rfm_b200._capi import check, lib, ptr
+    from rfm_b200.fm import FactorizationMachines, _FmTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d ...)"
+                             % (args.gpus, args.gpus))
+    dist = None
+    if world > 1:
+        from rfm_b200 import dist as rdist
+        dist = rdist.init(local_rank)
+    peaks, peak_kind = measured_peaks()
+    parity = dp_parity(dist, local_rank) if dist is not None else None
+
+    if args.workload == "stress":
+        roof = measure_stress(args, local_rank, peaks, peak_kind)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": roof["value"], "unit": UNIT, "n_gpus": 1, "steps": roof["steps"],
+                              "warmup": roof["warmup"], "ms_per_step": roof["ms_per_step"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32",
+                              "data": "synthetic", "config": {"workload": roof["workload"]}, "clocks": roof["clocks"],
+                              "roofline": roof, "gpu_launches": None}))
+        return
+
+    # data-parallel runs replicate the train set on every GPU: same seed everywhere
+    log, gen_s = make_data(args.rows, 2024)
+    X = log.fm_train["features"]
+    ftrain, fval = factored_dicts(log)
+    pinned = pin_host_arrays([X.indptr, X.indices, X.data, log.fm_train["labels"], log.fm_train["pscores"],
+                              ftrain["features"].users, ftrain["features"].items, ftrain["labels"]]
+                             + [b[1] for b in ftrain["features"].blocks if b[0] == "ctx"])
+    log.pinned_note = "%d train arrays page-locked (cudaHostRegister)" % len(pinned)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    s = 8 if args.dtype == "float64" else 4
+    dtype_tag = "f64" if args.dtype == "float64" else "f32"
+    train_in, val_in = (ftrain, fval) if args.input == "factored" else (log.fm_train, log.fm_val)
+
+    def device_run(train_d, val_d):
+        model = FactorizationMachines("IPS", K, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
+                                      sampler="feistel", device=local_rank)
+        ctx = model._context()
+        train_rows = model._rows(train_d["features"], train_d["labels"], train_d["pscores"])
+        val_rows = model._rows(val_d["features"], val_d["labels"], val_d["pscores"])
+        model.sync_to_device()
+        trainer = _FmTrainer(model._dev, train_rows, val_rows, B, W + 2 * K + 8)
+        dp = None
+        if dist is not None:
+            from rfm_b200 import dist as rdist
+            model.batch_size = B * world                       # weak scaling: B per GPU, global batch B*world
+            dp = rdist.make_fm_dp(model, trainer, dist, B * world, N_VAL, LR, lambda epoch: None)
+
+            def stepper(epoch, slot):
+                dp.step(epoch)
+        else:
+            def stepper(epoch, slot):
+                check(lib().rfm_fm_train_epoch_sampled(trainer.handle, 12345, epoch, B, LR, slot))
+        ms, launches, clk, prof = timed_steps(ctx, dist, stepper, W, K, local_rank)
+        tl = np.empty(W + 2 * K)
+        vl = np.empty(W + 2 * K)
+        if dist is None:
+            check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + 2 * K, ptr(tl), ptr(vl)))
+        else:
+            last = dp.flush().cpu().numpy()
+            tl[:] = last[0] / (B * world)
+            vl[:] = last[1] / N_VAL
+        assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl)), "non-finite loss in the timed region"
+        trainer.close()
+        return dict(ms=ms, launches=launches, clk=clk, prof=prof, tl=float(tl[W + K - 1]), vl=float(vl[W + K - 1]),
+                    rows_bytes=train_rows.h2d_bytes)
+
+    main = device_run(train_in, val_in)
+    other_fmt = "csr" if args.input == "factored" else "factored"
+    other = device_run(*((log.fm_train, log.fm_val) if other_fmt == "csr" else (ftrain, fval)))
+    ms, launches, clk, prof = main["ms"], main["launches"], main["clk"], main["prof"]
+    value = K * B * world / (ms * 1e-3)
 
     if rank != 0:
         if not args.no_e2e:
-            measure_e2e(args, log, local_rank, dist, world)
+            measure_e2e(args, log, ftrain, fval, local_rank, dist, world)
         if not args.no_scoring:
-            measure_scoring(local_rank, dist, world, *measured_peaks())
+            measure_scoring(local_rank, dist, world, peaks, peak_kind)
         dist.shutdown()
         return
 
     sample_rows = _capi.feistel_batch(X.shape[0], B, W, 12345)
     m, touched, step_bytes, per_kernel = algorithmic_bytes(X, sample_rows, K_FACTORS, s)
-    total_prof_ms = sum(v[1] for v in prof.values())
-    top = max((k for k in prof if k in per_kernel), key=lambda k: prof[k][1])
-    top_ms = prof[top][1] / prof[top][0]
-    peaks, peak_kind = measured_peaks()
-    achieved = per_kernel[top] * B / (top_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath) and B == (65536 if WORKLOAD == "kuairec_big" else 1 << 20) and args.dtype == "float64":
-        with open(tpath) as f:     # DRAM bytes per launch from the committed ncu --set full capture of this workload
-            traffic = json.load(f).get(WORKLOAD, {}).get(top, {}).get("dram_bytes")
-    roofline = {
-        "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": per_kernel[top] * B,
-        "peak_kind": peak_kind + " (HBM copy, burst)",
-        "algorithmic_bytes_per_interaction": per_kernel[top], "avg_launch_ms": top_ms,
-        "share_of_step": prof[top][1] / total_prof_ms,
-        "timing": "cudaEvent pair around each launch, separate pass of the same %d steps" % K,
-        "note": ("V (%.1f MB) and S (%.1f MB) are L2-resident at this shape, so the algorithmic gather traffic is "
-                 "served by L2, not HBM (SURVEY.md H7); achieved may therefore exceed the HBM peak"
-                 % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6)) if WORKLOAD != "stress" else
-                ("V (%.1f GB) and S (%.1f GB) exceed L2: id-column gathers and the s_t gather are HBM traffic"
-                 % (log.n_features * K_FACTORS * s / 1e9, B * K_FACTORS * s / 1e9)),
-        "step": {"algorithmic_bytes_per_interaction": step_bytes,
-                 "achieved": step_bytes * B * world / (ms / K * 1e-3) / 1e9 / world,
-                 "frac": step_bytes * B / (ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-        "kernels_ms_per_step": {k: round(v[1] / K, 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
-    }
-
-    e2e = None if args.no_e2e else measure_e2e(args, log, local_rank, dist, world)
+    roofline = step_roofline(prof, K, ms, B, world, m, touched, K_FACTORS, s, peaks, peak_kind, True,
+                             "V (%.1f MB) and S (%.1f MB) are L2-resident at this shape, so the algorithmic gather "
+                             "traffic is served by L2, not HBM (SURVEY.md H7): frac is the section-8(d) fraction, "
+                             "L2-assisted; the HBM-bound claim is roofline.stress"
+                             % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6), "kuairec_big")
+    roofline["other_input_format"] = {"input_format": other_fmt, "ms_per_step": other["ms"] / K,
+                                      "value": K * B * world / (other["ms"] * 1e-3)}
+    e2e = None if args.no_e2e else measure_e2e(args, log, ftrain, fval, local_rank, dist, world)
     scoring = None if args.no_scoring else measure_scoring(local_rank, dist, world, peaks, peak_kind)
+    if scoring is not None:
+        roofline["scoring"] = {name: {"pairs_per_s": v["value"], "ms_per_call": v["ms_per_call"],
+                                      "tensor_frac": (v.get("roofline") or {}).get("frac"),
+                                      "scoring_efficiency": v.get("scoring_efficiency")}
+                               for name, v in scoring.items() if isinstance(v, dict)}
+    if world == 1 and not args.no_stress:
+        roofline["stress"] = measure_stress(args, local_rank, peaks, peak_kind)
     cpu = None
     if not args.no_cpu_baseline:
         v1, st1, dt1 = cpu_port_run(log, B, 8, 1, budget_s=8.0)
         v, st, dt, cores = cpu_port_run_parallel(log, B, 160, 1, budget_s=15.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "host_cores_available": os.cpu_count(),
-               "sample": "%d epochs of B=%d on the %d-row train set, reference sampler included, %.1f s on %d "
-                         "processes" % (st, B, X.shape[0], dt, cores),
+               "sample": "%d epochs of B=%d on the %d-row train set (stacked CSR, the reference's input), reference "
+                         "sampler included, %.1f s on %d processes" % (st, B, X.shape[0], dt, cores),
                "single_core": {"value": v1, "sample": "%d epochs, %.1f s" % (st1, dt1)}}
+    if world == 1 and not args.no_scoring and (not args.no_cpu_baseline or not args.no_e2e):
+        s_cpu, s_e2e = scoring_cpu_and_e2e(local_rank)
+        if cpu is not None:
+            cpu["scoring"] = s_cpu
+        if e2e is not None:
+            e2e["scoring"] = s_e2e
+    if world == 1 and not args.no_mf:
+        mf, mf_cpu = measure_mf(local_rank, cpu is not None)
+        if e2e is not None:
+            e2e["mf"] = mf
+        if cpu is not None and mf_cpu is not None:
+            cpu["mf"] = mf_cpu
     cfg = workload_config(args, world)
-    cfg["l2"] = cfg["l2"].replace("train CSR", "%.1f GB train CSR" % (train_rows.h2d_bytes / 1e9))
-    if WORKLOAD == "stress":
-        cfg["l2"] = ("inputs larger than L2: %.1f GB CSR, %.1f GB parameter table and %.1f GB of per-batch s_t rows, "
-                     "all far beyond the 126 MB L2" % (train_rows.h2d_bytes / 1e9,
-                                                        log.n_features * K_FACTORS * s / 1e9, B * K_FACTORS * s / 1e9))
+    cfg["l2"] = cfg["l2"].replace("train rows", "%.2f GB of train rows" % (main["rows_bytes"] / 1e9))
     cfg.update(sampler="feistel (device, perf mode)", mean_nnz_per_row=round(m, 3),
-               touched_columns_per_step=int(touched), n_features=log.n_features, data_gen_s=round(gen_s, 1))
+               touched_columns_per_step=int(touched), n_features=log.n_features, data_gen_s=round(gen_s, 1),
+               input_format=("factored: user table + item table + (user, item, ctx) records, rows assembled on the "
+                             "device (SURVEY.md 8 f3)" if args.input == "factored" else
+                             "stacked CSR (the reference's own input) resident in HBM; e2e uploads the %s form"
+                             % args.e2e_input))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": dtype_tag, "data": "synthetic", "config": cfg, "clocks": clk, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "scoring": scoring,
-        "final_train_loss": float(tl[W + K - 1]), "final_val_loss": float(vl[W + K - 1]),
+        "final_train_loss": main["tl"], "final_val_loss": main["vl"],
     }
+    if parity is not None:
+        line["dp_parity"] = parity
+        line["config"]["dp_parity"] = parity
     print(json.dumps(line))
     for a in pinned:
         _capi.unpin_array(a)
@@ -567,20 +884,22 @@ def run_ours(args):
         dist.shutdown()
 
 
-def measure_e2e(args, log, device, dist, world):
+def measure_e2e(args, log, ftrain, fval, device, dist, world):
     """Public API on host arrays: FactorizationMachines.fit(train, val) for K epochs. Everything a
-    user pays is inside the timed region: CSR upload from pinned host memory, trainer set-up, K
+    user pays is inside the timed region: row upload from pinned host memory, trainer set-up, K
     epochs, loss read-back, parameter download."""
     from rfm_b200.fm import FactorizationMachines
     B, K = args.batch, args.steps
     out = {}
-    for sampler in ("feistel", "legacy"):
+    variants = [("factored", "feistel", ftrain, fval), ("csr", "feistel", log.fm_train, log.fm_val),
+                ("factored", "legacy", ftrain, fval)]
+    for fmt, sampler, train, val in variants:
         n_ep = K if sampler == "feistel" else min(K, 16)
         if dist is not None and sampler == "legacy":
             continue
         warm = FactorizationMachines("IPS", 2, K_FACTORS, LR, B * world, 12345, log.n_features, dtype=args.dtype,
                                      sampler=sampler, device=device, distributed=dist)
-        warm.fit(log.fm_train, log.fm_val)
+        warm.fit(train, val)
         del warm
         model = FactorizationMachines("IPS", n_ep, K_FACTORS, LR, B * world, 12345, log.n_features,
                                       dtype=args.dtype, sampler=sampler, device=device, distributed=dist)
@@ -588,41 +907,41 @@ def measure_e2e(args, log, device, dist, world):
             dist.barrier()
         model._context().synchronize()
         t0 = time.perf_counter()
-        tl, vl = model.fit(log.fm_train, log.fm_val)
+        tl, vl = model.fit(train, val)
         model._context().synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:
             dt = dist.max_over_ranks(dt)
         rows_bytes = model.last_fit_stats["h2d_bytes_rows"]
-        upload_s = model.last_fit_stats.get("upload_seconds")
-        out[sampler] = {
-            "value": n_ep * B * world / dt, "epochs": n_ep, "seconds": dt, "upload_seconds": upload_s,
+        out[(fmt, sampler)] = {
+            "value": n_ep * B * world / dt, "epochs": n_ep, "seconds": dt,
+            "upload_seconds": model.last_fit_stats.get("upload_seconds"),
             "phase_seconds": model.last_fit_stats.get("phase_seconds"),
             "h2d_bytes_per_step": rows_bytes / n_ep + (B * 8 if sampler == "legacy" else 0),
             "d2h_bytes_per_step": 16 + (1 + log.n_features * (K_FACTORS + 1)) * 8 / n_ep,
         }
-    main = out["feistel"]
+    head_fmt = args.e2e_input
+    main = out[(head_fmt, "feistel")]
+    apis = {"factored": "FactorizationMachines(sampler='feistel').fit(train, val), train['features'] a FactoredFeatures "
+                        "(the blocks the reference's preparer stacks + one (user, item, ctx) record per interaction) on "
+                        "pinned host arrays; includes the one-time upload, amortised over the epochs of this call",
+            "csr": "FactorizationMachines(sampler='feistel').fit(train, val) on the reference's stacked CSR in pinned "
+                   "host arrays; includes the one-time CSR upload, amortised over the epochs of this call"}
     res = {"value": main["value"], "unit": UNIT, "h2d_bytes_per_step": main["h2d_bytes_per_step"],
            "d2h_bytes_per_step": main["d2h_bytes_per_step"], "seconds": main["seconds"], "epochs": main["epochs"],
            "upload_seconds": main["upload_seconds"], "host_memory": getattr(log, "pinned_note", None),
-           "phase_seconds": main["phase_seconds"],
-           "api": "FactorizationMachines(sampler='feistel').fit(train, val) on pinned host arrays; includes the "
-                  "one-time CSR upload, amortised over the epochs of this call"}
-    if "legacy" in out:
-        res["legacy_sampler"] = dict(out["legacy"], note="reference batch order (RandomState(epoch) shuffle of all "
-                                     "N ids on host threads, SURVEY.md F14): host-bound by design")
+           "phase_seconds": main["phase_seconds"], "input_format": head_fmt, "api": apis[head_fmt]}
+    alt = "csr" if head_fmt == "factored" else "factored"
+    res["hstacked_csr" if alt == "csr" else "factored"] = dict(out[(alt, "feistel")], api=apis[alt])
+    if ("factored", "legacy") in out:
+        res["legacy_sampler"] = dict(out[("factored", "legacy")], input_format="factored",
+                                     note="reference batch order (RandomState(epoch) shuffle of all N ids on host "
+                                          "threads, SURVEY.md F14): host-bound by design")
     return res
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.workload == "stress":
-        WORKLOAD, N_USERS, N_ITEMS, K_FACTORS = "stress", 1_000_000, 1_000_000, 128
-        if a.rows == N_TRAIN:
-            a.rows = 20_000_000
-        if a.batch == 65536:
-            a.batch = 1 << 20
-        a.no_cpu_baseline = a.no_scoring = True
     if a.impl == "reference":
         run_reference(a)
     else:

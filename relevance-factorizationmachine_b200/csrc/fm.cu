@@ -49,6 +49,7 @@ struct FacDev {
   int n_seg, n_ctx, es, pad;  // es: bytes per value (4 or 8)
   const int32_t *user, *item;
   const void *ctx;          // T [n_rows][n_ctx]
+  const void *one;          // T [1] = 1.0: what an id block's entry loads as its value (keeps the entry fetch branch-free)
   FacSegDev seg[FAC_MAX_SEG];
 };
 
@@ -64,7 +65,7 @@ struct rfm_csr {
   bool factored = false;
   int n_seg = 0, n_ctx = 0;
   DevBuf<int32_t> f_user, f_item;
-  DevBuf<unsigned char> f_ctx;
+  DevBuf<unsigned char> f_ctx, f_one;
   struct Seg {
     int kind = 0, key = 0, width = 0, ctx0 = 0;
     uint32_t col0 = 0;
@@ -80,6 +81,7 @@ struct rfm_csr {
     f.user = f_user.p + row_offset;
     f.item = f_item.p + row_offset;
     f.ctx = f_ctx.p ? f_ctx.p + (size_t)row_offset * n_ctx * (dtype == RFM_F64 ? 8 : 4) : nullptr;
+    f.one = f_one.p;
     for (int s = 0; s < n_seg; ++s) {
       f.seg[s].kind = seg[s].kind;
       f.seg[s].key = seg[s].key;
@@ -316,9 +318,35 @@ __device__ __forceinline__ int fac_row_len(const FacDev &f, int u, int i, unsign
   }
   return at;
 }
-// entry `off` (< r.len) of row t: global column and value
+// The block descriptors the entry fetch indexes with a per-lane block number live in shared memory (structure of
+// arrays, two row sets): kernel parameters sit in the constant bank, where a warp's loads of different addresses
+// are serialised.
+struct FacSmem {
+  int kind[2 * FAC_MAX_SEG];
+  uint32_t col0[2 * FAC_MAX_SEG];
+  int ctx0[2 * FAC_MAX_SEG];
+  const int32_t *col[2 * FAC_MAX_SEG];
+  const void *val[2 * FAC_MAX_SEG];
+};
+__device__ __forceinline__ void fac_smem_fill(FacSmem &sm, const FacDev &f, const FacDev &f2, bool two) {
+  for (int i = threadIdx.x; i < 2 * FAC_MAX_SEG; i += blockDim.x) {
+    const bool second = i >= FAC_MAX_SEG;
+    const int s = second ? i - FAC_MAX_SEG : i;
+    const FacDev &src = (second && two) ? f2 : f;
+    const bool on = s < src.n_seg;
+    sm.kind[i] = on ? src.seg[s].kind : SEG_ID;
+    sm.col0[i] = on ? src.seg[s].col0 : 0u;
+    sm.ctx0[i] = on ? src.seg[s].ctx0 : 0;
+    sm.col[i] = on ? src.seg[s].col : nullptr;
+    sm.val[i] = on ? src.seg[s].val : nullptr;
+  }
+}
+// entry `off` (< r.len) of row t: global column and value. Branch-free: every lane issues exactly two loads (a
+// table block's column and value; an id / context block loads a dummy column and its value from `one` / the row's
+// context record), so the lanes of a row group, which sit in different blocks, do not diverge.
 template <typename T>
-__device__ __forceinline__ void fac_entry(const FacDev &f, const FacRow &r, int64_t t, int off, int &c, T &x) {
+__device__ __forceinline__ void fac_entry(const FacSmem &sm, int set, const FacDev &f, const FacRow &r, int64_t t,
+                                          int off, int &c, T &x) {
   int s = 0, b = r.base[0], start = 0;
 #pragma unroll
   for (int j = 1; j < FAC_MAX_SEG; ++j)
@@ -327,18 +355,18 @@ __device__ __forceinline__ void fac_entry(const FacDev &f, const FacRow &r, int6
       b = r.base[j];
       start = r.cum[j - 1];
     }
-  const FacSegDev &g = f.seg[s];
-  if (g.kind == SEG_ID) {
-    c = static_cast<int>(g.col0) + b;
-    x = T(1);
-  } else if (g.kind == SEG_TABLE) {
-    c = static_cast<int>(g.col0) + __ldg(g.col + b + off);
-    x = __ldg(static_cast<const T *>(g.val) + b + off);
-  } else {
-    const int j = __fns(static_cast<unsigned>(b), 0u, off - start + 1);     // the (off - start)-th non-zero column
-    c = static_cast<int>(g.col0) + j;
-    x = __ldg(static_cast<const T *>(f.ctx) + t * f.n_ctx + g.ctx0 + j);
-  }
+  const int at = set * FAC_MAX_SEG + s;
+  const int kind = sm.kind[at];
+  // context block: the (off - start)-th non-zero column of the block (b holds the block's non-zero mask)
+  const int j = f.n_ctx <= 1 ? 0 : (kind == SEG_CTX ? static_cast<int>(__fns(static_cast<unsigned>(b), 0u, off - start + 1)) : 0);
+  const int e = kind == SEG_TABLE ? b + off : 0;
+  const int32_t *cp = kind == SEG_TABLE ? sm.col[at] + e : f.user;
+  const T *xp = kind == SEG_TABLE ? static_cast<const T *>(sm.val[at]) + e
+              : kind == SEG_CTX   ? static_cast<const T *>(f.ctx) + t * f.n_ctx + sm.ctx0[at] + j
+                                  : static_cast<const T *>(f.one);
+  const int cv = __ldg(cp);
+  x = __ldg(xp);
+  c = static_cast<int>(sm.col0[at]) + (kind == SEG_TABLE ? cv : kind == SEG_ID ? b : j);
 }
 
 // ---- factored rows: upload helpers ---------------------------------------------------------------------------
@@ -475,6 +503,11 @@ fm_rows_kernel(const RowsArgs<T> a) {
     for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += ROWS_THREADS) hist[i] = 0;
     __syncthreads();
   }
+  __shared__ FacSmem fsm;
+  if (FAC) {
+    fac_smem_fill(fsm, a.fac, a.fac2, MODE == MODE_LOSS && a.n2 > 0);
+    __syncthreads();
+  }
   double partial = 0.0, partial2 = 0.0;
   const int64_t n_total = a.n + (MODE == MODE_LOSS ? a.n2 : 0);
   // Row metadata (row id, CSR extent, target) of the NEXT loop iteration is fetched while the current row is
@@ -555,8 +588,8 @@ fm_rows_kernel(const RowsArgs<T> a) {
       T x = T(0);
       if (off < len) {
         if (FAC) {
-          if (MODE == MODE_LOSS && second) fac_entry<T>(a.fac2, fr, t, off, c, x);
-          else fac_entry<T>(a.fac, fr, t, off, c, x);
+          if (MODE == MODE_LOSS && second) fac_entry<T>(fsm, 1, a.fac2, fr, t, off, c, x);
+          else fac_entry<T>(fsm, 0, a.fac, fr, t, off, c, x);
         } else {
           c = colp[beg + off];
           x = valp[beg + off];
@@ -1618,6 +1651,14 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
     RFM_TRY(r->f_item.alloc(nr));
     RFM_TRY(r->yp.alloc((size_t)nr * es));
     if (n_ctx) RFM_TRY(r->f_ctx.alloc((size_t)nr * n_ctx * es));
+    RFM_TRY(r->f_one.alloc(8));
+    {
+      const double one_d = 1.0;
+      const float one_f = 1.f;
+      RFM_CUDA(cudaMemcpyAsync(r->f_one.p, dtype == RFM_F64 ? (const void *)&one_d : (const void *)&one_f, es,
+                               cudaMemcpyHostToDevice, ctx->stream));
+      RFM_CUDA(cudaStreamSynchronize(ctx->stream));       // the source is on this stack frame
+    }
     DevBuf<int> bad;
     RFM_TRY(bad.alloc(4));
     RFM_CUDA(cudaMemsetAsync(bad.p, 0, 4 * sizeof(int), ctx->stream));

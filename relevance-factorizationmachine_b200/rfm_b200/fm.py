@@ -117,17 +117,19 @@ class FactorizationMachines(PointwiseBaseRecommender):
             self._synced = self._host_state()
 
     def sync_to_host(self) -> None:
-        """Refresh the holders' ndarrays in place from the device master copy."""
-        w0 = np.empty(1)
-        w = np.empty(self.n_features)
-        V = np.empty((self.n_features, self.n_factors))
-        check(lib().rfm_fm_get_params(self._dev.handle, ptr(w0), ptr(w), ptr(V)))
-        for holder, new in ((self.w0, w0), (self.w, w), (self.V, V)):
-            if (isinstance(holder.params, np.ndarray) and holder.params.shape == new.shape
-                    and holder.params.dtype == np.float64 and holder.params.flags.writeable):
-                holder.params[...] = new
+        """Refresh the holders' ndarrays in place from the device master copy (straight into the arrays the holders
+        already own when those are plain float64 buffers of the right shape: no intermediate copy)."""
+        shapes = ((self.w0, (1,)), (self.w, (self.n_features,)), (self.V, (self.n_features, self.n_factors)))
+        targets = []
+        for holder, shape in shapes:
+            p = holder.params
+            if (isinstance(p, np.ndarray) and p.shape == shape and p.dtype == np.float64 and p.flags.writeable
+                    and p.flags.c_contiguous):
+                targets.append(p)
             else:
-                holder.params = new
+                holder.params = np.empty(shape)
+                targets.append(holder.params)
+        check(lib().rfm_fm_get_params(self._dev.handle, ptr(targets[0]), ptr(targets[1]), ptr(targets[2])))
         self._synced = self._host_state()
 
     def _rows(self, X, labels=None, pscores=None):
