@@ -74,7 +74,11 @@ def parse():
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-mf", action="store_true")
     ap.add_argument("--stress-rows", type=int, default=20_000_000)
-    ap.add_argument("--workload", default="kuairec_big", choices=["kuairec_big", "stress"],
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] section that a default 8-GPU run carries")
+    ap.add_argument("--c5-rows", type=int, default=0, help="interactions of the c5 log (default: 125 M per GPU)")
+    ap.add_argument("--c5-users", type=int, default=1_000_000)
+    ap.add_argument("--c5-items", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="kuairec_big", choices=["kuairec_big", "stress", "c5"],
                     help="kuairec_big = BASELINE configs[2] (the headline; the stress shape runs as a section of it); "
                          "stress = only the configs[4]-shaped section: 1M users x 1M items, k=128, 8 non-zeros per row")
     return ap.parse_args()
@@ -626,7 +630,7 @@ def dp_parity(dist, device):
 
 
 # ---- our arm ----------------------------------------------------------------------------------------
-def timed_steps(ctx, dist, stepper, W, K, device):
+def timed_steps(ctx, dist, stepper, W, K, device, observe=True):
     """W warm-up steps, K timed steps (CUDA events on the launching stream, barrier + synchronize on both sides, max
     over ranks), nvidia-smi clocks sampled around a run of identical untimed steps, then a profiled pass of K steps."""
     def barrier():
@@ -649,7 +653,9 @@ def timed_steps(ctx, dist, stepper, W, K, device):
     # running (untimed, same stream, same data) until the sampler has seen the GPU under this load a few times.
     seen0, t_obs, extra = clocks.count(), time.perf_counter(), 0
     n_obs = 1 if dist is None else 0        # ranks must issue the same number of collective steps: fixed count there
-    while (dist is None and clocks.count() < seen0 + 3 and time.perf_counter() - t_obs < 3.0) or (dist is not None and n_obs < 1):
+    if not observe:                         # long steps: the timed region itself spans several sampling periods
+        n_obs = 1
+    while observe and (dist is None and clocks.count() < seen0 + 3 and time.perf_counter() - t_obs < 3.0) or (observe and dist is not None and n_obs < 1):
         for e in range(200 if dist is None else 1200):
             stepper(W + K + extra, W + 2 * K + 7)
             extra += 1
@@ -731,6 +737,133 @@ def measure_stress(args, device, peaks, peak_kind):
     return roof
 
 
+def measure_c5(args, device, dist, world, peaks, peak_kind):
+    """BASELINE configs[4]: 1 M users x 1 M items, 10^9 interactions, k = 128, full-catalog top-100 sharded over 8
+    GPUs. The log is generated ON EVERY GPU by the device-side click model (rfm_b200.clicks, SURVEY 8 f4: counter-
+    based, so every rank holds the same 10^9 factored rows, 16 bytes each) and trained data-parallel with the
+    reference's step (global batch 2^21 per GPU, one global Feistel permutation, NVLink reduce + apply); then every
+    item is ranked for every user, item-sharded, top-100."""
+    from rfm_b200._capi import check, lib, ptr
+    from rfm_b200.clicks import ClickModel, GeneratedRows
+    from rfm_b200.fm import FactorizationMachines, _FmTrainer
+    from rfm_b200.score import TopKScorer
+    from scipy.sparse import csr_matrix
+    U, I, k = args.c5_users, args.c5_items, STRESS_K
+    rows_total = args.c5_rows or 125_000_000 * world
+    B = min(1 << 21, max(1024, rows_total // (4 * world)))
+    K, W = max(3, min(args.steps, 6)), 3
+    t0 = time.perf_counter()
+    model_c = ClickModel(U, I, seed=2024)
+
+    def side(n, groups, mult0):
+        cols = np.empty((n, 3), dtype=np.int32)
+        ids = np.arange(n, dtype=np.int64)
+        off = 0
+        for j, g in enumerate(groups):
+            cols[:, j] = off + (ids * (j + mult0) + j) % g
+            off += g
+        return csr_matrix((np.ones(n * 3), cols.ravel(), np.arange(0, 3 * n + 1, 3, dtype=np.int32)), shape=(n, off))
+
+    blocks = [("id", "user", U), ("table", "user", side(U, STRESS_GROUPS[:3], 3)), ("id", "item", I),
+              ("table", "item", side(I, STRESS_GROUPS[3:], 5))]
+    n_features = U + I + sum(STRESS_GROUPS)
+    fm = FactorizationMachines("IPS", K, k, LR, B * world, 12345, n_features, dtype=args.dtype, sampler="feistel",
+                               device=device)
+    ctx = fm._context()
+    host_s = time.perf_counter() - t0
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    train = GeneratedRows(ctx, model_c, rows_total, blocks, row0=0, dtype=args.dtype)
+    val = GeneratedRows(ctx, model_c, N_VAL, blocks, row0=rows_total, dtype=args.dtype)
+    ctx.synchronize()
+    gen_s = time.perf_counter() - t0
+    fm.sync_to_device()
+    trainer = _FmTrainer(fm._dev, train, val, B, W + 2 * K + 8)
+    dp = None
+    if dist is not None:
+        from rfm_b200 import dist as rdist
+        dp = rdist.make_fm_dp(fm, trainer, dist, B * world, N_VAL, LR, lambda epoch: None)
+
+        def stepper(epoch, slot):
+            dp.step(epoch)
+    else:
+        def stepper(epoch, slot):
+            check(lib().rfm_fm_train_epoch_sampled(trainer.handle, 12345, epoch, B, LR, slot))
+    ms, launches, clk, prof = timed_steps(ctx, dist, stepper, W, K, device, observe=False)
+    if dist is None:
+        tl, vl = np.empty(W + K), np.empty(W + K)
+        check(lib().rfm_fm_trainer_losses(trainer.handle, 0, W + K, ptr(tl), ptr(vl)))
+        losses = (float(tl[-1]), float(vl[-1]))
+    else:
+        last = dp.flush().cpu().numpy()
+        losses = (float(last[0] / (B * world)), float(last[1] / N_VAL))
+    assert np.all(np.isfinite(losses)), "non-finite loss in the c5 section"
+    s = 8 if args.dtype == "float64" else 4
+    d = train.download(0, min(B, rows_total))
+    touched = np.unique(d["users"]).size + np.unique(d["items"]).size + sum(STRESS_GROUPS)
+    roof = step_roofline(prof, K, ms, B, world, 8.0, touched, k, s, peaks, peak_kind, False,
+                         "V (%.1f GB) and S (%.1f GB) exceed L2; per rank" % (n_features * k * s / 1e9, B * k * s / 1e9),
+                         "c5")
+    train_part = dict(roof, value=K * B * world / (ms * 1e-3), unit=UNIT, ms_per_step=ms / K, steps=K, warmup=W,
+                      batch_per_gpu=B, global_batch=B * world, interactions=rows_total, n_features=n_features,
+                      n_factors=k, rows_bytes_per_gpu=rows_total * (8 + s), generate_seconds=gen_s, host_setup_seconds=host_s,
+                      final_train_loss=losses[0], final_val_loss=losses[1], gpu_launches=launches,
+                      data="every rank generated all %d rows on its GPU (Philox click model), %.1f s" % (rows_total, gen_s))
+    trainer.close()
+    del train, val, trainer
+    # ---- scoring half: rank every item for every user, item-sharded, top-100
+    rng = np.random.default_rng(11)
+    A = rng.normal(size=(U, k)) * 0.3
+    C = rng.normal(size=(I, k)) * 0.3
+    beta = rng.normal(size=I) * 0.2
+    sc = TopKScorer(A, C, None, beta, 0.0, device=device)
+    Ktop = 100
+
+    def call():
+        if dist is not None:
+            from rfm_b200 import dist as rdist
+            return rdist.sharded_topk(sc, dist, Ktop, gather=False, copy=False)
+        return sc.topk(Ktop, copy=False)
+
+    call()
+    if dist is not None:
+        dist.barrier()
+    ctx.synchronize()
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = call()
+    ctx.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    if dist is not None:
+        dt = dist.max_over_ranks(dt)
+    ctx.profile_begin()
+    call()
+    sprof = ctx.profile_end()
+    fk = sum(v[0] * v[1] for k2, v in sprof.items() if k2 in ("score_sample", "score_collect"))
+    i_local = -(-I // world)
+    tf = 2.0 * (-(-U // 128) * 128) * (-(-i_local // 256) * 256) * 128 / (fk * 1e-3) / 1e12 if fk > 0 else None
+    # spot check: the first owned users' lists against a float64 argsort over the whole catalog
+    items_own = out[2] if dist is not None else out[0]
+    first_user = out[0] if dist is not None else 0
+    chk = min(4, items_own.shape[0])
+    S = A[first_user:first_user + chk] @ C.T + beta[None, :]
+    ref = np.argsort(S, axis=1, kind="stable")[:, ::-1][:, :Ktop]
+    exact = bool(np.array_equal(items_own[:chk], ref.astype(np.int32)))
+    score_part = {"users": U, "items": I, "n_factors": k, "top_k": Ktop, "value": U * I / dt, "unit": "pairs/s",
+                  "ms_per_call": dt * 1e3, "users_ranked_exactly": sc.last_stats.get("users_ranked_exactly"),
+                  "candidates_per_user": round(sc.last_stats.get("candidates", 0) / U, 2),
+                  "kernels_ms": {k2: [v[0], round(v[1], 3)] for k2, v in sprof.items()},
+                  "spot_check_vs_float64_argsort": exact,
+                  "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                               "frac": tf / peaks["bf16_tflops_sustained"] if tf else None,
+                               "note": "per rank; 2 U I_local k flops (one pass) over the time of both tensor passes"}}
+    assert exact, "c5 scoring spot check failed"
+    sc.close()
+    return {"workload": "BASELINE.json configs[4]: %d users x %d items, %d interactions, k=%d, top-%d, %d GPU(s)"
+                        % (U, I, rows_total, k, Ktop, world), "train": train_part, "scoring": score_part}
+
+
 def run_ours(args):
     from ctypes import byref
     from rfm_b200 import _capi
@@ -751,6 +884,19 @@ def run_ours(args):
     peaks, peak_kind = measured_peaks()
     parity = dp_parity(dist, local_rank) if dist is not None else None
 
+    if args.workload == "c5":
+        c5 = measure_c5(args, local_rank, dist, world, peaks, peak_kind)
+        if rank == 0:
+            tr = c5["train"]
+            print(json.dumps({"metric": METRIC, "value": tr["value"], "unit": UNIT, "n_gpus": world, "steps": tr["steps"],
+                              "warmup": tr["warmup"], "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32",
+                              "data": "synthetic", "config": {"workload": c5["workload"]}, "clocks": None,
+                              "roofline": dict(tr, scoring=c5["scoring"]), "gpu_launches": tr["gpu_launches"],
+                              "dp_parity": parity}))
+        if dist is not None:
+            dist.shutdown()
+        return
     if args.workload == "stress":
         roof = measure_stress(args, local_rank, peaks, peak_kind)
         if rank == 0:
@@ -813,11 +959,15 @@ def run_ours(args):
     ms, launches, clk, prof = main["ms"], main["launches"], main["clk"], main["prof"]
     value = K * B * world / (ms * 1e-3)
 
+    run_c5 = world == 8 and not args.no_c5
     if rank != 0:
         if not args.no_e2e:
             measure_e2e(args, log, ftrain, fval, local_rank, dist, world)
         if not args.no_scoring:
             measure_scoring(local_rank, dist, world, peaks, peak_kind)
+        if run_c5:
+            del log, X, ftrain, fval, train_in, val_in
+            measure_c5(args, local_rank, dist, world, peaks, peak_kind)
         dist.shutdown()
         return
 
@@ -839,6 +989,8 @@ def run_ours(args):
                                for name, v in scoring.items() if isinstance(v, dict)}
     if world == 1 and not args.no_stress:
         roofline["stress"] = measure_stress(args, local_rank, peaks, peak_kind)
+    if run_c5:      # BASELINE configs[4] rides in the 8-GPU line (roofline.c5): 10^9 interactions, 1 M x 1 M top-100
+        roofline["c5"] = measure_c5(args, local_rank, dist, world, peaks, peak_kind)
     cpu = None
     if not args.no_cpu_baseline:
         v1, st1, dt1 = cpu_port_run(log, B, 8, 1, budget_s=8.0)

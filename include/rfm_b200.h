@@ -147,6 +147,36 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
                         int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks,
                         const void *labels /* may be NULL */, int32_t label_bytes, const double *pscores, int dtype,
                         rfm_csr **out);
+/* Device-side generator of semi-synthetic interactions, mirroring the reference's
+ * simulation utils/dataloader/kuairec/_click.py:148-235: relevance gamma = clip(watch_ratio / relevance_clip, 0, 1)
+ * (:148-171), exposure theta_i = max(sigmoid(3 z_i - 1) ** exposure_bias, eps) per item (:173-205, computed by the
+ * caller: item_exposure), R ~ Be(gamma), O ~ Be(theta), click Y = O * R (:207-235); pscore = theta ** pow_used
+ * (kuairec/loader.py:167). The reference draws from NumPy's legacy global stream (sequential); this generator is
+ * counter-based (Philox4x32-10 keyed by seed, counter = global row index), so any shard of the log can be produced
+ * on any GPU: row g draws its user from user_cdf and its item from item_cdf (inclusive cumulative distributions,
+ * binary search), its context values ~ N(0, 1), its watch ratio = exp(hidden_scale <p_u, q_i> + noise_scale eps
+ * + watch_shift) with rank-n_hidden factors p_u, q_i ~ N(0, 1) that are themselves Philox functions of the id.
+ * Specification (bit-exact for ids, 1e-12 for values): oracle/clicks_oracle.py. rfm_factored_generate returns
+ * factored rows (blocks as rfm_factored_create; context blocks need no values) holding rows
+ * [row0, row0 + n_rows) of the log with targets y / pscore; keep_labels also keeps Y and R (rfm_rows_download). */
+typedef struct rfm_click_model {
+  uint64_t seed;
+  int64_t row0;
+  int64_t n_users, n_items;
+  const double *user_cdf;        /* [n_users], non-decreasing, last entry 1.0 */
+  const double *item_cdf;        /* [n_items] */
+  const double *item_exposure;   /* [n_items] theta_i in (0, 1] */
+  const double *item_pscore;     /* [n_items] theta_i ** pow_used, as the caller's NumPy computes it */
+  double pow_used;               /* informational */
+  int32_t n_hidden, keep_labels;
+  double hidden_scale, noise_scale, watch_shift, relevance_clip;
+} rfm_click_model;
+int rfm_factored_generate(rfm_ctx *ctx, int64_t n_rows, const rfm_click_model *model, const rfm_rows_block *blocks,
+                          int32_t n_blocks, int dtype, rfm_csr **out);
+/* Rows [first, first + n) of factored rows back on the host (any output may be NULL): ids, context values
+ * [n][n_ctx], targets y / pscore, and for generated rows with keep_labels the click and relevance labels. */
+int rfm_rows_download(rfm_csr *rows, int64_t first, int64_t n, int32_t *users, int32_t *items, double *ctx_values,
+                      double *targets, signed char *labels, signed char *relevance);
 /* Replace the per-row targets y/pscore with values the caller computed in float64 (fractional labels: the
  * reference divides whatever `labels` holds, src/fm.py:80; rfm_csr_create takes integer labels). */
 int rfm_csr_set_targets(rfm_csr *rows, const double *targets /* [n_rows] */);

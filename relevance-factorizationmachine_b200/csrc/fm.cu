@@ -23,79 +23,12 @@
 // fixed association, so results are bit-reproducible run to run.
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "rows.cuh"
 #include "sampler.cuh"
 
 using namespace rfm;
 
 // ---- handles ----------------------------------------------------------------------------------
-// Factored rows: what the reference's data layer holds BEFORE scipy.sparse.hstack
-// (utils/dataloader/coat/_preparer.py:154-170, kuairec/_feature.py:169-209) -- per-entity feature tables plus one
-// (user, item[, context]) record per interaction. A row is the concatenation, in column order, of up to FAC_MAX_SEG
-// blocks: the one-hot of an id, the table row of an id, or dense per-row context values. The row kernels assemble
-// x_t on the fly, so an interaction costs 8 + 8 n_ctx + 8 bytes of HBM instead of 12 m + 16.
-constexpr int FAC_MAX_SEG = 6;
-enum FacKind { SEG_ID = 0, SEG_TABLE = 1, SEG_CTX = 2 };
-struct FacSegDev {
-  int kind, key;            // key: 0 = the row's user id, 1 = its item id (SEG_ID, SEG_TABLE)
-  uint32_t col0;            // first global column of the block
-  int width;                // SEG_CTX: number of columns
-  const int32_t *ptr;       // SEG_TABLE: CSR of the table, columns local to the block
-  const int32_t *col;
-  const void *val;          // T
-  int ctx0;                 // SEG_CTX: first column of the block inside a row's context record
-  int pad;
-};
-struct FacDev {
-  int n_seg, n_ctx, es, pad;  // es: bytes per value (4 or 8)
-  const int32_t *user, *item;
-  const void *ctx;          // T [n_rows][n_ctx]
-  const void *one;          // T [1] = 1.0: what an id block's entry loads as its value (keeps the entry fetch branch-free)
-  FacSegDev seg[FAC_MAX_SEG];
-};
-
-struct rfm_csr {
-  rfm_ctx *ctx = nullptr;
-  int dtype = RFM_F64;
-  int64_t n_rows = 0, n_cols = 0, nnz = 0, max_row_len = 0;
-  bool has_targets = false;
-  DevBuf<int64_t> row_ptr;
-  DevBuf<int32_t> col;
-  DevBuf<unsigned char> val, yp;
-  // factored rows (rfm_factored_create): the CSR buffers above stay empty
-  bool factored = false;
-  int n_seg = 0, n_ctx = 0;
-  DevBuf<int32_t> f_user, f_item;
-  DevBuf<unsigned char> f_ctx, f_one;
-  struct Seg {
-    int kind = 0, key = 0, width = 0, ctx0 = 0;
-    uint32_t col0 = 0;
-    DevBuf<int32_t> ptr, col;
-    DevBuf<unsigned char> val;
-  } seg[FAC_MAX_SEG];
-  FacDev fac_dev(int64_t row_offset = 0) const {
-    FacDev f;
-    memset(&f, 0, sizeof(f));
-    f.n_seg = n_seg;
-    f.n_ctx = n_ctx;
-    f.es = dtype == RFM_F64 ? 8 : 4;
-    f.user = f_user.p + row_offset;
-    f.item = f_item.p + row_offset;
-    f.ctx = f_ctx.p ? f_ctx.p + (size_t)row_offset * n_ctx * (dtype == RFM_F64 ? 8 : 4) : nullptr;
-    f.one = f_one.p;
-    for (int s = 0; s < n_seg; ++s) {
-      f.seg[s].kind = seg[s].kind;
-      f.seg[s].key = seg[s].key;
-      f.seg[s].col0 = seg[s].col0;
-      f.seg[s].width = seg[s].width;
-      f.seg[s].ptr = seg[s].ptr.p;
-      f.seg[s].col = seg[s].col.p;
-      f.seg[s].val = seg[s].val.p;
-      f.seg[s].ctx0 = seg[s].ctx0;
-    }
-    return f;
-  }
-};
-
 struct rfm_fm {
   rfm_ctx *ctx = nullptr;
   int dtype = RFM_F64;
@@ -142,6 +75,12 @@ template <typename T>
 __global__ void convert_f64_kernel(const double *__restrict__ in, T *__restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = static_cast<T>(in[i]);
+}
+
+template <typename T>
+__global__ void widen_to_f64_kernel(const T *__restrict__ in, double *__restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = static_cast<double>(in[i]);
 }
 
 __global__ void widen_i32_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
@@ -1599,15 +1538,18 @@ int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev, void **col_dev, void 
   return RFM_OK;
 }
 
-int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64, const void *items,
-                        int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks, const void *labels,
-                        int32_t label_bytes, const double *pscores, int dtype, rfm_csr **out) {
+}  // extern "C" (pause)
+// gen != NULL: ids, context values and targets are generated on the device (rfm_factored_generate) instead of uploaded
+static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64,
+                                const void *items, int32_t items_is_int64, const rfm_rows_block *blocks,
+                                int32_t n_blocks, const void *labels, int32_t label_bytes, const double *pscores,
+                                int dtype, const rfm_click_model *gen, rfm_csr **out) {
   RFM_REQUIRE(ctx && out, "rfm_factored_create: NULL ctx/out");
   *out = nullptr;
   RFM_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffffLL, "rfm_factored_create: bad row count %lld", (long long)n_rows);
   RFM_REQUIRE(blocks && n_blocks >= 1 && n_blocks <= FAC_MAX_SEG, "rfm_factored_create: between 1 and %d blocks",
               FAC_MAX_SEG);
-  RFM_REQUIRE(n_rows == 0 || (users && items), "rfm_factored_create: users/items are NULL");
+  RFM_REQUIRE(n_rows == 0 || gen || (users && items), "rfm_factored_create: users/items are NULL");
   RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "rfm_factored_create: bad dtype %d", dtype);
   RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "rfm_factored_create: labels and pscores go together");
   RFM_REQUIRE(!labels || label_bytes == 1 || label_bytes == 4 || label_bytes == 8,
@@ -1621,7 +1563,7 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
                 "rfm_factored_create: block %d has unknown kind %d", b, k.kind);
     RFM_REQUIRE(k.n_cols >= 1, "rfm_factored_create: block %d has no columns", b);
     if (k.kind == RFM_BLOCK_CTX) {
-      RFM_REQUIRE(k.values || n_rows == 0, "rfm_factored_create: context block %d has no values", b);
+      RFM_REQUIRE(k.values || n_rows == 0 || gen, "rfm_factored_create: context block %d has no values", b);
       n_ctx += k.n_cols;
       RFM_REQUIRE(n_ctx <= 32, "rfm_factored_create: more than 32 context columns in total");
     } else {
@@ -1640,7 +1582,7 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
   r->dtype = dtype;
   r->n_rows = n_rows;
   r->n_cols = n_cols;
-  r->has_targets = labels != nullptr;
+  r->has_targets = labels != nullptr || gen != nullptr;
   r->factored = true;
   r->n_seg = n_blocks;
   r->n_ctx = (int)n_ctx;
@@ -1666,7 +1608,7 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
     int n_tmp = 0;
     const int g = grid_for(ctx, ceil_div(nr, 256), 8);
     // ids: 4 or 8 bytes per row over PCIe as the caller holds them, narrowed (and range-checked) on the device
-    for (int side = 0; side < 2 && n_rows > 0; ++side) {
+    for (int side = 0; side < 2 && n_rows > 0 && !gen; ++side) {
       const void *src = side == 0 ? users : items;
       const bool is64 = (side == 0 ? users_is_int64 : items_is_int64) != 0;
       int32_t *dst = side == 0 ? r->f_user.p : r->f_item.p;
@@ -1727,7 +1669,7 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
                        reinterpret_cast<const double *>(st.p), reinterpret_cast<float *>(sg.val.p), tnz);
           }
         }
-      } else if (sg.kind == SEG_CTX && n_rows > 0) {
+      } else if (sg.kind == SEG_CTX && n_rows > 0 && !gen) {
         if (dtype == RFM_F64 && n_ctx == k.n_cols) {      // the only context block, already in the record's layout
           RFM_TRY(upload(ctx, r->f_ctx.p, k.values, (size_t)n_rows * n_ctx * 8));
         } else {
@@ -1748,7 +1690,18 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
       col0 += (uint32_t)k.n_cols;
     }
     // targets
-    if (labels && n_rows > 0) {
+    if (gen) {
+      if (gen->keep_labels) {
+        RFM_TRY(r->g_label.alloc((size_t)nr));
+        RFM_TRY(r->g_relevance.alloc((size_t)nr));
+      }
+      if (n_rows > 0) {
+        RFM_REQUIRE(gen->n_users <= limit[0] && gen->n_items <= limit[1],
+                    "rfm_factored_generate: the click model draws ids the blocks do not cover");
+        RFM_TRY(rfm_synth_fill_rows(ctx, gen, n_rows, r->f_user.p, r->f_item.p, r->f_ctx.p, (int)n_ctx, r->yp.p,
+                                    r->g_label.p, r->g_relevance.p, dtype));
+      }
+    } else if (labels && n_rows > 0) {
       DevBuf<unsigned char> &ys = tmp[n_tmp++];
       DevBuf<unsigned char> &ps = tmp[n_tmp++];
       RFM_TRY(ys.alloc((size_t)n_rows * label_bytes));
@@ -1789,6 +1742,61 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
     return rc;
   }
   *out = r;
+  return RFM_OK;
+}
+
+extern "C" {
+
+int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64, const void *items,
+                        int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks, const void *labels,
+                        int32_t label_bytes, const double *pscores, int dtype, rfm_csr **out) {
+  return factored_create_impl(ctx, n_rows, users, users_is_int64, items, items_is_int64, blocks, n_blocks, labels,
+                              label_bytes, pscores, dtype, nullptr, out);
+}
+
+int rfm_factored_generate(rfm_ctx *ctx, int64_t n_rows, const rfm_click_model *model, const rfm_rows_block *blocks,
+                          int32_t n_blocks, int dtype, rfm_csr **out) {
+  RFM_REQUIRE(model, "rfm_factored_generate: model is NULL");
+  return factored_create_impl(ctx, n_rows, nullptr, 0, nullptr, 0, blocks, n_blocks, nullptr, 8, nullptr, dtype, model,
+                              out);
+}
+
+// ids, context values, targets (and, for generated rows that kept them, click / relevance labels) of rows
+// [first, first + n) back on the host: what a test compares with the generator's specification
+int rfm_rows_download(rfm_csr *rows, int64_t first, int64_t n, int32_t *users, int32_t *items, double *ctx_values,
+                      double *targets, signed char *labels, signed char *relevance) {
+  RFM_REQUIRE(rows && rows->factored, "rfm_rows_download: factored rows only");
+  RFM_REQUIRE(first >= 0 && n >= 0 && first + n <= rows->n_rows, "rfm_rows_download: row range out of bounds");
+  RFM_REQUIRE((!labels && !relevance) || rows->g_label.p, "rfm_rows_download: these rows kept no labels");
+  rfm_ctx *ctx = rows->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return RFM_OK;
+  const size_t es = dsize(rows->dtype);
+  if (users) RFM_CUDA(cudaMemcpyAsync(users, rows->f_user.p + first, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (items) RFM_CUDA(cudaMemcpyAsync(items, rows->f_item.p + first, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (labels) RFM_CUDA(cudaMemcpyAsync(labels, rows->g_label.p + first, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (relevance)
+    RFM_CUDA(cudaMemcpyAsync(relevance, rows->g_relevance.p + first, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  DevBuf<double> tmp;
+  const size_t nc = (size_t)n * rows->n_ctx;
+  RFM_TRY(tmp.alloc(nc + (size_t)n));
+  if (rows->dtype == RFM_F64) {
+    if (ctx_values && nc)
+      RFM_CUDA(cudaMemcpyAsync(ctx_values, rows->f_ctx.p + (size_t)first * rows->n_ctx * es, nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (targets) RFM_CUDA(cudaMemcpyAsync(targets, rows->yp.p + (size_t)first * es, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    if (ctx_values && nc) {
+      RFM_LAUNCH(ctx, widen_to_f64_kernel<float>, grid_for(ctx, ceil_div((int64_t)nc, 256), 8), 256, 0,
+                 reinterpret_cast<const float *>(rows->f_ctx.p) + (size_t)first * rows->n_ctx, tmp.p, (int64_t)nc);
+      RFM_CUDA(cudaMemcpyAsync(ctx_values, tmp.p, nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (targets) {
+      RFM_LAUNCH(ctx, widen_to_f64_kernel<float>, grid_for(ctx, ceil_div(n, 256), 8), 256, 0,
+                 reinterpret_cast<const float *>(rows->yp.p) + first, tmp.p + nc, n);
+      RFM_CUDA(cudaMemcpyAsync(targets, tmp.p + nc, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
 }
 
@@ -1894,15 +1902,6 @@ int rfm_fm_set_params(rfm_fm *m, const double *w0, const double *w, const double
   return RFM_OK;
 }
 
-}  // extern "C" (pause)
-namespace {
-template <typename T>
-__global__ void widen_to_f64_kernel(const T *__restrict__ in, double *__restrict__ out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = static_cast<double>(in[i]);
-}
-}  // namespace
-extern "C" {
 
 int rfm_fm_get_params(rfm_fm *m, double *w0, double *w, double *V) {
   RFM_REQUIRE(m && w0 && w && V, "rfm_fm_get_params: NULL argument");

@@ -556,6 +556,43 @@ __device__ __forceinline__ float key_to_float(uint32_t key) {
   return __uint_as_float((key & 0x80000000u) ? (key ^ 0x80000000u) : ~key);
 }
 
+// K-th largest of the keys a warp holds in registers (NJ per lane, 0 = none). For small K, K rounds of "take the
+// maximum out" (one warp reduction each) beat the 32 rounds of the bit-wise bisection.
+template <int NJ>
+__device__ __forceinline__ uint32_t warp_kth_largest(uint32_t (&key)[NJ], int K, int lane) {
+  if (K <= 24) {
+    uint32_t kth = 0u;
+    for (int r = 0; r < K; ++r) {
+      uint32_t m = 0u;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) m = max(m, key[j]);
+      kth = __reduce_max_sync(FULL, m);
+      if (kth == 0u) break;                                   // fewer than K keys
+      const unsigned holders = __ballot_sync(FULL, m == kth);
+      if (lane == __ffs(holders) - 1) {                       // one holder drops one instance of the maximum
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (!done && key[j] == kth) {
+            key[j] = 0u;
+            done = true;
+          }
+      }
+    }
+    return kth;
+  }
+  uint32_t thr = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand_thr = thr | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) cnt += key[j] >= cand_thr;
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (cnt >= K) thr = cand_thr;
+  }
+  return thr;
+}
+
 // One warp per user: the K-th largest group maximum of the sample is a lower bound on the user's K-th best
 // approximate score (K different items reach it). tau = that bound - 2 eps: every item whose EXACT score can
 // reach the exact K-th best has an approximate score >= tau (eps bounds |approximate - exact|).
@@ -601,7 +638,30 @@ score_threshold_kernel(const float *__restrict__ gmax, int64_t n_groups, int fol
       __syncwarp();
     }
     float t0 = -INFINITY;
-    if (n_groups >= K) {
+    bool exported = false;
+    if (NJ > 0 && K <= 24 && n_groups >= K) {
+      // small K: K rounds of "take the maximum out"; the extracted values ARE the K largest, exported as they come
+      uint32_t kth = 0u;
+      for (int r = 0; r < K; ++r) {
+        uint32_t m = 0u;
+#pragma unroll
+        for (int j = 0; j < (NJ > 0 ? NJ : 1); ++j) m = max(m, key[j]);
+        kth = __reduce_max_sync(FULL, m);
+        const unsigned holders = __ballot_sync(FULL, m == kth);
+        if (lane == __ffs(holders) - 1) {
+          bool done = false;
+#pragma unroll
+          for (int j = 0; j < (NJ > 0 ? NJ : 1); ++j)
+            if (!done && key[j] == kth) {
+              key[j] = 0u;
+              done = true;
+            }
+          if (gtop) gtop[u * (int64_t)K + r] = kth;
+        }
+      }
+      t0 = key_to_float(kth);
+      exported = true;
+    } else if (n_groups >= K) {
       uint32_t thr = 0u;                // bisection on the key bits for the K-th largest key
       for (int bit = 31; bit >= 0; --bit) {
         const uint32_t cand_thr = thr | (1u << bit);
@@ -619,7 +679,7 @@ score_threshold_kernel(const float *__restrict__ gmax, int64_t n_groups, int fol
       t0 = __uint_as_float(bits);
     }
     __syncwarp();
-    if (gtop) {
+    if (gtop && !exported) {
       // item-sharded runs: this rank's K largest group maxima (as keys, any order) go to the exchange region; the
       // K-th largest of the union over all ranks is the global bound (score_global_threshold_kernel)
       uint32_t *out = gtop + u * (int64_t)K;
@@ -827,18 +887,29 @@ score_rescore_kernel(const ExactArgs e, int64_t user0, int64_t n_users_chunk, co
   uint32_t *key = reinterpret_cast<uint32_t *>(it + kc);
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long seen = 0ull;        // candidates of this warp's users: ONE atomic per warp at the end (a per-user
+                                         // atomic on a single address serialised all 32,768 users of a pass at L2)
   for (int64_t row = gw; row < n_users_chunk; row += nw) {
     const int64_t u = user0 + row;
+    // the count and the first 32 candidates are requested together: one memory round trip instead of two
     const uint32_t cnt = cand_cnt[row];
-    if (lane == 0) atomicAdd(n_cand_total, (unsigned long long)cnt);
+    const int2 first = lane < kc ? cand[row * kc + lane] : make_int2(-1, 0);
+    seen += cnt;
     if (cnt > (uint32_t)kc) {            // more candidates than the buffer holds: rank this user exactly
       if (lane == 0) fail_list[atomicAdd(n_fail, 1u)] = (int32_t)u;
       continue;
     }
     int n_cand = (int)cnt;
+    if (n_cand == 0) {                   // nothing of this user's top-K can live in this range (sharded runs)
+      for (int r = lane; r < K; r += 32) {
+        out_items[u * K + r] = -1;
+        out_scores[u * K + r] = -INFINITY;
+      }
+      continue;
+    }
     for (int f = lane; f < e.k; f += 32) au[f] = e.A[u * e.k + f];
     for (int c = lane; c < n_cand; c += 32) {
-      const int2 v = cand[row * kc + c];
+      const int2 v = c == lane ? first : cand[row * kc + c];
       const uint32_t bits = (uint32_t)v.y;
       it[c] = v.x;
       key[c] = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);      // order-preserving uint key
@@ -903,6 +974,7 @@ score_rescore_kernel(const ExactArgs e, int64_t user0, int64_t n_users_chunk, co
     }
     __syncwarp();
   }
+  if (lane == 0 && seen) atomicAdd(n_cand_total, seen);
 }
 
 // one CTA per user: exact top-K over the whole catalog range (fallback and exact mode). The float64 scores of
@@ -1051,34 +1123,31 @@ __global__ void topk_xch_barrier_kernel(const XchPeers peers, size_t flags_off, 
   }
 }
 
-// One warp per user: K-th largest of the world x K group-maximum keys the ranks exported -> collect threshold
+// One warp per user: K-th largest of the world x K group-maximum keys the ranks exported -> collect threshold.
+// A lane keeps its NJ keys in registers and issues every peer load (2-3 us over NVLink) before the first use.
+template <int NJ>
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
 score_global_threshold_kernel(const XchPeers peers, size_t gtop_off, int world, int K, int64_t user0,
                               int64_t n_users_chunk, const float *__restrict__ eps, float *__restrict__ tau) {
-  extern __shared__ __align__(16) unsigned char gt_smem[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int n = world * K;
-  uint32_t *skey = reinterpret_cast<uint32_t *>(gt_smem) + (size_t)wid * n;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = gw; row < n_users_chunk; row += nw) {
     const int64_t u = user0 + row;
-    for (int i = lane; i < n; i += 32) {
-      const int q = i / K, j = i - q * K;
-      skey[i] = __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + gtop_off) + u * K + j);
+    uint32_t key[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int i = lane + 32 * j;
+      key[j] = 0u;
+      if (i < n) {
+        const int q = i / K, jj = i - q * K;
+        key[j] = __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + gtop_off) + u * K + jj);
+      }
     }
-    __syncwarp();
-    uint32_t thr = 0u;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand_thr = thr | (1u << bit);
-      int cnt = 0;
-      for (int i = lane; i < n; i += 32) cnt += skey[i] >= cand_thr;
-      cnt = __reduce_add_sync(FULL, cnt);
-      if (cnt >= K) thr = cand_thr;
-    }
+    const uint32_t thr = warp_kth_largest<NJ>(key, K, lane);
     const float t0 = key_to_float(thr);
     if (lane == 0) tau[row] = t0 > -INFINITY ? __double2float_rd((double)t0 - 2.0 * (double)eps[row]) : -INFINITY;
-    __syncwarp();
   }
 }
 
@@ -1099,12 +1168,29 @@ topk_xch_merge_kernel(const ListPtrs lists, int world, int K, int64_t user_begin
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t u = user_begin + gw; u < user_end; u += nw) {
     int valid = 0;
-    for (int i = lane; i < n; i += 32) {
-      const int q = i / K, j = i - q * K;
-      const int32_t it = __ldcg(lists.items[q] + u * K + j);
-      si[i] = it;
-      ss[i] = __ldcg(lists.scores[q] + u * K + j);
-      valid += it >= 0;
+    for (int i0 = 0; i0 < n; i0 += 32 * 4) {          // four peer loads of each kind in flight per lane
+      int32_t it[4];
+      double sv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + 32 * r + lane;
+        it[r] = -1;
+        sv[r] = 0.0;
+        if (i < n) {
+          const int q = i / K, j = i - q * K;
+          it[r] = __ldcg(lists.items[q] + u * K + j);
+          sv[r] = __ldcg(lists.scores[q] + u * K + j);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + 32 * r + lane;
+        if (i < n) {
+          si[i] = it[r];
+          ss[i] = sv[r];
+          valid += it[r] >= 0;
+        }
+      }
     }
     valid = __reduce_add_sync(FULL, valid);
     __syncwarp();
@@ -1521,7 +1607,7 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
       n_splits = (n_sample + pa.tiles_per_split - 1) / pa.tiles_per_split;
       RFM_TRY(launch_pass(ctx, t->kb, 0, gcols, dim3(n_ctas_x, n_splits), t->tmap_a, t->tmap_c, pa));
       const int tgrid = (int)std::min<int64_t>(((int64_t)nb * BM + SELECT_WARPS - 1) / SELECT_WARPS,
-                                               (int64_t)ctx->sm_count * 8);
+                                               (int64_t)ctx->sm_count * 16);
       RFM_TRY(launch_threshold(ctx, tgrid, t->gmax.p, n_groups / fold, fold, (int64_t)nb * BM, users_here, (int)K,
                                t->a_norm.p + user0, t->a_res.p + user0, t->c_norm_max.p, t->c_res_max.p,
                                t->beta_abs_max.p, t->kpad, t->tau.p, t->eps.p, t->cand_cnt.p,
@@ -1529,9 +1615,20 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
       if (plan.on) {
         // every rank's K largest group maxima are in place -> the global K-th largest replaces the local bound
         RFM_TRY(xch_barrier(t));
-        const size_t gsmem = (size_t)SELECT_WARPS * t->x_world * K * 4;
-        RFM_LAUNCH(ctx, score_global_threshold_kernel, tgrid, SELECT_WARPS * 32, gsmem, xch_peers(t), t->x_gtop_off,
-                   t->x_world, (int)K, user0, users_here, t->eps.p, t->tau.p);
+        const int per_lane = (t->x_world * K + 31) / 32;
+        const int ggrid = (int)std::min<int64_t>((users_here + SELECT_WARPS - 1) / SELECT_WARPS,
+                                                 (int64_t)ctx->sm_count * 16);
+#define RFM_GLOBAL_THRESHOLD(NJ)                                                                             \
+  do {                                                                                                       \
+    auto score_global_threshold = score_global_threshold_kernel<NJ>;                                         \
+    RFM_LAUNCH(ctx, score_global_threshold, ggrid, SELECT_WARPS * 32, 0, xch_peers(t), t->x_gtop_off,        \
+               t->x_world, (int)K, user0, users_here, t->eps.p, t->tau.p);                                   \
+  } while (0)
+        if (per_lane <= 4) RFM_GLOBAL_THRESHOLD(4);
+        else if (per_lane <= 8) RFM_GLOBAL_THRESHOLD(8);
+        else if (per_lane <= 16) RFM_GLOBAL_THRESHOLD(16);
+        else RFM_GLOBAL_THRESHOLD(30);           // world * K <= 8 * 120
+#undef RFM_GLOBAL_THRESHOLD
       }
       // pass 2: collect every item that reaches the threshold
       pa.tile_stride = 1;
@@ -1540,8 +1637,9 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
       pa.tiles_per_split = (n_item_tiles + n_splits - 1) / n_splits;
       n_splits = (n_item_tiles + pa.tiles_per_split - 1) / pa.tiles_per_split;
       RFM_TRY(launch_pass(ctx, t->kb, 1, 64, dim3(n_ctas_x, n_splits), t->tmap_a, t->tmap_c, pa));
+      const int rs_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / std::max<size_t>(rs_smem, 1)));
       const int rgrid = (int)std::min<int64_t>((users_here + RESCORE_WARPS - 1) / RESCORE_WARPS,
-                                               (int64_t)ctx->sm_count * 8);
+                                               (int64_t)ctx->sm_count * rs_per_sm);
       RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
                  t->cand.p, t->eps.p, kc, (int)K, dst_items, dst_scores, t->fail_list.p, t->n_fail.p, t->n_cand.p);
     }
@@ -1729,7 +1827,8 @@ int rfm_topk_run_sharded(rfm_topk *t, int32_t K, int32_t mode, int32_t *out_item
   if (n_own > 0) {
     const size_t msmem = (size_t)MERGE_WARPS * world * K * 12;
     RFM_CUDA(cudaFuncSetAttribute(topk_xch_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-    const int mgrid = (int)std::min<int64_t>((n_own + MERGE_WARPS - 1) / MERGE_WARPS, (int64_t)ctx->sm_count * 2);
+    const int mgrid = (int)std::min<int64_t>((n_own + MERGE_WARPS - 1) / MERGE_WARPS,
+                                             (int64_t)ctx->sm_count * std::max<int64_t>(1, std::min<int64_t>(8, (200 * 1024) / std::max<size_t>(msmem, 1))));
     ListPtrs lp;
     for (int q = 0; q < XCH_MAX_WORLD; ++q) {
       lp.items[q] = q < world ? reinterpret_cast<const int32_t *>(t->x_peer[q] + t->x_items_off) : nullptr;

@@ -152,6 +152,10 @@ class FactorizationMachines(PointwiseBaseRecommender):
         from .factored import FactoredFeatures, FactoredRows
         if isinstance(X, FactoredFeatures):     # user table + item table + (user, item, ctx) records: assembled on the device
             return FactoredRows(self._context(), X, labels, pscores, self.dtype)
+        if isinstance(X, _capi._Handle):        # rows that already live on the device (rfm_b200.clicks.GeneratedRows)
+            if X.dtype != self.dtype:
+                raise ValueError("device rows are %s, the model is %s" % (X.dtype, self.dtype))
+            return X
         env = self.distributed
         if (env is not None and labels is not None and env.backend == "nccl" and env.world > 1
                 and X.shape[0] >= int(os.environ.get("RFM_DP_UPLOAD_MIN_ROWS", "1000000"))
