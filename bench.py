@@ -417,7 +417,7 @@ def measure_scoring(device, dist, world, peaks, peak_kind):
         ctx.profile_begin()
         call()
         prof = ctx.profile_end()
-        fk = sum(v[0] * v[1] for k2, v in prof.items() if k2 in ("score_sample", "score_collect"))
+        fk = sum(v[1] for k2, v in prof.items() if k2 in ("score_sample", "score_collect"))       # v = (launches, total ms)
         i_local = I // world
         upad, ipad = -(-U // 128) * 128, -(-i_local // 256) * 256
         entry = {"users": U, "items": I, "n_factors": k, "top_k": K, "value": U * I / dt, "ms_per_call": dt * 1e3,
@@ -728,7 +728,7 @@ def measure_stress(args, device, peaks, peak_kind):
     roof = step_roofline(prof, K, ms, B, 1, 8.0, touched, STRESS_K, s, peaks, peak_kind, False,
                          "V (%.1f GB) and S (%.1f GB) exceed L2: id-column gathers and the s_t gather are HBM traffic"
                          % (n_features * STRESS_K * s / 1e9, B * STRESS_K * s / 1e9), "stress")
-    roof.update(value=K * B / (ms * 1e-3), unit=UNIT, ms_per_step=ms / K, steps=K, warmup=W, batch=B,
+    roof.update(value=K * B / (ms * 1e-3), value_unit=UNIT, ms_per_step=ms / K, steps=K, warmup=W, batch=B,
                 n_factors=STRESS_K, n_features=n_features, train_interactions=args.stress_rows,
                 input_format="factored", data_gen_s=round(gen_s, 1), clocks=clk,
                 workload="IPS-FM stress, BASELINE.json configs[4] shape on one GPU's share: 1M users x 1M items, "
@@ -804,7 +804,7 @@ def measure_c5(args, device, dist, world, peaks, peak_kind):
     roof = step_roofline(prof, K, ms, B, world, 8.0, touched, k, s, peaks, peak_kind, False,
                          "V (%.1f GB) and S (%.1f GB) exceed L2; per rank" % (n_features * k * s / 1e9, B * k * s / 1e9),
                          "c5")
-    train_part = dict(roof, value=K * B * world / (ms * 1e-3), unit=UNIT, ms_per_step=ms / K, steps=K, warmup=W,
+    train_part = dict(roof, value=K * B * world / (ms * 1e-3), value_unit=UNIT, ms_per_step=ms / K, steps=K, warmup=W,
                       batch_per_gpu=B, global_batch=B * world, interactions=rows_total, n_features=n_features,
                       n_factors=k, rows_bytes_per_gpu=rows_total * (8 + s), generate_seconds=gen_s, host_setup_seconds=host_s,
                       final_train_loss=losses[0], final_val_loss=losses[1], gpu_launches=launches,
@@ -840,7 +840,7 @@ def measure_c5(args, device, dist, world, peaks, peak_kind):
     ctx.profile_begin()
     call()
     sprof = ctx.profile_end()
-    fk = sum(v[0] * v[1] for k2, v in sprof.items() if k2 in ("score_sample", "score_collect"))
+    fk = sum(v[1] for k2, v in sprof.items() if k2 in ("score_sample", "score_collect"))      # v = (launches, total ms)
     i_local = -(-I // world)
     tf = 2.0 * (-(-U // 128) * 128) * (-(-i_local // 256) * 256) * 128 / (fk * 1e-3) / 1e12 if fk > 0 else None
     # spot check: the first owned users' lists against a float64 argsort over the whole catalog

@@ -621,13 +621,17 @@ score_threshold_kernel(const float *__restrict__ gmax, int64_t n_groups, int fol
       if (lane == 0) tau[u] = INFINITY;
       continue;
     }
-    // fold == 2: adjacent stored groups are merged on load (the maximum of two group maxima is the maximum of
-    // the doubled group), halving the keys when the sample holds more groups than the threshold needs
+    // fold = 2 or 4: adjacent stored groups are merged on load (the maximum of group maxima is the maximum of the
+    // wider group), shrinking the key set when the sample holds more groups than the threshold needs
     const float *g = gmax + u * n_groups * fold;
     auto group_max = [&](int64_t i) {
       if (fold == 1) return g[i];
-      const float2 p = *reinterpret_cast<const float2 *>(g + 2 * i);
-      return fmaxf(p.x, p.y);
+      if (fold == 2) {
+        const float2 p = *reinterpret_cast<const float2 *>(g + 2 * i);
+        return fmaxf(p.x, p.y);
+      }
+      const float4 p = *reinterpret_cast<const float4 *>(g + 4 * i);
+      return fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w));
     };
     uint32_t key[NJ > 0 ? NJ : 1];
     if (NJ > 0) {
@@ -1124,25 +1128,26 @@ __global__ void topk_xch_barrier_kernel(const XchPeers peers, size_t flags_off, 
 }
 
 // One warp per user: K-th largest of the world x K group-maximum keys the ranks exported -> collect threshold.
-// A lane keeps its NJ keys in registers and issues every peer load (2-3 us over NVLink) before the first use.
-template <int NJ>
+// A lane keeps XCH_MAX_WORLD x KJ keys in registers (KJ = ceil(K / 32) per peer; the peer loop is uniform, so the
+// peers' base pointers stay in uniform registers) and issues every peer load before the first use.
+template <int KJ>
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
 score_global_threshold_kernel(const XchPeers peers, size_t gtop_off, int world, int K, int64_t user0,
                               int64_t n_users_chunk, const float *__restrict__ eps, float *__restrict__ tau) {
+  constexpr int NJ = XCH_MAX_WORLD * KJ;
   const int lane = threadIdx.x & 31;
-  const int n = world * K;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = gw; row < n_users_chunk; row += nw) {
     const int64_t u = user0 + row;
     uint32_t key[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int i = lane + 32 * j;
-      key[j] = 0u;
-      if (i < n) {
-        const int q = i / K, jj = i - q * K;
-        key[j] = __ldcg(reinterpret_cast<const uint32_t *>(peers.base[q] + gtop_off) + u * K + jj);
+    for (int q = 0; q < XCH_MAX_WORLD; ++q) {
+      const uint32_t *src = q < world ? reinterpret_cast<const uint32_t *>(peers.base[q] + gtop_off) + u * K : nullptr;
+#pragma unroll
+      for (int r = 0; r < KJ; ++r) {
+        const int jj = lane + 32 * r;
+        key[q * KJ + r] = (src && jj < K) ? __ldcg(src + jj) : 0u;
       }
     }
     const uint32_t thr = warp_kth_largest<NJ>(key, K, lane);
@@ -1168,26 +1173,25 @@ topk_xch_merge_kernel(const ListPtrs lists, int world, int K, int64_t user_begin
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t u = user_begin + gw; u < user_end; u += nw) {
     int valid = 0;
-    for (int i0 = 0; i0 < n; i0 += 32 * 4) {          // four peer loads of each kind in flight per lane
+#pragma unroll
+    for (int q = 0; q < XCH_MAX_WORLD; ++q) {           // uniform loop: the list pointers stay in uniform registers
+      if (q >= world) break;
+      const int32_t *pi = lists.items[q] + u * K;
+      const double *ps = lists.scores[q] + u * K;
       int32_t it[4];
       double sv[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = i0 + 32 * r + lane;
-        it[r] = -1;
-        sv[r] = 0.0;
-        if (i < n) {
-          const int q = i / K, j = i - q * K;
-          it[r] = __ldcg(lists.items[q] + u * K + j);
-          sv[r] = __ldcg(lists.scores[q] + u * K + j);
-        }
+      for (int r = 0; r < 4; ++r) {                     // K <= 120: at most four entries per lane and list, all in flight
+        const int j = lane + 32 * r;
+        it[r] = j < K ? __ldcg(pi + j) : -1;
+        sv[r] = j < K ? __ldcg(ps + j) : 0.0;
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int i = i0 + 32 * r + lane;
-        if (i < n) {
-          si[i] = it[r];
-          ss[i] = sv[r];
+        const int j = lane + 32 * r;
+        if (j < K) {
+          si[q * K + j] = it[r];
+          ss[q * K + j] = sv[r];
           valid += it[r] >= 0;
         }
       }
@@ -1543,7 +1547,11 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
     const int64_t plan_groups = std::max<int64_t>(1, groups_of(plan_tiles, stride, gcols));
     // About c K stride items per user reach the threshold (negative binomial in the sampling, sd
     // stride sqrt(K (1 - 1/stride)); c = -ln(1 - f) / f corrects for top items sharing a group, f = K / groups).
-    const int fold = (!plan.on && n_groups % 2 == 0 && n_groups / 2 >= want_groups) ? 2 : 1;   // threshold over pairs of groups
+    // the threshold kernel merges `fold` adjacent stored groups on load when the sample holds more groups than the
+    // threshold needs: fewer keys per user to select from
+    int fold = 1;
+    for (int cand = 4; cand >= 2 && fold == 1; cand /= 2)
+      if (n_groups % cand == 0 && n_groups / cand >= want_groups) fold = cand;
     const double f = std::min(0.5, (double)K * fold / (double)plan_groups);
     const double cf = -std::log1p(-f) / f;
     const double sd = stride * std::sqrt((double)K * (1.0 - 1.0 / stride));
@@ -1615,19 +1623,19 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
       if (plan.on) {
         // every rank's K largest group maxima are in place -> the global K-th largest replaces the local bound
         RFM_TRY(xch_barrier(t));
-        const int per_lane = (t->x_world * K + 31) / 32;
+        const int kj = (K + 31) / 32;
         const int ggrid = (int)std::min<int64_t>((users_here + SELECT_WARPS - 1) / SELECT_WARPS,
                                                  (int64_t)ctx->sm_count * 16);
-#define RFM_GLOBAL_THRESHOLD(NJ)                                                                             \
+#define RFM_GLOBAL_THRESHOLD(KJ)                                                                             \
   do {                                                                                                       \
-    auto score_global_threshold = score_global_threshold_kernel<NJ>;                                         \
+    auto score_global_threshold = score_global_threshold_kernel<KJ>;                                         \
     RFM_LAUNCH(ctx, score_global_threshold, ggrid, SELECT_WARPS * 32, 0, xch_peers(t), t->x_gtop_off,        \
                t->x_world, (int)K, user0, users_here, t->eps.p, t->tau.p);                                   \
   } while (0)
-        if (per_lane <= 4) RFM_GLOBAL_THRESHOLD(4);
-        else if (per_lane <= 8) RFM_GLOBAL_THRESHOLD(8);
-        else if (per_lane <= 16) RFM_GLOBAL_THRESHOLD(16);
-        else RFM_GLOBAL_THRESHOLD(30);           // world * K <= 8 * 120
+        if (kj <= 1) RFM_GLOBAL_THRESHOLD(1);
+        else if (kj == 2) RFM_GLOBAL_THRESHOLD(2);
+        else if (kj == 3) RFM_GLOBAL_THRESHOLD(3);
+        else RFM_GLOBAL_THRESHOLD(4);            // K <= 120
 #undef RFM_GLOBAL_THRESHOLD
       }
       // pass 2: collect every item that reaches the threshold
