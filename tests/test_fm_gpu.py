@@ -74,14 +74,23 @@ def test_fit_is_bit_reproducible():
         np.testing.assert_array_equal(a, b)
 
 
-def test_float32_mode_tracks_reference():
-    g = load_golden("coat_fm_ips_alpha01")
+@pytest.mark.parametrize("name", ["coat_fm_ips_alpha01", "kuairec_small_fm_ips_alpha01", "kuairec_small_fm_ips"])
+def test_float32_mode_tracks_reference(name):
+    """float32 perf mode against the float64 reference at the north-star tolerance (1e-5): losses relative; the
+    parameters relative to the scale of their array (max |difference| <= 1e-5 max |reference|): an ELEMENT-wise 1e-5
+    cannot hold in float32 for entries that are themselves 1e-4 of the scale -- one rounding of the update
+    (2^-24 of the update's magnitude) already exceeds it -- so entries are held element-wise to 1e-4 + that floor."""
+    g = load_golden(name)
     train, val = _dicts(g)
     m = _model(g, train["features"].shape[1], dtype="float32")
     tl, vl = m.fit(train, val)
     np.testing.assert_allclose(tl, g["train_loss"], rtol=1e-5)
     np.testing.assert_allclose(vl, g["val_loss"], rtol=1e-5)
-    np.testing.assert_allclose(m.V(), g["V"], rtol=1e-4, atol=1e-6)
+    for mine, ref in ((m.V(), g["V"]), (m.w(), g["w"])):
+        scale = np.abs(ref).max()
+        assert np.abs(mine - ref).max() <= 1e-5 * scale
+        np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-5 * scale)
+    np.testing.assert_allclose(m.predict(X=golden_csr(g, "test")), g["test_scores"], rtol=1e-4, atol=1e-6)
 
 
 def test_feistel_sampler_on_device_matches_oracle():

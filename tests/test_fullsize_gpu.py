@@ -113,3 +113,23 @@ def test_large_grid_topk_properties(k, K):
     m_items, m_scores = merge_topk([p[0] for p in parts], [p[1] for p in parts], K)
     np.testing.assert_array_equal(m_items, items)
     np.testing.assert_array_equal(m_scores, scores)
+
+
+@pytest.mark.parametrize("sampler", ["legacy", "feistel"])
+def test_bench_shape_epochs_match_the_oracle(big_log, sampler):
+    """The benchmark's own shape (3 M of its 12 M rows, B = 65,536, k = 64) for three epochs against the CPU oracle's
+    fm_fit -- every loss and every parameter at 1e-9 -- with the reference's sampler and with the device sampler."""
+    from oracle import fm_oracle, sampler_oracle
+    from rfm_b200.fm import FactorizationMachines
+    n_epochs = 3
+    m = FactorizationMachines("IPS", n_epochs, K_FACTORS, LR, B, 12345, big_log.n_features, sampler=sampler)
+    w0, w, V = m.w0().copy(), m.w().copy(), m.V().copy()
+    tl, vl = m.fit(big_log.fm_train, big_log.fm_val)
+    pick = fm_oracle.legacy_batch if sampler == "legacy" else \
+        (lambda n, b, e: sampler_oracle.feistel_batch(n, b, e, 12345))
+    (rw0, rw, rV), rtl, rvl = fm_oracle.fm_fit(big_log.fm_train, big_log.fm_val, n_epochs, B, LR, w0, w, V, sampler=pick)
+    np.testing.assert_allclose(tl, rtl, rtol=1e-9)
+    np.testing.assert_allclose(vl, rvl, rtol=1e-9)
+    np.testing.assert_allclose(m.w0(), rw0, rtol=1e-9)
+    np.testing.assert_allclose(m.w(), rw, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(m.V(), rV, rtol=1e-9, atol=1e-13)
