@@ -65,6 +65,17 @@ class TopKScorer(_capi._Handle):
         self._xchg = None           # (world, k_cap) once rfm_b200.dist.connect_scorer has mapped the peers' regions
         self._xchg_env = None
 
+    def update(self, A, C, alpha=None, beta=None, bias=0.0):
+        """New factors of the same shapes (the model moved on: another epoch, another estimator) without
+        re-creating the device buffers, tensor maps and staging areas."""
+        A = _capi.as_array(A, np.float64)
+        C = _capi.as_array(C, np.float64)
+        if A.shape != (self.n_users, self.k) or C.shape != (self.n_items, self.k):
+            raise ValueError("update() keeps the shapes the scorer was created with")
+        alpha = None if alpha is None else _capi.as_array(alpha, np.float64)
+        beta = None if beta is None else _capi.as_array(beta, np.float64)
+        check(lib().rfm_topk_set_factors(self.handle, ptr(A), ptr(C), ptr(alpha), ptr(beta), float(bias)))
+
     def close(self):
         """Collective when the scorer is connected to peers: no rank may unmap / free its exchange region while
         another still merges from it."""
