@@ -147,6 +147,13 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
                         int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks,
                         const void *labels /* may be NULL */, int32_t label_bytes, const double *pscores, int dtype,
                         rfm_csr **out);
+/* The same with the propensity given per ITEM instead of per row: pscore[t] = item_pscores[item[t]]. In both of the
+ * reference's loaders the propensity is an item-level quantity gathered per row (coat/_preparer.py:56-62,
+ * kuairec/loader.py:160-168), so the factored hand-over can stop before that gather too. */
+int rfm_factored_create_item_pscores(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64,
+                                     const void *items, int32_t items_is_int64, const rfm_rows_block *blocks,
+                                     int32_t n_blocks, const void *labels, int32_t label_bytes,
+                                     const double *item_pscores, int64_t n_item_pscores, int dtype, rfm_csr **out);
 /* Device-side generator of semi-synthetic interactions, mirroring the reference's
  * simulation utils/dataloader/kuairec/_click.py:148-235: relevance gamma = clip(watch_ratio / relevance_clip, 0, 1)
  * (:148-171), exposure theta_i = max(sigmoid(3 z_i - 1) ** exposure_bias, eps) per item (:173-205, computed by the

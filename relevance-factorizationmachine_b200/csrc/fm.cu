@@ -328,6 +328,15 @@ __global__ void targets_any_kernel(const Y *__restrict__ y, const double *__rest
     yp[i] = static_cast<T>(static_cast<double>(y[i]) / ps[i]);
 }
 
+// the same with the propensity looked up per ITEM (pscore = theta_item ** pow_used is an item-level quantity in both of
+// the reference's loaders: coat/_preparer.py:56-62, kuairec/loader.py:160-168): 8 bytes per interaction less to upload
+template <typename T, typename Y>
+__global__ void targets_by_item_kernel(const Y *__restrict__ y, const int32_t *__restrict__ item,
+                                       const double *__restrict__ item_ps, T *__restrict__ yp, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    yp[i] = static_cast<T>(static_cast<double>(y[i]) / __ldg(item_ps + item[i]));
+}
+
 // one context block's columns into the per-row context record
 template <typename T>
 __global__ void ctx_pack_kernel(const double *__restrict__ in, int64_t n_rows, int width, T *__restrict__ out,
@@ -1543,7 +1552,8 @@ int rfm_csr_device_ptrs(rfm_csr *rows, void **row_ptr_dev, void **col_dev, void 
 static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64,
                                 const void *items, int32_t items_is_int64, const rfm_rows_block *blocks,
                                 int32_t n_blocks, const void *labels, int32_t label_bytes, const double *pscores,
-                                int dtype, const rfm_click_model *gen, rfm_csr **out) {
+                                const double *item_pscores, int64_t n_item_pscores, int dtype,
+                                const rfm_click_model *gen, rfm_csr **out) {
   RFM_REQUIRE(ctx && out, "rfm_factored_create: NULL ctx/out");
   *out = nullptr;
   RFM_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffffLL, "rfm_factored_create: bad row count %lld", (long long)n_rows);
@@ -1551,7 +1561,10 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
               FAC_MAX_SEG);
   RFM_REQUIRE(n_rows == 0 || gen || (users && items), "rfm_factored_create: users/items are NULL");
   RFM_REQUIRE(dtype == RFM_F32 || dtype == RFM_F64, "rfm_factored_create: bad dtype %d", dtype);
-  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr), "rfm_factored_create: labels and pscores go together");
+  RFM_REQUIRE((labels == nullptr) == (pscores == nullptr && item_pscores == nullptr),
+              "rfm_factored_create: labels and pscores go together");
+  RFM_REQUIRE(!(pscores && item_pscores), "rfm_factored_create: per-row OR per-item pscores");
+  RFM_REQUIRE(!item_pscores || n_item_pscores >= 1, "rfm_factored_create: empty per-item pscore table");
   RFM_REQUIRE(!labels || label_bytes == 1 || label_bytes == 4 || label_bytes == 8,
               "rfm_factored_create: labels must be int8, int32 or int64 (label_bytes = %d)", label_bytes);
   RFM_CUDA(cudaSetDevice(ctx->device));
@@ -1575,6 +1588,7 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
     }
     n_cols += k.n_cols;
   }
+  if (item_pscores) limit[1] = std::min(limit[1], n_item_pscores);
   RFM_REQUIRE(n_cols < 0xFFFFFFFFLL, "rfm_factored_create: too many columns");
   rfm_csr *r = new (std::nothrow) rfm_csr();
   if (!r) return fail(RFM_ERR_NOMEM, "rfm_factored_create: out of host memory");
@@ -1705,12 +1719,27 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
       DevBuf<unsigned char> &ys = tmp[n_tmp++];
       DevBuf<unsigned char> &ps = tmp[n_tmp++];
       RFM_TRY(ys.alloc((size_t)n_rows * label_bytes));
-      RFM_TRY(ps.alloc((size_t)n_rows * 8));
       RFM_TRY(upload(ctx, ys.p, labels, (size_t)n_rows * label_bytes));
-      RFM_TRY(upload(ctx, ps.p, pscores, (size_t)n_rows * 8));
+      if (item_pscores) {
+        RFM_TRY(ps.alloc((size_t)n_item_pscores * 8));
+        RFM_TRY(upload(ctx, ps.p, item_pscores, (size_t)n_item_pscores * 8));
+      } else {
+        RFM_TRY(ps.alloc((size_t)n_rows * 8));
+        RFM_TRY(upload(ctx, ps.p, pscores, (size_t)n_rows * 8));
+      }
       const double *psd = reinterpret_cast<const double *>(ps.p);
-#define RFM_TARGETS(T, Y) \
-  RFM_LAUNCH(ctx, (targets_any_kernel<T, Y>), g, 256, 0, reinterpret_cast<const Y *>(ys.p), psd, reinterpret_cast<T *>(r->yp.p), n_rows)
+      const int32_t *item_ids = r->f_item.p;
+      const bool by_item = item_pscores != nullptr;
+#define RFM_TARGETS(T, Y)                                                                                              \
+  do {                                                                                                                 \
+    if (by_item) {                                                                                                     \
+      RFM_LAUNCH(ctx, (targets_by_item_kernel<T, Y>), g, 256, 0, reinterpret_cast<const Y *>(ys.p), item_ids, psd,     \
+                 reinterpret_cast<T *>(r->yp.p), n_rows);                                                              \
+    } else {                                                                                                           \
+      RFM_LAUNCH(ctx, (targets_any_kernel<T, Y>), g, 256, 0, reinterpret_cast<const Y *>(ys.p), psd,                   \
+                 reinterpret_cast<T *>(r->yp.p), n_rows);                                                              \
+    }                                                                                                                  \
+  } while (0)
       if (dtype == RFM_F64) {
         if (label_bytes == 8) RFM_TARGETS(double, int64_t); else if (label_bytes == 4) RFM_TARGETS(double, int32_t); else RFM_TARGETS(double, int8_t);
       } else {
@@ -1751,14 +1780,23 @@ int rfm_factored_create(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t
                         int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks, const void *labels,
                         int32_t label_bytes, const double *pscores, int dtype, rfm_csr **out) {
   return factored_create_impl(ctx, n_rows, users, users_is_int64, items, items_is_int64, blocks, n_blocks, labels,
-                              label_bytes, pscores, dtype, nullptr, out);
+                              label_bytes, pscores, nullptr, 0, dtype, nullptr, out);
+}
+
+int rfm_factored_create_item_pscores(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64,
+                                     const void *items, int32_t items_is_int64, const rfm_rows_block *blocks,
+                                     int32_t n_blocks, const void *labels, int32_t label_bytes,
+                                     const double *item_pscores, int64_t n_item_pscores, int dtype, rfm_csr **out) {
+  RFM_REQUIRE(item_pscores, "rfm_factored_create_item_pscores: item_pscores is NULL");
+  return factored_create_impl(ctx, n_rows, users, users_is_int64, items, items_is_int64, blocks, n_blocks, labels,
+                              label_bytes, nullptr, item_pscores, n_item_pscores, dtype, nullptr, out);
 }
 
 int rfm_factored_generate(rfm_ctx *ctx, int64_t n_rows, const rfm_click_model *model, const rfm_rows_block *blocks,
                           int32_t n_blocks, int dtype, rfm_csr **out) {
   RFM_REQUIRE(model, "rfm_factored_generate: model is NULL");
-  return factored_create_impl(ctx, n_rows, nullptr, 0, nullptr, 0, blocks, n_blocks, nullptr, 8, nullptr, dtype, model,
-                              out);
+  return factored_create_impl(ctx, n_rows, nullptr, 0, nullptr, 0, blocks, n_blocks, nullptr, 8, nullptr, nullptr, 0,
+                              dtype, model, out);
 }
 
 // ids, context values, targets (and, for generated rows that kept them, click / relevance labels) of rows

@@ -47,6 +47,8 @@ _SIGNATURES = {
     "rfm_csr_device_ptrs": ([_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)], c_int),
     "rfm_factored_create": ([_P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int, POINTER(_P)],
                             c_int),
+    "rfm_factored_create_item_pscores": ([_P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int64,
+                                          c_int, POINTER(_P)], c_int),
     "rfm_factored_generate": ([_P, c_int64, _P, _P, c_int32, c_int, POINTER(_P)], c_int),
     "rfm_rows_download": ([_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P], c_int),
     "rfm_csr_set_targets": ([_P, _P], c_int),

@@ -201,6 +201,7 @@ def make_coat_shaped(seed: int = 2024, n_users: int = 290, n_items: int = 300,
     gamma = _sigmoid((hidden_p[users] * hidden_q[items]).sum(1) + rng.normal(size=users.size) * 0.3)
     labels = (rng.random(users.size) < gamma).astype(np.int64)
     pscores = theta[items] ** pow_used
+    tables["item_pscore"] = theta ** pow_used          # the per-item table the per-row pscores are gathered from
 
     perm = rng.permutation(users.size)
     n_val = int(round(users.size * val_ratio))
@@ -294,6 +295,7 @@ def make_kuairec_shaped(seed: int = 2024, n_users: int = 7176, n_items: int = 10
     pop = _popularity(n_items, rng)
     z = rng.normal(size=n_items)
     theta = np.maximum(_sigmoid(3.0 * z - 1.0) ** exposure_bias, 0.1)   # kuairec/_click.py:193-202
+    tables["item_pscore"] = theta ** pow_used          # the per-item table the per-row pscores are gathered from
     hidden_p = rng.normal(size=(n_users, 8)) * 0.5
     hidden_q = rng.normal(size=(n_items, 8)) * 0.5
     activity = rng.lognormal(sigma=0.6, size=n_users)

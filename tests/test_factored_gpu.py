@@ -125,3 +125,24 @@ def test_mixing_csr_train_with_factored_val_is_refused():
     m = FactorizationMachines("IPS", 2, 8, 1e-3, 100, 1, log.n_features)
     with pytest.raises(ValueError, match="both be CSR or both be factored"):
         m.fit(log.fm_train, _factored(log, log.fm_val))
+
+
+def test_per_item_pscores_equal_per_row_pscores():
+    """The propensity is an item-level table in the reference's loaders (kuairec/loader.py:160-168); handing the table
+    over (PerItem) instead of the gathered column gives the same bits."""
+    from rfm_b200.factored import PerItem
+    from rfm_b200.fm import FactorizationMachines
+    log, g = _log_and_golden("kuairec")
+    table = log.tables["item_pscore"]
+    np.testing.assert_array_equal(table[log.fm_train["items"]], log.fm_train["pscores"])
+    kw = dict(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]), lr=float(g["lr"]),
+              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]))
+    a, b = FactorizationMachines(**kw), FactorizationMachines(**kw)
+    ftrain, fval = _factored(log, log.fm_train), _factored(log, log.fm_val)
+    la = a.fit(ftrain, fval)
+    lb = b.fit(dict(ftrain, pscores=PerItem(table)), dict(fval, pscores=PerItem(table)))
+    assert la == lb
+    np.testing.assert_array_equal(a.V(), b.V())
+    np.testing.assert_allclose(lb[0], g["train_loss"], rtol=1e-9)
+    with pytest.raises(ValueError, match="item id"):
+        FactorizationMachines(**kw).fit(dict(ftrain, pscores=PerItem(table[:10])), fval)
