@@ -180,6 +180,10 @@ typedef struct rfm_click_model {
 } rfm_click_model;
 int rfm_factored_generate(rfm_ctx *ctx, int64_t n_rows, const rfm_click_model *model, const rfm_rows_block *blocks,
                           int32_t n_blocks, int dtype, rfm_csr **out);
+/* Factored rows -> the stacked CSR the reference would have built, assembled on the device (no PCIe traffic): the
+ * same entries in the same order, so nothing changes by a bit; the row kernels run ~10 % faster on resident CSR
+ * rows where everything is cached, at 12 m + 16 bytes of HBM per interaction instead of ~24. */
+int rfm_rows_materialize(const rfm_csr *rows, rfm_csr **out);
 /* Rows [first, first + n) of factored rows back on the host (any output may be NULL): ids, context values
  * [n][n_ctx], targets y / pscore, and for generated rows with keep_labels the click and relevance labels. */
 int rfm_rows_download(rfm_csr *rows, int64_t first, int64_t n, int32_t *users, int32_t *items, double *ctx_values,

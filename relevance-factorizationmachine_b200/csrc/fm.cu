@@ -378,6 +378,38 @@ __global__ void fac_row_len_kernel(const FacDev f, const int64_t *__restrict__ i
   }
 }
 
+// ---- factored rows -> stacked CSR on the device (rfm_rows_materialize) ------------------------------------------
+__global__ void fac_all_row_len_kernel(const FacDev f, int64_t n_rows, uint32_t *__restrict__ len) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_rows; t += (int64_t)gridDim.x * blockDim.x)
+    len[t] = static_cast<uint32_t>(fac_row_len(f, f.user[t], f.item[t], fac_ctx_mask(f, t)));
+}
+
+// row_ptr (int64) from the exclusive scan of the lengths, and the entries of every row in the stacked column order
+template <typename T>
+__global__ void __launch_bounds__(256)
+fac_fill_csr_kernel(const FacDev f, int64_t n_rows, const uint32_t *__restrict__ start, uint32_t total,
+                    int64_t *__restrict__ row_ptr, int32_t *__restrict__ col, T *__restrict__ val) {
+  __shared__ FacSmem fsm;
+  fac_smem_fill(fsm, f, f, false);
+  __syncthreads();
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= n_rows; t += (int64_t)gridDim.x * blockDim.x) {
+    if (t == n_rows) {
+      row_ptr[t] = total;
+      continue;
+    }
+    const uint32_t at = start[t];
+    row_ptr[t] = at;
+    const FacRow fr = fac_row(f, f.user[t], f.item[t], fac_ctx_mask(f, t));
+    for (int off = 0; off < fr.len; ++off) {
+      int c;
+      T x;
+      fac_entry<T>(fsm, 0, f, fr, t, off, c, x);
+      col[at + off] = c;
+      val[at + off] = x;
+    }
+  }
+}
+
 __device__ __forceinline__ double sigmoid_ref(double z) {
   // src/base.py:63-66
   z = fmin(fmax(z, -700.0), 700.0);
@@ -1797,6 +1829,64 @@ int rfm_factored_generate(rfm_ctx *ctx, int64_t n_rows, const rfm_click_model *m
   RFM_REQUIRE(model, "rfm_factored_generate: model is NULL");
   return factored_create_impl(ctx, n_rows, nullptr, 0, nullptr, 0, blocks, n_blocks, nullptr, 8, nullptr, nullptr, 0,
                               dtype, model, out);
+}
+
+// Factored rows -> the stacked CSR the reference would have built, assembled on the device (no PCIe): the row
+// kernels run ~10 % faster on resident CSR rows than on factored ones where everything is cached, so a
+// long fit uploads factored and trains stacked. Same entries in the same order: results do not change by a bit.
+int rfm_rows_materialize(const rfm_csr *rows, rfm_csr **out) {
+  RFM_REQUIRE(rows && out, "rfm_rows_materialize: NULL argument");
+  *out = nullptr;
+  RFM_REQUIRE(rows->factored, "rfm_rows_materialize: the rows are a stacked CSR already");
+  RFM_REQUIRE(rows->nnz < 0xFFFFFFF0LL, "rfm_rows_materialize: %lld non-zeros do not fit 32-bit offsets",
+              (long long)rows->nnz);
+  rfm_ctx *ctx = rows->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  rfm_csr *r = new (std::nothrow) rfm_csr();
+  if (!r) return fail(RFM_ERR_NOMEM, "rfm_rows_materialize: out of host memory");
+  r->ctx = ctx;
+  r->dtype = rows->dtype;
+  r->n_rows = rows->n_rows;
+  r->n_cols = rows->n_cols;
+  r->nnz = rows->nnz;
+  r->max_row_len = rows->max_row_len;
+  r->has_targets = rows->has_targets;
+  const size_t es = dsize(rows->dtype);
+  const int64_t n = rows->n_rows;
+  auto body = [&]() -> int {
+    RFM_TRY(r->row_ptr.alloc(n + 1));
+    RFM_TRY(r->col.alloc((size_t)rows->nnz));
+    RFM_TRY(r->val.alloc((size_t)rows->nnz * es));
+    RFM_TRY(r->yp.alloc((size_t)(n ? n : 1) * es));
+    RFM_CUDA(cudaMemcpyAsync(r->yp.p, rows->yp.p, (size_t)n * es, cudaMemcpyDeviceToDevice, ctx->stream));
+    DevBuf<uint32_t> len, start, sums, total;
+    RFM_TRY(len.alloc((size_t)(n ? n : 1)));
+    RFM_TRY(start.alloc((size_t)(n ? n : 1)));
+    RFM_TRY(sums.alloc((size_t)ceil_div(n ? n : 1, 4096) + 2));
+    RFM_TRY(total.alloc(1));
+    RFM_CUDA(cudaMemsetAsync(total.p, 0, 4, ctx->stream));
+    const int g = grid_for(ctx, ceil_div(n + 1, 256), 8);
+    if (n > 0) {
+      RFM_LAUNCH(ctx, fac_all_row_len_kernel, g, 256, 0, rows->fac_dev(), n, len.p);
+      RFM_TRY(exclusive_scan_u32(ctx, len.p, start.p, n, sums.p, total.p));
+    }
+    if (rows->dtype == RFM_F64) {
+      RFM_LAUNCH(ctx, fac_fill_csr_kernel<double>, g, 256, 0, rows->fac_dev(), n, start.p, (uint32_t)rows->nnz,
+                 r->row_ptr.p, r->col.p, reinterpret_cast<double *>(r->val.p));
+    } else {
+      RFM_LAUNCH(ctx, fac_fill_csr_kernel<float>, g, 256, 0, rows->fac_dev(), n, start.p, (uint32_t)rows->nnz,
+                 r->row_ptr.p, r->col.p, reinterpret_cast<float *>(r->val.p));
+    }
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RFM_OK;
+  };
+  const int rc = body();
+  if (rc != RFM_OK) {
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return RFM_OK;
 }
 
 // ids, context values, targets (and, for generated rows that kept them, click / relevance labels) of rows

@@ -878,7 +878,11 @@ __device__ __forceinline__ Best warp_best(Best b) {
 // candidates (item, exact score) are staged in shared memory so the K selection rounds never leave the SM.
 constexpr int RESCORE_WARPS = 4;
 
-__global__ void __launch_bounds__(RESCORE_WARPS * 32)
+// SHARDED: item-sharded runs leave a handful of candidates per user and rank, so the pass is a chain of memory
+// round trips per user, not arithmetic: twice the resident warps (registers capped at 64, the 32 partial sums of
+// lane_exact_dot spill to L1) beat the single-GPU register budget there.
+template <bool SHARDED>
+__global__ void __launch_bounds__(RESCORE_WARPS * 32, SHARDED ? 8 : 4)
 score_rescore_kernel(const ExactArgs e, int64_t user0, int64_t n_users_chunk, const uint32_t *__restrict__ cand_cnt,
                      const int2 *__restrict__ cand, const float *__restrict__ eps, int kc, int K,
                      int32_t *__restrict__ out_items, double *__restrict__ out_scores, int32_t *__restrict__ fail_list,
@@ -893,11 +897,35 @@ score_rescore_kernel(const ExactArgs e, int64_t user0, int64_t n_users_chunk, co
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long seen = 0ull;        // candidates of this warp's users: ONE atomic per warp at the end (a per-user
                                          // atomic on a single address serialised all 32,768 users of a pass at L2)
+  // A user's count, first 32 candidates and factor row are requested one loop iteration ahead (all independent
+  // loads), so that the chain per user is candidates' item rows -> rank -> store instead of four round trips.
+  struct Pre {
+    uint32_t cnt;
+    int2 first;
+    double a[4];        // factors lane, lane + 32, ... (k <= 128 on this path)
+  };
+  auto fetch = [&](int64_t row) {
+    Pre p;
+    p.cnt = 0u;
+    p.first = make_int2(-1, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p.a[j] = 0.0;
+    if (row < n_users_chunk) {
+      p.cnt = cand_cnt[row];
+      if (lane < kc) p.first = cand[row * kc + lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < e.k) p.a[j] = e.A[(user0 + row) * e.k + lane + 32 * j];
+    }
+    return p;
+  };
+  Pre nxt = fetch(gw);
   for (int64_t row = gw; row < n_users_chunk; row += nw) {
     const int64_t u = user0 + row;
-    // the count and the first 32 candidates are requested together: one memory round trip instead of two
-    const uint32_t cnt = cand_cnt[row];
-    const int2 first = lane < kc ? cand[row * kc + lane] : make_int2(-1, 0);
+    const Pre cur = nxt;
+    nxt = fetch(row + nw);
+    const uint32_t cnt = cur.cnt;
+    const int2 first = cur.first;
     seen += cnt;
     if (cnt > (uint32_t)kc) {            // more candidates than the buffer holds: rank this user exactly
       if (lane == 0) fail_list[atomicAdd(n_fail, 1u)] = (int32_t)u;
@@ -911,7 +939,9 @@ score_rescore_kernel(const ExactArgs e, int64_t user0, int64_t n_users_chunk, co
       }
       continue;
     }
-    for (int f = lane; f < e.k; f += 32) au[f] = e.A[u * e.k + f];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j < e.k) au[lane + 32 * j] = cur.a[j];
     for (int c = lane; c < n_cand; c += 32) {
       const int2 v = c == lane ? first : cand[row * kc + c];
       const uint32_t bits = (uint32_t)v.y;
@@ -1576,7 +1606,8 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
     RFM_CUDA(cudaMemsetAsync(t->n_cand.p, 0, sizeof(unsigned long long), ctx->stream));
     const size_t rs_smem = (size_t)RESCORE_WARPS * ((size_t)kc * 16 + (size_t)t->k * 8);
     RFM_REQUIRE(rs_smem <= 200 * 1024, "rfm_topk_run: %d candidates per user do not fit the re-scoring kernel", kc);
-    RFM_CUDA(cudaFuncSetAttribute(score_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    RFM_CUDA(cudaFuncSetAttribute(score_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    RFM_CUDA(cudaFuncSetAttribute(score_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
     uint32_t *gtop = plan.on ? reinterpret_cast<uint32_t *>(t->xchg + t->x_gtop_off) : nullptr;
     if (plan.on && empty) {     // nothing to rank here: no group maxima, empty lists
       RFM_LAUNCH(ctx, fill_u32_kernel, ctx->sm_count * 4, 256, 0, gtop, 0x007FFFFFu, (int64_t)t->n_users * K);
@@ -1648,8 +1679,15 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
       const int rs_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / std::max<size_t>(rs_smem, 1)));
       const int rgrid = (int)std::min<int64_t>((users_here + RESCORE_WARPS - 1) / RESCORE_WARPS,
                                                (int64_t)ctx->sm_count * rs_per_sm);
-      RFM_LAUNCH(ctx, score_rescore_kernel, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
-                 t->cand.p, t->eps.p, kc, (int)K, dst_items, dst_scores, t->fail_list.p, t->n_fail.p, t->n_cand.p);
+      if (plan.on && t->x_world >= 4) {
+        auto score_rescore = score_rescore_kernel<true>;
+        RFM_LAUNCH(ctx, score_rescore, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
+                   t->cand.p, t->eps.p, kc, (int)K, dst_items, dst_scores, t->fail_list.p, t->n_fail.p, t->n_cand.p);
+      } else {
+        auto score_rescore_kernel_ = score_rescore_kernel<false>;
+        RFM_LAUNCH(ctx, score_rescore_kernel_, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
+                   t->cand.p, t->eps.p, kc, (int)K, dst_items, dst_scores, t->fail_list.p, t->n_fail.p, t->n_cand.p);
+      }
     }
     if (!empty) {
       // users whose candidate buffer overflowed are ranked exactly against the whole catalog range

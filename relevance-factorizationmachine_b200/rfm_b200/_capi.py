@@ -50,6 +50,7 @@ _SIGNATURES = {
     "rfm_factored_create_item_pscores": ([_P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int64,
                                           c_int, POINTER(_P)], c_int),
     "rfm_factored_generate": ([_P, c_int64, _P, _P, c_int32, c_int, POINTER(_P)], c_int),
+    "rfm_rows_materialize": ([_P, POINTER(_P)], c_int),
     "rfm_rows_download": ([_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P], c_int),
     "rfm_csr_set_targets": ([_P, _P], c_int),
     "rfm_csr_destroy": ([_P], c_int),
@@ -315,6 +316,19 @@ class CsrRows(_Handle):
         out = [c_void_p() for _ in range(4)]
         check(lib().rfm_csr_device_ptrs(self.handle, *[byref(p) for p in out]))
         return tuple(p.value for p in out)
+
+
+class MaterializedRows(_Handle):
+    """Stacked CSR assembled on the device from factored rows (``rfm_rows_materialize``)."""
+
+    _destroy = "rfm_csr_destroy"
+
+    def __init__(self, factored_rows):
+        super().__init__()
+        check(lib().rfm_rows_materialize(factored_rows.handle, byref(self.handle)))
+        self.ctx, self.dtype, self.n_rows, self.shape = factored_rows.ctx, factored_rows.dtype, factored_rows.n_rows, \
+            factored_rows.shape
+        self.h2d_bytes = factored_rows.h2d_bytes        # what reached the device over PCIe
 
 
 class Optimizer(ctypes.Structure):

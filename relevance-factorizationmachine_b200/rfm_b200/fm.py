@@ -61,6 +61,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
     beta1: float = 0.9
     beta2: float = 0.999
     adam_eps: float = 1e-8
+    materialize: str = "auto"     # factored rows -> stacked CSR on the device before a fit: "auto" (long fits), "always", "never"
     _dev: object = field(default=None, init=False, repr=False, compare=False)
 
     def __post_init__(self) -> None:
@@ -70,6 +71,8 @@ class FactorizationMachines(PointwiseBaseRecommender):
             raise ValueError("optimizer must be 'sgd' or 'adam'")
         if self.l2 < 0:
             raise ValueError("l2 must be >= 0")
+        if self.materialize not in ("auto", "always", "never"):
+            raise ValueError("materialize must be 'auto', 'always' or 'never'")
         if self.distributed is not None and (self.optimizer != "sgd" or self.l2 != 0):
             raise ValueError("the data-parallel fit implements the reference's SGD step only")
         _capi.dtype_code(self.dtype)
@@ -168,6 +171,23 @@ class FactorizationMachines(PointwiseBaseRecommender):
     def reset_rows_cache(self) -> None:
         self._rows_cache.clear()
 
+    def _maybe_materialize(self, train_rows, val_rows):
+        """Factored rows reach the device in a ninth of the bytes, but where everything is cached the row kernels run
+        ~10 % faster on the stacked CSR. A long fit therefore assembles the CSR ON THE DEVICE from
+        the factored rows (same entries, same order: not a bit changes) and trains on that."""
+        from .factored import FactoredRows
+        is_fac = lambda r: isinstance(r, FactoredRows) or type(r).__name__ == "GeneratedRows"
+        if self.materialize == "never" or not (is_fac(train_rows) and is_fac(val_rows)):
+            return train_rows, val_rows
+        if self.materialize == "auto" and self.n_epochs < 128:
+            return train_rows, val_rows
+        try:
+            return _capi.MaterializedRows(train_rows), _capi.MaterializedRows(val_rows)
+        except (ValueError, _capi.RfmError):
+            if self.materialize == "always":
+                raise
+            return train_rows, val_rows        # too large for 32-bit offsets or for the device: stay factored
+
     # ---- reference API -----------------------------------------------------------------------
     def fit(self, train, val) -> tuple:
         ctx = self._context()
@@ -179,6 +199,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
         t_up = time.perf_counter()
         train_rows = self._rows(X, train["labels"], train["pscores"])
         val_rows = self._rows(val["features"], val["labels"], val["pscores"])
+        train_rows, val_rows = self._maybe_materialize(train_rows, val_rows)
         self.sync_to_device()
         self._upload_seconds = time.perf_counter() - t_up
         if self.distributed is not None:

@@ -146,3 +146,40 @@ def test_per_item_pscores_equal_per_row_pscores():
     np.testing.assert_allclose(lb[0], g["train_loss"], rtol=1e-9)
     with pytest.raises(ValueError, match="item id"):
         FactorizationMachines(**kw).fit(dict(ftrain, pscores=PerItem(table[:10])), fval)
+
+
+def test_materialized_on_device_equals_both_paths():
+    """rfm_rows_materialize assembles the stacked CSR on the device from factored rows: fit / predict through it are
+    bit-identical to the factored path and to the CSR uploaded from the host; it is what a long fit trains on."""
+    from rfm_b200 import _capi
+    from rfm_b200.factored import FactoredRows
+    from rfm_b200.fm import FactorizationMachines
+    log, g = _log_and_golden("kuairec")
+    kw = dict(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]), lr=float(g["lr"]),
+              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]))
+    ftrain, fval = _factored(log, log.fm_train), _factored(log, log.fm_val)
+    runs = []
+    for policy, data in (("never", (ftrain, fval)), ("always", (ftrain, fval)), ("never", (log.fm_train, log.fm_val))):
+        m = FactorizationMachines(materialize=policy, **kw)
+        runs.append((m.fit(*data), m.V().copy()))
+    assert runs[0][0] == runs[1][0] == runs[2][0]
+    np.testing.assert_array_equal(runs[0][1], runs[1][1])
+    np.testing.assert_array_equal(runs[0][1], runs[2][1])
+    np.testing.assert_allclose(runs[1][0][0], g["train_loss"], rtol=1e-9)
+    # the assembled arrays themselves: row pointers, columns, values, targets == the host CSR's device copy
+    import torch
+    from rfm_b200.dist import _DeviceArray
+    ctx = _capi.Context.default(0)
+    X = log.fm_train["features"]
+    host = _capi.CsrRows(ctx, X, log.fm_train["labels"], log.fm_train["pscores"])
+    mat = _capi.MaterializedRows(FactoredRows(ctx, ftrain["features"], ftrain["labels"], ftrain["pscores"]))
+    from ctypes import byref, c_void_p
+    ptrs = []
+    for rows in (host, mat):
+        out = [c_void_p() for _ in range(4)]
+        _capi.check(_capi.lib().rfm_csr_device_ptrs(rows.handle, *[byref(p) for p in out]))
+        ptrs.append([p.value for p in out])
+    for pa, pb, nbytes in zip(ptrs[0], ptrs[1], ((X.shape[0] + 1) * 8, X.nnz * 4, X.nnz * 8, X.shape[0] * 8)):
+        ta = torch.as_tensor(_DeviceArray(pa, nbytes, "|u1"), device="cuda:0")
+        tb = torch.as_tensor(_DeviceArray(pb, nbytes, "|u1"), device="cuda:0")
+        assert torch.equal(ta, tb)

@@ -13,11 +13,14 @@ rows_stress = int(sys.argv[2]) if len(sys.argv) > 2 else 4_000_000
 W, K = 0, 1
 
 
-def run(name, train, val, n_features, k, B):
+def run(name, train, val, n_features, k, B, materialize=False):
+    from rfm_b200 import _capi
     m = FactorizationMachines("IPS", K, k, bench.LR, B, 12345, n_features, sampler="feistel")
     ctx = m._context()
     trr = m._rows(train["features"], train["labels"], train["pscores"])
     var = m._rows(val["features"], val["labels"], val["pscores"])
+    if materialize:
+        trr, var = _capi.MaterializedRows(trr), _capi.MaterializedRows(var)
     m.sync_to_device()
     t = _FmTrainer(m._dev, trr, var, B, W + K + 2)
     l0 = ctx.launch_count()
@@ -34,3 +37,4 @@ run("kuairec_csr", log.fm_train, log.fm_val, log.n_features, 64, 65536)
 run("kuairec_factored", ftrain, fval, log.n_features, 64, 65536)
 train, val, n_features, _ = bench.make_stress_data(rows_stress, 2024)
 run("stress_factored", train, val, n_features, 128, 1 << 20)
+run("stress_csr", train, val, n_features, 128, 1 << 20, materialize=True)
