@@ -1679,7 +1679,9 @@ int topk_run_core(rfm_topk *t, int K, int mode, int64_t item_begin, int64_t item
       const int rs_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / std::max<size_t>(rs_smem, 1)));
       const int rgrid = (int)std::min<int64_t>((users_here + RESCORE_WARPS - 1) / RESCORE_WARPS,
                                                (int64_t)ctx->sm_count * rs_per_sm);
-      if (plan.on && t->x_world >= 4) {
+      // (measured at 8 GPUs: the register-capped variant is SLOWER -- 0.146 vs 0.115 ms at top-9, 0.27 vs 0.12 ms at
+      // top-100: the spilled partial sums cost more than the extra warps hide; kept behind an environment switch)
+      if (plan.on && getenv("RFM_RESCORE_LOWREG") != nullptr) {
         auto score_rescore = score_rescore_kernel<true>;
         RFM_LAUNCH(ctx, score_rescore, rgrid, RESCORE_WARPS * 32, rs_smem, e, user0, users_here, t->cand_cnt.p,
                    t->cand.p, t->eps.p, kc, (int)K, dst_items, dst_scores, t->fail_list.p, t->n_fail.p, t->n_cand.p);
