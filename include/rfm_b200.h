@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RFM_ABI_VERSION 4   /* 4: rfm_*_set_targets; factored rows, device-chained evaluation, sharded top-K exchange (round 2). 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
+#define RFM_ABI_VERSION 5   /* 5: rfm_fm_trainer_set_two_level. 4: rfm_*_set_targets; factored rows, device-chained evaluation, sharded top-K exchange (round 2). 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
 
 enum rfm_status {
   RFM_OK = 0,
@@ -215,6 +215,15 @@ int rfm_fm_logloss(rfm_fm *m, const rfm_csr *rows, double *out_loss);
 int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val /* may be NULL */,
                           int64_t max_batch, int64_t max_slots, rfm_fm_trainer **out);
 int rfm_fm_trainer_destroy(rfm_fm_trainer *t);
+/* Two-level step for FACTORED train rows (csrc/two_level.cuh). The same update as above (src/fm.py:80-88, 135-187),
+ * computed per entity first: the user-keyed part of x_t depends on the user alone (the reference stacks
+ * onehot[user], user_table[user], onehot[item], item_table[item]: coat/_preparer.py:154-170,
+ * kuairec/_feature.py:169-209), so s_t = A_user + C_item + context terms and
+ * grad v_j = sum_users x_uj (sum_{t of u} e_t s_t) - v_j sum_users x_uj^2 (sum_{t of u} e_t). A step then gathers
+ * 2 + n_ctx parameter rows per interaction instead of m, plus one pass over the entity tables. Same sums, associated
+ * per entity first: equal to the flat step to rounding, bit-reproducible run to run. mode 1 = on, 2 = on where the
+ * cost model predicts >= 1.5 x fewer gathered rows per step; call before the first epoch; *enabled = outcome. */
+int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabled);
 int rfm_fm_train_epoch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch, double lr,
                        int64_t slot);
 /* same step, batch drawn on the device by the Feistel sampler (perf mode). */

@@ -35,6 +35,8 @@ struct rfm_fm {
   int64_t n = 0;
   int k = 0, kp = 0, nch = 0;
   DevBuf<unsigned char> w0, w, V, vn;   // vn[j] = ||v_j||^2
+  uint64_t version = 0;                 // bumped by everything that changes the parameters (two-level trainers cache
+                                        // per-entity aggregates of them)
 };
 
 namespace {
@@ -673,20 +675,37 @@ struct ColsArgs {
   uint32_t unit;     // sorted entries covered by one carry record = one CTA iteration of the column pass
   T *carry_vec;      // [n_units][2][kp]    slot 0 = HEAD (run began in an earlier unit), 1 = TAIL
   T *carry_ac;       // [n_units][2][2]     (a, c)
-  // data-parallel mode: write the gradient instead of applying it
-  T *grad_w, *grad_V;
+  // OUT_GRAD (data-parallel mode): write the gradient instead of applying it.
+  // OUT_RAW (level 1 of the two-level step): the raw sums go out as they are: grad_V[j] = sum e x s, grad_w[j] = sum e x,
+  // raw_c[j] = sum e x^2
+  T *grad_w, *grad_V, *raw_c;
+  // L2 = true (level 2 of the two-level step): the list is the static (real column, virtual column, x) list and
+  // "S" holds level 1's vector sums: acc += x S[p], a += x Ea[p], c += x^2 Ec[p]
+  const T *Ea, *Ec;
   // fix-up work lists (order of the lists is irrelevant: every entry is handled independently)
   uint32_t *tails;       // chunks that own a column continuing into later chunks
   uint32_t *n_tails;
 };
 
-template <typename T, int TPR, int NCV, bool DP>
+enum ColsOut { OUT_SGD = 0, OUT_GRAD = 1, OUT_RAW = 2 };
+
+template <typename T, int TPR, int NCV, int OUT>
 __device__ __forceinline__ void finish_column(const ColsArgs<T> &a, uint32_t colj,
                                               const typename Vec2<T>::type (&acc)[NCV], T sa, T sc, int g,
                                               unsigned gmask) {
   using V2 = typename Vec2<T>::type;
+  if (OUT == OUT_RAW) {
+    V2 *grow = reinterpret_cast<V2 *>(a.grad_V + (size_t)colj * a.kp) + g;
+#pragma unroll
+    for (int ch = 0; ch < NCV; ++ch) grow[ch * TPR] = acc[ch];
+    if (g == 0) {
+      a.grad_w[colj] = sa;
+      a.raw_c[colj] = sc;
+    }
+    return;
+  }
   V2 *vrow = reinterpret_cast<V2 *>(a.V + (size_t)colj * a.kp) + g;
-  if (DP) {
+  if (OUT == OUT_GRAD) {
     V2 *grow = reinterpret_cast<V2 *>(a.grad_V + (size_t)colj * a.kp) + g;
 #pragma unroll
     for (int ch = 0; ch < NCV; ++ch) {
@@ -735,11 +754,14 @@ __device__ __forceinline__ void store_carry(const ColsArgs<T> &a, uint32_t chunk
 // the group where a run starts walks the following chunks' HEAD partials in chunk order and either finishes
 // the column (the run ends inside the unit) or emits ONE carry record for the unit. Only runs that cross
 // unit boundaries reach the global fix-up kernels.
-template <typename T, int TPR, int NCV, bool DP>
+// SMALL: chunks of TPR entries instead of 32 (a unit is then 256 entries for every TPR): four times the groups for
+// lists too short to fill the machine with 32-entry chunks (the two-level step's lists at the KuaiRec shape).
+template <typename T, int TPR, int NCV, int OUT, bool L2, bool SMALL = false>
 __global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? RFM_COLS_MIN_BLOCKS : 1)
 fm_cols_kernel(const ColsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
-  constexpr int GPW = 32 / TPR, NJ = 32 / TPR, GPC = ROWS_WARPS * GPW;
+  constexpr int GPW = 32 / TPR, NJ = SMALL ? 1 : 32 / TPR, GPC = ROWS_WARPS * GPW;
+  constexpr uint32_t CH = TPR * NJ;                              // entries per chunk
   extern __shared__ __align__(16) unsigned char cols_smem[];
   const int pstride = a.kp + 2;                                  // partial = kp values + (a, c)
   T *part = reinterpret_cast<T *>(cols_smem);                    // [GPC][2][pstride]
@@ -751,13 +773,13 @@ fm_cols_kernel(const ColsArgs<T> a) {
   const int gi = wid * GPW + grp;                                // this group's chunk inside the unit
   const unsigned gmask = TPR == 32 ? FULL : (((1u << TPR) - 1u) << (grp * TPR));
   const uint32_t M = *a.count;
-  const uint32_t n_chunks = (M + 31u) >> 5;
+  const uint32_t n_chunks = (M + CH - 1u) / CH;
   const uint32_t n_units = (n_chunks + GPC - 1) / GPC;
   for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {   // CTA-uniform trip count
     const uint32_t chunk = unit * GPC + gi;
-    const uint32_t base = chunk << 5;
+    const uint32_t base = chunk * CH;
     uint32_t key[NJ], p[NJ];
-    T xe[NJ], xxe[NJ];
+    T xe[NJ], xxe[NJ], xa[L2 ? NJ : 1];
     int n_valid = 0;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -768,15 +790,22 @@ fm_cols_kernel(const ColsArgs<T> a) {
       key[j] = k;
       p[j] = valid ? a.pos[e] : 0u;
       const T x = valid ? a.xs[e] : T(0);
-      const T ev = valid ? __ldg(a.E + p[j]) : T(0);
-      xe[j] = x * ev;
-      xxe[j] = x * x * ev;
+      if (L2) {
+        const T ea = valid ? __ldg(a.Ea + p[j]) : T(0), ec = valid ? __ldg(a.Ec + p[j]) : T(0);
+        xe[j] = x;
+        xa[L2 ? j : 0] = x * ea;
+        xxe[j] = x * x * ec;
+      } else {
+        const T ev = valid ? __ldg(a.E + p[j]) : T(0);
+        xe[j] = x * ev;
+        xxe[j] = x * x * ev;
+      }
       n_valid += __popc(__ballot_sync(FULL, valid) & gmask);   // padding sorts last: valid entries are a prefix
     }
     uint32_t prev_key = KEY_NONE, next_key = KEY_NONE;
     if (n_valid > 0) {
       if (base > 0) prev_key = a.keys[base - 1];
-      if (base + 32u < M) next_key = a.keys[base + 32u];
+      if (base + CH < M) next_key = a.keys[base + CH];
       if (next_key == a.sentinel) next_key = KEY_NONE;
     }
     V2 acc[NCV];
@@ -807,6 +836,7 @@ fm_cols_kernel(const ColsArgs<T> a) {
         const uint32_t pi = __shfl_sync(FULL, p[j], ii, TPR);
         const T xei = __shfl_sync(FULL, xe[j], ii, TPR);
         const T xxei = __shfl_sync(FULL, xxe[j], ii, TPR);
+        const T xai = L2 ? __shfl_sync(FULL, xa[L2 ? j : 0], ii, TPR) : xei;
         if (i < n_valid) {                                      // group-uniform
           const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)pi * a.kp) + g;
           V2 sv[NCV];
@@ -818,7 +848,7 @@ fm_cols_kernel(const ColsArgs<T> a) {
               if (g == 0) hkey[gi] = cur;
               my_flag |= 1u;
             } else {
-              finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
+              finish_column<T, TPR, NCV, OUT>(a, cur, acc, sa, sc, g, gmask);
             }
             head = false;
             cur = ki;
@@ -831,7 +861,7 @@ fm_cols_kernel(const ColsArgs<T> a) {
             acc[ch].x += xei * sv[ch].x;
             acc[ch].y += xei * sv[ch].y;
           }
-          sa += xei;
+          sa += xai;
           sc += xxei;
         }
       }
@@ -847,7 +877,7 @@ fm_cols_kernel(const ColsArgs<T> a) {
         if (g == 0) tkey[gi] = cur;
         my_flag |= 2u;
       } else {
-        finish_column<T, TPR, NCV, DP>(a, cur, acc, sa, sc, g, gmask);
+        finish_column<T, TPR, NCV, OUT>(a, cur, acc, sa, sc, g, gmask);
       }
     }
     if (g == 0) flag[gi] = my_flag;
@@ -884,7 +914,7 @@ fm_cols_kernel(const ColsArgs<T> a) {
         ++nx;
       }
       if (which == 1 && !open) {
-        finish_column<T, TPR, NCV, DP>(a, rkey, acc, sa, sc, g, gmask);       // began and ended inside the unit
+        finish_column<T, TPR, NCV, OUT>(a, rkey, acc, sa, sc, g, gmask);       // began and ended inside the unit
       } else {
         // crosses a unit boundary: one carry record for the whole unit (slot 0 = entering run, 1 = leaving run)
         V2 *cv = reinterpret_cast<V2 *>(a.carry_vec + ((size_t)unit * 2 + which) * a.kp) + g;
@@ -909,7 +939,7 @@ fm_cols_kernel(const ColsArgs<T> a) {
 constexpr int FIX_THREADS = 256;
 constexpr int FIX_WARPS = FIX_THREADS / 32;
 
-template <typename T, int NCH, bool DP>
+template <typename T, int NCH, int OUT>
 __global__ void __launch_bounds__(FIX_THREADS)
 fm_fixup_kernel(const ColsArgs<T> a) {
   using V2 = typename Vec2<T>::type;
@@ -1006,7 +1036,7 @@ fm_fixup_kernel(const ColsArgs<T> a) {
         sa += part[a.kp];
         sc += part[a.kp + 1];
       }
-      finish_column<T, 32, NCH, DP>(a, klast, acc, sa, sc, lane, FULL);
+      finish_column<T, 32, NCH, OUT>(a, klast, acc, sa, sc, lane, FULL);
     }
     __syncthreads();
   }
@@ -1164,6 +1194,8 @@ size_t cols_smem_bytes(int nch, int kp, size_t es) {
   return gpc * 2 * (size_t)(kp + 2) * es + 3 * gpc * sizeof(uint32_t);
 }
 
+#include "two_level.cuh"
+
 }  // namespace
 
 // ---- trainer handle -----------------------------------------------------------------------------
@@ -1194,6 +1226,7 @@ struct rfm_fm_trainer {
   unsigned char *grad_ptr() const { return xchg ? xchg + (size_t)dp_parity * xchg_grad_bytes : grad.p; }
   RadixSorter<float> sort32;
   RadixSorter<double> sort64;
+  TwoLevel *tl = nullptr;      // two-level step (factored rows; rfm_fm_trainer_set_two_level)
   // host staging ring for batch row ids
   static constexpr int RING = 4;
   PinnedBuf<int64_t> stage[RING];
@@ -1261,7 +1294,11 @@ int loss_pass(rfm_fm_trainer *t, const rfm_csr *rows, const int64_t *idx_dev, in
 // forward + residual + triples + sort + column pass (+ fix-up). DP=false applies SGD in place.
 // sampled: the batch is positions [q0, q0+batch) of the epoch's Feistel permutation, drawn on the device.
 template <typename T, bool DP>
+int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const FeistelKey &fkey, int64_t q0);
+
+template <typename T, bool DP>
 int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const FeistelKey &fkey, int64_t q0) {
+  if (t->tl) return step_two_level<T, DP>(t, batch, lr, sampled, fkey, q0);
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
   const rfm_csr *tr = t->train;
@@ -1346,16 +1383,252 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   const int tgrid = grid_for(ctx, unit_cap, 4);   // one CTA per leaving run; there are at most unit_cap of them
   const size_t csmem = cols_smem_bytes(m->nch, m->kp, sizeof(T));
   RFM_DISPATCH_TPR(m->nch, {
-    auto fm_cols = fm_cols_kernel<T, TPR, NCV, DP>;
+    auto fm_cols = fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, false>;
     if (csmem > 48 * 1024)
       RFM_CUDA(cudaFuncSetAttribute(fm_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
     RFM_LAUNCH(ctx, fm_cols, cgrid, ROWS_THREADS, csmem, c);
   });
   RFM_DISPATCH_NCH(m->nch, {
-    auto fm_fixup = fm_fixup_kernel<T, NCH, DP>;
+    auto fm_fixup = fm_fixup_kernel<T, NCH, DP ? OUT_GRAD : OUT_SGD>;
     const size_t fsmem = (size_t)FIX_WARPS * (m->kp + 2) * sizeof(T);
     RFM_LAUNCH(ctx, fm_fixup, tgrid, FIX_THREADS, fsmem, c);
   });
+  if (!DP) ++m->version;
+  return RFM_OK;
+}
+
+// ---- the two-level step (two_level.cuh) -------------------------------------------------------------------------
+template <typename T, int NCTX>
+int launch_vrows_as(rfm_ctx *ctx, int nch, int mode, bool sampled, const VRowsArgs<T> &args, int grid) {
+  RFM_DISPATCH_TPR(nch, {
+    if (mode == MODE_TRAIN) {
+      if (sampled) {
+        auto fm_vrows_train = fm_vrows_kernel<T, TPR, NCV, MODE_TRAIN, true, NCTX>;
+        RFM_LAUNCH(ctx, fm_vrows_train, grid, ROWS_THREADS, 0, args);
+      } else {
+        auto fm_vrows_train = fm_vrows_kernel<T, TPR, NCV, MODE_TRAIN, false, NCTX>;
+        RFM_LAUNCH(ctx, fm_vrows_train, grid, ROWS_THREADS, 0, args);
+      }
+    } else {
+      auto fm_vrows_loss = fm_vrows_kernel<T, TPR, NCV, MODE_LOSS, false, NCTX>;
+      RFM_LAUNCH(ctx, fm_vrows_loss, grid, ROWS_THREADS, 0, args);
+    }
+  });
+  return RFM_OK;
+}
+
+template <typename T>
+struct TlParams {
+  T *Vv, *wv, *vnv, *R, *Ra, *Rc;
+};
+template <typename T>
+TlParams<T> tl_params(const rfm_fm_trainer *t) {
+  const TwoLevel &L = *t->tl;
+  TlParams<T> p;
+  p.Vv = reinterpret_cast<T *>(L.Vv.p);
+  p.wv = reinterpret_cast<T *>(L.wv.p);
+  p.vnv = reinterpret_cast<T *>(L.vnv.p);
+  p.R = reinterpret_cast<T *>(L.R.p);
+  p.Ra = p.R + (size_t)L.nv * t->m->kp;
+  p.Rc = p.Ra + L.nv;
+  return p;
+}
+
+// per-entity aggregates of the CURRENT parameters (no-op while nothing changed them since the last call)
+template <typename T>
+int tl_refresh(rfm_fm_trainer *t) {
+  TwoLevel &L = *t->tl;
+  rfm_fm *m = t->m;
+  if (L.agg_version == m->version) return RFM_OK;
+  rfm_ctx *ctx = m->ctx;
+  const TlParams<T> p = tl_params<T>(t);
+  const int grid = grid_for(ctx, ceil_div(L.nv, units_per_block(m->nch)), 8);
+  RFM_DISPATCH_TPR(m->nch, {
+    auto fm_entity_fwd = fm_entity_fwd_kernel<T, TPR, NCV>;
+    RFM_LAUNCH(ctx, fm_entity_fwd, grid, ROWS_THREADS, 0, L.ent_ptr.p, L.ent_col.p,
+               reinterpret_cast<const T *>(L.ent_val.p), L.nv, reinterpret_cast<const T *>(m->V.p),
+               reinterpret_cast<const T *>(m->w.p), reinterpret_cast<const T *>(m->vn.p), m->kp, p.Vv, p.wv, p.vnv);
+  });
+  L.agg_version = m->version;
+  return RFM_OK;
+}
+
+template <typename T>
+RadixSorter<T> &tl_sorter_of(TwoLevel &L);
+template <>
+RadixSorter<float> &tl_sorter_of<float>(TwoLevel &L) { return L.l2_32; }
+template <>
+RadixSorter<double> &tl_sorter_of<double>(TwoLevel &L) { return L.l2_64; }
+
+template <typename T, bool DP>
+int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const FeistelKey &fkey, int64_t q0) {
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  TwoLevel &L = *t->tl;
+  const rfm_csr *tr = t->train;
+  RadixSorter<T> &sorter = sorter_of<T>(t);
+  const TlParams<T> p = tl_params<T>(t);
+  RFM_TRY(tl_refresh<T>(t));
+  const uint32_t cnt = (uint32_t)batch * t->stride;
+  if (cnt != t->count_host) {
+    t->count_host = cnt;
+    RFM_CUDA(cudaMemcpyAsync(t->count.p, &t->count_host, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RFM_CUDA(cudaMemsetAsync(L.R.p, 0, (size_t)L.nv * (m->kp + 2) * sizeof(T), ctx->stream));
+
+  // level 1: the row pass on virtual rows, with the aggregated table standing in for the parameters
+  const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), L.lean ? TL_VROWS_BLOCKS : t->rows_grid / ctx->sm_count);
+  RFM_TRY(sorter.clear_histograms(ctx));
+  Finish fin;
+  if (DP) {
+    T *g = reinterpret_cast<T *>(t->grad_ptr());
+    RFM_CUDA(cudaMemsetAsync(g, 0, (size_t)grad_total(m->n, m->kp) * sizeof(T), ctx->stream));
+    fin = make_finish(0, 1.0, g, nullptr, t->block_partials.p, t->ticket.p);
+  } else {
+    fin = make_finish(0, lr, m->w0.p, nullptr, t->block_partials.p, t->ticket.p);
+  }
+  if (L.lean) {
+    VRowsArgs<T> v;
+    memset(&v, 0, sizeof(v));
+    v.user = tr->f_user.p;
+    v.item = tr->f_item.p;
+    v.ctx = reinterpret_cast<const T *>(tr->f_ctx.p);
+    v.yp = reinterpret_cast<const T *>(tr->yp.p);
+    v.idx = t->idx.p;
+    v.n = batch;
+    v.w0 = reinterpret_cast<const T *>(m->w0.p);
+    v.A = p.Vv;
+    v.wv = p.wv;
+    v.vnv = p.vnv;
+    v.n_user = (uint32_t)L.n_ent[0];
+    v.ctx_col = (uint32_t)(L.n_ent[0] + L.n_ent[1]);
+    v.kp = m->kp;
+    v.S = reinterpret_cast<T *>(t->S.p);
+    v.E = reinterpret_cast<T *>(t->E.p);
+    v.stride = t->stride;
+    v.sentinel = (uint32_t)L.nv;
+    v.keys = sorter.keys[0].p;
+    v.pos = sorter.pos[0].p;
+    v.xs = sorter.val[0].p;
+    v.ghist = sorter.ghist();
+    v.n_passes = sorter.passes;
+    v.fkey = fkey;
+    v.q0 = q0;
+    v.idx_out = t->idx.p;
+    v.fin = fin;
+    if (tr->n_ctx) RFM_TRY((launch_vrows_as<T, 1>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
+    else RFM_TRY((launch_vrows_as<T, 0>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
+  } else {
+  RowsArgs<T> a = rows_args<T>(m, tr);
+  a.fac = tl_virtual_fac(tr->fac_dev(), L);
+  a.V = p.Vv;
+  a.w = p.wv;
+  a.vn = p.vnv;
+  a.idx = t->idx.p;
+  a.n = batch;
+  a.S = reinterpret_cast<T *>(t->S.p);
+  a.E = reinterpret_cast<T *>(t->E.p);
+  a.bptr = t->bptr.p;
+  a.stride = t->stride;
+  a.sentinel = (uint32_t)L.nv;
+  a.keys = sorter.keys[0].p;
+  a.pos = sorter.pos[0].p;
+  a.xs = sorter.val[0].p;
+  a.fkey = fkey;
+  a.q0 = q0;
+  a.idx_out = t->idx.p;
+  a.ghist = sorter.ghist();
+  a.n_passes = sorter.passes;
+  a.fin = fin;
+  RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, sampled, a, grid, true));
+  }
+  int sorted = 0;
+  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true));
+
+  ColsArgs<T> c;
+  memset(&c, 0, sizeof(c));
+  c.keys = sorter.keys[sorted].p;
+  c.pos = sorter.pos[sorted].p;
+  c.xs = sorter.val[sorted].p;
+  c.count = t->count.p;
+  c.sentinel = (uint32_t)L.nv;
+  c.E = reinterpret_cast<const T *>(t->E.p);
+  c.S = reinterpret_cast<const T *>(t->S.p);
+  c.kp = m->kp;
+  c.lr = static_cast<T>(lr);
+  c.unit = (uint32_t)cols_unit(m->nch);
+  c.carry_vec = reinterpret_cast<T *>(t->carry_vec.p);
+  c.carry_ac = reinterpret_cast<T *>(t->carry_ac.p);
+  c.tails = t->tails.p;
+  c.n_tails = t->n_tails.p;
+  c.grad_V = p.R;
+  c.grad_w = p.Ra;
+  c.raw_c = p.Rc;
+  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
+  const size_t csmem = cols_smem_bytes(m->nch, m->kp, sizeof(T));
+  const size_t fsmem = (size_t)FIX_WARPS * (m->kp + 2) * sizeof(T);
+  // lists too short to fill the machine with 32-entry chunks are walked in chunks of TPR entries (unit = 256)
+  auto small_chunks = [&](int64_t entries) { return ceil_div(entries, cols_unit(m->nch)) < 2 * (int64_t)ctx->sm_count; };
+  {
+    const bool small = small_chunks(cnt);
+    c.unit = small ? (uint32_t)ROWS_THREADS : (uint32_t)cols_unit(m->nch);
+    const int64_t unit_cap = ceil_div((int64_t)cnt, (int64_t)c.unit);
+    const int cgrid = grid_for(ctx, unit_cap, t->rows_grid / ctx->sm_count);
+    const int tgrid = grid_for(ctx, unit_cap, 4);
+    RFM_DISPATCH_TPR(m->nch, {
+      auto fm_cols_level1 = small ? fm_cols_kernel<T, TPR, NCV, OUT_RAW, false, true>
+                                  : fm_cols_kernel<T, TPR, NCV, OUT_RAW, false, false>;
+      if (csmem > 48 * 1024)
+        RFM_CUDA(cudaFuncSetAttribute(fm_cols_level1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      RFM_LAUNCH(ctx, fm_cols_level1, cgrid, ROWS_THREADS, csmem, c);
+    });
+    RFM_DISPATCH_NCH(m->nch, {
+      auto fm_fixup_level1 = fm_fixup_kernel<T, NCH, OUT_RAW>;
+      RFM_LAUNCH(ctx, fm_fixup_level1, tgrid, FIX_THREADS, fsmem, c);
+    });
+  }
+
+  // level 2: the static (real column, virtual column, x) list over level 1's sums -> the reference's update
+  RadixSorter<T> &l2 = tl_sorter_of<T>(L);
+  ColsArgs<T> d = c;
+  d.keys = l2.keys[L.l2_buf].p;
+  d.pos = l2.pos[L.l2_buf].p;
+  d.xs = l2.val[L.l2_buf].p;
+  d.count = L.m2_dev.p;
+  d.sentinel = KEY_NONE;
+  d.E = nullptr;
+  d.S = p.R;
+  d.Ea = p.Ra;
+  d.Ec = p.Rc;
+  d.V = reinterpret_cast<T *>(m->V.p);
+  d.w = reinterpret_cast<T *>(m->w.p);
+  d.vn = reinterpret_cast<T *>(m->vn.p);
+  d.grad_V = d.grad_w = d.raw_c = nullptr;
+  if (DP) {
+    T *g = reinterpret_cast<T *>(t->grad_ptr());
+    d.grad_w = g + GRAD_W_OFF;
+    d.grad_V = g + grad_v_off(m->n);
+  }
+  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
+  {
+    const bool small = small_chunks(L.m2);
+    d.unit = small ? (uint32_t)ROWS_THREADS : (uint32_t)cols_unit(m->nch);
+    const int64_t unit_cap = ceil_div(L.m2, (int64_t)d.unit);
+    const int cgrid = grid_for(ctx, unit_cap, t->rows_grid / ctx->sm_count);
+    const int tgrid = grid_for(ctx, unit_cap, 4);
+    RFM_DISPATCH_TPR(m->nch, {
+      auto fm_cols_level2 = small ? fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, true, true>
+                                  : fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, true, false>;
+      if (csmem > 48 * 1024)
+        RFM_CUDA(cudaFuncSetAttribute(fm_cols_level2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      RFM_LAUNCH(ctx, fm_cols_level2, cgrid, ROWS_THREADS, csmem, d);
+    });
+    RFM_DISPATCH_NCH(m->nch, {
+      auto fm_fixup_level2 = fm_fixup_kernel<T, NCH, DP ? OUT_GRAD : OUT_SGD>;
+      RFM_LAUNCH(ctx, fm_fixup_level2, tgrid, FIX_THREADS, fsmem, d);
+    });
+  }
+  if (!DP) ++m->version;
   return RFM_OK;
 }
 
@@ -1382,6 +1655,73 @@ int batch_and_val_losses(rfm_fm_trainer *t, int64_t batch, double scale_b, doubl
                          int64_t val_end, double scale_v, double *dst_v) {
   rfm_fm *m = t->m;
   rfm_ctx *ctx = m->ctx;
+  if (t->tl) {     // the batch (and val rows keyed by the same tables) as virtual rows over the aggregated table
+    TwoLevel &L = *t->tl;
+    RFM_TRY(tl_refresh<T>(t));
+    const TlParams<T> p = tl_params<T>(t);
+    if (L.lean) {
+      const rfm_csr *tr = t->train, *va = t->val;
+      VRowsArgs<T> v;
+      memset(&v, 0, sizeof(v));
+      v.user = tr->f_user.p;
+      v.item = tr->f_item.p;
+      v.ctx = reinterpret_cast<const T *>(tr->f_ctx.p);
+      v.yp = reinterpret_cast<const T *>(tr->yp.p);
+      v.idx = t->idx.p;
+      v.n = batch;
+      v.w0 = reinterpret_cast<const T *>(m->w0.p);
+      v.A = p.Vv;
+      v.wv = p.wv;
+      v.vnv = p.vnv;
+      v.n_user = (uint32_t)L.n_ent[0];
+      v.ctx_col = (uint32_t)(L.n_ent[0] + L.n_ent[1]);
+      v.kp = m->kp;
+      v.fin = make_finish(1, scale_b, nullptr, dst_b, t->block_partials.p, t->ticket.p);
+      int64_t n_all = batch;
+      const bool val_here = va && val_end > val_begin;
+      if (val_here && L.val_virtual) {
+        v.user2 = va->f_user.p + val_begin;
+        v.item2 = va->f_item.p + val_begin;
+        v.ctx2 = va->f_ctx.p ? reinterpret_cast<const T *>(va->f_ctx.p) + val_begin * va->n_ctx : nullptr;
+        v.yp2 = reinterpret_cast<const T *>(va->yp.p) + val_begin;
+        v.n2 = val_end - val_begin;
+        v.fin2 = make_finish(1, scale_v, nullptr, dst_v, t->block_partials.p + t->rows_grid, t->ticket.p + 1);
+        n_all += v.n2;
+      } else if (!val_here) {
+        RFM_CUDA(cudaMemsetAsync(dst_v, 0, sizeof(double), ctx->stream));
+      }
+      const int grid = grid_for(ctx, ceil_div(n_all, units_per_block(m->nch)), TL_VROWS_BLOCKS);
+      if (tr->n_ctx) RFM_TRY((launch_vrows_as<T, 1>(ctx, m->nch, MODE_LOSS, false, v, grid)));
+      else RFM_TRY((launch_vrows_as<T, 0>(ctx, m->nch, MODE_LOSS, false, v, grid)));
+      if (val_here && !L.val_virtual)
+        RFM_TRY(loss_pass<T>(t, va, nullptr, val_begin, val_end - val_begin, scale_v, dst_v));
+      return RFM_OK;
+    }
+    RowsArgs<T> a = rows_args<T>(m, t->train);
+    a.fac = tl_virtual_fac(t->train->fac_dev(), L);
+    a.V = p.Vv;
+    a.w = p.wv;
+    a.vn = p.vnv;
+    a.idx = t->idx.p;
+    a.n = batch;
+    a.fin = make_finish(1, scale_b, nullptr, dst_b, t->block_partials.p, t->ticket.p);
+    int64_t n_all = batch;
+    const bool val_here = t->val && val_end > val_begin;
+    if (val_here && L.val_virtual) {
+      a.fac2 = tl_virtual_fac(t->val->fac_dev(val_begin), L);
+      a.yp2 = reinterpret_cast<const T *>(t->val->yp.p) + val_begin;
+      a.n2 = val_end - val_begin;
+      a.fin2 = make_finish(1, scale_v, nullptr, dst_v, t->block_partials.p + t->rows_grid, t->ticket.p + 1);
+      n_all += a.n2;
+    } else if (!val_here) {
+      RFM_CUDA(cudaMemsetAsync(dst_v, 0, sizeof(double), ctx->stream));
+    }
+    const int grid = grid_for(ctx, ceil_div(n_all, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
+    RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_LOSS, false, a, grid, true));
+    if (val_here && !L.val_virtual)     // other tables: the flat row pass on the real parameters
+      RFM_TRY(loss_pass<T>(t, t->val, nullptr, val_begin, val_end - val_begin, scale_v, dst_v));
+    return RFM_OK;
+  }
   RowsArgs<T> a = rows_args<T>(m, t->train);
   a.idx = t->idx.p;
   a.n = batch;
@@ -1694,6 +2034,8 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
           ptr[(size_t)i] = (int32_t)v;
         }
         const int64_t tnz = ptr[(size_t)ne];
+        sg.n_entities = ne;
+        sg.tnz = tnz;
         RFM_REQUIRE(tnz == 0 || (k.indices && k.data), "rfm_factored_create: table block %d has no indices/data", b);
         for (int64_t z = 0; z < tnz; ++z)
           RFM_REQUIRE(k.indices[z] >= 0 && k.indices[z] < k.n_cols,
@@ -2027,6 +2369,7 @@ int rfm_fm_set_params(rfm_fm *m, const double *w0, const double *w, const double
                reinterpret_cast<const float *>(m->V.p), reinterpret_cast<float *>(m->vn.p), m->n, m->kp);
   }
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  ++m->version;
   return RFM_OK;
 }
 
@@ -2209,6 +2552,140 @@ int rfm_fm_trainer_create(rfm_fm *m, const rfm_csr *train, const rfm_csr *val, i
   return RFM_OK;
 }
 
+// Two-level step for factored train rows (two_level.cuh). mode 1: switch it on; 2: only where the cost model
+// (gathered parameter rows per pass: batch x mean row length, against batch x virtual row length + the entity
+// tables' entries) predicts at least 1.5 x. Call before the first epoch. *enabled reports the outcome.
+int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabled) {
+  RFM_REQUIRE(t, "rfm_fm_trainer_set_two_level: trainer is NULL");
+  if (enabled) *enabled = t->tl ? 1 : 0;
+  RFM_REQUIRE(mode == 1 || mode == 2, "rfm_fm_trainer_set_two_level: mode must be 1 (on) or 2 (auto)");
+  if (t->tl) return RFM_OK;
+  const rfm_csr *tr = t->train;
+  if (!tr->factored) {
+    RFM_REQUIRE(mode == 2, "rfm_fm_trainer_set_two_level: the train rows are not factored");
+    return RFM_OK;
+  }
+  rfm_fm *m = t->m;
+  rfm_ctx *ctx = m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  TwoLevel *Lp = new (std::nothrow) TwoLevel();
+  if (!Lp) return fail(RFM_ERR_NOMEM, "rfm_fm_trainer_set_two_level: out of host memory");
+  TwoLevel &L = *Lp;
+  int64_t lim[2] = {INT64_MAX, INT64_MAX}, m2_est = tr->n_ctx;
+  int n_key_segs[2] = {0, 0};
+  for (int s = 0; s < tr->n_seg; ++s) {
+    const rfm_csr::Seg &g = tr->seg[s];
+    if (g.kind == SEG_CTX) {
+      for (int j = 0; j < g.width; ++j) L.ctx_cols.c[g.ctx0 + j] = g.col0 + (uint32_t)j;
+      continue;
+    }
+    lim[g.key] = std::min<int64_t>(lim[g.key], g.kind == SEG_ID ? g.width : g.n_entities);
+    ++n_key_segs[g.key];
+  }
+  for (int key = 0; key < 2; ++key) L.n_ent[key] = n_key_segs[key] ? lim[key] : 0;
+  for (int s = 0; s < tr->n_seg; ++s) {
+    const rfm_csr::Seg &g = tr->seg[s];
+    if (g.kind == SEG_ID) m2_est += L.n_ent[g.key];
+    if (g.kind == SEG_TABLE) m2_est += g.tnz;
+  }
+  L.nv = L.n_ent[0] + L.n_ent[1] + tr->n_ctx;
+  L.stride = (uint32_t)((L.n_ent[0] > 0) + (L.n_ent[1] > 0) + tr->n_ctx);
+  const double mean_len = tr->n_rows > 0 ? (double)tr->nnz / (double)tr->n_rows : 0.0;
+  const double flat = (double)t->max_batch * mean_len;
+  const double two = (double)t->max_batch * (double)L.stride + (double)m2_est;
+  const int64_t cap1 = t->max_batch * (int64_t)L.stride;
+  const bool fits = L.nv >= 1 && L.nv < 0xFFFFFFF0LL && cap1 < 0xFFFFFFF0LL && m2_est < 0x7FFFFFF0LL;
+  if (mode == 2 && (!fits || flat < 1.5 * two)) {
+    delete Lp;
+    return RFM_OK;
+  }
+  const size_t es = dsize(m->dtype);
+  auto body = [&]() -> int {
+    RFM_REQUIRE(fits, "rfm_fm_trainer_set_two_level: too many entities or batch entries for 32-bit offsets");
+    const FacDev f = tr->fac_dev();
+    const int g = grid_for(ctx, ceil_div(L.nv, 256), 8);
+    // entity lists: lengths -> scan -> fill (also the triples of the level-2 list, sorted by real column below)
+    DevBuf<uint32_t> len, scan_tmp;
+    RFM_TRY(len.alloc((size_t)L.nv));
+    RFM_TRY(scan_tmp.alloc((size_t)ceil_div(L.nv, 4096) + 2));
+    RFM_TRY(L.ent_ptr.alloc((size_t)L.nv + 1));
+    RFM_TRY(L.m2_dev.alloc(1));
+    RFM_LAUNCH(ctx, tl_ent_len_kernel, g, 256, 0, f, L.n_ent[0], L.n_ent[1], L.nv, len.p);
+    RFM_TRY(exclusive_scan_u32(ctx, len.p, L.ent_ptr.p, L.nv, scan_tmp.p, L.m2_dev.p));
+    uint32_t m2 = 0;
+    RFM_CUDA(cudaMemcpyAsync(L.ent_ptr.p + L.nv, L.m2_dev.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    RFM_CUDA(cudaMemcpyAsync(&m2, L.m2_dev.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    L.m2 = m2;
+    RFM_REQUIRE(L.m2 >= 1, "rfm_fm_trainer_set_two_level: the blocks hold no entries");
+    RFM_TRY(L.ent_col.alloc((size_t)L.m2));
+    RFM_TRY(L.ent_val.alloc((size_t)L.m2 * es));
+    int sorted = 0;
+    if (m->dtype == RFM_F64) {
+      RFM_TRY(L.l2_64.init(L.m2, m->n));
+      RFM_LAUNCH(ctx, tl_ent_fill_kernel<double>, g, 256, 0, f, L.n_ent[0], L.n_ent[1], L.nv, L.ctx_cols, L.ent_ptr.p,
+                 L.ent_col.p, reinterpret_cast<double *>(L.ent_val.p), L.l2_64.keys[0].p, L.l2_64.pos[0].p,
+                 L.l2_64.val[0].p);
+      RFM_TRY(L.l2_64.sort(ctx, L.m2_dev.p, &sorted));
+      RFM_TRY(L.l2_64.check(ctx));
+    } else {
+      RFM_TRY(L.l2_32.init(L.m2, m->n));
+      RFM_LAUNCH(ctx, tl_ent_fill_kernel<float>, g, 256, 0, f, L.n_ent[0], L.n_ent[1], L.nv, L.ctx_cols, L.ent_ptr.p,
+                 L.ent_col.p, reinterpret_cast<float *>(L.ent_val.p), L.l2_32.keys[0].p, L.l2_32.pos[0].p,
+                 L.l2_32.val[0].p);
+      RFM_TRY(L.l2_32.sort(ctx, L.m2_dev.p, &sorted));
+      RFM_TRY(L.l2_32.check(ctx));
+    }
+    L.l2_buf = sorted;
+    RFM_TRY(L.Vv.alloc((size_t)L.nv * m->kp * es));
+    RFM_TRY(L.wv.alloc((size_t)L.nv * es));
+    RFM_TRY(L.vnv.alloc((size_t)L.nv * es));
+    RFM_TRY(L.R.alloc((size_t)L.nv * (m->kp + 2) * es));
+    // val rows ride in the virtual loss launch when they are keyed by the same tables (same blocks, same bytes)
+    const rfm_csr *va = t->val;
+    bool same = va && va->factored && va->n_seg == tr->n_seg && va->n_ctx == tr->n_ctx;
+    DevBuf<int> differ;
+    RFM_TRY(differ.alloc(1));
+    RFM_CUDA(cudaMemsetAsync(differ.p, 0, sizeof(int), ctx->stream));
+    for (int s = 0; same && s < tr->n_seg; ++s) {
+      const rfm_csr::Seg &a = tr->seg[s], &b = va->seg[s];
+      same = a.kind == b.kind && a.key == b.key && a.col0 == b.col0 && a.width == b.width && a.ctx0 == b.ctx0 &&
+             a.n_entities == b.n_entities && a.tnz == b.tnz;
+      if (!same || a.kind != SEG_TABLE) continue;
+      const struct { const void *x, *y; int64_t words; } arrays[3] = {
+          {a.ptr.p, b.ptr.p, a.n_entities + 1}, {a.col.p, b.col.p, a.tnz}, {a.val.p, b.val.p, a.tnz * (int64_t)(es / 4)}};
+      for (const auto &ar : arrays)
+        if (ar.words > 0 && ar.x != ar.y)
+          RFM_LAUNCH(ctx, tl_compare_kernel, grid_for(ctx, ceil_div(ar.words, 256), 8), 256, 0,
+                     static_cast<const uint32_t *>(ar.x), static_cast<const uint32_t *>(ar.y), ar.words, differ.p);
+    }
+    int differ_host = 0;
+    RFM_CUDA(cudaMemcpyAsync(&differ_host, differ.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+    L.val_virtual = same && differ_host == 0;
+    // the lean row kernel covers [user | item | at most one context column]; RFM_TL_GENERIC=1 keeps the generic one
+    L.lean = L.n_ent[0] > 0 && L.n_ent[1] > 0 && tr->n_ctx <= 1 && getenv("RFM_TL_GENERIC") == nullptr;
+    // level 1 sorts batch x stride virtual entries by virtual column; the carry records serve both levels
+    t->stride = L.stride;
+    t->nnz_cap = cap1;
+    t->count_host = 0;
+    if (m->dtype == RFM_F64) RFM_TRY(t->sort64.init(cap1, L.nv + 1)); else RFM_TRY(t->sort32.init(cap1, L.nv + 1));
+    const int64_t chunk_cap = ceil_div(std::max<int64_t>(cap1, L.m2), (int64_t)ROWS_THREADS) + 1;   // the smaller unit
+    RFM_TRY(t->carry_vec.alloc((size_t)chunk_cap * 2 * m->kp * es));
+    RFM_TRY(t->carry_ac.alloc((size_t)chunk_cap * 4 * es));
+    RFM_TRY(t->tails.alloc((size_t)chunk_cap));
+    return RFM_OK;
+  };
+  const int rc = body();
+  if (rc != RFM_OK) {
+    delete Lp;
+    return rc;
+  }
+  t->tl = Lp;
+  if (enabled) *enabled = 1;
+  return RFM_OK;
+}
+
 int rfm_fm_trainer_destroy(rfm_fm_trainer *t) {
   if (t) {
     cudaSetDevice(t->m->ctx->device);
@@ -2222,6 +2699,7 @@ int rfm_fm_trainer_destroy(rfm_fm_trainer *t) {
         if (q != t->dp_rank && t->peer_base[q]) cudaIpcCloseMemHandle(t->peer_base[q]);
       if (t->xchg) cudaFree(t->xchg);
     }
+    delete t->tl;
     delete t;
   }
   return RFM_OK;
@@ -2326,6 +2804,7 @@ int rfm_fm_apply_grad(rfm_fm_trainer *t, double lr) {
                reinterpret_cast<float *>(m->vn.p), gr, gr + GRAD_W_OFF, gr + grad_v_off(m->n), m->n, m->kp,
                (float)lr);
   }
+  ++m->version;
   return RFM_OK;
 }
 
@@ -2636,6 +3115,7 @@ int rfm_fm_dp_exchange_apply(rfm_fm_trainer *t, double lr) {
                reinterpret_cast<float *>(m->w.p), reinterpret_cast<float *>(m->V.p),
                reinterpret_cast<float *>(m->vn.p), m->n, m->kp, (float)lr);
   }
+  ++m->version;
   t->dp_parity ^= 1;           // the next gradient goes to the other buffer
   t->dp_pending_loss = true;   // rfm_fm_loss_sums of this step will ride in the next exchange
   return RFM_OK;
@@ -2685,6 +3165,7 @@ int opt_epoch_impl(rfm_fm_trainer *t, int64_t batch, int64_t slot, bool sampled,
                reinterpret_cast<T *>(m->V.p), reinterpret_cast<T *>(m->vn.p), gr, (T *)nullptr, (T *)nullptr, m->n,
                m->k, m->kp, GRAD_W_OFF, grad_v_off(m->n), o);
   }
+  ++m->version;
   return post_update_losses<T>(t, batch, slot);
 }
 }  // namespace

@@ -46,6 +46,7 @@ struct rfm_csr {
   struct Seg {
     int kind = 0, key = 0, width = 0, ctx0 = 0;
     uint32_t col0 = 0;
+    int64_t n_entities = 0, tnz = 0;   // SEG_TABLE: rows and stored entries of the table
     DevBuf<int32_t> ptr, col;
     DevBuf<unsigned char> val;
   } seg[FAC_MAX_SEG];

@@ -76,6 +76,7 @@ class GeneratedRows(_capi._Handle):
     """Factored rows generated on the device; stands where ``train["features"]`` does (labels / pscores: None)."""
 
     _destroy = "rfm_csr_destroy"
+    factored = True
 
     def __init__(self, ctx, model: ClickModel, n_rows: int, blocks, row0: int = 0, dtype="float64", keep_labels=False):
         super().__init__()

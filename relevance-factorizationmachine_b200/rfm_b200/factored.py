@@ -161,6 +161,7 @@ class FactoredRows(_capi._Handle):
     """Device copy of a ``FactoredFeatures`` (+ labels / pscores): an ``rfm_csr`` handle of the factored kind."""
 
     _destroy = "rfm_csr_destroy"
+    factored = True
 
     def __init__(self, ctx, X: FactoredFeatures, labels=None, pscores=None, dtype="float64"):
         super().__init__()

@@ -43,6 +43,15 @@ class _FmTrainer(_capi._Handle):
         self._keep = [model, train, val]
         check(lib().rfm_fm_trainer_create(model.handle, train.handle, val.handle if val is not None else None,
                                           max_batch, max_slots, byref(self.handle)))
+        self.two_level = False
+
+    def set_two_level(self, mode: int) -> bool:
+        """mode 1: on; 2: where the cost model predicts a gain (``rfm_fm_trainer_set_two_level``)."""
+        from ctypes import c_int32
+        on = c_int32(0)
+        check(lib().rfm_fm_trainer_set_two_level(self.handle, mode, byref(on)))
+        self.two_level = bool(on.value)
+        return self.two_level
 
 
 @dataclass
@@ -62,6 +71,8 @@ class FactorizationMachines(PointwiseBaseRecommender):
     beta2: float = 0.999
     adam_eps: float = 1e-8
     materialize: str = "auto"     # factored rows -> stacked CSR on the device before a fit: "auto" (long fits), "always", "never"
+    step: str = "auto"            # factored rows: "two_level" = per-entity aggregates (csrc/two_level.cuh), "flat" = one
+                                  # gathered parameter row per stored non-zero, "auto" = two-level where it gathers >= 1.5 x less
     _dev: object = field(default=None, init=False, repr=False, compare=False)
 
     def __post_init__(self) -> None:
@@ -73,6 +84,8 @@ class FactorizationMachines(PointwiseBaseRecommender):
             raise ValueError("l2 must be >= 0")
         if self.materialize not in ("auto", "always", "never"):
             raise ValueError("materialize must be 'auto', 'always' or 'never'")
+        if self.step not in ("auto", "flat", "two_level"):
+            raise ValueError("step must be 'auto', 'flat' or 'two_level'")
         if self.distributed is not None and (self.optimizer != "sgd" or self.l2 != 0):
             raise ValueError("the data-parallel fit implements the reference's SGD step only")
         _capi.dtype_code(self.dtype)
@@ -188,6 +201,20 @@ class FactorizationMachines(PointwiseBaseRecommender):
                 raise
             return train_rows, val_rows        # too large for 32-bit offsets or for the device: stay factored
 
+    def _make_trainer(self, train_rows, val_rows, max_batch, max_slots):
+        """(trainer, train rows, val rows): factored rows train with the two-level step where it is asked for or
+        pays (then they stay factored); otherwise a long fit may assemble the stacked CSR on the device first."""
+        is_fac = lambda r: getattr(r, "factored", False)
+        if is_fac(train_rows) and (self.step == "two_level" or (self.step == "auto" and self.materialize != "always")):
+            trainer = _FmTrainer(self._dev, train_rows, val_rows, max_batch, max_slots)
+            if trainer.set_two_level(1 if self.step == "two_level" else 2):
+                return trainer, train_rows, val_rows
+            trainer.close()
+        elif self.step == "two_level":
+            raise ValueError("step='two_level' needs FactoredFeatures (or generated rows) as train['features']")
+        train_rows, val_rows = self._maybe_materialize(train_rows, val_rows)
+        return _FmTrainer(self._dev, train_rows, val_rows, max_batch, max_slots), train_rows, val_rows
+
     # ---- reference API -----------------------------------------------------------------------
     def fit(self, train, val) -> tuple:
         ctx = self._context()
@@ -199,13 +226,12 @@ class FactorizationMachines(PointwiseBaseRecommender):
         t_up = time.perf_counter()
         train_rows = self._rows(X, train["labels"], train["pscores"])
         val_rows = self._rows(val["features"], val["labels"], val["pscores"])
-        train_rows, val_rows = self._maybe_materialize(train_rows, val_rows)
         self.sync_to_device()
         self._upload_seconds = time.perf_counter() - t_up
         if self.distributed is not None:
             return self._fit_data_parallel(train_rows, val_rows, n_rows)
         t_phase = time.perf_counter()
-        trainer = _FmTrainer(self._dev, train_rows, val_rows, self.batch_size, max(self.n_epochs, 1))
+        trainer, train_rows, val_rows = self._make_trainer(train_rows, val_rows, self.batch_size, max(self.n_epochs, 1))
         phases = {"upload": self._upload_seconds, "trainer_create": time.perf_counter() - t_phase}
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
@@ -260,7 +286,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
         t_phase = time.perf_counter()
         self.sync_to_host()
         phases["download_params"] = time.perf_counter() - t_phase
-        self.last_fit_stats = {"gpu_launches": launches,
+        self.last_fit_stats = {"gpu_launches": launches, "two_level": getattr(trainer, "two_level", False),
                                "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes,
                                "upload_seconds": self._upload_seconds,
                                "phase_seconds": {k: round(v, 5) for k, v in phases.items()}}
@@ -275,7 +301,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
         begin, end = rdist.slice_bounds(self.batch_size, env.world, env.rank)
         phases = {"upload": self._upload_seconds}
         t_phase = time.perf_counter()
-        trainer = _FmTrainer(self._dev, train_rows, val_rows, max(end - begin, 1), 1)
+        trainer, train_rows, val_rows = self._make_trainer(train_rows, val_rows, max(end - begin, 1), 1)
         phases["trainer_create"] = time.perf_counter() - t_phase
         epochs = range(self.n_epochs)
         prefetch = LegacyBatchPrefetcher(n_rows, self.batch_size, epochs) if self.sampler == "legacy" else None
@@ -322,7 +348,7 @@ class FactorizationMachines(PointwiseBaseRecommender):
         t_phase = time.perf_counter()
         self.sync_to_host()
         phases["download_params"] = time.perf_counter() - t_phase
-        self.last_fit_stats = {"gpu_launches": launches,
+        self.last_fit_stats = {"gpu_launches": launches, "two_level": getattr(trainer, "two_level", False),
                                "h2d_bytes_rows": train_rows.h2d_bytes + val_rows.h2d_bytes,
                                "upload_seconds": self._upload_seconds,
                                "phase_seconds": {k: round(v, 5) for k, v in phases.items()}}
