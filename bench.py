@@ -61,10 +61,13 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="interactions per step per GPU")
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--rows", type=int, default=N_TRAIN, help="train interactions in the job")
-    ap.add_argument("--input", default="csr", choices=["factored", "csr"],
-                    help="row format RESIDENT IN HBM for the device-timed steps (value): csr = the reference's stacked "
-                         "matrix, factored = user table + item table + (user, item, ctx) records (SURVEY 8 f3); the "
-                         "other one is timed next to it (roofline.other_input_format)")
+    ap.add_argument("--input", default="factored", choices=["factored", "csr"],
+                    help="row format RESIDENT IN HBM for the device-timed steps (value): factored = user table + item "
+                         "table + (user, item, ctx) records (SURVEY 8 f3; what the e2e uploads), csr = the reference's "
+                         "stacked matrix; the other formats / steps are timed next to it (roofline.other_input_formats)")
+    ap.add_argument("--step", default="auto", choices=["auto", "flat", "two_level"],
+                    help="factored rows: two_level = per-entity aggregates (csrc/two_level.cuh), flat = one gathered "
+                         "parameter row per stored non-zero, auto = what FactorizationMachines.fit picks")
     ap.add_argument("--e2e-input", default="factored", choices=["factored", "csr"],
                     help="row format the headline e2e uploads from host memory; the other one is e2e.hstacked_csr / "
                          "e2e.factored")
@@ -181,6 +184,15 @@ def algorithmic_bytes_of(m, touched, B, k, s):
         "fm_rows_loss": 8 + 16 + m * (4 + s) + s + m * (k + 1) * s,
     }
     return step, per_kernel
+
+
+def two_level_bytes(B, k, s, n_ctx, entity_entries, n_features):
+    """Bytes one interaction must move in the two-level step, counted the way section 8(d) counts the flat one: the
+    row record, the forward gathers of both passes (user row, item row, context columns), and per STEP the entity
+    pass (entity_entries parameter rows gathered forward, as many rows of per-entity sums gathered backward, every
+    parameter row read and written once), spread over the B interactions of the step."""
+    stream = 4 + 4 + 4 + n_ctx * s + 4 + s
+    return stream + 2 * (2 + n_ctx) * (k + 1) * s + (2 * entity_entries + 2 * n_features) * (k + 1) * s / B
 
 
 class ClockSampler:
@@ -684,6 +696,11 @@ def timed_steps(ctx, dist, stepper, W, K, device, observe=True):
 def step_roofline(prof, K, ms, B, world, m, touched, k, s, peaks, peak_kind, l2_assisted, note, traffic_key):
     step_bytes, per_kernel = algorithmic_bytes_of(m, touched, B, k, s)
     total_prof_ms = sum(v[1] for v in prof.values())
+    if not any(kk in per_kernel for kk in prof):      # two-level step: its row passes gather 2 + n_ctx rows per interaction
+        per_kernel = {"fm_vrows_train": 8 + 16 + 3 * (k + 1) * s + k * s + s + 3 * (8 + s),
+                      "fm_vrows_loss": 8 + 16 + 3 * (k + 1) * s,
+                      "fm_rows_train": 8 + 16 + 3 * (k + 1) * s + k * s + s + 3 * (8 + s),
+                      "fm_rows_loss": 8 + 16 + 3 * (k + 1) * s}
     top = max((kk for kk in prof if kk in per_kernel), key=lambda kk: prof[kk][1])
     top_ms = prof[top][1] / prof[top][0]
     achieved = step_bytes * B / (ms / K * 1e-3) / 1e9
@@ -941,7 +958,7 @@ def run_ours(args):
     dtype_tag = "f64" if args.dtype == "float64" else "f32"
     train_in, val_in = (ftrain, fval) if args.input == "factored" else (log.fm_train, log.fm_val)
 
-    def device_run(train_d, val_d):
+    def device_run(train_d, val_d, step="flat"):
         model = FactorizationMachines("IPS", K, K_FACTORS, LR, B, 12345, log.n_features, dtype=args.dtype,
                                       sampler="feistel", device=local_rank)
         ctx = model._context()
@@ -949,6 +966,8 @@ def run_ours(args):
         val_rows = model._rows(val_d["features"], val_d["labels"], val_d["pscores"])
         model.sync_to_device()
         trainer = _FmTrainer(model._dev, train_rows, val_rows, B, W + 2 * K + 8)
+        if step != "flat" and getattr(train_rows, "factored", False):
+            trainer.set_two_level(1 if step == "two_level" else 2)
         dp = None
         if dist is not None:
             from rfm_b200 import dist as rdist
@@ -972,11 +991,19 @@ def run_ours(args):
         assert np.all(np.isfinite(tl)) and np.all(np.isfinite(vl)), "non-finite loss in the timed region"
         trainer.close()
         return dict(ms=ms, launches=launches, clk=clk, prof=prof, tl=float(tl[W + K - 1]), vl=float(vl[W + K - 1]),
-                    rows_bytes=train_rows.h2d_bytes)
+                    rows_bytes=train_rows.h2d_bytes, two_level=trainer.two_level)
 
-    main = device_run(train_in, val_in)
-    other_fmt = "csr" if args.input == "factored" else "factored"
-    other = device_run(*((log.fm_train, log.fm_val) if other_fmt == "csr" else (ftrain, fval)))
+    main = device_run(train_in, val_in, args.step if args.input == "factored" else "flat")
+    others = []
+    for fmt, step in (("csr", "flat"), ("factored", "flat"), ("factored", "two_level")):
+        if fmt == args.input and (fmt == "csr" or (step == "two_level") == main["two_level"]):
+            continue                                         # that is the headline run itself
+        o = device_run(*((log.fm_train, log.fm_val) if fmt == "csr" else (ftrain, fval)), step)
+        others.append({"input_format": fmt, "step": "two_level" if o["two_level"] else "flat",
+                       "ms_per_step": o["ms"] / K, "value": K * B * world / (o["ms"] * 1e-3),
+                       "final_train_loss": o["tl"],
+                       "kernels_ms_per_step": {kk: round(v[1] / K, 5) for kk, v in
+                                               sorted(o["prof"].items(), key=lambda kv: -kv[1][1])}})
     ms, launches, clk, prof = main["ms"], main["launches"], main["clk"], main["prof"]
     value = K * B * world / (ms * 1e-3)
 
@@ -998,9 +1025,27 @@ def run_ours(args):
                              "V (%.1f MB) and S (%.1f MB) are L2-resident at this shape, so the algorithmic gather "
                              "traffic is served by L2, not HBM (SURVEY.md H7): frac is the section-8(d) fraction, "
                              "L2-assisted; the HBM-bound claim is roofline.stress"
-                             % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6), "kuairec_big")
-    roofline["other_input_format"] = {"input_format": other_fmt, "ms_per_step": other["ms"] / K,
-                                      "value": K * B * world / (other["ms"] * 1e-3)}
+                             % (log.n_features * K_FACTORS * s / 1e6, B * K_FACTORS * s / 1e6),
+                             "kuairec_two_level" if main["two_level"] else
+                             ("kuairec_factored" if args.input == "factored" else "kuairec_big"))
+    roofline["other_input_formats"] = others
+    roofline["step"] = "two_level" if main["two_level"] else "flat"
+    if main["two_level"]:
+        ff = ftrain["features"]
+        n_ctx = sum(b[1].shape[1] for b in ff.blocks if b[0] == "ctx")
+        entries = n_ctx + sum(b[2] for b in ff.blocks if b[0] == "id") + sum(b[2].nnz for b in ff.blocks if b[0] == "table")
+        own = two_level_bytes(B, K_FACTORS, s, n_ctx, entries, log.n_features)
+        own_achieved = own * B / (ms / K * 1e-3) / 1e9
+        roofline["two_level"] = {
+            "algorithmic_bytes_per_interaction": own, "achieved": own_achieved, "frac": own_achieved / peaks["hbm_gbs"],
+            "entity_entries": int(entries),
+            "note": "the two-level step (csrc/two_level.cuh) computes the same update from per-user / per-item "
+                    "aggregates: it gathers 2 + n_ctx parameter rows per interaction and pass instead of m = %.1f, plus "
+                    "one pass over the entity tables per step, i.e. %.0f bytes per interaction where section 8(d) "
+                    "counts %.0f. roofline.frac keeps the section-8(d) numerator (the contract's definition), so it "
+                    "measures the step against the bytes the FLAT formulation must move and may exceed what a "
+                    "byte-for-byte implementation could reach; this object holds the fraction in the step's own bytes"
+                    % (m, own, roofline["algorithmic_bytes_per_interaction"])}
     e2e = None if args.no_e2e else measure_e2e(args, log, ftrain, fval, local_rank, dist, world)
     scoring = None if args.no_scoring else measure_scoring(local_rank, dist, world, peaks, peak_kind)
     if scoring is not None:
@@ -1036,8 +1081,9 @@ def run_ours(args):
     cfg["l2"] = cfg["l2"].replace("train rows", "%.2f GB of train rows" % (main["rows_bytes"] / 1e9))
     cfg.update(sampler="feistel (device, perf mode)", mean_nnz_per_row=round(m, 3),
                touched_columns_per_step=int(touched), n_features=log.n_features, data_gen_s=round(gen_s, 1),
-               input_format=("factored: user table + item table + (user, item, ctx) records, rows assembled on the "
-                             "device (SURVEY.md 8 f3)" if args.input == "factored" else
+               input_format=("factored rows resident in HBM: user table + item table + (user, item, ctx) records "
+                             "(SURVEY.md 8 f3), %s step" % ("two-level" if main["two_level"] else "flat")
+                             if args.input == "factored" else
                              "stacked CSR (the reference's own input) resident in HBM; e2e uploads the %s form"
                              % args.e2e_input))
     line = {

@@ -1442,7 +1442,7 @@ int tl_refresh(rfm_fm_trainer *t) {
   if (L.agg_version == m->version) return RFM_OK;
   rfm_ctx *ctx = m->ctx;
   const TlParams<T> p = tl_params<T>(t);
-  const int grid = grid_for(ctx, ceil_div(L.nv, units_per_block(m->nch)), 8);
+  const int grid = grid_for(ctx, ceil_div(L.nv, units_per_block(m->nch)), 4);     // one wave
   RFM_DISPATCH_TPR(m->nch, {
     auto fm_entity_fwd = fm_entity_fwd_kernel<T, TPR, NCV>;
     RFM_LAUNCH(ctx, fm_entity_fwd, grid, ROWS_THREADS, 0, L.ent_ptr.p, L.ent_col.p,

@@ -154,7 +154,7 @@ __global__ void tl_compare_kernel(const uint32_t *__restrict__ a, const uint32_t
 // Entity forward: a group of TPR lanes per virtual column sums x v_j, x w_j and x^2 ||v_j||^2 over the entity's
 // entries, in entry order (the same lane layout and per-entry order as the row pass).
 template <typename T, int TPR, int NCV>
-__global__ void __launch_bounds__(ROWS_THREADS)
+__global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? 4 : 1)
 fm_entity_fwd_kernel(const uint32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent_col,
                      const T *__restrict__ ent_val, int64_t nv, const T *__restrict__ V, const T *__restrict__ w,
                      const T *__restrict__ vn, int kp, T *__restrict__ Vv, T *__restrict__ wv, T *__restrict__ vnv) {
