@@ -126,6 +126,23 @@ def main():
     la, lb = ma.fit(kr.fm_train, kr.fm_val), mb.fit(fac(kr.fm_train), fac(kr.fm_val))
     assert la == lb
     np.testing.assert_array_equal(ma.V(), mb.V())
+    # the two-level step (csrc/two_level.cuh) feeding the same exchange: against the flat data-parallel fit and
+    # against the single-GPU two-level fit (two associations of the same sums), ranks bit-identical
+    mc = FactorizationMachines(step="two_level", **kw2)
+    lc = mc.fit(fac(kr.fm_train), fac(kr.fm_val))
+    assert mc.last_fit_stats["two_level"] is True
+    md = FactorizationMachines(step="two_level", **dict(kw2, distributed=None))
+    ld = md.fit(fac(kr.fm_train), fac(kr.fm_val))
+    for ref_l, ref_m in ((lb, mb), (ld, md)):
+        np.testing.assert_allclose(lc[0], ref_l[0], rtol=1e-11)
+        np.testing.assert_allclose(lc[1], ref_l[1], rtol=1e-11)
+        np.testing.assert_allclose(mc.V(), ref_m.V(), rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(mc.w(), ref_m.w(), rtol=1e-9, atol=1e-13)
+    mine = torch.from_numpy(mc.V().copy()).cuda(local_rank)
+    lo, hi = mine.clone(), mine.clone()
+    env.dist.all_reduce(lo, op=env.dist.ReduceOp.MIN)
+    env.dist.all_reduce(hi, op=env.dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks diverged (two-level)"
     if env.rank == 0:
         print("DP_OK world=%d exchange=%s" % (env.world, os.environ.get("RFM_DP_EXCHANGE", "nvlink")))
     env.shutdown()

@@ -51,7 +51,7 @@ def test_two_level_fit_matches_the_reference_goldens_and_the_flat_step(which):
     np.testing.assert_allclose(w0, g["w0"], rtol=1e-9, atol=1e-13)
     np.testing.assert_allclose(tl_b, tl_a, rtol=1e-11)                 # the flat step: same sums, other association
     np.testing.assert_allclose(vl_b, vl_a, rtol=1e-11)
-    np.testing.assert_allclose(V, flat.V(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(V, flat.V(), rtol=1e-9, atol=1e-13)
     np.testing.assert_allclose(m.predict(X=fval["features"]), flat.predict(X=fval["features"]), rtol=1e-11)
 
 
@@ -68,8 +68,8 @@ def test_two_level_with_the_device_sampler_and_the_evaluator_chain():
     la, lb = a.fit(ftrain, fval), b.fit(ftrain, fval)
     np.testing.assert_allclose(lb[0], la[0], rtol=1e-11)
     np.testing.assert_allclose(lb[1], la[1], rtol=1e-11)
-    np.testing.assert_allclose(b.V(), a.V(), rtol=1e-10, atol=1e-14)
-    np.testing.assert_allclose(b.w(), a.w(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(b.V(), a.V(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(b.w(), a.w(), rtol=1e-9, atol=1e-13)
     # the evaluator hook reads the REAL parameters between two-level epochs: the Coat golden's per-epoch val_metrics
     from conftest import golden_csr, golden_frame
     from rfm_b200.synth import make_coat_shaped
@@ -115,8 +115,8 @@ def test_ragged_tables_empty_entities_wide_context_and_foreign_val_tables():
     assert b.last_fit_stats["two_level"] is True
     np.testing.assert_allclose(lb[0], la[0], rtol=1e-11)
     np.testing.assert_allclose(lb[1], la[1], rtol=1e-11)
-    np.testing.assert_allclose(b.V(), a.V(), rtol=1e-10, atol=1e-14)
-    np.testing.assert_allclose(b.w(), a.w(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(b.V(), a.V(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(b.w(), a.w(), rtol=1e-9, atol=1e-13)
     # val rows keyed by a different user table
     ut2 = (ut * 2.0).tocsr()
     fv = FactoredFeatures(blocks(ut2, ctx[val_sel]), users[val_sel], items[val_sel])
