@@ -682,6 +682,15 @@ struct ColsArgs {
   // L2 = true (level 2 of the two-level step): the list is the static (real column, virtual column, x) list and
   // "S" holds level 1's vector sums: acc += x S[p], a += x Ea[p], c += x^2 Ec[p]
   const T *Ea, *Ec;
+  // Level 1 of the two-level step with one dense context column: the first ctx_blocks CTAs of the launch do not walk
+  // the sorted list but sum that column over all ctx_rows batch positions (c_q = Cq[q]; every row holds the column, so
+  // it needs no sort): per-CTA partials in cpart, combined by the last of them into the OUT_RAW outputs of
+  // virtual column ctx_col
+  uint32_t ctx_blocks, ctx_col;
+  int64_t ctx_rows;
+  const T *Cq;
+  T *cpart;
+  uint32_t *ctx_ticket;
   // fix-up work lists (order of the lists is irrelevant: every entry is handled independently)
   uint32_t *tails;       // chunks that own a column continuing into later chunks
   uint32_t *n_tails;
@@ -747,6 +756,97 @@ __device__ __forceinline__ void store_carry(const ColsArgs<T> &a, uint32_t chunk
   }
 }
 
+// The dense context column of level 1 (see ColsArgs::ctx_blocks): sum over q of (c_q e_q) s_q, c_q e_q and c_q^2 e_q.
+// Rows are dealt to the CTAs in contiguous ranges and inside a CTA to the row groups round-robin; every group adds
+// its rows in order, groups of a warp combine by xor butterfly, warps in warp order, CTAs in three contiguous
+// blocks of CTA order by the last CTA to finish: one fixed association per (batch, launch shape).
+template <typename T, int TPR, int NCV>
+__device__ __forceinline__ void ctx_column_sums(const ColsArgs<T> &a, unsigned char *smem) {
+  using V2 = typename Vec2<T>::type;
+  constexpr int GPW = 32 / TPR;
+  const int lane = lane_id(), g = lane % TPR, grp = lane / TPR, wid = threadIdx.x >> 5;
+  const int pstride = a.kp + 2;
+  T *wpart = reinterpret_cast<T *>(smem);            // [ROWS_WARPS][pstride], then [3][pstride]
+  __shared__ bool ctx_last;
+  const int64_t nb = a.ctx_blocks, per = (a.ctx_rows + nb - 1) / nb;
+  const int64_t lo = blockIdx.x * per, hi = min(a.ctx_rows, lo + per);
+  V2 acc[NCV];
+#pragma unroll
+  for (int ch = 0; ch < NCV; ++ch) acc[ch].x = acc[ch].y = T(0);
+  T sa = T(0), sc = T(0);
+  RFM_UNROLL(4)
+  for (int64_t r = lo + wid * GPW + grp; r < hi; r += ROWS_WARPS * GPW) {
+    const T c = __ldg(a.Cq + r), ev = __ldg(a.E + r);
+    const T xe = c * ev, xxe = c * c * ev;
+    const V2 *srow = reinterpret_cast<const V2 *>(a.S + (size_t)r * a.kp) + g;
+#pragma unroll
+    for (int ch = 0; ch < NCV; ++ch) {
+      const V2 sv = __ldg(srow + ch * TPR);
+      acc[ch].x += xe * sv.x;
+      acc[ch].y += xe * sv.y;
+    }
+    sa += xe;
+    sc += xxe;
+  }
+#pragma unroll
+  for (int o = TPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int ch = 0; ch < NCV; ++ch) {
+      acc[ch].x += __shfl_xor_sync(FULL, acc[ch].x, o);
+      acc[ch].y += __shfl_xor_sync(FULL, acc[ch].y, o);
+    }
+    sa += __shfl_xor_sync(FULL, sa, o);
+    sc += __shfl_xor_sync(FULL, sc, o);
+  }
+  if (lane < TPR) {
+#pragma unroll
+    for (int ch = 0; ch < NCV; ++ch) {
+      wpart[wid * pstride + (ch * TPR + g) * 2] = acc[ch].x;
+      wpart[wid * pstride + (ch * TPR + g) * 2 + 1] = acc[ch].y;
+    }
+    if (lane == 0) {
+      wpart[wid * pstride + a.kp] = sa;
+      wpart[wid * pstride + a.kp + 1] = sc;
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < pstride; f += ROWS_THREADS) {
+    T s = T(0);
+    for (int w = 0; w < ROWS_WARPS; ++w) s += wpart[w * pstride + f];
+    a.cpart[(size_t)blockIdx.x * pstride + f] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ctx_last = atomicAdd(a.ctx_ticket, 1u) == a.ctx_blocks - 1u;
+  __syncthreads();
+  if (!ctx_last) return;
+  __threadfence();
+  const unsigned seg_len = (a.ctx_blocks + 2u) / 3u;
+  for (int i = threadIdx.x; i < 3 * pstride; i += ROWS_THREADS) {
+    const unsigned sg = i / pstride, f = i - sg * pstride;
+    const unsigned b0 = min(a.ctx_blocks, sg * seg_len), b1 = min(a.ctx_blocks, b0 + seg_len);
+    T s = T(0);
+    unsigned b = b0;
+    for (; b + 8 <= b1; b += 8) {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(a.cpart + (size_t)(b + u) * pstride + f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; b < b1; ++b) s += __ldcg(a.cpart + (size_t)b * pstride + f);
+    wpart[i] = s;
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < pstride; f += ROWS_THREADS) {
+    const T s = (wpart[f] + wpart[pstride + f]) + wpart[2 * pstride + f];
+    if (f < a.kp) a.grad_V[(size_t)a.ctx_col * a.kp + f] = s;
+    else if (f == a.kp) a.grad_w[a.ctx_col] = s;
+    else a.raw_c[a.ctx_col] = s;
+  }
+  if (threadIdx.x == 0) *a.ctx_ticket = 0u;
+}
+
 // Column pass. A group of TPR lanes walks one chunk of 32 consecutive entries of the column-sorted list
 // (entry i lives in lane i % TPR, register i / TPR); a CTA covers GPC = 8 * 32/TPR consecutive chunks per
 // iteration ("unit"). Columns that live inside one chunk are finished by their group. Partial sums of a
@@ -772,10 +872,15 @@ fm_cols_kernel(const ColsArgs<T> a) {
   const int wid = threadIdx.x >> 5;
   const int gi = wid * GPW + grp;                                // this group's chunk inside the unit
   const unsigned gmask = TPR == 32 ? FULL : (((1u << TPR) - 1u) << (grp * TPR));
+  if (OUT == OUT_RAW && blockIdx.x < a.ctx_blocks) {             // block-uniform: these CTAs sum the dense context column
+    ctx_column_sums<T, TPR, NCV>(a, cols_smem);
+    return;
+  }
   const uint32_t M = *a.count;
   const uint32_t n_chunks = (M + CH - 1u) / CH;
   const uint32_t n_units = (n_chunks + GPC - 1) / GPC;
-  for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {   // CTA-uniform trip count
+  const uint32_t first_cta = OUT == OUT_RAW ? a.ctx_blocks : 0u, n_ctas = gridDim.x - first_cta;
+  for (uint32_t unit = blockIdx.x - first_cta; unit < n_units; unit += n_ctas) {   // CTA-uniform trip count
     const uint32_t chunk = unit * GPC + gi;
     const uint32_t base = chunk * CH;
     uint32_t key[NJ], p[NJ];
@@ -1516,6 +1621,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
     v.q0 = q0;
     v.idx_out = t->idx.p;
     v.fin = fin;
+    v.Cq = reinterpret_cast<T *>(L.Cq.p);
     if (tr->n_ctx) RFM_TRY((launch_vrows_as<T, 1>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
     else RFM_TRY((launch_vrows_as<T, 0>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
   } else {
@@ -1573,7 +1679,15 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
     const bool small = small_chunks(cnt);
     c.unit = small ? (uint32_t)ROWS_THREADS : (uint32_t)cols_unit(m->nch);
     const int64_t unit_cap = ceil_div((int64_t)cnt, (int64_t)c.unit);
-    const int cgrid = grid_for(ctx, unit_cap, t->rows_grid / ctx->sm_count);
+    if (L.lean && tr->n_ctx == 1) {      // the dense context column is summed by extra CTAs of this launch
+      c.ctx_blocks = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, batch / 256));
+      c.ctx_col = (uint32_t)(L.n_ent[0] + L.n_ent[1]);
+      c.ctx_rows = batch;
+      c.Cq = reinterpret_cast<const T *>(L.Cq.p);
+      c.cpart = reinterpret_cast<T *>(L.cpart.p);
+      c.ctx_ticket = L.ctx_ticket.p;
+    }
+    const int cgrid = grid_for(ctx, unit_cap, t->rows_grid / ctx->sm_count) + (int)c.ctx_blocks;
     const int tgrid = grid_for(ctx, unit_cap, 4);
     RFM_DISPATCH_TPR(m->nch, {
       auto fm_cols_level1 = small ? fm_cols_kernel<T, TPR, NCV, OUT_RAW, false, true>
@@ -1591,6 +1705,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
   // level 2: the static (real column, virtual column, x) list over level 1's sums -> the reference's update
   RadixSorter<T> &l2 = tl_sorter_of<T>(L);
   ColsArgs<T> d = c;
+  d.ctx_blocks = 0;
   d.keys = l2.keys[L.l2_buf].p;
   d.pos = l2.pos[L.l2_buf].p;
   d.xs = l2.val[L.l2_buf].p;
@@ -2589,7 +2704,11 @@ int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabl
     if (g.kind == SEG_TABLE) m2_est += g.tnz;
   }
   L.nv = L.n_ent[0] + L.n_ent[1] + tr->n_ctx;
-  L.stride = (uint32_t)((L.n_ent[0] > 0) + (L.n_ent[1] > 0) + tr->n_ctx);
+  // the lean row kernel covers [user | item | at most one context column]; that column is dense, so it skips the sort
+  // (extra CTAs of the level-1 column pass sum it) and a virtual row has two sorted entries. RFM_TL_GENERIC=1 keeps
+  // the generic factored row kernel with every context column in the sort.
+  L.lean = L.n_ent[0] > 0 && L.n_ent[1] > 0 && tr->n_ctx <= 1 && getenv("RFM_TL_GENERIC") == nullptr;
+  L.stride = L.lean ? 2u : (uint32_t)((L.n_ent[0] > 0) + (L.n_ent[1] > 0) + tr->n_ctx);
   const double mean_len = tr->n_rows > 0 ? (double)tr->nnz / (double)tr->n_rows : 0.0;
   const double flat = (double)t->max_batch * mean_len;
   const double two = (double)t->max_batch * (double)L.stride + (double)m2_est;
@@ -2663,8 +2782,12 @@ int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabl
     RFM_CUDA(cudaMemcpyAsync(&differ_host, differ.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RFM_CUDA(cudaStreamSynchronize(ctx->stream));
     L.val_virtual = same && differ_host == 0;
-    // the lean row kernel covers [user | item | at most one context column]; RFM_TL_GENERIC=1 keeps the generic one
-    L.lean = L.n_ent[0] > 0 && L.n_ent[1] > 0 && tr->n_ctx <= 1 && getenv("RFM_TL_GENERIC") == nullptr;
+    if (L.lean && tr->n_ctx == 1) {
+      RFM_TRY(L.Cq.alloc((size_t)t->max_batch * es));
+      RFM_TRY(L.cpart.alloc((size_t)ctx->sm_count * (m->kp + 2) * es));
+      RFM_TRY(L.ctx_ticket.alloc(1));
+      RFM_CUDA(cudaMemsetAsync(L.ctx_ticket.p, 0, sizeof(uint32_t), ctx->stream));
+    }
     // level 1 sorts batch x stride virtual entries by virtual column; the carry records serve both levels
     t->stride = L.stride;
     t->nnz_cap = cap1;

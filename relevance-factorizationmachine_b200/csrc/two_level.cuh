@@ -40,6 +40,8 @@ struct TwoLevel {
   bool val_virtual = false;    // val rows are keyed by the same tables: their loss rides in the virtual loss launch
   DevBuf<unsigned char> Vv, wv, vnv;    // aggregated parameter table [nv][kp], [nv], [nv]
   DevBuf<unsigned char> R;              // level-1 sums [nv][kp] | a [nv] | c [nv]   (zeroed every step)
+  DevBuf<unsigned char> Cq, cpart;      // lean, one context column: c_q per batch position; per-CTA sums of the column
+  DevBuf<uint32_t> ctx_ticket;
   DevBuf<uint32_t> ent_ptr, m2_dev;     // entity lists: CSR by virtual column
   DevBuf<int32_t> ent_col;
   DevBuf<unsigned char> ent_val;
@@ -228,6 +230,7 @@ struct VRowsArgs {
   uint32_t n_user, ctx_col;       // ctx_col = U + I
   int kp;
   T *S, *E;
+  T *Cq;                          // NCTX == 1, train: the row's context value by batch position (summed in level 1)
   uint32_t stride, sentinel;
   uint32_t *keys, *pos;
   T *xs;
@@ -349,17 +352,15 @@ fm_vrows_kernel(const VRowsArgs<T> a) {
           a.E[q] = static_cast<T>(e);
           partial += e;
         }
-        if (g < static_cast<int>(a.stride)) {
-          const bool live = g < 2 || cur.c != T(0);       // an exact zero is no entry (scipy stores none)
-          const uint32_t key = g == 0 ? cu : g == 1 ? ci : (live ? a.ctx_col : a.sentinel);
-          const uint32_t o = static_cast<uint32_t>(q) * a.stride + static_cast<uint32_t>(g);
+        if (g < 2) {                                      // the sort sees the user and the item entry (x = 1); the
+          const uint32_t key = g == 0 ? cu : ci;          // context column is dense and summed by position in level 1
+          const uint32_t o = static_cast<uint32_t>(q) * 2u + static_cast<uint32_t>(g);
           a.keys[o] = key;
-          if (live) {
-            a.pos[o] = static_cast<uint32_t>(q);
-            a.xs[o] = g < 2 ? T(1) : cur.c;
-          }
+          a.pos[o] = static_cast<uint32_t>(q);
+          a.xs[o] = T(1);
           for (int ps = 0; ps < a.n_passes; ++ps) atomicAdd(&hist[ps * RS_RADIX + ((key >> (8 * ps)) & 0xFF)], 1u);
         }
+        if (NCTX && g == 2) a.Cq[q] = cur.c;
       } else if (MODE == MODE_LOSS) {
         if (g == 0) {
           const double r = static_cast<double>(cur.ypv);

@@ -114,7 +114,20 @@ class FactorizationMachines(PointwiseBaseRecommender):
         if self._ctx is None:
             self._ctx = _capi.Context.default(self.device)
             self._dev = _FmDevice(self._ctx, self.n_features, self.n_factors, self.dtype)
+            self._pin_params()
         return self._ctx
+
+    def _pin_params(self) -> None:
+        """Page-lock the holders' arrays (once, when the model first meets its device): fit() uploads them at its start
+        and refreshes them in place at its end, and a pageable 9 MB copy each way costs ~1.5 ms of a 10 ms fit.
+        The registration is dropped when the array is garbage collected. RFM_PIN_PARAMS=0 switches it off."""
+        if os.environ.get("RFM_PIN_PARAMS", "1") == "0":
+            return
+        for holder in (self.w, self.V):
+            a = holder.params
+            if (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.owndata
+                    and a.nbytes >= (1 << 20) and _capi.pin_array(a)):
+                weakref.finalize(a, _capi.lib().rfm_host_unregister, c_void_p(a.ctypes.data))
 
     def _host_state(self):
         return (id(self.w0.params), self.w0.version, id(self.w.params), self.w.version,

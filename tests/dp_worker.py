@@ -121,17 +121,17 @@ def main():
     fac = lambda d: {"features": factored_from_tables(kr.tables, d["users"], d["items"], d["ctx"]),
                      "labels": d["labels"], "pscores": d["pscores"]}
     kw2 = dict(estimator="IPS", n_epochs=5, n_factors=32, lr=1e-4, batch_size=2000, seed=1, n_features=kr.n_features,
-               alpha=0.1, sampler="feistel", device=local_rank, distributed=env)
+               alpha=0.1, sampler="feistel", device=local_rank, distributed=env, step="flat")
     ma, mb = FactorizationMachines(**kw2), FactorizationMachines(**kw2)
     la, lb = ma.fit(kr.fm_train, kr.fm_val), mb.fit(fac(kr.fm_train), fac(kr.fm_val))
     assert la == lb
     np.testing.assert_array_equal(ma.V(), mb.V())
     # the two-level step (csrc/two_level.cuh) feeding the same exchange: against the flat data-parallel fit and
     # against the single-GPU two-level fit (two associations of the same sums), ranks bit-identical
-    mc = FactorizationMachines(step="two_level", **kw2)
+    mc = FactorizationMachines(**dict(kw2, step="two_level"))
     lc = mc.fit(fac(kr.fm_train), fac(kr.fm_val))
     assert mc.last_fit_stats["two_level"] is True
-    md = FactorizationMachines(step="two_level", **dict(kw2, distributed=None))
+    md = FactorizationMachines(**dict(kw2, step="two_level", distributed=None))
     ld = md.fit(fac(kr.fm_train), fac(kr.fm_val))
     for ref_l, ref_m in ((lb, mb), (ld, md)):
         np.testing.assert_allclose(lc[0], ref_l[0], rtol=1e-11)

@@ -1,6 +1,7 @@
-"""GPU parity of the factored input format: the row kernels assemble x_t on the fly
-from [id | table row | context] blocks and must reproduce the hstacked-CSR path BIT FOR BIT (same column order,
-same summation order), hence the reference goldens at 1e-9."""
+"""GPU parity of the factored input format: with the flat step (step="flat") the row kernels
+assemble x_t on the fly from [id | table row | context] blocks and must reproduce the hstacked-CSR path BIT FOR BIT
+(same column order, same summation order), hence the reference goldens at 1e-9. The two-level step, which
+step="auto" picks where it pays, has its own file (tests/test_two_level_gpu.py)."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -32,7 +33,7 @@ def test_fit_on_factored_rows_equals_csr_fit_and_the_reference(which, dtype):
     log, g = _log_and_golden(which)
     kw = dict(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]), lr=float(g["lr"]),
               batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]),
-              dtype=dtype)
+              dtype=dtype, step="flat")
     train = {"features": golden_csr(g, "train"), "labels": g["train_labels"], "pscores": g["train_pscores"]}
     val = {"features": golden_csr(g, "val"), "labels": g["val_labels"], "pscores": g["val_pscores"]}
     a = FactorizationMachines(**kw)
@@ -66,7 +67,7 @@ def test_device_sampler_and_row_subsets_agree_with_csr():
     from rfm_b200.fm import FactorizationMachines
     log, g = _log_and_golden("kuairec")
     kw = dict(estimator="IPS", n_epochs=6, n_factors=16, lr=1e-4, batch_size=1500, seed=3, n_features=log.n_features,
-              alpha=0.1, sampler="feistel")
+              alpha=0.1, sampler="feistel", step="flat")
     a, b = FactorizationMachines(**kw), FactorizationMachines(**kw)
     la = a.fit(log.fm_train, log.fm_val)
     lb = b.fit(_factored(log, log.fm_train), _factored(log, log.fm_val))
@@ -96,7 +97,7 @@ def test_ragged_tables_empty_rows_and_wide_context():
     ps = rng.uniform(0.2, 1.0, n)
     val_sel = np.arange(0, n, 7)
     kw = dict(estimator="IPS", n_epochs=8, n_factors=20, lr=5e-4, batch_size=700, seed=5, n_features=X.shape[1],
-              alpha=0.2)
+              alpha=0.2, step="flat")
     a, b = FactorizationMachines(**kw), FactorizationMachines(**kw)
     la = a.fit({"features": X, "labels": y.astype(np.int64), "pscores": ps},
                {"features": X[val_sel], "labels": y[val_sel].astype(np.int64), "pscores": ps[val_sel]})
@@ -136,7 +137,8 @@ def test_per_item_pscores_equal_per_row_pscores():
     table = log.tables["item_pscore"]
     np.testing.assert_array_equal(table[log.fm_train["items"]], log.fm_train["pscores"])
     kw = dict(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]), lr=float(g["lr"]),
-              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]))
+              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]),
+              step="flat")
     a, b = FactorizationMachines(**kw), FactorizationMachines(**kw)
     ftrain, fval = _factored(log, log.fm_train), _factored(log, log.fm_val)
     la = a.fit(ftrain, fval)
@@ -156,7 +158,8 @@ def test_materialized_on_device_equals_both_paths():
     from rfm_b200.fm import FactorizationMachines
     log, g = _log_and_golden("kuairec")
     kw = dict(estimator="IPS", n_epochs=int(g["n_epochs"]), n_factors=int(g["k"]), lr=float(g["lr"]),
-              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]))
+              batch_size=int(g["B"]), seed=int(g["seed"]), n_features=log.n_features, alpha=float(g["alpha"]),
+              step="flat")
     ftrain, fval = _factored(log, log.fm_train), _factored(log, log.fm_val)
     runs = []
     for policy, data in (("never", (ftrain, fval)), ("always", (ftrain, fval)), ("never", (log.fm_train, log.fm_val))):
