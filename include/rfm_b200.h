@@ -272,6 +272,9 @@ int rfm_fm_dp_export(rfm_fm_trainer *t, void *handle_out /* RFM_DP_HANDLE_BYTES 
 int rfm_fm_dp_connect(rfm_fm_trainer *t, int32_t rank, int32_t world,
                       const void *all_handles /* world x RFM_DP_HANDLE_BYTES */);
 int rfm_fm_dp_exchange_apply(rfm_fm_trainer *t, double lr);
+/* Diagnostic (RFM_DPX_TRACE=1): %globaltimer (ns) of the last exchange kernel's CTA 0 at [start, first barrier passed,
+ * own slice reduced, second barrier passed, parameters applied]; stamps_ns: uint64 [8]. */
+int rfm_fm_dp_trace(rfm_fm_trainer *t, uint64_t *stamps_ns);
 int rfm_fm_dp_prev_loss_ptr_dev(rfm_fm_trainer *t, void **sums_dev /* double[2] */,
                                 void **status_dev /* uint32, may be NULL */);
 /* post-update loss of a batch slice / of val rows [row_begin, row_end): SUM of the per-row

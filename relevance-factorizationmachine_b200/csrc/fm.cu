@@ -2954,7 +2954,16 @@ struct DpxArgs {
   uint32_t *local;          // [arrive counter, go flag, error flag] of this rank
   const double *loss_in;    // this rank's previous-step loss sums, or nullptr
   double *loss_out;         // global loss sums of the previous step (read back from the header)
+  unsigned long long *trace;   // RFM_DPX_TRACE=1: %globaltimer of CTA 0 at [start, barrier 0 passed, slice reduced,
+                               // barrier 1 passed, applied] (rfm_fm_dp_trace), else nullptr
 };
+__device__ __forceinline__ void dpx_stamp(const DpxArgs &a, int i) {
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[i] = t;
+  }
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -3024,7 +3033,9 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
     mine[1] = static_cast<T>(a.loss_in[0]);
     mine[2] = static_cast<T>(a.loss_in[1]);
   }
+  dpx_stamp(a, 0);
   if (!dpx_barrier(a, 0)) return;   // every rank's gradient is complete (or the exchange is abandoned: status set)
+  dpx_stamp(a, 1);
   {
     const int64_t lo = min(a.total, (int64_t)a.rank * a.slice), hi = min(a.total, lo + a.slice);
     using V2 = typename Vec2<T>::type;
@@ -3049,7 +3060,9 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
       reinterpret_cast<V2 *>(mine + lo)[i] = acc;
     }
   }
+  dpx_stamp(a, 2);
   if (!dpx_barrier(a, 1)) return;   // every slice is reduced
+  dpx_stamp(a, 3);
   auto at = [&](int64_t i) -> const T * {      // element i of the reduced gradient, in its owner's buffer
     const int64_t owner = min((int64_t)a.world - 1, i / a.slice);
     return reinterpret_cast<const T *>(a.peer[owner] + a.grad_off) + i;
@@ -3067,6 +3080,12 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
   const int64_t v_off = grad_v_off_dev(n);
   constexpr int R = 4;                             // feature rows in flight per warp (peer loads)
   for (int64_t j0 = gwarp; j0 < n; j0 += R * nw) {
+    T gwv[R];                                      // the rows' w gradients: peer loads issued with the first V loads
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t j = j0 + r * nw;
+      gwv[r] = (lane == 0 && j < n) ? *at(GRAD_W_OFF + j) : T(0);
+    }
     for (int f = lane * 2; f < kp; f += 64) {      // same association as row_norms_kernel / apply_grad_rows_kernel
       T g0[R], g1[R];
 #pragma unroll
@@ -3099,10 +3118,11 @@ fm_dp_exchange_apply_kernel(const DpxArgs a, T *__restrict__ w0, T *__restrict__
       s = warp_sum(s);
       if (lane == 0) {
         vn[j] = s;
-        w[j] += lr * *at(GRAD_W_OFF + j);
+        w[j] += lr * gwv[r];
       }
     }
   }
+  dpx_stamp(a, 4);
 }
 
 }  // namespace
@@ -3146,8 +3166,8 @@ int rfm_fm_dp_export(rfm_fm_trainer *t, void *handle_out) {
   }
   RFM_CUDA(cudaMemsetAsync(t->xchg, 0, bytes, ctx->stream));
   RFM_TRY(t->dp_prev_loss.alloc(2));
-  RFM_TRY(t->dp_local.alloc(4));
-  RFM_CUDA(cudaMemsetAsync(t->dp_local.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+  RFM_TRY(t->dp_local.alloc(4 + 16));     // + 8 x uint64 of RFM_DPX_TRACE time stamps
+  RFM_CUDA(cudaMemsetAsync(t->dp_local.p, 0, (4 + 16) * sizeof(uint32_t), ctx->stream));
   RFM_CUDA(cudaMemsetAsync(t->dp_prev_loss.p, 0, 2 * sizeof(double), ctx->stream));
   RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   memcpy(handle_out, &h, sizeof(h));
@@ -3223,6 +3243,7 @@ int rfm_fm_dp_exchange_apply(rfm_fm_trainer *t, double lr) {
   a.total = grad_total(m->n, m->kp);
   a.slice = (ceil_div(a.total, (int64_t)t->dp_world) + 1) / 2 * 2;
   a.local = t->dp_local.p;
+  a.trace = getenv("RFM_DPX_TRACE") ? reinterpret_cast<unsigned long long *>(t->dp_local.p + 4) : nullptr;
   a.loss_in = t->dp_pending_loss ? t->loss_sums.p : nullptr;
   a.loss_out = t->dp_prev_loss.p;
   // every CTA must be resident at once (the kernel spins on flags): one wave, four CTAs per SM
@@ -3241,6 +3262,15 @@ int rfm_fm_dp_exchange_apply(rfm_fm_trainer *t, double lr) {
   ++m->version;
   t->dp_parity ^= 1;           // the next gradient goes to the other buffer
   t->dp_pending_loss = true;   // rfm_fm_loss_sums of this step will ride in the next exchange
+  return RFM_OK;
+}
+
+int rfm_fm_dp_trace(rfm_fm_trainer *t, uint64_t *stamps_ns) {
+  RFM_REQUIRE(t && stamps_ns && t->dp_local.p, "rfm_fm_dp_trace: not exported");
+  rfm_ctx *ctx = t->m->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  RFM_CUDA(cudaMemcpyAsync(stamps_ns, t->dp_local.p + 4, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
   return RFM_OK;
 }
 

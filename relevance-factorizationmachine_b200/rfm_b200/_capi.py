@@ -64,6 +64,7 @@ _SIGNATURES = {
     "rfm_fm_trainer_create": ([_P, _P, _P, c_int64, c_int64, POINTER(_P)], c_int),
     "rfm_fm_trainer_destroy": ([_P], c_int),
     "rfm_fm_trainer_set_two_level": ([_P, c_int32, POINTER(c_int32)], c_int),
+    "rfm_fm_dp_trace": ([_P, _P], c_int),
     "rfm_fm_train_epoch": ([_P, _P, c_int64, c_double, c_int64], c_int),
     "rfm_fm_train_epoch_sampled": ([_P, c_uint32, c_uint32, c_int64, c_double, c_int64], c_int),
     "rfm_fm_grad_size": ([_P, POINTER(c_int64)], c_int),
