@@ -1064,12 +1064,25 @@ fm_fixup_kernel(const ColsArgs<T> a) {
       uint32_t last_unit = first + 1u;
       const uint32_t probe = base + 2u * a.unit - 1u;
       if (probe < M && a.keys[probe] == klast) {            // the next unit is entirely this column: search on
-        uint32_t lo = probe + 1u, hi = M;
+        // A unit belongs to the run iff its FIRST key is the column (the list is sorted), so the search runs over
+        // units, galloping from the run's start: 2 log2(run length in units) dependent probes instead of log2(M)
+        const uint32_t n_units = (M + a.unit - 1u) / a.unit;
+        uint32_t known = first + 1u, step = 1u, hi = n_units;        // unit `known` is in the run
+        while (known + step < n_units) {
+          if (a.keys[(known + step) * a.unit] == klast) {
+            known += step;
+            step <<= 1;
+          } else {
+            hi = known + step;
+            break;
+          }
+        }
+        uint32_t lo = known + 1u;                                    // first unit not known to be in the run
         while (lo < hi) {
           const uint32_t mid = lo + ((hi - lo) >> 1);
-          if (a.keys[mid] == klast) lo = mid + 1; else hi = mid;
+          if (a.keys[mid * a.unit] == klast) lo = mid + 1; else hi = mid;
         }
-        last_unit = (lo - 1u) / a.unit;
+        last_unit = lo - 1u;
       }
       s_last = last_unit;
       s_key = klast;
