@@ -133,6 +133,7 @@ struct rfm_ctx {
     std::vector<unsigned char *> retired;   // outgrown regions: peers may still map them, freed with the context
   } dp;
   bool dp_cache = true;
+  bool pdl = true;              // programmatic dependent launch along the FM step's kernel chain (RFM_PDL=0: off)
 };
 
 namespace rfm {
@@ -160,6 +161,39 @@ void prof_end(rfm_ctx *ctx);
                          cudaGetErrorString(err__), __FILE__, __LINE__);                    \
   } while (0)
 
+// The same launch with programmatic stream serialization allowed (ctx->pdl): the kernel may be scheduled while its
+// predecessor in the stream drains. Only for kernels whose first statement is pdl_wait_and_release(): their bodies
+// still run strictly after the predecessor has completed and flushed; what overlaps is the launch latency and the
+// block scheduling of the dependent kernel with the tail of the primary.
+#define RFM_LAUNCH_PDL(ctx, kernel, grid, block, smem, ...)                                 \
+  do {                                                                                      \
+    if ((ctx)->profiling) ::rfm::prof_begin((ctx), #kernel);                                \
+    cudaLaunchConfig_t cfg__ = {};                                                          \
+    cfg__.gridDim = dim3((unsigned)(grid));                                                 \
+    cfg__.blockDim = dim3((unsigned)(block));                                               \
+    cfg__.dynamicSmemBytes = (smem);                                                        \
+    cfg__.stream = (ctx)->stream;                                                           \
+    cudaLaunchAttribute attr__[1];                                                          \
+    attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+    attr__[0].val.programmaticStreamSerializationAllowed = (ctx)->pdl ? 1 : 0;              \
+    cfg__.attrs = attr__;                                                                   \
+    cfg__.numAttrs = 1;                                                                     \
+    cudaError_t lerr__ = cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                   \
+    (ctx)->launches++;                                                                      \
+    if ((ctx)->profiling) ::rfm::prof_end((ctx));                                           \
+    if (lerr__ == cudaSuccess && (ctx)->sync_launches) {                                    \
+      cudaError_t serr__ = cudaStreamSynchronize((ctx)->stream);                            \
+      if (serr__ != cudaSuccess)                                                            \
+        return ::rfm::fail(RFM_ERR_CUDA, "kernel %s faulted: %s (%s:%d)", #kernel,          \
+                           cudaGetErrorString(serr__), __FILE__, __LINE__);                 \
+    }                                                                                       \
+    if (lerr__ != cudaSuccess) {                                                            \
+      cudaGetLastError();                                                                   \
+      return ::rfm::fail(RFM_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,          \
+                         cudaGetErrorString(lerr__), __FILE__, __LINE__);                   \
+    }                                                                                       \
+  } while (0)
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers -------------------------------------------------------------------------
@@ -185,6 +219,25 @@ __device__ __forceinline__ T warp_sum(T v) {
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// First statement of a kernel that may be launched with RFM_LAUNCH_PDL: wait until the preceding kernel of the stream
+// has completed and its writes are visible (a no-op under a plain launch), then let the NEXT kernel's blocks be
+// scheduled as slots free up (they park at their own wait).
+// The fence in between matters: a block launched programmatically becomes resident while the predecessor still
+// runs, i.e. AFTER the L1 invalidation that a kernel boundary implies, so its SM's L1 can hold lines the predecessor's
+// own blocks fetched and other SMs then overwrote; loads through the non-coherent path (__ldg, const __restrict__)
+// would hit them (observed: a stale V row in the first loss pass after a fix-up on a 4-block problem). A gpu-scope
+// fence makes ptxas emit CCTL.IVALL, which drops the SM's L1 lines, as the launch boundary would have.
+// release: let the dependents go early. ONLY when the next operation of the stream is a kernel that starts with this
+// call -- measured: after a kernel that released early, a following operation that does not wait (the next epoch's
+// batch upload) did overtake it (a first-epoch loss computed on a half-overwritten batch, 15 of 25 runs of a 4-block
+// problem). Every launch therefore says explicitly whether its successor waits (pdl_release in the argument
+// structs, 0 by default).
+__device__ __forceinline__ void pdl_wait_and_release(bool release = true) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __threadfence();
+  if (release) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // host-callable device-wide utilities (scan.cu)
 int exclusive_scan_u32(rfm_ctx *ctx, const uint32_t *in_dev, uint32_t *out_dev, int64_t n,

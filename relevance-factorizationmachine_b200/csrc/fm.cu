@@ -193,6 +193,7 @@ struct RowsArgs {
   Finish fin2;
   // FAC kernels: the rows (and the optional second row set) are factored; row_ptr / col / val are unused
   FacDev fac, fac2;
+  int pdl_release;        // the next operation of the stream is a kernel that waits (common.cuh: pdl_wait_and_release)
 };
 
 // ---- factored rows: per-row block layout --------------------------------------------------------------------
@@ -471,6 +472,7 @@ __device__ __forceinline__ T group_sum(T v, unsigned mask) {
 template <typename T, int TPR, int NCV, int MODE, bool SAMPLED, bool FAC>
 __global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? RFM_ROWS_MIN_BLOCKS : 1)
 fm_rows_kernel(const RowsArgs<T> a) {
+  pdl_wait_and_release(a.pdl_release != 0);
   using V2 = typename Vec2<T>::type;
   constexpr int GPW = 32 / TPR;
   const int lane = lane_id(), g = lane % TPR, grp = lane / TPR;
@@ -694,6 +696,7 @@ struct ColsArgs {
   // fix-up work lists (order of the lists is irrelevant: every entry is handled independently)
   uint32_t *tails;       // chunks that own a column continuing into later chunks
   uint32_t *n_tails;
+  int pdl_release;       // the next operation of the stream is a kernel that waits (set per launch)
 };
 
 enum ColsOut { OUT_SGD = 0, OUT_GRAD = 1, OUT_RAW = 2 };
@@ -859,6 +862,7 @@ __device__ __forceinline__ void ctx_column_sums(const ColsArgs<T> &a, unsigned c
 template <typename T, int TPR, int NCV, int OUT, bool L2, bool SMALL = false>
 __global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? RFM_COLS_MIN_BLOCKS : 1)
 fm_cols_kernel(const ColsArgs<T> a) {
+  pdl_wait_and_release(a.pdl_release != 0);
   using V2 = typename Vec2<T>::type;
   constexpr int GPW = 32 / TPR, NJ = SMALL ? 1 : 32 / TPR, GPC = ROWS_WARPS * GPW;
   constexpr uint32_t CH = TPR * NJ;                              // entries per chunk
@@ -1047,6 +1051,7 @@ constexpr int FIX_WARPS = FIX_THREADS / 32;
 template <typename T, int NCH, int OUT>
 __global__ void __launch_bounds__(FIX_THREADS)
 fm_fixup_kernel(const ColsArgs<T> a) {
+  pdl_wait_and_release(a.pdl_release != 0);
   using V2 = typename Vec2<T>::type;
   constexpr int FIX_UNROLL = NCH <= 1 ? 8 : NCH <= 2 ? 4 : NCH <= 4 ? 2 : 1;
   extern __shared__ __align__(16) unsigned char fix_smem[];
@@ -1281,17 +1286,17 @@ int launch_rows_as(rfm_ctx *ctx, int nch, int mode, bool sampled, const RowsArgs
     if (mode == MODE_TRAIN) {
       if (sampled) {
         auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, true, FAC>;
-        RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
+        RFM_LAUNCH_PDL(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
       } else {
         auto fm_rows_train = fm_rows_kernel<T, TPR, NCV, MODE_TRAIN, false, FAC>;
-        RFM_LAUNCH(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
+        RFM_LAUNCH_PDL(ctx, fm_rows_train, grid, ROWS_THREADS, 0, args);
       }
     } else if (mode == MODE_LOSS) {
       auto fm_rows_loss = fm_rows_kernel<T, TPR, NCV, MODE_LOSS, false, FAC>;
-      RFM_LAUNCH(ctx, fm_rows_loss, grid, ROWS_THREADS, 0, args);
+      RFM_LAUNCH_PDL(ctx, fm_rows_loss, grid, ROWS_THREADS, 0, args);
     } else {
       auto fm_rows_predict = fm_rows_kernel<T, TPR, NCV, MODE_PREDICT, false, FAC>;
-      RFM_LAUNCH(ctx, fm_rows_predict, grid, ROWS_THREADS, 0, args);
+      RFM_LAUNCH_PDL(ctx, fm_rows_predict, grid, ROWS_THREADS, 0, args);
     }
   });
   return RFM_OK;
@@ -1456,6 +1461,10 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
   a.q0 = q0;
   a.idx_out = t->idx.p;
   RFM_TRY(sorter.clear_histograms(ctx));
+  // every memset of the step happens before the row pass, so that its kernels follow each other in the stream
+  // (RFM_LAUNCH_PDL)
+  RFM_TRY(sorter.prepare(ctx));
+  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
   a.ghist = sorter.ghist();
   a.n_passes = sorter.passes;
   if (DP) {
@@ -1467,9 +1476,10 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
     a.fin = make_finish(0, lr, m->w0.p, nullptr, t->block_partials.p, t->ticket.p);
   }
   const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
+  a.pdl_release = 1;       // the sort passes, the column pass and the fix-up follow back to back, each waiting
   RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, fused_draw, a, grid, tr->factored));
   int sorted = 0;
-  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true));
+  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true, /*prepared=*/true));
 
   ColsArgs<T> c;
   memset(&c, 0, sizeof(c));
@@ -1495,7 +1505,6 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
     c.grad_w = g + GRAD_W_OFF;
     c.grad_V = g + grad_v_off(m->n);
   }
-  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
   const int64_t unit_cap = ceil_div(t->nnz_cap, cols_unit(m->nch));
   const int cgrid = grid_for(ctx, unit_cap, t->rows_grid / ctx->sm_count);
   const int tgrid = grid_for(ctx, unit_cap, 4);   // one CTA per leaving run; there are at most unit_cap of them
@@ -1504,12 +1513,14 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
     auto fm_cols = fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, false>;
     if (csmem > 48 * 1024)
       RFM_CUDA(cudaFuncSetAttribute(fm_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-    RFM_LAUNCH(ctx, fm_cols, cgrid, ROWS_THREADS, csmem, c);
+    c.pdl_release = 1;
+    RFM_LAUNCH_PDL(ctx, fm_cols, cgrid, ROWS_THREADS, csmem, c);
+    c.pdl_release = 0;     // what follows the fix-up is the caller's business (exchange, optimizer, loss pass, memsets)
   });
   RFM_DISPATCH_NCH(m->nch, {
     auto fm_fixup = fm_fixup_kernel<T, NCH, DP ? OUT_GRAD : OUT_SGD>;
     const size_t fsmem = (size_t)FIX_WARPS * (m->kp + 2) * sizeof(T);
-    RFM_LAUNCH(ctx, fm_fixup, tgrid, FIX_THREADS, fsmem, c);
+    RFM_LAUNCH_PDL(ctx, fm_fixup, tgrid, FIX_THREADS, fsmem, c);
   });
   if (!DP) ++m->version;
   return RFM_OK;
@@ -1522,14 +1533,14 @@ int launch_vrows_as(rfm_ctx *ctx, int nch, int mode, bool sampled, const VRowsAr
     if (mode == MODE_TRAIN) {
       if (sampled) {
         auto fm_vrows_train = fm_vrows_kernel<T, TPR, NCV, MODE_TRAIN, true, NCTX>;
-        RFM_LAUNCH(ctx, fm_vrows_train, grid, ROWS_THREADS, 0, args);
+        RFM_LAUNCH_PDL(ctx, fm_vrows_train, grid, ROWS_THREADS, 0, args);
       } else {
         auto fm_vrows_train = fm_vrows_kernel<T, TPR, NCV, MODE_TRAIN, false, NCTX>;
-        RFM_LAUNCH(ctx, fm_vrows_train, grid, ROWS_THREADS, 0, args);
+        RFM_LAUNCH_PDL(ctx, fm_vrows_train, grid, ROWS_THREADS, 0, args);
       }
     } else {
       auto fm_vrows_loss = fm_vrows_kernel<T, TPR, NCV, MODE_LOSS, false, NCTX>;
-      RFM_LAUNCH(ctx, fm_vrows_loss, grid, ROWS_THREADS, 0, args);
+      RFM_LAUNCH_PDL(ctx, fm_vrows_loss, grid, ROWS_THREADS, 0, args);
     }
   });
   return RFM_OK;
@@ -1553,8 +1564,9 @@ TlParams<T> tl_params(const rfm_fm_trainer *t) {
 }
 
 // per-entity aggregates of the CURRENT parameters (no-op while nothing changed them since the last call)
+// release_next: the caller launches a waiting kernel right after this call, with nothing in between
 template <typename T>
-int tl_refresh(rfm_fm_trainer *t) {
+int tl_refresh(rfm_fm_trainer *t, bool release_next = false) {
   TwoLevel &L = *t->tl;
   rfm_fm *m = t->m;
   if (L.agg_version == m->version) return RFM_OK;
@@ -1563,9 +1575,10 @@ int tl_refresh(rfm_fm_trainer *t) {
   const int grid = grid_for(ctx, ceil_div(L.nv, units_per_block(m->nch)), 4);     // one wave
   RFM_DISPATCH_TPR(m->nch, {
     auto fm_entity_fwd = fm_entity_fwd_kernel<T, TPR, NCV>;
-    RFM_LAUNCH(ctx, fm_entity_fwd, grid, ROWS_THREADS, 0, L.ent_ptr.p, L.ent_col.p,
-               reinterpret_cast<const T *>(L.ent_val.p), L.nv, reinterpret_cast<const T *>(m->V.p),
-               reinterpret_cast<const T *>(m->w.p), reinterpret_cast<const T *>(m->vn.p), m->kp, p.Vv, p.wv, p.vnv);
+    RFM_LAUNCH_PDL(ctx, fm_entity_fwd, grid, ROWS_THREADS, 0, (const uint32_t *)L.ent_ptr.p, (const int32_t *)L.ent_col.p,
+                   reinterpret_cast<const T *>(L.ent_val.p), L.nv, reinterpret_cast<const T *>(m->V.p),
+                   reinterpret_cast<const T *>(m->w.p), reinterpret_cast<const T *>(m->vn.p), m->kp, p.Vv, p.wv, p.vnv,
+                   release_next ? 1 : 0);
   });
   L.agg_version = m->version;
   return RFM_OK;
@@ -1593,6 +1606,9 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
     RFM_CUDA(cudaMemcpyAsync(t->count.p, &t->count_host, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   RFM_CUDA(cudaMemsetAsync(L.R.p, 0, (size_t)L.nv * (m->kp + 2) * sizeof(T), ctx->stream));
+  // every memset of the step happens here, so that its nine kernels follow each other in the stream (RFM_LAUNCH_PDL)
+  RFM_TRY(sorter.prepare(ctx));
+  RFM_CUDA(cudaMemsetAsync(L.n_tails2.p, 0, 2 * sizeof(uint32_t), ctx->stream));
 
   // level 1: the row pass on virtual rows, with the aggregated table standing in for the parameters
   const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), L.lean ? TL_VROWS_BLOCKS : t->rows_grid / ctx->sm_count);
@@ -1634,6 +1650,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
     v.q0 = q0;
     v.idx_out = t->idx.p;
     v.fin = fin;
+    v.pdl_release = 1;     // sort, level 1, level 2 follow back to back, each waiting
     v.Cq = reinterpret_cast<T *>(L.Cq.p);
     if (tr->n_ctx) RFM_TRY((launch_vrows_as<T, 1>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
     else RFM_TRY((launch_vrows_as<T, 0>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
@@ -1659,10 +1676,11 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
   a.ghist = sorter.ghist();
   a.n_passes = sorter.passes;
   a.fin = fin;
+  a.pdl_release = 1;
   RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, sampled, a, grid, true));
   }
   int sorted = 0;
-  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true));
+  RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true, /*prepared=*/true));
 
   ColsArgs<T> c;
   memset(&c, 0, sizeof(c));
@@ -1679,11 +1697,10 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
   c.carry_vec = reinterpret_cast<T *>(t->carry_vec.p);
   c.carry_ac = reinterpret_cast<T *>(t->carry_ac.p);
   c.tails = t->tails.p;
-  c.n_tails = t->n_tails.p;
+  c.n_tails = L.n_tails2.p;
   c.grad_V = p.R;
   c.grad_w = p.Ra;
   c.raw_c = p.Rc;
-  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
   const size_t csmem = cols_smem_bytes(m->nch, m->kp, sizeof(T));
   const size_t fsmem = (size_t)FIX_WARPS * (m->kp + 2) * sizeof(T);
   // lists too short to fill the machine with 32-entry chunks are walked in chunks of TPR entries (unit = 256)
@@ -1707,11 +1724,12 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
                                   : fm_cols_kernel<T, TPR, NCV, OUT_RAW, false, false>;
       if (csmem > 48 * 1024)
         RFM_CUDA(cudaFuncSetAttribute(fm_cols_level1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-      RFM_LAUNCH(ctx, fm_cols_level1, cgrid, ROWS_THREADS, csmem, c);
+      c.pdl_release = 1;
+      RFM_LAUNCH_PDL(ctx, fm_cols_level1, cgrid, ROWS_THREADS, csmem, c);
     });
     RFM_DISPATCH_NCH(m->nch, {
       auto fm_fixup_level1 = fm_fixup_kernel<T, NCH, OUT_RAW>;
-      RFM_LAUNCH(ctx, fm_fixup_level1, tgrid, FIX_THREADS, fsmem, c);
+      RFM_LAUNCH_PDL(ctx, fm_fixup_level1, tgrid, FIX_THREADS, fsmem, c);
     });
   }
 
@@ -1737,7 +1755,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
     d.grad_w = g + GRAD_W_OFF;
     d.grad_V = g + grad_v_off(m->n);
   }
-  RFM_CUDA(cudaMemsetAsync(t->n_tails.p, 0, sizeof(uint32_t), ctx->stream));
+  d.n_tails = L.n_tails2.p + 1;
   {
     const bool small = small_chunks(L.m2);
     d.unit = small ? (uint32_t)ROWS_THREADS : (uint32_t)cols_unit(m->nch);
@@ -1749,11 +1767,13 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
                                   : fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, true, false>;
       if (csmem > 48 * 1024)
         RFM_CUDA(cudaFuncSetAttribute(fm_cols_level2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-      RFM_LAUNCH(ctx, fm_cols_level2, cgrid, ROWS_THREADS, csmem, d);
+      d.pdl_release = 1;
+      RFM_LAUNCH_PDL(ctx, fm_cols_level2, cgrid, ROWS_THREADS, csmem, d);
+      d.pdl_release = 0;   // what follows the last fix-up is the caller's business
     });
     RFM_DISPATCH_NCH(m->nch, {
       auto fm_fixup_level2 = fm_fixup_kernel<T, NCH, DP ? OUT_GRAD : OUT_SGD>;
-      RFM_LAUNCH(ctx, fm_fixup_level2, tgrid, FIX_THREADS, fsmem, d);
+      RFM_LAUNCH_PDL(ctx, fm_fixup_level2, tgrid, FIX_THREADS, fsmem, d);
     });
   }
   if (!DP) ++m->version;
@@ -1785,7 +1805,9 @@ int batch_and_val_losses(rfm_fm_trainer *t, int64_t batch, double scale_b, doubl
   rfm_ctx *ctx = m->ctx;
   if (t->tl) {     // the batch (and val rows keyed by the same tables) as virtual rows over the aggregated table
     TwoLevel &L = *t->tl;
-    RFM_TRY(tl_refresh<T>(t));
+    // the entity forward may release the loss launch early only when nothing sits between them in the stream
+    const bool direct = t->val && val_end > val_begin;      // no memset of dst_v before the loss launch
+    RFM_TRY(tl_refresh<T>(t, /*release_next=*/direct));
     const TlParams<T> p = tl_params<T>(t);
     if (L.lean) {
       const rfm_csr *tr = t->train, *va = t->val;
@@ -2773,6 +2795,7 @@ int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabl
     RFM_TRY(L.wv.alloc((size_t)L.nv * es));
     RFM_TRY(L.vnv.alloc((size_t)L.nv * es));
     RFM_TRY(L.R.alloc((size_t)L.nv * (m->kp + 2) * es));
+    RFM_TRY(L.n_tails2.alloc(2));
     // val rows ride in the virtual loss launch when they are keyed by the same tables (same blocks, same bytes)
     const rfm_csr *va = t->val;
     bool same = va && va->factored && va->n_seg == tr->n_seg && va->n_ctx == tr->n_ctx;

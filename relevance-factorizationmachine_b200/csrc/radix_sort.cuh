@@ -66,7 +66,8 @@ rs_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restr
                    const uint32_t *__restrict__ count_dev, int shift,
                    const uint32_t *__restrict__ ghist /* [256] of this pass */,
                    uint32_t *status /* [n_tiles][256], zeroed */, uint32_t *tile_counter /* zeroed */,
-                   uint32_t *error_flag) {
+                   uint32_t *error_flag, int pdl_release) {
+  pdl_wait_and_release(pdl_release != 0);
   __shared__ uint32_t wcnt[RS_WARPS][RS_RADIX];
   __shared__ uint32_t digit_base[RS_RADIX];
   __shared__ uint32_t gbase[RS_RADIX];        // global position of tile-local slot 0 of each digit's run
@@ -265,11 +266,17 @@ struct RadixSorter {
   }
   // input is in buffer 0; returns the index of the buffer holding the sorted output. histograms_ready: the
   // producer of the keys already accumulated ghist() (after clear_histograms), so the histogram pass is skipped.
-  int sort(rfm_ctx *ctx, const uint32_t *count_dev, int *out_buf, bool histograms_ready = false) {
-    int cur = 0;
-    // zero the tile counters and status words; the error flag in between is sticky
+  // zero the tile counters and status words (the error flag in between is sticky); sort() does it itself unless the
+  // caller did it earlier in the stream (prepared = true: no memset then sits between the producer of the keys
+  // and the sort kernels, which lets them launch programmatically)
+  int prepare(rfm_ctx *ctx) {
     RFM_CUDA(cudaMemsetAsync(tile_counter(0), 0, RS_MAX_PASSES * sizeof(uint32_t), ctx->stream));
     RFM_CUDA(cudaMemsetAsync(status(0), 0, (size_t)passes * n_tiles_cap * RS_RADIX * sizeof(uint32_t), ctx->stream));
+    return RFM_OK;
+  }
+  int sort(rfm_ctx *ctx, const uint32_t *count_dev, int *out_buf, bool histograms_ready = false, bool prepared = false) {
+    int cur = 0;
+    if (!prepared) RFM_TRY(prepare(ctx));
     if (!histograms_ready) {
       RFM_TRY(clear_histograms(ctx));
       const int hgrid = n_tiles_cap < ctx->sm_count * 4 ? n_tiles_cap : ctx->sm_count * 4;
@@ -277,9 +284,16 @@ struct RadixSorter {
     }
     const int grid = n_tiles_cap < ctx->sm_count * 4 ? n_tiles_cap : ctx->sm_count * 4;
     for (int p = 0; p < passes; ++p) {
-      RFM_LAUNCH(ctx, rs_onesweep_kernel<T>, grid, RS_THREADS, 0, keys[cur].p, pos[cur].p, val[cur].p,
-                 keys[cur ^ 1].p, pos[cur ^ 1].p, val[cur ^ 1].p, count_dev, 8 * p, ghist() + p * RS_RADIX,
-                 status(p), tile_counter(p), error_flag());
+      if (prepared) {
+        RFM_LAUNCH_PDL(ctx, rs_onesweep_kernel<T>, grid, RS_THREADS, 0, (const uint32_t *)keys[cur].p,
+                       (const uint32_t *)pos[cur].p, (const T *)val[cur].p, keys[cur ^ 1].p, pos[cur ^ 1].p,
+                       val[cur ^ 1].p, count_dev, 8 * p, (const uint32_t *)(ghist() + p * RS_RADIX), status(p),
+                       tile_counter(p), error_flag(), 1);     // prepared: the caller's next kernel waits
+      } else {
+        RFM_LAUNCH(ctx, rs_onesweep_kernel<T>, grid, RS_THREADS, 0, keys[cur].p, pos[cur].p, val[cur].p,
+                   keys[cur ^ 1].p, pos[cur ^ 1].p, val[cur ^ 1].p, count_dev, 8 * p, ghist() + p * RS_RADIX,
+                   status(p), tile_counter(p), error_flag(), 0);
+      }
       cur ^= 1;
     }
     *out_buf = cur;

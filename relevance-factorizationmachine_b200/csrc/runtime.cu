@@ -182,6 +182,8 @@ int rfm_ctx_create(int device, void *cuda_stream, rfm_ctx **out) {
   }
   const char *dc = getenv("RFM_DP_CACHE");
   ctx->dp_cache = !(dc && dc[0] == '0');
+  const char *pd = getenv("RFM_PDL");
+  ctx->pdl = !(pd && pd[0] == '0');     // on unless RFM_PDL=0
   const char *sl = getenv("RFM_SYNC_LAUNCHES");
   ctx->sync_launches = sl && sl[0] == '1';
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {

@@ -41,7 +41,7 @@ struct TwoLevel {
   DevBuf<unsigned char> Vv, wv, vnv;    // aggregated parameter table [nv][kp], [nv], [nv]
   DevBuf<unsigned char> R;              // level-1 sums [nv][kp] | a [nv] | c [nv]   (zeroed every step)
   DevBuf<unsigned char> Cq, cpart;      // lean, one context column: c_q per batch position; per-CTA sums of the column
-  DevBuf<uint32_t> ctx_ticket;
+  DevBuf<uint32_t> ctx_ticket, n_tails2;   // n_tails2: tail counters of level 1 and level 2 (both zeroed at the step's start)
   DevBuf<uint32_t> ent_ptr, m2_dev;     // entity lists: CSR by virtual column
   DevBuf<int32_t> ent_col;
   DevBuf<unsigned char> ent_val;
@@ -159,7 +159,9 @@ template <typename T, int TPR, int NCV>
 __global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? 4 : 1)
 fm_entity_fwd_kernel(const uint32_t *__restrict__ ent_ptr, const int32_t *__restrict__ ent_col,
                      const T *__restrict__ ent_val, int64_t nv, const T *__restrict__ V, const T *__restrict__ w,
-                     const T *__restrict__ vn, int kp, T *__restrict__ Vv, T *__restrict__ wv, T *__restrict__ vnv) {
+                     const T *__restrict__ vn, int kp, T *__restrict__ Vv, T *__restrict__ wv, T *__restrict__ vnv,
+                     int pdl_release) {
+  pdl_wait_and_release(pdl_release != 0);
   using V2 = typename Vec2<T>::type;
   constexpr int GPW = 32 / TPR;
   const int lane = lane_id(), g = lane % TPR, grp = lane / TPR;
@@ -240,6 +242,7 @@ struct VRowsArgs {
   int64_t q0;
   int64_t *idx_out;
   Finish fin;
+  int pdl_release;                // the next operation of the stream is a kernel that waits
   // MODE_LOSS: optional second row set (val rows keyed by the same tables)
   const int32_t *user2, *item2;
   const T *ctx2, *yp2;
@@ -255,6 +258,7 @@ constexpr int TL_VROWS_BLOCKS = RFM_TL_VROWS_BLOCKS;     // resident CTAs per SM
 template <typename T, int TPR, int NCV, int MODE, bool SAMPLED, int NCTX>
 __global__ void __launch_bounds__(ROWS_THREADS, NCV <= 4 ? TL_VROWS_BLOCKS : 1)
 fm_vrows_kernel(const VRowsArgs<T> a) {
+  pdl_wait_and_release(a.pdl_release != 0);
   using V2 = typename Vec2<T>::type;
   constexpr int GPW = 32 / TPR;
   const int lane = lane_id(), g = lane % TPR, grp = lane / TPR;
