@@ -71,3 +71,18 @@ def test_reference_arm_prints_the_contract_line():
     cfg = line["config"]
     assert "workload" in cfg and cfg["train_interactions"] == 60000 and cfg["batch_per_gpu"] == 2048
     assert "model" not in cfg
+
+
+def test_two_level_bytes_formula_and_step_argument():
+    """bench.py's own-bytes model of the two-level step at the KuaiRec shape (row record + 2 passes x 3 gathered rows +
+    the entity pass spread over the batch), and the drop-in's `step` argument."""
+    import bench
+    import pytest
+    got = bench.two_level_bytes(65536, 64, 8, 1, 138000, 18030)
+    want = (4 + 4 + 4 + 8 + 4 + 8) + 2 * 3 * 65 * 8 + (2 * 138000 + 2 * 18030) * 65 * 8 / 65536
+    assert abs(got - want) < 1e-9 and 5000 < got < 6000
+    assert got < bench.algorithmic_bytes_of(16.479, 17187, 65536, 64, 8)[0] / 3
+    from rfm_b200.fm import FactorizationMachines
+    with pytest.raises(ValueError, match="step must be"):
+        FactorizationMachines("IPS", 1, 4, 1e-3, 10, 1, 20, step="fast")
+    assert FactorizationMachines("IPS", 1, 4, 1e-3, 10, 1, 20).step == "auto"

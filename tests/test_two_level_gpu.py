@@ -131,6 +131,38 @@ def test_ragged_tables_empty_entities_wide_context_and_foreign_val_tables():
     assert not np.allclose(lc[1], la[1], rtol=1e-6)        # the other table does change the val loss
 
 
+@pytest.mark.parametrize("k", [65, 130, 300])
+@pytest.mark.parametrize("n_ctx", [0, 1, 2])
+def test_two_level_factor_counts_and_context_widths(k, n_ctx):
+    """n_factors beyond one 64-wide chunk (16- and 32-lane row groups, the reference's own 300) with no, one (the lean
+    row kernel + the dense-column CTAs of level 1) and two context columns (the generic row kernel, every context
+    column in the sort): against the flat step on the stacked matrix."""
+    from rfm_b200.factored import FactoredFeatures
+    from rfm_b200.fm import FactorizationMachines
+    rng = np.random.default_rng(100 * k + n_ctx)
+    n_users, n_items, n = 60, 45, 2500
+    ut = sp.random(n_users, 12, density=0.4, format="csr", random_state=1)
+    it = sp.random(n_items, 7, density=0.5, format="csr", random_state=2)
+    users, items = rng.integers(0, n_users, n), rng.integers(0, n_items, n)
+    blocks = [("id", "user", n_users), ("id", "item", n_items)]
+    if n_ctx:
+        blocks.append(("ctx", rng.normal(size=(n, n_ctx))))
+    blocks += [("table", "user", ut), ("table", "item", it)]
+    ff = FactoredFeatures(blocks, users, items)
+    X = ff.tocsr()
+    y, ps = (rng.random(n) < 0.5).astype(np.int64), rng.uniform(0.3, 1.0, n)
+    kw = dict(estimator="IPS", n_epochs=5, n_factors=k, lr=3e-4, batch_size=900, seed=k, n_features=X.shape[1], alpha=0.2)
+    a, b = FactorizationMachines(**kw), FactorizationMachines(step="two_level", **kw)
+    la = a.fit({"features": X, "labels": y, "pscores": ps}, {"features": X[:300], "labels": y[:300], "pscores": ps[:300]})
+    lb = b.fit({"features": ff, "labels": y, "pscores": ps}, {"features": ff[:300], "labels": y[:300], "pscores": ps[:300]})
+    assert b.last_fit_stats["two_level"] is True
+    np.testing.assert_allclose(lb[0], la[0], rtol=1e-11)
+    np.testing.assert_allclose(lb[1], la[1], rtol=1e-11)
+    np.testing.assert_allclose(b.V(), a.V(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(b.w(), a.w(), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(b.w0(), a.w0(), rtol=1e-9, atol=1e-13)
+
+
 @pytest.mark.parametrize("opt", ["adam", "sgd_l2"])
 def test_two_level_feeds_the_dense_optimizers(opt):
     """Adam / SGD + L2 take the batch gradient from the two-level passes (the gradient buffer the data-parallel step
