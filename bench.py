@@ -1063,6 +1063,7 @@ def run_ours(args):
     if rank != 0:
         if not args.no_e2e:
             measure_e2e(args, log, ftrain, fval, local_rank, dist, world)
+            measure_sharded_predict(args, log, ftrain, local_rank, dist, world)
         if not args.no_scoring:
             measure_scoring(local_rank, dist, world, peaks, peak_kind)
         if run_c5:
@@ -1099,6 +1100,8 @@ def run_ours(args):
                     "byte-for-byte implementation could reach; this object holds the fraction in the step's own bytes"
                     % (m, own, roofline["algorithmic_bytes_per_interaction"])}
     e2e = None if args.no_e2e else measure_e2e(args, log, ftrain, fval, local_rank, dist, world)
+    if e2e is not None and dist is not None:
+        e2e["sharded_predict"] = measure_sharded_predict(args, log, ftrain, local_rank, dist, world)
     scoring = None if args.no_scoring else measure_scoring(local_rank, dist, world, peaks, peak_kind)
     if scoring is not None:
         roofline["scoring"] = {name: {"pairs_per_s": v["value"], "ms_per_call": v["ms_per_call"],
@@ -1159,6 +1162,39 @@ def run_ours(args):
         _capi.unpin_array(a)
     if dist is not None:
         dist.shutdown()
+
+
+def measure_sharded_predict(args, log, ftrain, device, dist, world):
+    """Row-sharded predict (independent rows): every rank scores 1/N of the rows with its replica
+    of the parameters, the score slices are all-gathered. Timed from host rows to host scores on every rank, next to
+    the single-process predict of the same rows in the same run; bit-equality of the two is asserted."""
+    from rfm_b200 import dist as rdist
+    from rfm_b200.fm import FactorizationMachines
+    n = min(4_000_000, ftrain["features"].shape[0])
+    X = ftrain["features"][:n]
+    m = FactorizationMachines("IPS", 1, K_FACTORS, LR, args.batch, 12345, log.n_features, dtype=args.dtype, device=device)
+    m.sync_to_device()
+
+    def timed(fn, reps=3):
+        m.reset_rows_cache()
+        out = np.array(fn())             # warm-up and the result that is compared (a copy: the sharded call returns a
+        m.reset_rows_cache()             # view of a page-locked buffer, which must go back to torch's cache)
+        fn()                             # steady state from here on: that buffer (a 14 ms cudaHostAlloc) is reused
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m.reset_rows_cache()         # every call uploads its rows again, as a fresh call would
+            fn()
+        return dist.max_over_ranks((time.perf_counter() - t0) / reps), out
+
+    t_single, ref = timed(lambda: m.predict(X=X))
+    t_shard, got = timed(lambda: rdist.sharded_predict(m, X, dist))
+    assert np.array_equal(ref, got), "row-sharded predict differs from the single-process predict"
+    return {"rows": int(n), "unit": "rows/s", "value": n / t_shard, "ms_per_call": t_shard * 1e3,
+            "single_gpu_ms": t_single * 1e3, "speedup_vs_1gpu": t_single / t_shard, "bit_identical": True,
+            "api": "rfm_b200.dist.sharded_predict(model, FactoredFeatures, env): host rows -> each rank uploads and scores "
+                   "its slice (rfm_fm_predict_dev into the send buffer) -> NCCL all-gather -> one copy into page-locked "
+                   "host memory on every rank; steady state (the first call also allocates that buffer)"}
 
 
 def measure_e2e(args, log, ftrain, fval, device, dist, world):

@@ -410,8 +410,33 @@ def sharded_predict(model, X, env: DistEnv) -> np.ndarray:
     torch = env.torch
     n = X.shape[0]
     begin, end = slice_bounds(n, env.world, env.rank)
-    mine = model.predict(X=X[begin:end]) if end > begin else np.empty(0)
     width = -(-n // env.world) if n else 0                 # slices differ by at most one row: pad to the widest
+    if env.backend == "nccl" and type(model).__name__ == "FactorizationMachines" and n > 0:
+        # device path: the slice's scores are written by rfm_fm_predict_dev straight into the all-gather's send buffer,
+        # the gathered [world][width] block comes back in ONE copy into page-locked memory
+        from ctypes import c_void_p
+        from ._capi import check, lib
+        dev = "cuda:%d" % env.device
+        model.sync_to_device()
+        send = torch.zeros(max(width, 1), dtype=torch.float64, device=dev)
+        if end > begin:
+            rows = model._rows(X[begin:end])
+            check(lib().rfm_fm_predict_dev(model._dev.handle, rows.handle, c_void_p(send.data_ptr())))
+            model._ctx.synchronize()                       # the library's stream -> torch's stream
+        recv = torch.empty(env.world * max(width, 1), dtype=torch.float64, device=dev)
+        env.dist.all_gather_into_tensor(recv, send)
+        host = torch.empty(recv.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(recv, non_blocking=True)
+        torch.cuda.synchronize(env.device)
+        flat = host.numpy()
+        if n % env.world == 0:
+            return flat[:n]                                # slices are contiguous: no reassembly
+        out = np.empty(n)
+        for r in range(env.world):
+            b, e = slice_bounds(n, env.world, r)
+            out[b:e] = flat[r * width: r * width + (e - b)]
+        return out
+    mine = model.predict(X=X[begin:end]) if end > begin else np.empty(0)
     dev = "cuda:%d" % env.device if env.backend == "nccl" else "cpu"
     buf = torch.zeros(max(width, 1), dtype=torch.float64, device=dev)
     buf[: end - begin] = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64)).to(dev)
