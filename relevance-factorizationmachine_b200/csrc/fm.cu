@@ -1350,6 +1350,7 @@ struct rfm_fm_trainer {
   RadixSorter<float> sort32;
   RadixSorter<double> sort64;
   TwoLevel *tl = nullptr;      // two-level step (factored rows; rfm_fm_trainer_set_two_level)
+  bool broken = false;         // a failed rfm_fm_trainer_set_two_level left the batch buffers half re-sized
   // host staging ring for batch row ids
   static constexpr int RING = 4;
   PinnedBuf<int64_t> stage[RING];
@@ -1912,6 +1913,7 @@ int stage_batch(rfm_fm_trainer *t, const int64_t *batch_rows, int64_t batch) {
 
 int check_batch(const rfm_fm_trainer *t, int64_t batch, int64_t slot, const char *who) {
   RFM_REQUIRE(t != nullptr, "%s: trainer is NULL", who);
+  RFM_REQUIRE(!t->broken, "%s: rfm_fm_trainer_set_two_level failed on this trainer; create a new one", who);
   RFM_REQUIRE(batch >= 1 && batch <= t->max_batch, "%s: batch %lld outside [1, %lld]", who, (long long)batch,
               (long long)t->max_batch);
   RFM_REQUIRE(batch <= t->train->n_rows,
@@ -2824,7 +2826,9 @@ int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabl
       RFM_TRY(L.ctx_ticket.alloc(1));
       RFM_CUDA(cudaMemsetAsync(L.ctx_ticket.p, 0, sizeof(uint32_t), ctx->stream));
     }
-    // level 1 sorts batch x stride virtual entries by virtual column; the carry records serve both levels
+    // level 1 sorts batch x stride virtual entries by virtual column; the carry records serve both levels.
+    // From here on the trainer's own buffers change: a failure leaves it unusable (broken), not silently flat.
+    t->broken = true;
     t->stride = L.stride;
     t->nnz_cap = cap1;
     t->count_host = 0;
@@ -2841,6 +2845,7 @@ int rfm_fm_trainer_set_two_level(rfm_fm_trainer *t, int32_t mode, int32_t *enabl
     return rc;
   }
   t->tl = Lp;
+  t->broken = false;
   if (enabled) *enabled = 1;
   return RFM_OK;
 }
