@@ -161,7 +161,11 @@ void prof_end(rfm_ctx *ctx);
                          cudaGetErrorString(err__), __FILE__, __LINE__);                    \
   } while (0)
 
-// The same launch with programmatic stream serialization allowed (ctx->pdl): the kernel may be scheduled while its
+// Dependent launch is used (and kernels may release their dependents early) only on the plain path: the per-kernel
+// profile and RFM_SYNC_LAUNCHES put events / synchronisations between the kernels, i.e. operations that do not wait.
+inline bool pdl_on(const rfm_ctx *ctx) { return ctx->pdl && !ctx->profiling && !ctx->sync_launches; }
+
+// The same launch with programmatic stream serialization allowed (pdl_on(ctx)): the kernel may be scheduled while its
 // predecessor in the stream drains. Only for kernels whose first statement is pdl_wait_and_release(): their bodies
 // still run strictly after the predecessor has completed and flushed; what overlaps is the launch latency and the
 // block scheduling of the dependent kernel with the tail of the primary.
@@ -175,7 +179,7 @@ void prof_end(rfm_ctx *ctx);
     cfg__.stream = (ctx)->stream;                                                           \
     cudaLaunchAttribute attr__[1];                                                          \
     attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
-    attr__[0].val.programmaticStreamSerializationAllowed = (ctx)->pdl ? 1 : 0;              \
+    attr__[0].val.programmaticStreamSerializationAllowed = ::rfm::pdl_on(ctx) ? 1 : 0;      \
     cfg__.attrs = attr__;                                                                   \
     cfg__.numAttrs = 1;                                                                     \
     cudaError_t lerr__ = cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                   \

@@ -1477,7 +1477,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
     a.fin = make_finish(0, lr, m->w0.p, nullptr, t->block_partials.p, t->ticket.p);
   }
   const int grid = grid_for(ctx, ceil_div(batch, units_per_block(m->nch)), t->rows_grid / ctx->sm_count);
-  a.pdl_release = 1;       // the sort passes, the column pass and the fix-up follow back to back, each waiting
+  a.pdl_release = pdl_on(ctx) ? 1 : 0;       // the sort passes, the column pass and the fix-up follow back to back, each waiting
   RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, fused_draw, a, grid, tr->factored));
   int sorted = 0;
   RFM_TRY(sorter.sort(ctx, t->count.p, &sorted, /*histograms_ready=*/true, /*prepared=*/true));
@@ -1514,7 +1514,7 @@ int step_core(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, const F
     auto fm_cols = fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, false>;
     if (csmem > 48 * 1024)
       RFM_CUDA(cudaFuncSetAttribute(fm_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-    c.pdl_release = 1;
+    c.pdl_release = pdl_on(ctx) ? 1 : 0;
     RFM_LAUNCH_PDL(ctx, fm_cols, cgrid, ROWS_THREADS, csmem, c);
     c.pdl_release = 0;     // what follows the fix-up is the caller's business (exchange, optimizer, loss pass, memsets)
   });
@@ -1579,7 +1579,7 @@ int tl_refresh(rfm_fm_trainer *t, bool release_next = false) {
     RFM_LAUNCH_PDL(ctx, fm_entity_fwd, grid, ROWS_THREADS, 0, (const uint32_t *)L.ent_ptr.p, (const int32_t *)L.ent_col.p,
                    reinterpret_cast<const T *>(L.ent_val.p), L.nv, reinterpret_cast<const T *>(m->V.p),
                    reinterpret_cast<const T *>(m->w.p), reinterpret_cast<const T *>(m->vn.p), m->kp, p.Vv, p.wv, p.vnv,
-                   release_next ? 1 : 0);
+                   release_next && pdl_on(ctx) ? 1 : 0);
   });
   L.agg_version = m->version;
   return RFM_OK;
@@ -1651,7 +1651,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
     v.q0 = q0;
     v.idx_out = t->idx.p;
     v.fin = fin;
-    v.pdl_release = 1;     // sort, level 1, level 2 follow back to back, each waiting
+    v.pdl_release = pdl_on(ctx) ? 1 : 0;     // sort, level 1, level 2 follow back to back, each waiting
     v.Cq = reinterpret_cast<T *>(L.Cq.p);
     if (tr->n_ctx) RFM_TRY((launch_vrows_as<T, 1>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
     else RFM_TRY((launch_vrows_as<T, 0>(ctx, m->nch, MODE_TRAIN, sampled, v, grid)));
@@ -1677,7 +1677,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
   a.ghist = sorter.ghist();
   a.n_passes = sorter.passes;
   a.fin = fin;
-  a.pdl_release = 1;
+  a.pdl_release = pdl_on(ctx) ? 1 : 0;
   RFM_TRY(launch_rows<T>(ctx, m->nch, MODE_TRAIN, sampled, a, grid, true));
   }
   int sorted = 0;
@@ -1725,7 +1725,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
                                   : fm_cols_kernel<T, TPR, NCV, OUT_RAW, false, false>;
       if (csmem > 48 * 1024)
         RFM_CUDA(cudaFuncSetAttribute(fm_cols_level1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-      c.pdl_release = 1;
+      c.pdl_release = pdl_on(ctx) ? 1 : 0;
       RFM_LAUNCH_PDL(ctx, fm_cols_level1, cgrid, ROWS_THREADS, csmem, c);
     });
     RFM_DISPATCH_NCH(m->nch, {
@@ -1768,7 +1768,7 @@ int step_two_level(rfm_fm_trainer *t, int64_t batch, double lr, bool sampled, co
                                   : fm_cols_kernel<T, TPR, NCV, DP ? OUT_GRAD : OUT_SGD, true, false>;
       if (csmem > 48 * 1024)
         RFM_CUDA(cudaFuncSetAttribute(fm_cols_level2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-      d.pdl_release = 1;
+      d.pdl_release = pdl_on(ctx) ? 1 : 0;
       RFM_LAUNCH_PDL(ctx, fm_cols_level2, cgrid, ROWS_THREADS, csmem, d);
       d.pdl_release = 0;   // what follows the last fix-up is the caller's business
     });

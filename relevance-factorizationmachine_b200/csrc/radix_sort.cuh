@@ -288,7 +288,7 @@ struct RadixSorter {
         RFM_LAUNCH_PDL(ctx, rs_onesweep_kernel<T>, grid, RS_THREADS, 0, (const uint32_t *)keys[cur].p,
                        (const uint32_t *)pos[cur].p, (const T *)val[cur].p, keys[cur ^ 1].p, pos[cur ^ 1].p,
                        val[cur ^ 1].p, count_dev, 8 * p, (const uint32_t *)(ghist() + p * RS_RADIX), status(p),
-                       tile_counter(p), error_flag(), 1);     // prepared: the caller's next kernel waits
+                       tile_counter(p), error_flag(), pdl_on(ctx) ? 1 : 0);     // prepared: the caller's next kernel waits
       } else {
         RFM_LAUNCH(ctx, rs_onesweep_kernel<T>, grid, RS_THREADS, 0, keys[cur].p, pos[cur].p, val[cur].p,
                    keys[cur ^ 1].p, pos[cur ^ 1].p, val[cur ^ 1].p, count_dev, 8 * p, ghist() + p * RS_RADIX,
