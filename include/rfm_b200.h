@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RFM_ABI_VERSION 5   /* 5: rfm_fm_trainer_set_two_level. 4: rfm_*_set_targets; factored rows, device-chained evaluation, sharded top-K exchange (round 2). 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
+#define RFM_ABI_VERSION 6   /* 6: rfm_factored_create_range, rfm_rows_device_ptrs, rfm_factored_finalize. 5: rfm_fm_trainer_set_two_level, rfm_fm_dp_trace. 4: rfm_*_set_targets; factored rows, device-chained evaluation, sharded top-K exchange (round 2). 3: rfm_csr_create_range, rfm_csr_device_ptrs added. 2: rfm_topk_run stats grew to int64[4]; rfm_topk_result_host, rfm_fm_dp_*, rfm_fm_train_epoch_opt added */
 
 enum rfm_status {
   RFM_OK = 0,
@@ -154,6 +154,18 @@ int rfm_factored_create_item_pscores(rfm_ctx *ctx, int64_t n_rows, const void *u
                                      const void *items, int32_t items_is_int64, const rfm_rows_block *blocks,
                                      int32_t n_blocks, const void *labels, int32_t label_bytes,
                                      const double *item_pscores, int64_t n_item_pscores, int dtype, rfm_csr **out);
+/* The same rows when each data-parallel rank uploads 1/G of them (no reference counterpart): rows
+ * [row_begin, row_end) are copied from the host -- the host pointers are those of the FULL arrays, pscores OR
+ * item_pscores is NULL --, the object has the full shape, the caller fills the other rows on the device through
+ * rfm_rows_device_ptrs (user int32[n_rows], item int32[n_rows], ctx T[n_rows][n_ctx] or NULL, targets T[n_rows];
+ * rfm_b200.dist.sharded_factored_rows broadcasts every slice from its owner over NVLink) and then calls
+ * rfm_factored_finalize (row statistics: total non-zeros, longest row). Byte-identical to rfm_factored_create. */
+int rfm_factored_create_range(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64, const void *items,
+                              int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks, const void *labels,
+                              int32_t label_bytes, const double *pscores, const double *item_pscores,
+                              int64_t n_item_pscores, int dtype, int64_t row_begin, int64_t row_end, rfm_csr **out);
+int rfm_rows_device_ptrs(rfm_csr *rows, void **user_dev, void **item_dev, void **ctx_dev, void **targets_dev);
+int rfm_factored_finalize(rfm_csr *rows);
 /* Device-side generator of semi-synthetic interactions, mirroring the reference's
  * simulation utils/dataloader/kuairec/_click.py:148-235: relevance gamma = clip(watch_ratio / relevance_clip, 0, 1)
  * (:148-171), exposure theta_i = max(sigmoid(3 z_i - 1) ** exposure_bias, eps) per item (:173-205, computed by the

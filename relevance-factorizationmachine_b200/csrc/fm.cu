@@ -2077,9 +2077,17 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
                                 const void *items, int32_t items_is_int64, const rfm_rows_block *blocks,
                                 int32_t n_blocks, const void *labels, int32_t label_bytes, const double *pscores,
                                 const double *item_pscores, int64_t n_item_pscores, int dtype,
-                                const rfm_click_model *gen, rfm_csr **out) {
+                                const rfm_click_model *gen, rfm_csr **out, int64_t rb = 0, int64_t re = -1) {
+  // rows [rb, re) are copied from the host (re < 0: all of them); with a partial range the rest is for the caller to
+  // fill on the device (rfm_rows_device_ptrs) and the row statistics wait for rfm_factored_finalize
   RFM_REQUIRE(ctx && out, "rfm_factored_create: NULL ctx/out");
   *out = nullptr;
+  if (re < 0) re = n_rows;
+  RFM_REQUIRE(rb >= 0 && rb <= re && re <= n_rows, "rfm_factored_create_range: bad row range [%lld, %lld) of %lld",
+              (long long)rb, (long long)re, (long long)n_rows);
+  const bool partial = rb > 0 || re < n_rows;
+  RFM_REQUIRE(!(partial && gen), "rfm_factored_create_range: generated rows have no range");
+  const int64_t nsel = re - rb;
   RFM_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffffLL, "rfm_factored_create: bad row count %lld", (long long)n_rows);
   RFM_REQUIRE(blocks && n_blocks >= 1 && n_blocks <= FAC_MAX_SEG, "rfm_factored_create: between 1 and %d blocks",
               FAC_MAX_SEG);
@@ -2146,20 +2154,20 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
     int n_tmp = 0;
     const int g = grid_for(ctx, ceil_div(nr, 256), 8);
     // ids: 4 or 8 bytes per row over PCIe as the caller holds them, narrowed (and range-checked) on the device
-    for (int side = 0; side < 2 && n_rows > 0 && !gen; ++side) {
-      const void *src = side == 0 ? users : items;
+    for (int side = 0; side < 2 && nsel > 0 && !gen; ++side) {
+      const unsigned char *src = static_cast<const unsigned char *>(side == 0 ? users : items);
       const bool is64 = (side == 0 ? users_is_int64 : items_is_int64) != 0;
-      int32_t *dst = side == 0 ? r->f_user.p : r->f_item.p;
+      int32_t *dst = (side == 0 ? r->f_user.p : r->f_item.p) + rb;
       const int64_t lim = limit[side] == INT64_MAX ? 0x7fffffffLL : limit[side];
       if (is64) {
         DevBuf<unsigned char> &st = tmp[n_tmp++];
-        RFM_TRY(st.alloc((size_t)n_rows * 8));
-        RFM_TRY(upload(ctx, st.p, src, (size_t)n_rows * 8));
-        RFM_LAUNCH(ctx, narrow_ids_kernel<int64_t>, g, 256, 0, reinterpret_cast<const int64_t *>(st.p), dst, n_rows, lim,
+        RFM_TRY(st.alloc((size_t)nsel * 8));
+        RFM_TRY(upload(ctx, st.p, src + (size_t)rb * 8, (size_t)nsel * 8));
+        RFM_LAUNCH(ctx, narrow_ids_kernel<int64_t>, g, 256, 0, reinterpret_cast<const int64_t *>(st.p), dst, nsel, lim,
                    bad.p + side);
       } else {
-        RFM_TRY(upload(ctx, dst, src, (size_t)n_rows * 4));
-        RFM_LAUNCH(ctx, narrow_ids_kernel<int32_t>, g, 256, 0, dst, dst, n_rows, lim, bad.p + side);
+        RFM_TRY(upload(ctx, dst, src + (size_t)rb * 4, (size_t)nsel * 4));
+        RFM_LAUNCH(ctx, narrow_ids_kernel<int32_t>, g, 256, 0, dst, dst, nsel, lim, bad.p + side);
       }
     }
     // blocks
@@ -2209,20 +2217,22 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
                        reinterpret_cast<const double *>(st.p), reinterpret_cast<float *>(sg.val.p), tnz);
           }
         }
-      } else if (sg.kind == SEG_CTX && n_rows > 0 && !gen) {
+      } else if (sg.kind == SEG_CTX && nsel > 0 && !gen) {
+        const unsigned char *vsrc = reinterpret_cast<const unsigned char *>(k.values) + (size_t)rb * k.n_cols * 8;
+        unsigned char *cdst = r->f_ctx.p + (size_t)rb * n_ctx * es;
         if (dtype == RFM_F64 && n_ctx == k.n_cols) {      // the only context block, already in the record's layout
-          RFM_TRY(upload(ctx, r->f_ctx.p, k.values, (size_t)n_rows * n_ctx * 8));
+          RFM_TRY(upload(ctx, cdst, vsrc, (size_t)nsel * n_ctx * 8));
         } else {
           DevBuf<unsigned char> &st = tmp[n_tmp++];
-          RFM_TRY(st.alloc((size_t)n_rows * k.n_cols * 8));
-          RFM_TRY(upload(ctx, st.p, k.values, (size_t)n_rows * k.n_cols * 8));
-          const int gg = grid_for(ctx, ceil_div(n_rows * k.n_cols, 256), 8);
+          RFM_TRY(st.alloc((size_t)nsel * k.n_cols * 8));
+          RFM_TRY(upload(ctx, st.p, vsrc, (size_t)nsel * k.n_cols * 8));
+          const int gg = grid_for(ctx, ceil_div(nsel * k.n_cols, 256), 8);
           if (dtype == RFM_F64) {
-            RFM_LAUNCH(ctx, ctx_pack_kernel<double>, gg, 256, 0, reinterpret_cast<const double *>(st.p), n_rows,
-                       (int)k.n_cols, reinterpret_cast<double *>(r->f_ctx.p), (int)n_ctx, ctx0);
+            RFM_LAUNCH(ctx, ctx_pack_kernel<double>, gg, 256, 0, reinterpret_cast<const double *>(st.p), nsel,
+                       (int)k.n_cols, reinterpret_cast<double *>(cdst), (int)n_ctx, ctx0);
           } else {
-            RFM_LAUNCH(ctx, ctx_pack_kernel<float>, gg, 256, 0, reinterpret_cast<const double *>(st.p), n_rows,
-                       (int)k.n_cols, reinterpret_cast<float *>(r->f_ctx.p), (int)n_ctx, ctx0);
+            RFM_LAUNCH(ctx, ctx_pack_kernel<float>, gg, 256, 0, reinterpret_cast<const double *>(st.p), nsel,
+                       (int)k.n_cols, reinterpret_cast<float *>(cdst), (int)n_ctx, ctx0);
           }
         }
       }
@@ -2241,29 +2251,31 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
         RFM_TRY(rfm_synth_fill_rows(ctx, gen, n_rows, r->f_user.p, r->f_item.p, r->f_ctx.p, (int)n_ctx, r->yp.p,
                                     r->g_label.p, r->g_relevance.p, dtype));
       }
-    } else if (labels && n_rows > 0) {
+    } else if (labels && nsel > 0) {
       DevBuf<unsigned char> &ys = tmp[n_tmp++];
       DevBuf<unsigned char> &ps = tmp[n_tmp++];
-      RFM_TRY(ys.alloc((size_t)n_rows * label_bytes));
-      RFM_TRY(upload(ctx, ys.p, labels, (size_t)n_rows * label_bytes));
+      RFM_TRY(ys.alloc((size_t)nsel * label_bytes));
+      RFM_TRY(upload(ctx, ys.p, static_cast<const unsigned char *>(labels) + (size_t)rb * label_bytes,
+                     (size_t)nsel * label_bytes));
       if (item_pscores) {
         RFM_TRY(ps.alloc((size_t)n_item_pscores * 8));
         RFM_TRY(upload(ctx, ps.p, item_pscores, (size_t)n_item_pscores * 8));
       } else {
-        RFM_TRY(ps.alloc((size_t)n_rows * 8));
-        RFM_TRY(upload(ctx, ps.p, pscores, (size_t)n_rows * 8));
+        RFM_TRY(ps.alloc((size_t)nsel * 8));
+        RFM_TRY(upload(ctx, ps.p, pscores + rb, (size_t)nsel * 8));
       }
       const double *psd = reinterpret_cast<const double *>(ps.p);
-      const int32_t *item_ids = r->f_item.p;
+      const int32_t *item_ids = r->f_item.p + rb;
+      unsigned char *ypd = r->yp.p + (size_t)rb * es;
       const bool by_item = item_pscores != nullptr;
 #define RFM_TARGETS(T, Y)                                                                                              \
   do {                                                                                                                 \
     if (by_item) {                                                                                                     \
       RFM_LAUNCH(ctx, (targets_by_item_kernel<T, Y>), g, 256, 0, reinterpret_cast<const Y *>(ys.p), item_ids, psd,     \
-                 reinterpret_cast<T *>(r->yp.p), n_rows);                                                              \
+                 reinterpret_cast<T *>(ypd), nsel);                                                                    \
     } else {                                                                                                           \
       RFM_LAUNCH(ctx, (targets_any_kernel<T, Y>), g, 256, 0, reinterpret_cast<const Y *>(ys.p), psd,                   \
-                 reinterpret_cast<T *>(r->yp.p), n_rows);                                                              \
+                 reinterpret_cast<T *>(ypd), nsel);                                                                    \
     }                                                                                                                  \
   } while (0)
       if (dtype == RFM_F64) {
@@ -2279,7 +2291,7 @@ static int factored_create_impl(rfm_ctx *ctx, int64_t n_rows, const void *users,
     DevBuf<unsigned long long> nnz_dev;
     RFM_TRY(nnz_dev.alloc(1));
     RFM_CUDA(cudaMemsetAsync(nnz_dev.p, 0, 8, ctx->stream));
-    if (n_rows > 0) RFM_LAUNCH(ctx, fac_stats_kernel, g, 256, 0, r->fac_dev(), n_rows, nnz_dev.p, bad.p + 2);
+    if (n_rows > 0 && !partial) RFM_LAUNCH(ctx, fac_stats_kernel, g, 256, 0, r->fac_dev(), n_rows, nnz_dev.p, bad.p + 2);
     unsigned long long nnz_host = 0;
     int bad_host[4] = {0, 0, 0, 0};
     RFM_CUDA(cudaMemcpyAsync(&nnz_host, nnz_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2316,6 +2328,52 @@ int rfm_factored_create_item_pscores(rfm_ctx *ctx, int64_t n_rows, const void *u
   RFM_REQUIRE(item_pscores, "rfm_factored_create_item_pscores: item_pscores is NULL");
   return factored_create_impl(ctx, n_rows, users, users_is_int64, items, items_is_int64, blocks, n_blocks, labels,
                               label_bytes, nullptr, item_pscores, n_item_pscores, dtype, nullptr, out);
+}
+
+// Rows [row_begin, row_end) are copied from the host (the host pointers are those of the FULL arrays); the object has
+// the full shape. The caller fills the other rows on the device (rfm_rows_device_ptrs: NVLink broadcasts from the
+// ranks that uploaded them, rfm_b200.dist.sharded_factored_rows) and then calls rfm_factored_finalize.
+int rfm_factored_create_range(rfm_ctx *ctx, int64_t n_rows, const void *users, int32_t users_is_int64, const void *items,
+                              int32_t items_is_int64, const rfm_rows_block *blocks, int32_t n_blocks, const void *labels,
+                              int32_t label_bytes, const double *pscores, const double *item_pscores,
+                              int64_t n_item_pscores, int dtype, int64_t row_begin, int64_t row_end, rfm_csr **out) {
+  RFM_REQUIRE(ctx && out, "rfm_factored_create_range: NULL ctx/out");
+  RFM_REQUIRE(row_end >= 0, "rfm_factored_create_range: bad row range");
+  return factored_create_impl(ctx, n_rows, users, users_is_int64, items, items_is_int64, blocks, n_blocks, labels,
+                              label_bytes, pscores, item_pscores, n_item_pscores, dtype, nullptr, out, row_begin, row_end);
+}
+
+int rfm_rows_device_ptrs(rfm_csr *rows, void **user_dev, void **item_dev, void **ctx_dev, void **targets_dev) {
+  RFM_REQUIRE(rows && rows->factored, "rfm_rows_device_ptrs: not factored rows");
+  if (user_dev) *user_dev = rows->f_user.p;
+  if (item_dev) *item_dev = rows->f_item.p;
+  if (ctx_dev) *ctx_dev = rows->n_ctx ? rows->f_ctx.p : nullptr;
+  if (targets_dev) *targets_dev = rows->yp.p;
+  return RFM_OK;
+}
+
+// row statistics of factored rows whose arrays were completed on the device: total non-zeros, longest row
+int rfm_factored_finalize(rfm_csr *rows) {
+  RFM_REQUIRE(rows && rows->factored, "rfm_factored_finalize: not factored rows");
+  rfm_ctx *ctx = rows->ctx;
+  RFM_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<unsigned long long> nnz_dev;
+  DevBuf<int> mx;
+  RFM_TRY(nnz_dev.alloc(1));
+  RFM_TRY(mx.alloc(1));
+  RFM_CUDA(cudaMemsetAsync(nnz_dev.p, 0, 8, ctx->stream));
+  RFM_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), ctx->stream));
+  if (rows->n_rows > 0)
+    RFM_LAUNCH(ctx, fac_stats_kernel, grid_for(ctx, ceil_div(rows->n_rows, 256), 8), 256, 0, rows->fac_dev(), rows->n_rows,
+               nnz_dev.p, mx.p);
+  unsigned long long nnz_host = 0;
+  int mx_host = 0;
+  RFM_CUDA(cudaMemcpyAsync(&nnz_host, nnz_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaMemcpyAsync(&mx_host, mx.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RFM_CUDA(cudaStreamSynchronize(ctx->stream));
+  rows->nnz = (int64_t)nnz_host;
+  rows->max_row_len = mx_host;
+  return RFM_OK;
 }
 
 int rfm_factored_generate(rfm_ctx *ctx, int64_t n_rows, const rfm_click_model *model, const rfm_rows_block *blocks,

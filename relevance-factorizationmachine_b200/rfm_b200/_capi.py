@@ -47,6 +47,10 @@ _SIGNATURES = {
     "rfm_csr_device_ptrs": ([_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)], c_int),
     "rfm_factored_create": ([_P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int, POINTER(_P)],
                             c_int),
+    "rfm_factored_create_range": ([_P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, _P, _P, c_int64, c_int,
+                                   c_int64, c_int64, POINTER(_P)], c_int),
+    "rfm_rows_device_ptrs": ([_P, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P)], c_int),
+    "rfm_factored_finalize": ([_P], c_int),
     "rfm_factored_create_item_pscores": ([_P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, _P, c_int64,
                                           c_int, POINTER(_P)], c_int),
     "rfm_factored_generate": ([_P, c_int64, _P, _P, c_int32, c_int, POINTER(_P)], c_int),
@@ -123,7 +127,7 @@ class RfmError(RuntimeError):
     pass
 
 
-ABI_VERSION = 5        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
+ABI_VERSION = 6        # RFM_ABI_VERSION of include/rfm_b200.h this shim was written against
 
 
 def lib():

@@ -141,6 +141,46 @@ def sharded_csr_rows(ctx, X, labels, pscores, dtype: str, env: DistEnv):
     return rows
 
 
+def sharded_factored_rows(ctx, X, labels, pscores, dtype: str, env: DistEnv):
+    """Factored rows for a data-parallel fit with 1/G of the PCIe traffic per rank: rank r copies only rows
+    ``slice_bounds(N, G, r)`` of the per-interaction arrays from the host (``rfm_factored_create_range``; the small
+    per-entity tables go to every rank), then every slice of (user, item, context, target) is broadcast from its
+    owner into the same offsets on all ranks over NVLink. Byte-identical to ``FactoredRows(ctx, X, labels, pscores,
+    dtype)`` on every rank: eight ranks pulling the same 0.2 GB through the host's memory system was what bounded the
+    8-GPU fit end to end. All ranks must call this with the same data."""
+    from .factored import FactoredRows
+    if env.backend != "nccl":
+        raise RuntimeError("sharded_factored_rows needs the NCCL backend (the slices are exchanged on the device)")
+    torch = env.torch
+    n = X.shape[0]
+    begin, end = slice_bounds(n, env.world, env.rank)
+    err = None
+    try:
+        rows = FactoredRows(ctx, X, labels, pscores, dtype, row_range=(begin, end))
+    except Exception as e:                      # noqa: BLE001 -- every rank must learn about it before the collectives
+        rows, err = None, e
+    if env.max_over_ranks(0.0 if err is None else 1.0) > 0:
+        raise err if err is not None else RuntimeError("sharded_factored_rows: the upload failed on another rank")
+    ctx.synchronize()
+    user, item, cvals, targets = rows.device_ptrs()
+    es = 8 if dtype == "float64" else 4
+    arrays = [(user, 4), (item, 4)]
+    if cvals and rows.n_ctx:
+        arrays.append((cvals, rows.n_ctx * es))
+    if rows.has_targets:
+        arrays.append((targets, es))
+    dev = "cuda:%d" % env.device
+    for src in range(env.world):
+        b, e = slice_bounds(n, env.world, src)
+        for base, per_row in arrays:
+            if e > b:
+                t = torch.as_tensor(_DeviceArray(base + b * per_row, (e - b) * per_row, "|u1"), device=dev)
+                env.dist.broadcast(t, src=src)
+    torch.cuda.synchronize(env.device)
+    rows.finalize()
+    return rows
+
+
 class DataParallelFM:
     """The DP step, independent of where the arithmetic runs.
 

@@ -163,10 +163,14 @@ class FactoredRows(_capi._Handle):
     _destroy = "rfm_csr_destroy"
     factored = True
 
-    def __init__(self, ctx, X: FactoredFeatures, labels=None, pscores=None, dtype="float64"):
+    def __init__(self, ctx, X: FactoredFeatures, labels=None, pscores=None, dtype="float64", row_range=None):
+        """row_range=(begin, end): copy only those rows from the host (the object keeps the full shape; the caller fills
+        the rest on the device and calls ``finalize()``, see rfm_b200.dist.sharded_factored_rows)."""
         super().__init__()
         n_rows = X.shape[0]
         self.ctx, self.shape, self.dtype, self.n_rows = ctx, X.shape, dtype, n_rows
+        self.n_ctx = sum(b[1].shape[1] for b in X.blocks if b[0] == "ctx")
+        self.has_targets = labels is not None
         arr = (RowsBlock * len(X.blocks))()
         keep = []
         for slot, b in zip(arr, X.blocks):
@@ -200,6 +204,18 @@ class FactoredRows(_capi._Handle):
                 y, targets = _capi.integer_labels(lab, pscores.rows(X.items) if by_item else ps)
         common = (ctx.handle, n_rows, ptr(X.users), int(X.users.dtype == np.int64), ptr(X.items),
                   int(X.items.dtype == np.int64), arr, len(X.blocks), ptr(y), label_bytes)
+        if row_range is not None:
+            if targets is not None:
+                raise ValueError("a ranged upload takes integer labels")
+            begin, end = row_range
+            per_row, per_item = (None, ptr(ps)) if (by_item and y is not None) else (ptr(ps), None)
+            check(lib().rfm_factored_create_range(*common, per_row, per_item, ps.shape[0] if per_item is not None else 0,
+                                                  _capi.dtype_code(dtype), begin, end, byref(self.handle)))
+            frac = (end - begin) / max(n_rows, 1)
+            tables = sum(t.indptr.nbytes + t.indices.nbytes + t.data.nbytes for t in (b[2] for b in X.blocks if b[0] == "table"))
+            rows_bytes = X.nbytes - tables + ((y.nbytes + (0 if by_item else ps.nbytes)) if y is not None else 0)
+            self.h2d_bytes = int(tables + frac * rows_bytes + (ps.nbytes if (by_item and y is not None) else 0))
+            return
         if by_item and y is not None:
             check(lib().rfm_factored_create_item_pscores(*common, ptr(ps), ps.shape[0], _capi.dtype_code(dtype),
                                                          byref(self.handle)))
@@ -208,3 +224,12 @@ class FactoredRows(_capi._Handle):
         if targets is not None:
             check(lib().rfm_csr_set_targets(self.handle, ptr(targets)))
         self.h2d_bytes = X.nbytes + ((y.nbytes + ps.nbytes) if y is not None else 0)
+
+    def device_ptrs(self):
+        """(user, item, ctx or None, targets) device addresses."""
+        out = [c_void_p() for _ in range(4)]
+        check(lib().rfm_rows_device_ptrs(self.handle, *[byref(p) for p in out]))
+        return tuple(p.value for p in out)
+
+    def finalize(self):
+        check(lib().rfm_factored_finalize(self.handle))

@@ -180,6 +180,15 @@ class FactorizationMachines(PointwiseBaseRecommender):
     def _make_rows(self, X, labels, pscores):
         from .factored import FactoredFeatures, FactoredRows
         if isinstance(X, FactoredFeatures):     # user table + item table + (user, item, ctx) records: assembled on the device
+            env = self.distributed
+            lab = None if labels is None else np.asarray(labels)
+            if (env is not None and lab is not None and lab.dtype in (np.int8, np.int32, np.int64)
+                    and env.backend == "nccl" and env.world > 1
+                    and X.shape[0] >= int(os.environ.get("RFM_DP_UPLOAD_MIN_ROWS", "1000000"))
+                    and os.environ.get("RFM_DP_UPLOAD", "sharded") == "sharded"):
+                # data-parallel fit on a large train set: each rank uploads 1/G of the rows, NVLink carries the rest
+                from .dist import sharded_factored_rows
+                return sharded_factored_rows(self._context(), X, labels, pscores, self.dtype, env)
             return FactoredRows(self._context(), X, labels, pscores, self.dtype)
         if isinstance(X, _capi._Handle):        # rows that already live on the device (rfm_b200.clicks.GeneratedRows)
             if X.dtype != self.dtype:

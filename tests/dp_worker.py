@@ -126,6 +126,29 @@ def main():
     la, lb = ma.fit(kr.fm_train, kr.fm_val), mb.fit(fac(kr.fm_train), fac(kr.fm_val))
     assert la == lb
     np.testing.assert_array_equal(ma.V(), mb.V())
+    # sharded upload of factored rows (1/G of the per-interaction arrays per rank over PCIe, NVLink broadcasts for the
+    # rest) == the replicated upload, byte for byte; and a whole fit through it gives the same bits
+    from rfm_b200.factored import FactoredRows, PerItem
+    from rfm_b200.dist import sharded_factored_rows
+    ftr = fac(kr.fm_train)
+    for dtype in ("float64", "float32"):
+        for ps_arg in (ftr["pscores"], PerItem(kr.tables["item_pscore"])):
+            y8 = ftr["labels"].astype(np.int8)
+            full = FactoredRows(mb._context(), ftr["features"], y8, ps_arg, dtype)
+            part = sharded_factored_rows(mb._context(), ftr["features"], y8, ps_arg, dtype, env)
+            es = 8 if dtype == "float64" else 4
+            n_r = ftr["features"].shape[0]
+            for pa, pb, nbytes in zip(full.device_ptrs(), part.device_ptrs(), (n_r * 4, n_r * 4, n_r * es * full.n_ctx, n_r * es)):
+                if nbytes and pa and pb:
+                    ta = torch.as_tensor(_DeviceArray(pa, nbytes, "|u1"), device="cuda:%d" % local_rank)
+                    tb = torch.as_tensor(_DeviceArray(pb, nbytes, "|u1"), device="cuda:%d" % local_rank)
+                    assert torch.equal(ta, tb), "sharded factored upload differs from the replicated one (%s)" % dtype
+    os.environ["RFM_DP_UPLOAD_MIN_ROWS"] = "0"
+    me = FactorizationMachines(**kw2)
+    le = me.fit(fac(kr.fm_train), fac(kr.fm_val))
+    os.environ["RFM_DP_UPLOAD_MIN_ROWS"] = "1000000"
+    assert le == lb
+    np.testing.assert_array_equal(me.V(), mb.V())
     # the two-level step (csrc/two_level.cuh) feeding the same exchange: against the flat data-parallel fit and
     # against the single-GPU two-level fit (two associations of the same sums), ranks bit-identical
     mc = FactorizationMachines(**dict(kw2, step="two_level"))
